@@ -1,0 +1,147 @@
+"""1:1 port of the reference's test/test_mcts.jl and test/test_features.jl onto the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import go, features
+from oracle import mcts as M
+from oracle.go import BLACK, WHITE, GoPosition, PlayerMove
+from refboards import load_board, ALMOST_DONE_BOARD, EMPTY_ROW9 as EMPTY_ROW
+
+env = go.GoEnv(9)
+A = env.action_space
+f32 = np.float32
+kgs = lambda s: go.from_kgs(s, env)
+
+
+def send_two_return_one():                               # test_mcts.jl:34-43
+    return GoPosition(env, board=load_board(ALMOST_DONE_BOARD, env), n=75, komi=0.5, caps=(0, 0), ko=None,
+                      recent=[PlayerMove(BLACK, (0, 1)), PlayerMove(WHITE, (0, 8)), PlayerMove(BLACK, (1, 0))],
+                      to_play=WHITE)
+
+
+def test_action_flipping():                              # :45-59
+    rs = np.random.RandomState(1)
+    probs = (0.02 * np.ones(A) + rs.rand(A) * 0.001).astype(f32)
+    black_root = M.MCTSNode(GoPosition(env))
+    white_root = M.MCTSNode(GoPosition(env, to_play=WHITE))
+    M.incorporate_results(M.select_leaf(black_root), probs, 0, black_root)
+    M.incorporate_results(M.select_leaf(white_root), probs, 0, white_root)
+    bl = M.select_leaf(black_root)
+    wl = M.select_leaf(white_root)
+    assert bl.fmove == wl.fmove
+    # (the reference compares the two score vectors; after the selections above they are equal)
+    assert (M.child_action_score(black_root) == M.child_action_score(white_root)).all()
+
+
+def test_select_leaf():                                  # :61-70
+    flattened = go.to_flat(kgs("D9"), env)
+    probs = (0.02 * np.ones(A)).astype(f32)
+    probs[flattened] = 0.4
+    root = M.MCTSNode(send_two_return_one())
+    M.incorporate_results(M.select_leaf(root), probs, 0, root)
+    assert root.position.to_play == WHITE
+    assert M.select_leaf(root) is root.children[flattened]
+
+
+def test_backup_incorporate_results():                   # :72-114
+    probs = (0.02 * np.ones(A)).astype(f32)
+    root = M.MCTSNode(send_two_return_one())
+    M.incorporate_results(M.select_leaf(root), probs, 0, root)
+    leaf = M.select_leaf(root)
+    M.incorporate_results(leaf, probs, -1, root)
+    assert root.N == 2
+    assert root.Q == pytest.approx(-1 / 3, rel=1e-6)
+    assert root.child_N[leaf.fmove] == 1
+    assert leaf.N == 1
+    assert M.child_Q(root)[leaf.fmove] == -0.5
+    assert leaf.Q == pytest.approx(-0.5)
+    assert root.position.to_play == WHITE
+    leaf2 = M.select_leaf(root)
+    M.incorporate_results(leaf2, probs, -0.2, root)
+    assert root.N == 3
+    assert root.Q == pytest.approx(-0.3, rel=1e-6)
+    assert leaf.N == 2
+    assert leaf2.N == 1
+    assert leaf2.parent is leaf      # the reference's stated assumption (root -> leaf -> leaf2)
+    assert leaf.Q == pytest.approx(M.child_Q(root)[leaf.fmove])
+    assert leaf.Q == pytest.approx(-0.4, rel=1e-6)
+    assert M.child_Q(leaf)[leaf2.fmove] == pytest.approx(-0.6, rel=1e-6)
+    assert leaf2.Q == pytest.approx(-0.6, rel=1e-6)
+
+
+def test_do_not_explore_past_finish():                   # :116-127
+    probs = (0.02 * np.ones(A)).astype(f32)
+    root = M.MCTSNode(GoPosition(env))
+    M.incorporate_results(M.select_leaf(root), probs, 0, root)
+    first_pass = M.maybe_add_child(root, go.to_flat(None, env))
+    M.incorporate_results(first_pass, probs, 0, root)
+    second_pass = M.maybe_add_child(first_pass, go.to_flat(None, env))
+    with pytest.raises(AssertionError):
+        M.incorporate_results(second_pass, probs, 0, root)
+    node_to_explore = M.select_leaf(second_pass)
+    assert node_to_explore is second_pass
+
+
+def test_add_child():                                    # :129-135 (reference fmove 17 -> 0-based 16)
+    root = M.MCTSNode(GoPosition(env))
+    child = M.maybe_add_child(root, 16)
+    assert 16 in root.children
+    assert child.parent is root
+    assert child.fmove == 16
+
+
+def test_add_child_idempotency():                        # :137-144
+    root = M.MCTSNode(GoPosition(env))
+    child = M.maybe_add_child(root, 16)
+    current = dict(root.children)
+    child2 = M.maybe_add_child(root, 16)
+    assert child is child2
+    assert current == root.children
+
+
+def test_never_select_illegal_moves():                   # :146-167 (reference index 2 -> 0-based 1)
+    probs = (0.02 * np.ones(A)).astype(f32)
+    probs[1] = 0.99
+    root = M.MCTSNode(send_two_return_one())
+    M.incorporate_results(root, probs, 0, root)
+    root.N = 10000
+    root.child_N[go.all_legal_moves(root.position).astype(bool)] = 10000
+    leaf = M.select_leaf(root)
+    assert leaf.fmove != 1
+    for _ in range(10):
+        M.inject_noise(root)
+        leaf = M.select_leaf(root)
+        assert leaf.fmove != 1
+
+
+def test_dont_pick_unexpanded_child():                   # :169-183 (reference index 18 -> 17)
+    probs = (0.02 * np.ones(A)).astype(f32)
+    probs[17] = 0.999
+    root = M.MCTSNode(GoPosition(env))
+    M.incorporate_results(root, probs, 0, root)
+    leaf1 = M.select_leaf(root)
+    assert leaf1.fmove == 17
+    M.add_virtual_loss(leaf1, root)
+    leaf2 = M.select_leaf(root)
+    assert leaf1 is leaf2
+
+
+# ------------------------------------------------------------ test_features.jl
+def test_stone_features():                               # test_features.jl:39-79
+    pos = GoPosition(env)
+    for c in ((0, 0), (0, 1), (0, 2), (0, 3), (1, 1)):
+        go.play_move(pos, c, mutate=True)
+    f = features.stone_features(pos)
+    assert pos.to_play == WHITE
+    assert f.shape == (9, 9, 16)
+    lb = lambda two_rows: load_board(two_rows + EMPTY_ROW * 7, env)
+    assert (f[:, :, 0] == lb("...X.....\n.........\n")).all()
+    assert (f[:, :, 1] == lb("X.X......\n.X.......\n")).all()
+    assert (f[:, :, 2] == lb(".X.X.....\n.........\n")).all()
+    assert (f[:, :, 3] == lb("X.X......\n.........\n")).all()
+    assert (f[:, :, 4] == lb(".X.......\n.........\n")).all()
+    assert (f[:, :, 5] == lb("X.X......\n.........\n")).all()
+    for i in range(10, 16):
+        assert (f[:, :, i] == 0).all()
+    full = features.get_feats(pos)
+    assert full.shape == (9, 9, 17) and (full[:, :, 16] == -1).all()
