@@ -1,0 +1,999 @@
+// engine.cu -- host side of libagz: owns device memory, launches the warp-per-game kernels of ops.cuh and the
+// network kernels, and exports the C ABI of include/agz.h.  There is no CPU execution path in this library.
+// (The same file is compiled with -DAGZ_EMU by tests/emu to run the tree kernels on the fiber emulator; the
+// network and NCCL parts are compiled out there.)
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/agz.h"
+#include "devrt.h"
+#include "ops.cuh"
+#if AGZ_CUDA
+#include "nn.h"
+#include "replay.h"
+#endif
+
+using namespace agz;
+
+static thread_local char g_err[512] = "";
+
+struct agz_engine {
+  Cfg c;
+  View v;
+  agz_config cfg;
+  devrt::stream_t stream;
+  int smem_per_warp;
+  std::vector<void*> allocs;
+  char err[512];
+  int evaluator;
+  // evaluator buffers
+  float* d_dummy_pi;
+  float* d_dummy_v;
+  float* d_eval_pi;  // [n_games*pmax][A]
+  float* d_eval_v;
+  float* d_feats_f32;  // [n_games*pmax][17][N2]
+  // hook scratch
+  int* d_hook_result;
+  float* d_hook_probs;
+  agz_position *d_pos_in, *d_pos_out;
+  int8_t* d_hook_legal;
+  uint8_t* d_hook_libs;
+  float* d_hook_feats;
+  long long launches;
+  bool started;
+  unsigned long long ring_head;
+  int timing;
+  float phase_ms[4];
+  long long phase_launches[4];
+#if AGZ_CUDA
+  NNet* nn;
+  cudaEvent_t ev[5];
+  ReplayState* replay;
+#endif
+};
+
+static int fail(agz_engine* e, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  char buf[512];
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  snprintf(g_err, sizeof(g_err), "%s", buf);
+  if (e) snprintf(e->err, sizeof(e->err), "%s", buf);
+  return code;
+}
+
+#define DCHECK(e, call)                                                                                  \
+  do {                                                                                                   \
+    int rc__ = (call);                                                                                   \
+    if (rc__ != 0) return fail((e), AGZ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, devrt::last_error_string(rc__), __FILE__, __LINE__); \
+  } while (0)
+
+#define DISPATCH_KA(e, ...)                                      \
+  switch ((e)->c.KA) {                                           \
+    case 3: { constexpr int KA = 3; __VA_ARGS__; } break;        \
+    case 6: { constexpr int KA = 6; __VA_ARGS__; } break;        \
+    default: { constexpr int KA = 12; __VA_ARGS__; } break;      \
+  }
+
+template <class T>
+static int dalloc(agz_engine* e, T** p, size_t count) {
+  void* q = nullptr;
+  int rc = devrt::dmalloc(&q, count * sizeof(T));
+  if (rc) return rc;
+  e->allocs.push_back(q);
+  *p = (T*)q;
+  return devrt::dmemset(q, 0, count * sizeof(T), e->stream);
+}
+
+extern "C" int32_t agz_version(void) { return 100; }
+
+extern "C" const char* agz_last_error(agz_engine* e) { return e ? e->err : g_err; }
+
+extern "C" int32_t agz_config_default(agz_config* cfg, int32_t board_n) {
+  if (!cfg || board_n < 2 || board_n > AGZ_MAX_N) return fail(nullptr, AGZ_ERR_ARG, "board_n must be in [2, %d]", AGZ_MAX_N);
+  memset(cfg, 0, sizeof(*cfg));
+  const int N = board_n, A = N * N + 1;
+  cfg->board_n = N;
+  cfg->planes = 17;
+  cfg->filters = 256;
+  cfg->tower_height = 19;                                   // neural_net.jl:13
+  cfg->c_puct = 0.96;                                       // mcts.jl:11
+  cfg->noise_weight = 0.25;                                 // mcts.jl:13
+  cfg->noise_alpha = (double)(float)(0.03 * 361.0 / A);     // mcts.jl:22 (stored as Float32)
+  cfg->max_game_length = (N * N * 7) / 5;                   // mcts.jl:21
+  cfg->tau_threshold = (N * N / 12) / 2 * 2;                // mcts_play.jl:19
+  cfg->parallel_readouts = 8;                               // mcts_play.jl:73
+  cfg->max_parallel = 8;
+  cfg->komi = 7.5f;                                         // board.jl:297
+  cfg->resign_threshold = -0.9;                             // mcts_play.jl:18
+  cfg->resign_disable_frac = 0.05;                          // selfplay.jl:9
+  cfg->n_games = 1;
+  cfg->readouts = 800;                                      // mcts_play.jl:17
+  cfg->nodes_per_game = 0;
+  cfg->seed = 0;
+  cfg->device = 0;
+  cfg->world_size = 1;
+  cfg->rank = 0;
+  cfg->record_ring = 0;
+  cfg->evaluator = AGZ_EVAL_DUMMY;
+  cfg->inject_noise = 1;
+  return AGZ_OK;
+}
+
+extern "C" void agz_engine_destroy(agz_engine* e) {
+  if (!e) return;
+#if AGZ_CUDA
+  cudaSetDevice(e->cfg.device);
+  cudaStreamSynchronize(e->stream);
+  if (e->replay) replay_destroy(e->replay);
+  if (e->nn) nn_destroy(e->nn);
+  for (int i = 0; i < 5; ++i) cudaEventDestroy(e->ev[i]);
+#endif
+  for (void* p : e->allocs) devrt::dfree(p);
+#if AGZ_CUDA
+  cudaStreamDestroy(e->stream);
+#endif
+  delete e;
+}
+
+extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
+  if (!cfg || !out) return fail(nullptr, AGZ_ERR_ARG, "null argument");
+  *out = nullptr;
+  const int N = cfg->board_n;
+  if (N < 2 || N > AGZ_MAX_N) return fail(nullptr, AGZ_ERR_ARG, "board_n out of range");
+  if (cfg->n_games < 1) return fail(nullptr, AGZ_ERR_ARG, "n_games must be >= 1");
+  if (cfg->parallel_readouts < 1 || cfg->max_parallel < cfg->parallel_readouts) return fail(nullptr, AGZ_ERR_ARG, "need 1 <= parallel_readouts <= max_parallel");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(nullptr, AGZ_ERR_ARG, "bad rank/world_size");
+  if (cfg->max_game_length < 1 || cfg->max_game_length > 32000) return fail(nullptr, AGZ_ERR_ARG, "bad max_game_length");
+#if AGZ_CUDA
+  {
+    int ndev = 0;
+    cudaError_t rc = cudaGetDeviceCount(&ndev);
+    if (rc != cudaSuccess || ndev <= 0)
+      return fail(nullptr, AGZ_ERR_CUDA, "no CUDA device: libagz has no CPU fallback (%s)", cudaGetErrorString(rc));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, AGZ_ERR_ARG, "device %d of %d", cfg->device, ndev);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major != 10) return fail(nullptr, AGZ_ERR_CUDA, "device is sm_%d%d; libagz is built for sm_100a only", prop.major, prop.minor);
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, AGZ_ERR_CUDA, "cudaSetDevice failed");
+  }
+#endif
+  agz_engine* e = new agz_engine();
+  memset(&e->c, 0, sizeof(e->c));
+  memset(&e->v, 0, sizeof(e->v));
+  e->cfg = *cfg;
+  e->err[0] = 0;
+  e->launches = 0;
+  e->started = false;
+  e->ring_head = 0;
+  e->timing = 0;
+  memset(e->phase_ms, 0, sizeof(e->phase_ms));
+  memset(e->phase_launches, 0, sizeof(e->phase_launches));
+#if AGZ_CUDA
+  e->nn = nullptr;
+  e->replay = nullptr;
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return fail(nullptr, AGZ_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  for (int i = 0; i < 5; ++i) cudaEventCreate(&e->ev[i]);
+#else
+  e->stream = 0;
+#endif
+  Cfg& c = e->c;
+  c.N = N;
+  c.N2 = N * N;
+  c.A = N * N + 1;
+  int ka = (c.A + 31) / 32;
+  c.KA = ka <= 3 ? 3 : (ka <= 6 ? 6 : 12);
+  c.AS = c.KA * 32;
+  c.KB = (c.N2 + 31) / 32;
+  c.pmax = cfg->max_parallel;
+  c.parallel = cfg->parallel_readouts;
+  c.max_game_length = cfg->max_game_length;
+  c.maxd = cfg->max_game_length + 4;
+  c.tau_threshold = cfg->tau_threshold;
+  c.readouts = cfg->readouts;
+  c.n_games = cfg->n_games;
+  c.world = cfg->world_size;
+  c.rank = cfg->rank;
+  c.inject_noise = cfg->inject_noise;
+  c.komi = cfg->komi;
+  c.c_puct = cfg->c_puct;
+  c.noise_weight = cfg->noise_weight;
+  c.noise_alpha = cfg->noise_alpha;
+  c.resign_threshold = cfg->resign_threshold;
+  c.resign_disable_frac = cfg->resign_disable_frac;
+  c.seed = cfg->seed;
+  c.total_games = 0;
+  const int need = cfg->readouts + 2 * c.pmax + 4;
+  c.cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : std::max(256, 4 * need);
+  if (c.cap < need + 2) c.cap = need + 2;
+  c.ring_cap = cfg->record_ring > 0 ? cfg->record_ring : 2 * cfg->n_games;
+  e->smem_per_warp = (int)((c.KB * 32 * 7 + 15) / 16 * 16);
+  e->evaluator = cfg->evaluator;
+
+  const size_t G = c.n_games, nodes = G * c.cap, L = c.max_game_length + 2, rows = G * c.pmax;
+  View& v = e->v;
+  int rc = 0;
+  rc |= dalloc(e, &v.N, nodes * c.AS);
+  rc |= dalloc(e, &v.W, nodes * c.AS);
+  rc |= dalloc(e, &v.P, nodes * c.AS);
+  rc |= dalloc(e, &v.child, nodes * c.AS);
+  rc |= dalloc(e, &v.meta, nodes);
+  rc |= dalloc(e, &v.bits, nodes * 3 * c.KB);
+  rc |= dalloc(e, &v.gs, G);
+  rc |= dalloc(e, &v.hist, G * 7 * 2 * c.KB);
+  rc |= dalloc(e, &v.path, rows * c.maxd);
+  rc |= dalloc(e, &v.leaf_node, rows);
+  rc |= dalloc(e, &v.leaf_plen, rows);
+  rc |= dalloc(e, &v.remap, nodes);
+  rc |= dalloc(e, &v.rec_moves, G * L);
+  rc |= dalloc(e, &v.rec_q, G * L);
+  rc |= dalloc(e, &v.rec_pi, G * L * c.A);
+  rc |= dalloc(e, &v.rec_vis, G * L * c.A);
+  rc |= dalloc(e, &v.ring_hdr, (size_t)c.ring_cap);
+  rc |= dalloc(e, &v.ring_moves, (size_t)c.ring_cap * L);
+  rc |= dalloc(e, &v.ring_q, (size_t)c.ring_cap * L);
+  rc |= dalloc(e, &v.ring_pi, (size_t)c.ring_cap * L * c.A);
+  rc |= dalloc(e, &v.ring_vis, (size_t)c.ring_cap * L * c.A);
+  rc |= dalloc(e, &v.ctr, (size_t)CTR_COUNT);
+  rc |= dalloc(e, &e->d_dummy_pi, (size_t)c.A);
+  rc |= dalloc(e, &e->d_dummy_v, (size_t)1);
+  rc |= dalloc(e, &e->d_eval_pi, rows * c.A);
+  rc |= dalloc(e, &e->d_eval_v, rows);
+  rc |= dalloc(e, &e->d_hook_result, (size_t)8);
+  rc |= dalloc(e, &e->d_hook_probs, (size_t)c.A);
+  rc |= dalloc(e, &e->d_pos_in, (size_t)1);
+  rc |= dalloc(e, &e->d_pos_out, (size_t)1);
+  rc |= dalloc(e, &e->d_hook_legal, (size_t)AGZ_MAX_ACTIONS);
+  rc |= dalloc(e, &e->d_hook_libs, (size_t)AGZ_MAX_POINTS);
+  rc |= dalloc(e, &e->d_hook_feats, (size_t)17 * c.N2);
+  e->d_feats_f32 = nullptr;
+  if (rc) {
+    int code = fail(nullptr, AGZ_ERR_CUDA, "device allocation failed (n_games=%d, nodes_per_game=%d)", c.n_games, c.cap);
+    agz_engine_destroy(e);
+    return code;
+  }
+  // DummyNet default: uniform priors, value 0 (test_mcts_player.jl:14-18)
+  std::vector<float> pri((size_t)c.A, (float)(1.0 / c.A));
+  devrt::h2d(e->d_dummy_pi, pri.data(), pri.size() * sizeof(float), e->stream);
+#if AGZ_CUDA
+  {
+    NNShape s{N, cfg->planes, cfg->filters, cfg->tower_height};
+    char nerr[256] = "";
+    if (cfg->planes != 17) {
+      agz_engine_destroy(e);
+      return fail(nullptr, AGZ_ERR_ARG, "planes must be 17");
+    }
+    e->nn = nn_create(s, (int)rows, nerr, sizeof(nerr));
+    if (!e->nn) {
+      int code = fail(nullptr, AGZ_ERR_CUDA, "nn_create: %s", nerr);
+      agz_engine_destroy(e);
+      return code;
+    }
+    int r2 = dalloc(e, &e->d_feats_f32, rows * 17 * c.N2);
+    if (r2) {
+      agz_engine_destroy(e);
+      return fail(nullptr, AGZ_ERR_CUDA, "feature buffer allocation failed");
+    }
+  }
+#endif
+  int src = devrt::sync(e->stream);
+  if (src) {
+    agz_engine_destroy(e);
+    return fail(nullptr, AGZ_ERR_CUDA, "engine init failed: %s", devrt::last_error_string(src));
+  }
+  *out = e;
+  return AGZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------- evaluator
+static void bind_evaluator(agz_engine* e) {
+  if (e->evaluator == AGZ_EVAL_DUMMY) {
+    e->v.eval_pi = e->d_dummy_pi;
+    e->v.eval_v = e->d_dummy_v;
+    e->v.pi_stride = 0;
+    e->v.v_stride = 0;
+  } else {
+    e->v.eval_pi = e->d_eval_pi;
+    e->v.eval_v = e->d_eval_v;
+    e->v.pi_stride = e->c.A;
+    e->v.v_stride = 1;
+  }
+}
+
+extern "C" int32_t agz_set_dummy_evaluator(agz_engine* e, const float* priors, float value) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  std::vector<float> pri((size_t)e->c.A, (float)(1.0 / e->c.A));
+  if (priors) memcpy(pri.data(), priors, pri.size() * sizeof(float));
+  DCHECK(e, devrt::h2d(e->d_dummy_pi, pri.data(), pri.size() * sizeof(float), e->stream));
+  DCHECK(e, devrt::h2d(e->d_dummy_v, &value, sizeof(float), e->stream));
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_set_evaluator(agz_engine* e, int32_t evaluator) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  if (evaluator != AGZ_EVAL_DUMMY && evaluator != AGZ_EVAL_NN_TC && evaluator != AGZ_EVAL_NN_F32) return fail(e, AGZ_ERR_ARG, "unknown evaluator %d", evaluator);
+#if !AGZ_CUDA
+  if (evaluator != AGZ_EVAL_DUMMY) return fail(e, AGZ_ERR_ARG, "network evaluators need the CUDA build");
+#endif
+  e->evaluator = evaluator;
+  return AGZ_OK;
+}
+
+#if AGZ_CUDA
+// features + network for batch rows [row0, row0 + nrows): writes d_eval_pi / d_eval_v
+static int run_network(agz_engine* e, int row0, int nrows) {
+  char nerr[256] = "";
+  if (!nn_ready(e->nn)) {
+    if (nn_commit(e->nn, e->stream, nerr, sizeof(nerr))) return fail(e, AGZ_ERR_ARG, "network not ready: %s", nerr);
+  }
+  if (e->timing) cudaEventRecord(e->ev[1], e->stream);
+  if (e->evaluator == AGZ_EVAL_NN_F32) {
+    float* feats = e->d_feats_f32 + (size_t)row0 * 17 * e->c.N2;
+    DISPATCH_KA(e, {
+      LeafFeaturesF32Op<KA> op{e->c, e->v, e->d_feats_f32};
+      // the op indexes rows from 0; launch all rows up to row0+nrows and let it skip (cheap), or offset:
+      (void)feats;
+      DCHECK(e, devrt::launch_warps(op, row0 + nrows, e->smem_per_warp, e->stream));
+    });
+    e->launches += 1;
+    if (e->timing) cudaEventRecord(e->ev[2], e->stream);
+    int rc = nn_forward_f32(e->nn, e->d_feats_f32 + (size_t)row0 * 17 * e->c.N2, nrows, e->d_eval_pi + (size_t)row0 * e->c.A, e->d_eval_v + row0, e->stream);
+    if (rc) return fail(e, AGZ_ERR_CUDA, "nn_forward_f32: %s", cudaGetErrorString((cudaError_t)rc));
+    e->launches += nn_f32_launches_per_forward(e->nn);
+  } else {
+    int rc = engine_tc_features(e->c, e->v, e->nn, row0, nrows, e->smem_per_warp, e->stream);
+    if (rc) return fail(e, AGZ_ERR_CUDA, "tc feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    e->launches += 1;
+    if (e->timing) cudaEventRecord(e->ev[2], e->stream);
+    rc = nn_forward_tc(e->nn, row0 + nrows, e->d_eval_pi, e->d_eval_v, e->stream, nerr, sizeof(nerr));
+    if (rc) return fail(e, AGZ_ERR_CUDA, "nn_forward_tc: %s", nerr);
+    e->launches += nn_tc_launches_per_forward(e->nn);
+  }
+  return AGZ_OK;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------- self-play
+static int read_progress(agz_engine* e, agz_progress* p) {
+  unsigned long long ctr[CTR_COUNT];
+  DCHECK(e, devrt::d2h(ctr, e->v.ctr, sizeof(ctr), e->stream));
+  std::vector<GameState> gs((size_t)e->c.n_games);
+  DCHECK(e, devrt::d2h(gs.data(), e->v.gs, gs.size() * sizeof(GameState), e->stream));
+  p->moves_played = (int64_t)ctr[CTR_MOVES];
+  p->games_finished = (int64_t)ctr[CTR_FINISHED];
+  p->games_started = (int64_t)ctr[CTR_STARTED];
+  p->positions_evaluated = (int64_t)ctr[CTR_POSITIONS];
+  p->readouts = (int64_t)ctr[CTR_READOUTS];
+  p->path_nodes = (int64_t)ctr[CTR_PATHNODES];
+  p->games_live = 0;
+  p->error = 0;
+  for (auto& g : gs) {
+    if (g.phase == PH_SEED || g.phase == PH_SEARCH || g.phase == PH_WAIT_RING) p->games_live++;
+    if (g.err && !p->error) p->error = g.err;
+  }
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_selfplay_start(agz_engine* e, int64_t total_games) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  e->c.total_games = total_games;
+  DCHECK(e, devrt::dmemset(e->v.ctr, 0, sizeof(unsigned long long) * CTR_COUNT, e->stream));
+  e->ring_head = 0;
+  bind_evaluator(e);
+  DISPATCH_KA(e, {
+    StartOp<KA> op{e->c, e->v};
+    DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+  });
+  e->launches += 1;
+  e->started = true;
+  DCHECK(e, devrt::sync(e->stream));
+  return AGZ_OK;
+}
+
+static int one_round(agz_engine* e) {
+#if AGZ_CUDA
+  if (e->timing) cudaEventRecord(e->ev[0], e->stream);
+#endif
+  DISPATCH_KA(e, {
+    SelectOp<KA> op{e->c, e->v, -1, e->c.parallel};
+    DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+  });
+  e->launches += 1;
+#if AGZ_CUDA
+  if (e->evaluator != AGZ_EVAL_DUMMY) {
+    int rc = run_network(e, 0, e->c.n_games * e->c.pmax);
+    if (rc) return rc;
+  } else if (e->timing) {
+    cudaEventRecord(e->ev[1], e->stream);
+    cudaEventRecord(e->ev[2], e->stream);
+  }
+  if (e->timing) cudaEventRecord(e->ev[3], e->stream);
+#endif
+  DISPATCH_KA(e, {
+    IncorporateOp<KA> op{e->c, e->v, -1};
+    DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+  });
+  e->launches += 1;
+#if AGZ_CUDA
+  if (e->timing) {
+    cudaEventRecord(e->ev[4], e->stream);
+    cudaEventSynchronize(e->ev[4]);
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
+      e->phase_ms[i] += ms;
+    }
+    e->phase_launches[0] += 1;
+    e->phase_launches[1] += e->evaluator != AGZ_EVAL_DUMMY ? 1 : 0;
+    e->phase_launches[2] += e->evaluator == AGZ_EVAL_NN_TC ? nn_tc_launches_per_forward(e->nn) : (e->evaluator == AGZ_EVAL_NN_F32 ? nn_f32_launches_per_forward(e->nn) : 0);
+    e->phase_launches[3] += 1;
+  }
+#endif
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_selfplay_step(agz_engine* e, int32_t rounds, agz_progress* progress) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  if (!e->started) return fail(e, AGZ_ERR_ARG, "agz_selfplay_start has not been called");
+  bind_evaluator(e);
+  for (int r = 0; r < rounds; ++r) {
+    int rc = one_round(e);
+    if (rc) return rc;
+  }
+  if (progress) {
+    DCHECK(e, devrt::sync(e->stream));
+    return read_progress(e, progress);
+  }
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_selfplay_harvest(agz_engine* e, int32_t max_records, agz_game_header* headers, int16_t* moves, float* qs,
+                                        float* pis, float* visits, int32_t* n_out) {
+  if (!e || !n_out) return fail(e, AGZ_ERR_ARG, "null argument");
+  *n_out = 0;
+  DCHECK(e, devrt::sync(e->stream));
+  unsigned long long ctr[CTR_COUNT];
+  DCHECK(e, devrt::d2h(ctr, e->v.ctr, sizeof(ctr), e->stream));
+  const unsigned long long tail = ctr[CTR_RING_TAIL];
+  const size_t L = e->c.max_game_length + 2, A = e->c.A;
+  int n = 0;
+  while (e->ring_head < tail && n < max_records) {
+    const size_t rs = (size_t)(e->ring_head % (unsigned long long)e->c.ring_cap);
+    RingHeader hd;
+    DCHECK(e, devrt::d2h(&hd, e->v.ring_hdr + rs, sizeof(hd), e->stream));
+    if (headers) {
+      headers[n].game_id = hd.game_id; headers[n].n_moves = hd.n_moves; headers[n].result = hd.result;
+      headers[n].resigned = hd.resigned; headers[n].final_score = hd.final_score; headers[n].resign_threshold = hd.resign_threshold;
+    }
+    const size_t nm = (size_t)hd.n_moves;
+    if (moves) { memset(moves + n * L, 0, L * sizeof(int16_t)); if (nm) DCHECK(e, devrt::d2h(moves + n * L, e->v.ring_moves + rs * L, nm * sizeof(int16_t), e->stream)); }
+    if (qs) { memset(qs + n * L, 0, L * sizeof(float)); if (nm) DCHECK(e, devrt::d2h(qs + n * L, e->v.ring_q + rs * L, nm * sizeof(float), e->stream)); }
+    if (pis) { memset(pis + n * L * A, 0, L * A * sizeof(float)); if (nm) DCHECK(e, devrt::d2h(pis + n * L * A, e->v.ring_pi + rs * L * A, nm * A * sizeof(float), e->stream)); }
+    if (visits) { memset(visits + n * L * A, 0, L * A * sizeof(float)); if (nm) DCHECK(e, devrt::d2h(visits + n * L * A, e->v.ring_vis + rs * L * A, nm * A * sizeof(float), e->stream)); }
+    ++n;
+    ++e->ring_head;
+  }
+  unsigned long long h = e->ring_head;
+  DCHECK(e, devrt::h2d(e->v.ctr + CTR_RING_HEAD, &h, sizeof(h), e->stream));
+  *n_out = n;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_selfplay_run(agz_engine* e, int32_t total_games, agz_game_header* headers, int16_t* moves, float* qs, float* pis,
+                                    float* visits) {
+  if (!e || total_games < 1) return fail(e, AGZ_ERR_ARG, "bad argument");
+  int rc = agz_selfplay_start(e, total_games);
+  if (rc) return rc;
+  // games of this rank: ids rank, rank+world, ... < total
+  const int mine = (total_games - e->c.rank + e->c.world - 1) / e->c.world;
+  const size_t L = e->c.max_game_length + 2, A = e->c.A;
+  std::vector<agz_game_header> hd((size_t)std::max(1, e->c.ring_cap));
+  std::vector<int16_t> mv; std::vector<float> q, pi, vis;
+  if (moves) mv.resize(hd.size() * L);
+  if (qs) q.resize(hd.size() * L);
+  if (pis) pi.resize(hd.size() * L * A);
+  if (visits) vis.resize(hd.size() * L * A);
+  int got = 0;
+  const int chunk = 8;
+  long long guard = 0;
+  while (got < mine) {
+    agz_progress pr;
+    rc = agz_selfplay_step(e, chunk, &pr);
+    if (rc) return rc;
+    if (pr.error) return fail(e, pr.error, "a game stopped with error %d (6 = node arena full: raise nodes_per_game)", pr.error);
+    int n = 0;
+    rc = agz_selfplay_harvest(e, (int)hd.size(), hd.data(), moves ? mv.data() : nullptr, qs ? q.data() : nullptr, pis ? pi.data() : nullptr,
+                              visits ? vis.data() : nullptr, &n);
+    if (rc) return rc;
+    for (int i = 0; i < n; ++i) {
+      // records are returned in local game order: index = (game_id - rank) / world
+      long long idx = (hd[i].game_id - e->c.rank) / e->c.world;
+      if (idx < 0 || idx >= mine) continue;
+      if (headers) headers[idx] = hd[i];
+      if (moves) memcpy(moves + idx * L, mv.data() + i * L, L * sizeof(int16_t));
+      if (qs) memcpy(qs + idx * L, q.data() + i * L, L * sizeof(float));
+      if (pis) memcpy(pis + idx * L * A, pi.data() + i * L * A, L * A * sizeof(float));
+      if (visits) memcpy(visits + idx * L * A, vis.data() + i * L * A, L * A * sizeof(float));
+      ++got;
+    }
+    if (pr.games_live == 0 && got < mine && n == 0) return fail(e, AGZ_ERR_ASSERT, "self-play stalled with %d of %d games", got, mine);
+    if (++guard > 100000000LL) return fail(e, AGZ_ERR_ASSERT, "self-play did not terminate");
+  }
+  return AGZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ hooks
+static int run_hook(agz_engine* e, HookParams& h, int* ival, float* fval) {
+  h.result = e->d_hook_result;
+  bind_evaluator(e);
+  DISPATCH_KA(e, {
+    HookOp<KA> op{e->c, e->v, h};
+    DCHECK(e, devrt::launch_warps(op, 1, e->smem_per_warp, e->stream));
+  });
+  e->launches += 1;
+  int res[4];
+  DCHECK(e, devrt::d2h(res, e->d_hook_result, sizeof(res), e->stream));
+  if (ival) *ival = res[1];
+  if (fval) memcpy(fval, &res[3], sizeof(float));
+  if (res[0] == E_ILLEGAL) return fail(e, AGZ_ERR_ILLEGAL_MOVE, "illegal move");
+  if (res[0] == E_ASSERT) return fail(e, AGZ_ERR_ASSERT, "assertion failed on device");
+  if (res[0] == E_CAPACITY) return fail(e, AGZ_ERR_CAPACITY, "node arena full");
+  if (res[0]) return fail(e, AGZ_ERR_ASSERT, "device status %d", res[0]);
+  return AGZ_OK;
+}
+
+static int check_slot(agz_engine* e, int slot) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  if (slot < 0 || slot >= e->c.n_games) return fail(e, AGZ_ERR_ARG, "slot %d out of range", slot);
+  return AGZ_OK;
+}
+
+static int check_node(agz_engine* e, int slot, int node) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  GameState gs;
+  DCHECK(e, devrt::d2h(&gs, e->v.gs + slot, sizeof(gs), e->stream));
+  if (node < 0 || node >= gs.count) return fail(e, AGZ_ERR_ARG, "node %d out of range (count %d)", node, gs.count);
+  return AGZ_OK;
+}
+
+static HookParams hp(int kind, int slot) {
+  HookParams h;
+  memset(&h, 0, sizeof(h));
+  h.kind = kind;
+  h.slot = slot;
+  h.node = -1;
+  return h;
+}
+
+extern "C" int32_t agz_tree_init(agz_engine* e, int32_t slot, const agz_position* pos, int64_t game_id) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  HookParams h = hp(HK_INIT, slot);
+  h.game_id = game_id;
+  if (pos) {
+    if (pos->to_play != 1 && pos->to_play != -1) return fail(e, AGZ_ERR_ARG, "to_play must be +-1");
+    DCHECK(e, devrt::h2d(e->d_pos_in, pos, sizeof(*pos), e->stream));
+    h.pos_in = e->d_pos_in;
+  }
+  return run_hook(e, h, nullptr, nullptr);
+}
+
+extern "C" int32_t agz_tree_select_leaf(agz_engine* e, int32_t slot, int32_t from_node, int32_t* leaf) {
+  int rc = from_node >= 0 ? check_node(e, slot, from_node) : check_slot(e, slot);
+  if (rc) return rc;
+  HookParams h = hp(HK_SELECT, slot);
+  h.node = from_node;
+  int iv = -1;
+  rc = run_hook(e, h, &iv, nullptr);
+  if (leaf) *leaf = iv;
+  return rc;
+}
+
+static int node_hook(agz_engine* e, int kind, int slot, int node, const float* probs, float value) {
+  int rc = check_node(e, slot, node);
+  if (rc) return rc;
+  HookParams h = hp(kind, slot);
+  h.node = node;
+  h.value = value;
+  if (probs) {
+    DCHECK(e, devrt::h2d(e->d_hook_probs, probs, sizeof(float) * e->c.A, e->stream));
+    h.probs = e->d_hook_probs;
+  }
+  return run_hook(e, h, nullptr, nullptr);
+}
+
+extern "C" int32_t agz_tree_incorporate(agz_engine* e, int32_t slot, int32_t node, const float* probs, float value) {
+  if (!probs) return fail(e, AGZ_ERR_ARG, "probs is null");
+  return node_hook(e, HK_INCORPORATE, slot, node, probs, value);
+}
+extern "C" int32_t agz_tree_backup_value(agz_engine* e, int32_t slot, int32_t node, float value) { return node_hook(e, HK_BACKUP, slot, node, nullptr, value); }
+extern "C" int32_t agz_tree_add_virtual_loss(agz_engine* e, int32_t slot, int32_t node) { return node_hook(e, HK_VLOSS_ADD, slot, node, nullptr, 0.f); }
+extern "C" int32_t agz_tree_revert_virtual_loss(agz_engine* e, int32_t slot, int32_t node) { return node_hook(e, HK_VLOSS_REVERT, slot, node, nullptr, 0.f); }
+
+extern "C" int32_t agz_tree_maybe_add_child(agz_engine* e, int32_t slot, int32_t node, int32_t fmove, int32_t* child) {
+  int rc = check_node(e, slot, node);
+  if (rc) return rc;
+  if (fmove < 0 || fmove >= e->c.A) return fail(e, AGZ_ERR_ARG, "move out of range");
+  HookParams h = hp(HK_ADD_CHILD, slot);
+  h.node = node;
+  h.fmove = fmove;
+  int iv = -1;
+  rc = run_hook(e, h, &iv, nullptr);
+  if (child) *child = iv;
+  return rc;
+}
+
+extern "C" int32_t agz_tree_search(agz_engine* e, int32_t slot, int32_t parallel_readouts, int32_t* n_leaves) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  if (parallel_readouts < 1 || parallel_readouts > e->c.pmax) return fail(e, AGZ_ERR_ARG, "parallel_readouts must be in [1, max_parallel=%d]", e->c.pmax);
+  bind_evaluator(e);
+  DISPATCH_KA(e, {
+    SelectOp<KA> op{e->c, e->v, slot, parallel_readouts};
+    DCHECK(e, devrt::launch_warps(op, 1, e->smem_per_warp, e->stream));
+  });
+  e->launches += 1;
+  GameState gs;
+  DCHECK(e, devrt::d2h(&gs, e->v.gs + slot, sizeof(gs), e->stream));
+  if (n_leaves) *n_leaves = gs.nleaf;
+  if (gs.err) return fail(e, gs.err == E_CAPACITY ? AGZ_ERR_CAPACITY : AGZ_ERR_ASSERT, "select failed with device status %d", gs.err);
+#if AGZ_CUDA
+  if (e->evaluator != AGZ_EVAL_DUMMY && gs.nleaf > 0) {
+    rc = run_network(e, slot * e->c.pmax, gs.nleaf);
+    if (rc) return rc;
+  }
+#endif
+  DISPATCH_KA(e, {
+    IncorporateOp<KA> op{e->c, e->v, slot};
+    DCHECK(e, devrt::launch_warps(op, 1, e->smem_per_warp, e->stream));
+  });
+  e->launches += 1;
+  DCHECK(e, devrt::d2h(&gs, e->v.gs + slot, sizeof(gs), e->stream));
+  if (gs.err) return fail(e, AGZ_ERR_ASSERT, "incorporate failed with device status %d", gs.err);
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_tree_inject_noise(agz_engine* e, int32_t slot) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  HookParams h = hp(HK_NOISE, slot);
+  return run_hook(e, h, nullptr, nullptr);
+}
+
+extern "C" int32_t agz_tree_pick_move(agz_engine* e, int32_t slot, int32_t* fmove) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  HookParams h = hp(HK_PICK, slot);
+  int iv = -1;
+  rc = run_hook(e, h, &iv, nullptr);
+  if (fmove) *fmove = iv;
+  return rc;
+}
+
+extern "C" int32_t agz_tree_play_move(agz_engine* e, int32_t slot, int32_t fmove) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  if (fmove < 0 || fmove >= e->c.A) return fail(e, AGZ_ERR_ARG, "move out of range");
+  HookParams h = hp(HK_PLAY, slot);
+  h.fmove = fmove;
+  return run_hook(e, h, nullptr, nullptr);
+}
+
+extern "C" int32_t agz_tree_should_resign(agz_engine* e, int32_t slot, double threshold, int32_t* yes) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  HookParams h = hp(HK_RESIGN, slot);
+  h.thr = threshold;
+  int iv = 0;
+  rc = run_hook(e, h, &iv, nullptr);
+  if (yes) *yes = iv;
+  return rc;
+}
+
+extern "C" int32_t agz_tree_root(agz_engine* e, int32_t slot, int32_t* root, int32_t* node_count) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  GameState gs;
+  DCHECK(e, devrt::d2h(&gs, e->v.gs + slot, sizeof(gs), e->stream));
+  if (root) *root = gs.root;
+  if (node_count) *node_count = gs.count;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_tree_pending_vlosses(agz_engine* e, int32_t slot, int32_t* pending) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  GameState gs;
+  DCHECK(e, devrt::d2h(&gs, e->v.gs + slot, sizeof(gs), e->stream));
+  if (pending) *pending = gs.vloss_balance;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_tree_read_node(agz_engine* e, int32_t slot, int32_t node, agz_node_view* out) {
+  int rc = check_node(e, slot, node);
+  if (rc) return rc;
+  if (!out) return fail(e, AGZ_ERR_ARG, "null out");
+  memset(out, 0, sizeof(*out));
+  const Cfg& c = e->c;
+  const size_t gi = (size_t)slot * c.cap + node, r = gi * c.AS;
+  NodeMeta m;
+  GameState gs;
+  DCHECK(e, devrt::d2h(&m, e->v.meta + gi, sizeof(m), e->stream));
+  DCHECK(e, devrt::d2h(&gs, e->v.gs + slot, sizeof(gs), e->stream));
+  DCHECK(e, devrt::d2h(out->child_N, e->v.N + r, sizeof(float) * c.A, e->stream));
+  DCHECK(e, devrt::d2h(out->child_W, e->v.W + r, sizeof(float) * c.A, e->stream));
+  DCHECK(e, devrt::d2h(out->child_prior, e->v.P + r, sizeof(float) * c.A, e->stream));
+  DCHECK(e, devrt::d2h(out->children, e->v.child + r, sizeof(int32_t) * c.A, e->stream));
+  std::vector<uint32_t> bits((size_t)3 * c.KB);
+  DCHECK(e, devrt::d2h(bits.data(), e->v.bits + gi * 3 * c.KB, bits.size() * sizeof(uint32_t), e->stream));
+  out->parent = m.parent; out->fmove = m.fmove; out->to_play = m.to_play; out->n = m.n; out->ko = m.ko;
+  out->is_expanded = (m.flags & F_EXPANDED) ? 1 : 0;
+  out->done = (m.flags & F_DONE) ? 1 : 0;
+  out->last_move_pass = (m.flags & F_LASTPASS) ? 1 : 0;
+  for (int p = 0; p < c.N2; ++p) {
+    int b = (bits[p >> 5] >> (p & 31)) & 1, w = (bits[c.KB + (p >> 5)] >> (p & 31)) & 1;
+    out->board[p] = (int8_t)(b - w);
+    out->legal[p] = (int8_t)((bits[2 * c.KB + (p >> 5)] >> (p & 31)) & 1);
+  }
+  out->legal[c.N2] = 1;
+  if (m.parent < 0) { out->N = gs.root_N; out->W = gs.root_W; }
+  else {
+    const size_t pr = ((size_t)slot * c.cap + m.parent) * c.AS + m.fmove;
+    DCHECK(e, devrt::d2h(&out->N, e->v.N + pr, sizeof(float), e->stream));
+    DCHECK(e, devrt::d2h(&out->W, e->v.W + pr, sizeof(float), e->stream));
+  }
+  // child_action_score (mcts.jl:86-92) with the reference's float widths; host doubles, no contraction
+  volatile float one_plus = 1.0f + out->N;
+  volatile double cu = c.c_puct * (double)sqrtf(one_plus);
+  for (int a = 0; a < c.A; ++a) {
+    volatile float den = 1.0f + out->child_N[a];
+    volatile float q = out->child_W[a] / den;
+    volatile float qt = q * (float)m.to_play;
+    volatile double u1 = cu * (double)out->child_prior[a];
+    volatile double u = u1 / (double)den;
+    out->action_score[a] = (double)qt + u;
+  }
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_tree_set_stats(agz_engine* e, int32_t slot, int32_t node, const float* self_N, const float* child_N, const int32_t* n_override) {
+  int rc = check_node(e, slot, node);
+  if (rc) return rc;
+  const Cfg& c = e->c;
+  const size_t gi = (size_t)slot * c.cap + node;
+  NodeMeta m;
+  DCHECK(e, devrt::d2h(&m, e->v.meta + gi, sizeof(m), e->stream));
+  if (self_N) {
+    if (m.parent < 0) {
+      GameState gs;
+      DCHECK(e, devrt::d2h(&gs, e->v.gs + slot, sizeof(gs), e->stream));
+      gs.root_N = *self_N;
+      DCHECK(e, devrt::h2d(e->v.gs + slot, &gs, sizeof(gs), e->stream));
+    } else {
+      DCHECK(e, devrt::h2d(e->v.N + ((size_t)slot * c.cap + m.parent) * c.AS + m.fmove, self_N, sizeof(float), e->stream));
+    }
+  }
+  if (child_N) DCHECK(e, devrt::h2d(e->v.N + gi * c.AS, child_N, sizeof(float) * c.A, e->stream));
+  if (n_override) {
+    m.n = (int16_t)*n_override;
+    DCHECK(e, devrt::h2d(e->v.meta + gi, &m, sizeof(m), e->stream));
+  }
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_tree_read_record(agz_engine* e, int32_t slot, int32_t* n_moves, int16_t* moves, float* qs, float* pis) {
+  int rc = check_slot(e, slot);
+  if (rc) return rc;
+  GameState gs;
+  DCHECK(e, devrt::d2h(&gs, e->v.gs + slot, sizeof(gs), e->stream));
+  const size_t L = e->c.max_game_length + 2, A = e->c.A, nm = (size_t)gs.n_moves;
+  if (n_moves) *n_moves = gs.n_moves;
+  if (nm && moves) DCHECK(e, devrt::d2h(moves, e->v.rec_moves + slot * L, nm * sizeof(int16_t), e->stream));
+  if (nm && qs) DCHECK(e, devrt::d2h(qs, e->v.rec_q + slot * L, nm * sizeof(float), e->stream));
+  if (nm && pis) DCHECK(e, devrt::d2h(pis, e->v.rec_pi + slot * L * A, nm * A * sizeof(float), e->stream));
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_tree_node_features(agz_engine* e, int32_t slot, int32_t node, float* out) {
+  int rc = check_node(e, slot, node);
+  if (rc) return rc;
+  HookParams h = hp(HK_FEATURES, slot);
+  h.node = node;
+  h.f_out = e->d_hook_feats;
+  rc = run_hook(e, h, nullptr, nullptr);
+  if (rc) return rc;
+  DCHECK(e, devrt::d2h(out, e->d_hook_feats, sizeof(float) * 17 * e->c.N2, e->stream));
+  return AGZ_OK;
+}
+
+// ---- position hooks
+static int pos_hook(agz_engine* e, int kind, const agz_position* in, int fmove, int* ival, float* fval) {
+  if (!e || !in) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (in->to_play != 1 && in->to_play != -1) return fail(e, AGZ_ERR_ARG, "to_play must be +-1");
+  DCHECK(e, devrt::h2d(e->d_pos_in, in, sizeof(*in), e->stream));
+  HookParams h = hp(kind, 0);
+  h.fmove = fmove;
+  h.pos_in = e->d_pos_in;
+  h.pos_out = e->d_pos_out;
+  h.legal_out = e->d_hook_legal;
+  h.libs_out = e->d_hook_libs;
+  return run_hook(e, h, ival, fval);
+}
+
+extern "C" int32_t agz_pos_play_move(agz_engine* e, const agz_position* in, int32_t fmove, agz_position* out) {
+  if (!e || !out) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (fmove < 0 || fmove >= e->c.A) return fail(e, AGZ_ERR_ARG, "move out of range");
+  // note: the reference's `@assert !new_pos.done` (board.jl:462) is vacuous (deepcopy resets `done`, board.jl:304),
+  // and test_go.jl:490-491 plays on after two passes, so a done position is accepted here too.
+  DCHECK(e, devrt::dmemset(e->d_pos_out, 0, sizeof(agz_position), e->stream));
+  int rc = pos_hook(e, HK_POS_PLAY, in, fmove, nullptr, nullptr);
+  if (rc) return rc;
+  DCHECK(e, devrt::d2h(out, e->d_pos_out, sizeof(*out), e->stream));
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_pos_legal_moves(agz_engine* e, const agz_position* in, int8_t* legal) {
+  int rc = pos_hook(e, HK_POS_LEGAL, in, 0, nullptr, nullptr);
+  if (rc) return rc;
+  DCHECK(e, devrt::d2h(legal, e->d_hook_legal, (size_t)e->c.A, e->stream));
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_pos_score(agz_engine* e, const agz_position* in, float* score) {
+  float f = 0.f;
+  int rc = pos_hook(e, HK_POS_SCORE, in, 0, nullptr, &f);
+  if (rc) return rc;
+  if (score) *score = f;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_pos_liberties(agz_engine* e, const agz_position* in, uint8_t* liberty_cache) {
+  int rc = pos_hook(e, HK_POS_LIBS, in, 0, nullptr, nullptr);
+  if (rc) return rc;
+  DCHECK(e, devrt::d2h(liberty_cache, e->d_hook_libs, (size_t)e->c.N2, e->stream));
+  return AGZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------- introspection
+extern "C" int32_t agz_kernel_launches(agz_engine* e, int64_t* n) {
+  if (!e || !n) return fail(e, AGZ_ERR_ARG, "null argument");
+  *n = e->launches;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_set_timing(agz_engine* e, int32_t enabled) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  e->timing = enabled;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_phase_times(agz_engine* e, float ms[4], int64_t launches[4], int32_t reset) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  for (int i = 0; i < 4; ++i) {
+    if (ms) ms[i] = e->phase_ms[i];
+    if (launches) launches[i] = e->phase_launches[i];
+  }
+  if (reset) {
+    memset(e->phase_ms, 0, sizeof(e->phase_ms));
+    memset(e->phase_launches, 0, sizeof(e->phase_launches));
+  }
+  return AGZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------- network ABI
+#if AGZ_CUDA
+extern "C" size_t agz_net_param_count(agz_engine* e, int32_t chain) { return e ? nn_param_count(e->nn, chain) : 0; }
+extern "C" size_t agz_net_bn_count(agz_engine* e, int32_t chain) { return e ? nn_bn_count(e->nn, chain) : 0; }
+
+extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t chain, const float* flat, size_t n) {
+  if (!e || !flat) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
+  if (n != nn_param_count(e->nn, chain)) return fail(e, AGZ_ERR_ARG, "chain %d expects %zu parameters, got %zu", chain, nn_param_count(e->nn, chain), n);
+  cudaSetDevice(e->cfg.device);
+  return nn_set_params(e->nn, chain, flat, n) ? fail(e, AGZ_ERR_ARG, "nn_set_params failed") : AGZ_OK;
+}
+
+extern "C" int32_t agz_net_set_bn_stats(agz_engine* e, int32_t chain, const float* mu, const float* sigma, size_t n_each, int32_t bn_mode) {
+  if (!e || !mu || !sigma) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
+  if (n_each != nn_bn_count(e->nn, chain)) return fail(e, AGZ_ERR_ARG, "chain %d has %zu BatchNorm channels, got %zu", chain, nn_bn_count(e->nn, chain), n_each);
+  if (bn_mode != AGZ_BN_VAR_EPS && bn_mode != AGZ_BN_STD) return fail(e, AGZ_ERR_ARG, "bad bn_mode");
+  return nn_set_bn(e->nn, chain, mu, sigma, n_each, bn_mode) ? fail(e, AGZ_ERR_ARG, "nn_set_bn failed") : AGZ_OK;
+}
+
+extern "C" int32_t agz_features(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, int32_t B, float* out) {
+  if (!e || !boards_hist || !to_play || !out || B < 1) return fail(e, AGZ_ERR_ARG, "bad argument");
+  cudaSetDevice(e->cfg.device);
+  int rc = engine_host_features(e->c, boards_hist, to_play, B, out, nullptr, e->stream);
+  if (rc) return fail(e, AGZ_ERR_CUDA, "feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
+  e->launches += 1;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_net_forward(agz_engine* e, int32_t evaluator, const int8_t* boards_hist, const int8_t* to_play, int32_t B, float* pi, float* v) {
+  if (!e || !boards_hist || !to_play || !pi || !v || B < 1) return fail(e, AGZ_ERR_ARG, "bad argument");
+  if (evaluator != AGZ_EVAL_NN_TC && evaluator != AGZ_EVAL_NN_F32) return fail(e, AGZ_ERR_ARG, "evaluator must be a network");
+  cudaSetDevice(e->cfg.device);
+  char nerr[256] = "";
+  if (!nn_ready(e->nn) && nn_commit(e->nn, e->stream, nerr, sizeof(nerr))) return fail(e, AGZ_ERR_ARG, "network not ready: %s", nerr);
+  const int maxb = e->c.n_games * e->c.pmax;
+  const size_t A = e->c.A, N2 = e->c.N2;
+  for (int b0 = 0; b0 < B; b0 += maxb) {
+    const int nb = std::min(maxb, B - b0);
+    int rc;
+    if (evaluator == AGZ_EVAL_NN_F32) {
+      rc = engine_host_features(e->c, boards_hist + (size_t)b0 * 8 * N2, to_play + b0, nb, nullptr, e->d_feats_f32, e->stream);
+      if (rc) return fail(e, AGZ_ERR_CUDA, "feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
+      rc = nn_forward_f32(e->nn, e->d_feats_f32, nb, e->d_eval_pi, e->d_eval_v, e->stream);
+      if (rc) return fail(e, AGZ_ERR_CUDA, "nn_forward_f32: %s", cudaGetErrorString((cudaError_t)rc));
+      e->launches += 1 + nn_f32_launches_per_forward(e->nn);
+    } else {
+      rc = engine_host_features_tc(e->c, e->nn, boards_hist + (size_t)b0 * 8 * N2, to_play + b0, nb, e->stream);
+      if (rc) return fail(e, AGZ_ERR_CUDA, "tc feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
+      rc = nn_forward_tc(e->nn, nb, e->d_eval_pi, e->d_eval_v, e->stream, nerr, sizeof(nerr));
+      if (rc) return fail(e, AGZ_ERR_CUDA, "nn_forward_tc: %s", nerr);
+      e->launches += 1 + nn_tc_launches_per_forward(e->nn);
+    }
+    DCHECK(e, devrt::d2h(pi + (size_t)b0 * A, e->d_eval_pi, sizeof(float) * A * nb, e->stream));
+    DCHECK(e, devrt::d2h(v + b0, e->d_eval_v, sizeof(float) * nb, e->stream));
+  }
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_nccl_unique_id(uint8_t id_out[128]) { return replay_unique_id(id_out) ? fail(nullptr, AGZ_ERR_NCCL, "ncclGetUniqueId failed") : AGZ_OK; }
+
+extern "C" int32_t agz_nccl_init(agz_engine* e, const uint8_t id[128]) {
+  if (!e || !id) return fail(e, AGZ_ERR_ARG, "null argument");
+  cudaSetDevice(e->cfg.device);
+  char rerr[256] = "";
+  if (!e->replay) e->replay = replay_create(e->c, rerr, sizeof(rerr));
+  if (!e->replay) return fail(e, AGZ_ERR_CUDA, "replay_create: %s", rerr);
+  if (replay_nccl_init(e->replay, id, e->c.world, e->c.rank, rerr, sizeof(rerr))) return fail(e, AGZ_ERR_NCCL, "%s", rerr);
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_replay_gather(agz_engine* e, int64_t* n_tuples_total) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  cudaSetDevice(e->cfg.device);
+  char rerr[256] = "";
+  if (!e->replay) e->replay = replay_create(e->c, rerr, sizeof(rerr));
+  if (!e->replay) return fail(e, AGZ_ERR_CUDA, "replay_create: %s", rerr);
+  long long nl = 0;
+  int rc = replay_gather(e->replay, e->c, e->v, e->smem_per_warp, e->stream, n_tuples_total, &nl, rerr, sizeof(rerr));
+  e->launches += nl;
+  if (rc) return fail(e, rc, "%s", rerr);
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_replay_read(agz_engine* e, int64_t first, int32_t count, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs) {
+  if (!e || !e->replay) return fail(e, AGZ_ERR_ARG, "no replay ring (call agz_replay_gather first)");
+  cudaSetDevice(e->cfg.device);
+  char rerr[256] = "";
+  int rc = replay_read(e->replay, e->c, first, count, boards, to_play, pis, zs, e->stream, rerr, sizeof(rerr));
+  if (rc) return fail(e, rc, "%s", rerr);
+  return AGZ_OK;
+}
+#else
+extern "C" size_t agz_net_param_count(agz_engine*, int32_t) { return 0; }
+extern "C" size_t agz_net_bn_count(agz_engine*, int32_t) { return 0; }
+extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t, const float*, size_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
+extern "C" int32_t agz_net_set_bn_stats(agz_engine* e, int32_t, const float*, const float*, size_t, int32_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
+extern "C" int32_t agz_features(agz_engine* e, const int8_t*, const int8_t*, int32_t, float*) { return fail(e, AGZ_ERR_CUDA, "not in the emulation build"); }
+extern "C" int32_t agz_net_forward(agz_engine* e, int32_t, const int8_t*, const int8_t*, int32_t, float*, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
+extern "C" int32_t agz_nccl_unique_id(uint8_t*) { return AGZ_ERR_NCCL; }
+extern "C" int32_t agz_nccl_init(agz_engine* e, const uint8_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
+extern "C" int32_t agz_replay_gather(agz_engine* e, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
+extern "C" int32_t agz_replay_read(agz_engine* e, int64_t, int32_t, int8_t*, int8_t*, float*, int8_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
+#endif

@@ -1,0 +1,53 @@
+// nn.h -- policy/value network of the engine (src/neural_net.jl:13-33,57-68; src/resnet.jl:2-32).
+// Two device implementations of the same network:
+//   NN_F32: fp32 SIMT kernels (cross-check path),
+//   NN_TC : TMA-staged tcgen05 implicit-GEMM 3x3 convolutions, fp16 operands / fp32 accumulation in TMEM,
+//           fused bias+BatchNorm+ReLU(+residual) epilogue, fused heads.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <cuda_runtime.h>
+
+namespace agz {
+
+struct NNet;
+
+struct NNShape {
+  int N, planes, filters, tower;
+};
+
+NNet* nn_create(const NNShape& s, int max_batch, char* err, size_t errlen);
+void nn_destroy(NNet* n);
+size_t nn_param_count(const NNet* n, int chain);
+size_t nn_bn_count(const NNet* n, int chain);  // BatchNorm channels of the chain (mu / sigma are this long each)
+int nn_set_params(NNet* n, int chain, const float* flat, size_t cnt);
+int nn_set_bn(NNet* n, int chain, const float* mu, const float* sigma, size_t cnt, int mode);
+// fold BatchNorm, reorder weights for both paths and upload; called lazily before the first forward
+int nn_commit(NNet* n, cudaStream_t s, char* err, size_t errlen);
+bool nn_ready(const NNet* n);
+
+// Input of both paths: packed history planes written by the feature kernels.
+//   feats_f32 : [B][17][N2] float, reference (W x H x C x B) order               (NN_F32)
+//   feats_tc  : see nn_tc_input_layout()                                          (NN_TC)
+// Output: pi [B][A] float (softmax over all A actions, no legality masking), v [B] float (Black's view).
+int nn_forward_f32(NNet* n, const float* feats_f32, int B, float* pi, float* v, cudaStream_t s);
+
+// The tensor-core path consumes activations as fp16 rows of `cin_pad` channels in a zero-bordered board
+// layout: every board is (N+1) rows of (N+1) points plus one leading pad row, so a 3x3 tap is a constant
+// row offset.  The feature kernel writes straight into this buffer.
+struct TCInput {
+  void* act;          // __half [rows_total][cin_pad]
+  int rows_per_board; // (N+1)*(N+1)
+  int row_stride_pts; // N+1
+  int cin_pad;        // 32
+  long long rows_total;
+};
+TCInput nn_tc_input(NNet* n);
+int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen);
+// 2*MACs of one position through the network (stem + tower + heads), for the roofline
+double nn_flops_per_position(const NNShape& s);
+long long nn_tc_launches_per_forward(const NNet* n);
+long long nn_f32_launches_per_forward(const NNet* n);
+
+}  // namespace agz

@@ -1,0 +1,306 @@
+// ops.cuh -- the warp-per-game kernels of the engine, written as functors: op(warp_index, smem).
+// k_warps<Op> (engine.cu) runs one functor instance per warp; the CPU test build runs the same functors on
+// fibers (tests/emu).  Reference functions each op stands for are named at the op.
+#pragma once
+#include "../../include/agz.h"
+#include "tree.cuh"
+
+namespace agz {
+
+// selfplay.jl:11-14 for every slot: global slot s = rank + world*g plays games s, s+S, s+2S, ...
+template <int KA>
+struct StartOp {
+  Cfg c;
+  View v;
+  AGZ_DEV void operator()(int g, char* smem) const {
+    Warp<KA> w(c, v, g, smem);
+    long long id = (long long)c.rank + (long long)c.world * g;
+    if (c.total_games < 0 || id < c.total_games) w.start_game(id);
+    else w.st.phase = PH_IDLE;
+    w.store_state();
+  }
+};
+
+// tree_search! part 1 (mcts_play.jl:74-87) / the seed selection of selfplay.jl:18
+template <int KA>
+struct SelectOp {
+  Cfg c;
+  View v;
+  int only_slot;  // >= 0: hook mode, run this slot with `parallel` leaves regardless of phase
+  int parallel;
+  AGZ_DEV void operator()(int wi, char* smem) const {
+    const int g = only_slot >= 0 ? only_slot : wi;
+    Warp<KA> w(c, v, g, smem);
+    if (only_slot >= 0) {
+      w.search_select(parallel, false);
+    } else if (w.st.phase == PH_SEED) {
+      w.search_select(1, true);
+    } else if (w.st.phase == PH_SEARCH) {
+      w.search_select(c.parallel, false);
+    } else {
+      w.st.nleaf = 0;
+      w.st.seed_round = 0;
+    }
+    w.store_state();
+  }
+};
+
+// tree_search! part 2 (mcts_play.jl:88-96) + the per-move logic of selfplay.jl:22-43
+template <int KA>
+struct IncorporateOp {
+  Cfg c;
+  View v;
+  int only_slot;
+  AGZ_DEV void operator()(int wi, char* smem) const {
+    const int g = only_slot >= 0 ? only_slot : wi;
+    Warp<KA> w(c, v, g, smem);
+    w.search_incorporate();
+    if (only_slot < 0) w.after_round();
+    w.st.seed_round = 0;
+    w.store_state();
+  }
+};
+
+// get_feats for every leaf collected this round, reference layout: out[b][17][N2] float (N x N x 17 x B)
+template <int KA>
+struct LeafFeaturesF32Op {
+  Cfg c;
+  View v;
+  float* out;
+  AGZ_DEV void operator()(int b, char* smem) const {
+    const int g = b / c.pmax, k = b % c.pmax;
+    Warp<KA> w(c, v, g, smem);
+    float* o = out + (size_t)b * 17 * c.N2;
+    const int lane = simt::lane();
+    if (k >= w.st.nleaf) {
+      for (int i = lane; i < 17 * c.N2; i += 32) o[i] = 0.f;
+      return;
+    }
+    const int node = v.leaf_node[b];
+    const int N2 = c.N2;
+    int tp = w.gather_features(node, [&](int hb, int p, uint32_t mine, uint32_t theirs) {
+      o[(2 * hb) * N2 + p] = (float)mine;
+      o[(2 * hb + 1) * N2 + p] = (float)theirs;
+    });
+    for (int p = lane; p < N2; p += 32) o[16 * N2 + p] = (float)tp;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ hooks
+enum {
+  HK_INIT = 1, HK_SELECT, HK_INCORPORATE, HK_BACKUP, HK_VLOSS_ADD, HK_VLOSS_REVERT, HK_ADD_CHILD, HK_NOISE, HK_PICK,
+  HK_PLAY, HK_FEATURES, HK_RESIGN, HK_POS_PLAY, HK_POS_LEGAL, HK_POS_SCORE, HK_POS_LIBS
+};
+
+struct HookParams {
+  int kind, slot, node, fmove;
+  float value;
+  double thr;
+  long long game_id;
+  const float* probs;
+  const agz_position* pos_in;
+  agz_position* pos_out;
+  int8_t* legal_out;
+  uint8_t* libs_out;
+  float* f_out;
+  int* result;  // [0] status, [1] int result, [2] float bits
+};
+
+template <int KA>
+struct HookOp {
+  Cfg c;
+  View v;
+  HookParams h;
+
+  AGZ_DEV void finish(Warp<KA>& w, int status, int ival, float fval) const {
+    simt::sync();
+    if (simt::lane() == 0) {
+      h.result[0] = status;
+      h.result[1] = ival;
+      h.result[2] = 0;
+      reinterpret_cast<float*>(h.result)[3] = fval;
+    }
+    (void)w;
+  }
+
+  AGZ_DEV void operator()(int, char* smem) const {
+    Warp<KA> w(c, v, h.slot, smem);
+    const int lane = simt::lane();
+    w.st.err = 0;
+    switch (h.kind) {
+      case HK_INIT: {  // initialize_game!(player, pos) (mcts_play.jl:110-118)
+        const agz_position* p = h.pos_in;
+        w.st.game_id = h.game_id;
+        w.st.game_id_lo = (uint32_t)h.game_id;
+        w.st.resign_thr = c.resign_threshold;
+        w.st.phase = PH_MANUAL;
+        w.st.target_N = 0.f;
+        if (p == nullptr) {
+          w.st.hist_len = 0;
+          for (int k = 0; k < c.KB; ++k) w.rs.bd[k * 32 + lane] = 0;
+          simt::sync();
+          w.init_root_from_scratch(0, -1, 1, 0);
+        } else {
+          uint32_t* hh = v.hist + (size_t)h.slot * (7 * 2 * c.KB);
+          int nh = p->n_hist < 0 ? 0 : (p->n_hist > 7 ? 7 : p->n_hist);
+          for (int r = 0; r < nh; ++r) {
+            for (int k = 0; k < c.KB; ++k) {
+              int pt = k * 32 + lane;
+              int x = pt < c.N2 ? p->hist[r][pt] : 0;
+              unsigned b = simt::ballot(x == 1), wv = simt::ballot(x == -1);
+              if (lane == 0) {
+                hh[(size_t)r * 2 * c.KB + k] = b;
+                hh[(size_t)r * 2 * c.KB + c.KB + k] = wv;
+              }
+            }
+          }
+          w.st.hist_len = nh;
+          rules_load_bytes(w.B, w.rs, p->board);
+          int flags = (p->last_move_pass ? F_LASTPASS : 0) | (p->done ? F_DONE : 0);
+          w.init_root_from_scratch(p->n, p->ko, p->to_play, flags);
+        }
+        finish(w, 0, 0, 0.f);
+        break;
+      }
+      case HK_SELECT: {
+        PathEnt* path = w.path_of(0);
+        int plen = 0;
+        int leaf = w.select_leaf(h.node < 0 ? w.st.root : h.node, path, plen);
+        finish(w, w.st.err, leaf, 0.f);
+        break;
+      }
+      case HK_INCORPORATE:
+      case HK_BACKUP:
+      case HK_VLOSS_ADD:
+      case HK_VLOSS_REVERT: {
+        PathEnt* path = w.path_of(0);
+        int plen = w.build_path(h.node, path);
+        if (!w.st.err) {
+          if (h.kind == HK_INCORPORATE) w.incorporate(h.node, path, plen, h.probs, h.value);
+          else if (h.kind == HK_BACKUP) w.apply_path(path, plen, OP_BACKUP, h.value);
+          else w.apply_path(path, plen, h.kind == HK_VLOSS_ADD ? OP_VLOSS_ADD : OP_VLOSS_REVERT, 0.f);
+        }
+        finish(w, w.st.err, 0, 0.f);
+        break;
+      }
+      case HK_ADD_CHILD: {  // maybe_add_child! (mcts.jl:140-147)
+        const size_t r = w.row(h.node);
+        int child = v.child[r + h.fmove];
+        if (child < 0) {
+          NodeMeta m = w.load_meta(h.node);
+          child = w.create_child(h.node, m, h.fmove, true);
+          if (child >= 0 && lane == 0) v.child[r + h.fmove] = child;
+        }
+        finish(w, w.st.err, child, 0.f);
+        break;
+      }
+      case HK_NOISE:
+        w.inject_noise();
+        finish(w, 0, 0, 0.f);
+        break;
+      case HK_PICK: {
+        int mv = w.pick_move();
+        finish(w, w.st.err, mv, 0.f);
+        break;
+      }
+      case HK_PLAY: {
+        int rc = w.play_move(h.fmove, true);
+        finish(w, rc, w.st.root, 0.f);
+        break;
+      }
+      case HK_RESIGN: {  // should_resign (mcts_play.jl:124)
+        NodeMeta rm = w.load_meta(w.st.root);
+        float q = simt::fdiv(w.st.root_W, simt::fadd(1.0f, w.st.root_N));
+        float qp = simt::fmul(q, (float)rm.to_play);
+        finish(w, 0, (double)qp < h.thr ? 1 : 0, qp);
+        break;
+      }
+      case HK_FEATURES: {
+        float* o = h.f_out;
+        const int N2 = c.N2;
+        int tp = w.gather_features(h.node, [&](int hb, int p, uint32_t mine, uint32_t theirs) {
+          o[(2 * hb) * N2 + p] = (float)mine;
+          o[(2 * hb + 1) * N2 + p] = (float)theirs;
+        });
+        for (int p = lane; p < N2; p += 32) o[16 * N2 + p] = (float)tp;
+        finish(w, 0, 0, 0.f);
+        return;  // no state change
+      }
+      case HK_POS_PLAY: {  // play_move!(pos, c) (board.jl:451-509) on a caller-supplied position
+        const agz_position* p = h.pos_in;
+        agz_position* o = h.pos_out;
+        rules_load_bytes(w.B, w.rs, p->board);
+        int status = 0, ko = -1, ncap = 0;
+        const int mv = h.fmove;
+        if (mv != c.N2) {
+          if (mv == p->ko) status = E_ILLEGAL;
+          else if (rules_play(w.B, w.rs, mv, p->to_play, true, ko, ncap)) status = E_ILLEGAL;
+        }
+        if (status == 0) {
+          for (int k = 0; k < c.KB; ++k) {
+            int pt = k * 32 + lane;
+            if (pt < c.N2) {
+              o->board[pt] = w.rs.bd[pt];
+              o->hist[0][pt] = p->board[pt];
+              for (int r = 1; r < 7; ++r) o->hist[r][pt] = p->hist[r - 1][pt];
+            }
+          }
+          if (lane == 0) {
+            o->n_hist = p->n_hist < 7 ? p->n_hist + 1 : 7;
+            o->n = p->n + 1;
+            o->to_play = -p->to_play;
+            o->ko = mv == c.N2 ? -1 : ko;
+            o->last_move_pass = mv == c.N2;
+            o->done = (mv == c.N2 && p->last_move_pass) ? 1 : 0;
+            o->caps[0] = p->caps[0] + (p->to_play == 1 ? ncap : 0);
+            o->caps[1] = p->caps[1] + (p->to_play == 1 ? 0 : ncap);
+            o->komi = p->komi;
+          }
+        }
+        finish(w, status, ncap, 0.f);
+        return;
+      }
+      case HK_POS_LEGAL: {  // all_legal_moves (board.jl:393-424)
+        const agz_position* p = h.pos_in;
+        rules_load_bytes(w.B, w.rs, p->board);
+        rules_label(w.B, w.rs, 0);
+        rules_count_liberties(w.B, w.rs);
+        uint32_t lw[KA];
+        rules_legal_mask<KA>(w.B, w.rs, p->to_play, p->ko, lw);
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+          int pt = k * 32 + lane;
+          if (pt < c.N2) h.legal_out[pt] = (int8_t)((lw[k] >> lane) & 1u);
+        }
+        if (lane == 0) h.legal_out[c.N2] = 1;
+        finish(w, 0, 0, 0.f);
+        return;
+      }
+      case HK_POS_SCORE: {
+        const agz_position* p = h.pos_in;
+        rules_load_bytes(w.B, w.rs, p->board);
+        float sc = rules_score(w.B, w.rs, p->komi);
+        finish(w, 0, 0, sc);
+        return;
+      }
+      case HK_POS_LIBS: {  // liberty_cache
+        const agz_position* p = h.pos_in;
+        rules_load_bytes(w.B, w.rs, p->board);
+        rules_label(w.B, w.rs, 0);
+        rules_count_liberties(w.B, w.rs);
+        for (int k = 0; k < c.KB; ++k) {
+          int pt = k * 32 + lane;
+          if (pt < c.N2) h.libs_out[pt] = (uint8_t)(w.rs.bd[pt] != 0 ? w.rs.cnt[w.rs.lab[pt]] : 0);
+        }
+        finish(w, 0, 0, 0.f);
+        return;
+      }
+      default:
+        finish(w, E_ASSERT, 0, 0.f);
+        return;
+    }
+    w.store_state();
+  }
+};
+
+}  // namespace agz

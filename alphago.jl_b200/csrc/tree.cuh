@@ -1,0 +1,867 @@
+// tree.cuh -- the MCTS search tree in HBM and the warp-per-tree device functions that walk it.
+//
+// Replaces (reference paths): src/mcts.jl  MCTSNode :41-82, select_leaf :108-138, maybe_add_child! :140-147,
+// add/revert_virtual_loss! :149-171, revert_visits! :173-186, incorporate_results! :188-213,
+// backup_value! :215-225, is_done :230-231, inject_noise! :233-239, children_as_pi :241-252;
+// src/mcts_play.jl  tree_search! :73-98, pick_move :52-71, play_move! :26-50, should_resign :124;
+// src/selfplay.jl :1-45 (per-game state machine).
+//
+// Layout (struct of arrays, one arena of `cap` nodes per game slot, node id local to the slot):
+//   N, W, P      float [slot][node][AS]   AS = 32*KA >= A, rows are 128-byte aligned -> coalesced warp loads
+//   child        int32 [slot][node][AS]   child node id or -1
+//   meta         NodeMeta [slot][node]    16 bytes
+//   bits         uint32 [slot][node][3*KB] black plane, white plane, legal-move mask
+// A node's own N / W live in its parent's row (as in the reference, mcts.jl:94-102); the root's live in the
+// per-game state.  One warp owns one game: the 8 selections of a tree_search! round are serial inside the
+// warp (they are order dependent through virtual loss), parallelism comes from thousands of games.
+#pragma once
+#include "go_rules.cuh"
+#include "rng.cuh"
+#include "simt.h"
+
+namespace agz {
+
+enum { PH_IDLE = 0, PH_SEED = 1, PH_SEARCH = 2, PH_WAIT_RING = 3, PH_MANUAL = 4 };
+enum { F_EXPANDED = 1, F_DONE = 2, F_LASTPASS = 4 };
+enum { E_OK = 0, E_ILLEGAL = 1, E_ASSERT = 2, E_CAPACITY = 6 };
+enum { OP_VLOSS_ADD = 0, OP_VLOSS_REVERT = 1, OP_BACKUP = 2, OP_REVERT_VISITS = 3 };
+static const uint32_t SLOT_ROOT = 0xFFFFFFFFu;
+
+struct NodeMeta {  // 16 bytes
+  int32_t parent;
+  int16_t fmove;  // move that led here (-1 for an arena root)
+  int16_t n;      // position.n
+  int16_t ko;     // flat point or -1
+  int8_t to_play;
+  uint8_t flags;
+  int32_t pad;
+};
+
+struct PathEnt {  // 16 bytes; where this path node's own N / W live
+  uint32_t slot;  // index into N / W, or SLOT_ROOT
+  int32_t node;
+  int32_t to_play;
+  int32_t pad;
+};
+
+struct GameState {
+  int32_t phase, root, count, err;
+  float root_N, root_W, target_N;
+  int32_t n_moves;       // plies recorded for the current game
+  uint32_t sel_ctr, noise_ctr;
+  uint32_t game_id_lo;
+  int32_t hist_len;
+  double resign_thr;
+  int64_t game_id;
+  int32_t nleaf, seed_round;
+  int32_t vloss_balance;  // path entries with a virtual loss outstanding
+  int32_t result, resigned;
+  float final_score;
+  int32_t pad[2];
+};
+
+struct Cfg {
+  int N, N2, A, KA, AS, KB;
+  int cap, maxd, pmax;
+  int max_game_length, tau_threshold, readouts, parallel;
+  int n_games, world, rank, inject_noise;
+  int ring_cap;
+  float komi;
+  double c_puct, noise_weight, noise_alpha, resign_threshold, resign_disable_frac;
+  uint64_t seed;
+  long long total_games;
+};
+
+enum { CTR_MOVES = 0, CTR_FINISHED, CTR_STARTED, CTR_POSITIONS, CTR_READOUTS, CTR_PATHNODES, CTR_RING_TAIL, CTR_RING_HEAD, CTR_COUNT };
+
+struct RingHeader {  // mirrors agz_game_header
+  int64_t game_id;
+  int32_t n_moves, result, resigned;
+  float final_score;
+  double resign_threshold;
+};
+
+struct View {
+  float *N, *W, *P;
+  int32_t* child;
+  NodeMeta* meta;
+  uint32_t* bits;
+  GameState* gs;
+  uint32_t* hist;  // [slot][7][2*KB]
+  PathEnt* path;   // [slot][pmax][maxd]
+  int32_t *leaf_node, *leaf_plen;  // [slot][pmax]
+  int32_t* remap;  // [slot][cap]
+  const float* eval_pi;  // row b at eval_pi + b*pi_stride
+  const float* eval_v;   // eval_v[b*v_stride]
+  long long pi_stride;
+  int v_stride;
+  int16_t* rec_moves;  // [slot][L]
+  float *rec_q, *rec_pi, *rec_vis;  // [slot][L], [slot][L][A], [slot][L][A]
+  RingHeader* ring_hdr;
+  int16_t* ring_moves;
+  float *ring_q, *ring_pi, *ring_vis;
+  unsigned long long* ctr;
+};
+
+template <int KA>
+struct Warp {
+  const Cfg& c;
+  const View& v;
+  const int g;
+  const int lane;
+  Board B;
+  RulesScratch rs;
+  GameState st;  // register copy (warp-uniform); written back by store_state()
+  size_t nbase;
+
+  AGZ_DEV Warp(const Cfg& c_, const View& v_, int g_, char* smem) : c(c_), v(v_), g(g_), lane(simt::lane()) {
+    B.N = c.N; B.N2 = c.N2; B.KB = c.KB;
+    rs = rules_scratch_at(smem, c.KB);
+    st = v.gs[g];
+    nbase = (size_t)g * c.cap;
+  }
+  AGZ_DEV void store_state() {
+    simt::sync();
+    if (lane == 0) v.gs[g] = st;
+  }
+  AGZ_DEV size_t row(int node) const { return (nbase + node) * (size_t)c.AS; }
+  AGZ_DEV uint32_t* bits_of(int node) const { return v.bits + (nbase + node) * (size_t)(3 * c.KB); }
+  AGZ_DEV NodeMeta load_meta(int node) const { return v.meta[nbase + node]; }
+  AGZ_DEV bool terminal(const NodeMeta& m) const { return (m.flags & F_DONE) || m.n >= c.max_game_length; }
+  AGZ_DEV PathEnt* path_of(int k) const { return v.path + ((size_t)g * c.pmax + k) * c.maxd; }
+  AGZ_DEV void count(int which, unsigned long long n) {
+    if (lane == 0) simt::atomic_add(&v.ctr[which], n);
+  }
+
+  // ---- node creation -----------------------------------------------------------------------
+  AGZ_DEV void init_rows(int node) {
+    size_t r = row(node);
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      int a = k * 32 + lane;
+      v.N[r + a] = 0.f;
+      v.W[r + a] = 0.f;
+      v.P[r + a] = 0.f;
+      v.child[r + a] = -1;
+    }
+  }
+
+  // Write a node whose position is on the rules scratch (labels/liberties valid unless `skip_legal`).
+  AGZ_DEV void write_node(int node, int parent, int fmove, int n, int ko, int to_play, int flags, bool skip_legal) {
+    uint32_t bw[KA], ww[KA], lw[KA];
+    rules_pack<KA>(B, rs, bw, ww);
+#pragma unroll
+    for (int k = 0; k < KA; ++k) lw[k] = 0;
+    if (!skip_legal) rules_legal_mask<KA>(B, rs, to_play, ko, lw);
+    uint32_t* bp = bits_of(node);
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      if (k < c.KB && lane == 0) {
+        bp[k] = bw[k];
+        bp[c.KB + k] = ww[k];
+        bp[2 * c.KB + k] = lw[k];
+      }
+    }
+    if (lane == 0) {
+      NodeMeta m;
+      m.parent = parent; m.fmove = (int16_t)fmove; m.n = (int16_t)n; m.ko = (int16_t)ko;
+      m.to_play = (int8_t)to_play; m.flags = (uint8_t)flags; m.pad = 0;
+      v.meta[nbase + node] = m;
+    }
+    init_rows(node);
+  }
+
+  // maybe_add_child! when the child is missing: play `move` from `parent` (mcts.jl:140-147 -> board.jl:451-509).
+  // Returns the new node id, or -1 with st.err set (E_CAPACITY, or E_ILLEGAL when check_legal).
+  AGZ_DEV int create_child(int parent, const NodeMeta& pm, int move, bool check_legal) {
+    if (st.count >= c.cap) { st.err = E_CAPACITY; return -1; }
+    const uint32_t* pb = bits_of(parent);
+    if (check_legal && move != c.N2) {
+      uint32_t lw = pb[2 * c.KB + (move >> 5)];
+      if (!((lw >> (move & 31)) & 1u)) { st.err = E_ILLEGAL; return -1; }
+    }
+    int idx = st.count++;
+    rules_load(B, rs, pb, pb + c.KB);
+    int color = pm.to_play;
+    int n = pm.n + 1;
+    int ko = -1, flags = 0, ncap = 0;
+    bool term;
+    if (move == c.N2) {  // pass_move! (board.jl:426-440)
+      flags = F_LASTPASS | ((pm.flags & F_LASTPASS) ? F_DONE : 0);
+      term = (flags & F_DONE) || n >= c.max_game_length;
+      if (!term) { rules_label(B, rs, 0); rules_count_liberties(B, rs); }
+    } else {
+      rules_play(B, rs, move, color, false, ko, ncap);
+      term = n >= c.max_game_length;
+    }
+    write_node(idx, parent, move, n, ko, -color, flags, term);
+    simt::sync();
+    return idx;
+  }
+
+  // ---- path updates (virtual loss, backup, visit reverts) -------------------------------------
+  // Entries are distinct nodes, so the read-modify-writes of one path go out in parallel, one per lane.
+  AGZ_DEV void apply_path(const PathEnt* path, int plen, int op, float value) {
+    simt::sync();
+    for (int d0 = 0; d0 < plen; d0 += 32) {
+      int d = d0 + lane;
+      if (d < plen) {
+        PathEnt e = path[d];
+        if (e.slot != SLOT_ROOT) {
+          if (op == OP_REVERT_VISITS) v.N[e.slot] = simt::fsub(v.N[e.slot], 1.0f);
+          else {
+            float add = op == OP_BACKUP ? value : (op == OP_VLOSS_ADD ? (float)e.to_play : (float)(-e.to_play));
+            v.W[e.slot] = simt::fadd(v.W[e.slot], add);
+          }
+        }
+      }
+    }
+    PathEnt e0 = path[0];
+    if (e0.slot == SLOT_ROOT) {
+      if (op == OP_REVERT_VISITS) st.root_N = simt::fsub(st.root_N, 1.0f);
+      else {
+        float add = op == OP_BACKUP ? value : (op == OP_VLOSS_ADD ? (float)e0.to_play : (float)(-e0.to_play));
+        st.root_W = simt::fadd(st.root_W, add);
+      }
+    }
+    if (op == OP_VLOSS_ADD) st.vloss_balance += plen;
+    if (op == OP_VLOSS_REVERT) st.vloss_balance -= plen;
+    simt::sync();
+  }
+
+  // Rebuild the path root..node by walking parent pointers (used by the single-node hooks only).
+  AGZ_DEV int build_path(int node, PathEnt* path) {
+    int len = 0;
+    for (int x = node; x >= 0; x = load_meta(x).parent) ++len;
+    if (len > c.maxd) { st.err = E_ASSERT; return 0; }
+    int d = len - 1;
+    for (int x = node; x >= 0;) {
+      NodeMeta m = load_meta(x);
+      if (lane == 0) {
+        PathEnt e;
+        e.slot = m.parent < 0 ? SLOT_ROOT : (uint32_t)(row(m.parent) + m.fmove);
+        e.node = x; e.to_play = m.to_play; e.pad = 0;
+        path[d] = e;
+      }
+      --d;
+      x = m.parent;
+    }
+    simt::sync();
+    return len;
+  }
+
+  // ---- select_leaf (mcts.jl:108-138) ------------------------------------------------------------
+  AGZ_DEV int select_leaf(int from, PathEnt* path, int& plen) {
+    uint32_t sel_idx = st.sel_ctr++;
+    uint32_t move_no = (uint32_t)load_meta(st.root).n;
+    int cur = from;
+    int depth = 0;
+    uint32_t slot;
+    float cur_N;
+    {
+      NodeMeta fm = load_meta(cur);
+      if (fm.parent < 0) {
+        slot = SLOT_ROOT;
+        st.root_N = simt::fadd(st.root_N, 1.0f);
+        cur_N = st.root_N;
+      } else {
+        slot = (uint32_t)(row(fm.parent) + fm.fmove);
+        cur_N = simt::fadd(v.N[slot], 1.0f);
+        simt::sync();
+        if (lane == 0) v.N[slot] = cur_N;
+      }
+    }
+    for (;;) {
+      NodeMeta m = load_meta(cur);
+      if (lane == 0) {
+        PathEnt e;
+        e.slot = slot; e.node = cur; e.to_play = m.to_play; e.pad = 0;
+        path[depth] = e;
+      }
+      if (!(m.flags & F_EXPANDED)) break;
+      if (depth + 1 >= c.maxd) { st.err = E_ASSERT; break; }
+      const size_t r = row(cur);
+      float n[KA], w[KA], p[KA];
+      int ch[KA];
+#pragma unroll
+      for (int k = 0; k < KA; ++k) {
+        int a = k * 32 + lane;
+        n[k] = v.N[r + a];
+        w[k] = v.W[r + a];
+        p[k] = v.P[r + a];
+        ch[k] = v.child[r + a];
+      }
+      const int pass = c.N2;
+      int best;
+      // HACK of the reference: after a pass, look at the double pass first (mcts.jl:119-126)
+      float n_pass = 0.f;
+#pragma unroll
+      for (int k = 0; k < KA; ++k)
+        if (k == (pass >> 5)) n_pass = n[k];
+      n_pass = simt::shfl(n_pass, pass & 31);
+      if ((m.flags & F_LASTPASS) && n_pass == 0.f) {
+        best = pass;
+      } else {
+        // score = Float64(Float32(W/(1+N)) * to_play) + ((c_puct * Float64(sqrt_f32(1+N_parent))) * Float64(P)) / Float64(1+N)
+        const uint32_t* lw = bits_of(cur) + 2 * c.KB;
+        const double cu = simt::dmul(c.c_puct, (double)simt::fsqrt(simt::fadd(1.0f, cur_N)));
+        const float tp = (float)m.to_play;
+        double s[KA];
+        double mx = -1.0e300;
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+          int a = k * 32 + lane;
+          bool legal = false;
+          if (a < c.N2) legal = (lw[k] >> lane) & 1u;  // word k is a warp-uniform address
+          else if (a == pass) legal = true;
+          float den = simt::fadd(1.0f, n[k]);
+          float q = simt::fmul(simt::fdiv(w[k], den), tp);
+          double u = simt::ddiv(simt::dmul(cu, (double)p[k]), (double)den);
+          s[k] = legal ? simt::dadd((double)q, u) : -1.0e300;
+          mx = s[k] > mx ? s[k] : mx;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          double o = simt::shfl_xor(mx, off);
+          mx = o > mx ? o : mx;
+        }
+        unsigned tm[KA];
+        int total = 0;
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+          tm[k] = simt::ballot(s[k] == mx);
+          total += simt::popc(tm[k]);
+        }
+        U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_SELECT, move_no, sel_idx, (uint32_t)depth);
+        int pick = (int)simt::mulhi(rr.x, (uint32_t)total);
+        best = pass;
+        bool found = false;
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+          int cntk = simt::popc(tm[k]);
+          if (!found) {
+            if (pick < cntk) {
+              unsigned mk = tm[k];
+              for (int t = 0; t < pick; ++t) mk &= mk - 1;  // drop the `pick` lowest set bits
+              best = k * 32 + simt::ffs(mk) - 1;
+              found = true;
+            } else {
+              pick -= cntk;
+            }
+          }
+        }
+      }
+      const int ok = best >> 5, ol = best & 31;
+      float n_old = 0.f;
+      int child = -1;
+#pragma unroll
+      for (int k = 0; k < KA; ++k)
+        if (k == ok) { n_old = n[k]; child = ch[k]; }
+      n_old = simt::shfl(n_old, ol);
+      child = simt::shfl(child, ol);
+      const float n_new = simt::fadd(n_old, 1.0f);
+      if (child < 0) {
+        child = create_child(cur, m, best, false);
+        if (child < 0) break;
+        if (lane == ol) v.child[r + best] = child;
+      }
+      if (lane == ol) v.N[r + best] = n_new;  // N(child) += 1 (mcts.jl:113-114)
+      slot = (uint32_t)(r + best);
+      cur_N = n_new;
+      cur = child;
+      ++depth;
+    }
+    plen = depth + 1;
+    simt::sync();
+    return cur;
+  }
+
+  // ---- tree_search! first half: collect leaves (mcts_play.jl:74-87) ------------------------------
+  AGZ_DEV void search_select(int parallel, bool seed_mode) {
+    int nleaf = 0, attempts = 0;
+    const int want = seed_mode ? 1 : parallel;
+    while (nleaf < want && attempts < 2 * want) {
+      ++attempts;
+      PathEnt* path = path_of(nleaf);
+      int plen = 0;
+      int leaf = select_leaf(st.root, path, plen);
+      if (st.err) break;
+      count(CTR_READOUTS, 1);
+      count(CTR_PATHNODES, (unsigned long long)plen);
+      NodeMeta lm = load_meta(leaf);
+      if (terminal(lm)) {  // game over: back up the true result, do not evaluate (mcts_play.jl:80-84)
+        const uint32_t* lb = bits_of(leaf);
+        rules_load(B, rs, lb, lb + c.KB);
+        float sc = rules_score(B, rs, c.komi);
+        float value = sc > 0.f ? 1.f : (sc < 0.f ? -1.f : 0.f);
+        apply_path(path, plen, OP_BACKUP, value);
+        continue;
+      }
+      if (!seed_mode) apply_path(path, plen, OP_VLOSS_ADD, 0.f);
+      if (lane == 0) {
+        v.leaf_node[(size_t)g * c.pmax + nleaf] = leaf;
+        v.leaf_plen[(size_t)g * c.pmax + nleaf] = plen;
+      }
+      ++nleaf;
+    }
+    st.nleaf = nleaf;
+    st.seed_round = seed_mode ? 1 : 0;
+    count(CTR_POSITIONS, (unsigned long long)nleaf);
+  }
+
+  // incorporate_results! for one node given its path (mcts.jl:188-213)
+  AGZ_DEV void incorporate(int leaf, const PathEnt* path, int plen, const float* probs, float value) {
+    NodeMeta lm = load_meta(leaf);
+    simt::sync();  // every lane has read the flags before lane 0 rewrites them below
+    if (lm.flags & F_DONE) { st.err = E_ASSERT; return; }  // @assert !position.done (mcts.jl:196)
+    if (lm.flags & F_EXPANDED) {
+      apply_path(path, plen, OP_REVERT_VISITS, 0.f);
+      return;
+    }
+    if (lane == 0) v.meta[nbase + leaf].flags = (uint8_t)(lm.flags | F_EXPANDED);
+    const size_t r = row(leaf);
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      int a = k * 32 + lane;
+      bool in = a < c.A;
+      v.P[r + a] = in ? probs[a] : 0.f;
+      v.W[r + a] = in ? value : 0.f;  // children start from the parent's value (mcts.jl:211)
+    }
+    apply_path(path, plen, OP_BACKUP, value);
+  }
+
+  // ---- tree_search! second half (mcts_play.jl:88-96) ---------------------------------------------
+  AGZ_DEV void search_incorporate() {
+    const bool seed_mode = st.seed_round != 0;
+    for (int k = 0; k < st.nleaf; ++k) {
+      const PathEnt* path = path_of(k);
+      int leaf = v.leaf_node[(size_t)g * c.pmax + k];
+      int plen = v.leaf_plen[(size_t)g * c.pmax + k];
+      if (!seed_mode) apply_path(path, plen, OP_VLOSS_REVERT, 0.f);
+      size_t b = (size_t)g * c.pmax + k;
+      incorporate(leaf, path, plen, v.eval_pi + b * v.pi_stride, v.eval_v[b * v.v_stride]);
+      if (st.err) break;
+    }
+    st.nleaf = 0;
+  }
+
+  // ---- inject_noise! (mcts.jl:233-239) -------------------------------------------------------------
+  AGZ_DEV void inject_noise() {
+    const size_t r = row(st.root);
+    const uint32_t move_no = (uint32_t)load_meta(st.root).n;
+    const uint32_t call = st.noise_ctr++;
+    double gm[KA];
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      int a = k * 32 + lane;
+      gm[k] = 0.0;
+      if (a < c.A) {
+        gm[k] = gamma_small(c.noise_alpha, c.seed, st.game_id_lo, move_no, (uint32_t)a, call);
+        acc = simt::dadd(acc, gm[k]);
+      }
+    }
+    const double total = butterfly_sum(acc);
+    const double keep = simt::dsub(1.0, c.noise_weight);
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      int a = k * 32 + lane;
+      if (a < c.A) {
+        double mixed = simt::dadd(simt::dmul((double)v.P[r + a], keep), simt::dmul(simt::ddiv(gm[k], total), c.noise_weight));
+        v.P[r + a] = (float)mixed;
+      }
+    }
+    simt::sync();
+  }
+
+  // ---- pick_move (mcts_play.jl:52-71): returns the flat move, or -1 with st.err = E_ASSERT -------------
+  AGZ_DEV int pick_move() {
+    const size_t r = row(st.root);
+    const NodeMeta m = load_meta(st.root);
+    float n[KA];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      int a = k * 32 + lane;
+      n[k] = a < c.A ? v.N[r + a] : -1.f;
+    }
+    if (m.n >= c.tau_threshold) {
+      float mx = -1.f;
+#pragma unroll
+      for (int k = 0; k < KA; ++k) mx = n[k] > mx ? n[k] : mx;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        float o = simt::shfl_xor(mx, off);
+        mx = o > mx ? o : mx;
+      }
+      unsigned tm[KA];
+      int total = 0;
+#pragma unroll
+      for (int k = 0; k < KA; ++k) {
+        tm[k] = simt::ballot(n[k] == mx);
+        total += simt::popc(tm[k]);
+      }
+      U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_PICK_MAX, (uint32_t)m.n, 0, 0);
+      int pick = (int)simt::mulhi(rr.x, (uint32_t)total);
+      int best = -1;
+#pragma unroll
+      for (int k = 0; k < KA; ++k) {
+        int cntk = simt::popc(tm[k]);
+        if (best < 0) {
+          if (pick < cntk) {
+            unsigned mk = tm[k];
+            for (int t = 0; t < pick; ++t) mk &= mk - 1;
+            best = k * 32 + simt::ffs(mk) - 1;
+          } else {
+            pick -= cntk;
+          }
+        }
+      }
+      return best;
+    }
+    // soft pick: cdf = cumsum(child_N) / cdf[end-1]; first index with cdf >= rand()
+    float cum[KA];
+    float carry = 0.f;
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      float x = n[k] > 0.f ? n[k] : 0.f;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        float o = simt::shfl(x, lane - off);
+        if (lane >= off) x = simt::fadd(x, o);
+      }
+      cum[k] = simt::fadd(x, carry);
+      carry = simt::shfl(cum[k], 31);
+    }
+    const int last = c.N2 - 1;  // cdf[end-1]: pass is excluded from the normaliser
+    float denom = 0.f;
+#pragma unroll
+    for (int k = 0; k < KA; ++k)
+      if (k == (last >> 5)) denom = cum[k];
+    denom = simt::shfl(denom, last & 31);
+    if (denom == 0.f) { st.err = E_ASSERT; return -1; }
+    U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_PICK_SOFT, (uint32_t)m.n, 0, 0);
+    const double sel = u53(rr.x, rr.y);
+    int best = -1;
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      int a = k * 32 + lane;
+      bool ge = a < c.A && (double)simt::fdiv(cum[k], denom) >= sel;
+      unsigned mk = simt::ballot(ge);
+      if (best < 0 && mk) best = k * 32 + simt::ffs(mk) - 1;
+    }
+    if (best < 0) { st.err = E_ASSERT; return -1; }
+    float nb = 0.f;
+#pragma unroll
+    for (int k = 0; k < KA; ++k)
+      if (k == (best >> 5)) nb = n[k];
+    nb = simt::shfl(nb, best & 31);
+    if (nb == 0.f) { st.err = E_ASSERT; return -1; }  // @assert child_N[fcoord] != 0 (mcts_play.jl:68)
+    return best;
+  }
+
+  // ---- arena compaction: keep the subtree of the root, slide it to the front (stable) -------------------
+  AGZ_DEV void compact() {
+    int32_t* remap = v.remap + (size_t)g * c.cap;
+    const int count = st.count;
+    int base = 0;
+    for (int c0 = 0; c0 < count; c0 += 32) {
+      int i = c0 + lane;
+      int parent = -2;
+      if (i < count) parent = load_meta(i).parent;
+      unsigned mask = 0;
+      for (;;) {  // a parent always has a smaller id than its child; resolve same-chunk parents by iteration
+        bool live = false;
+        if (i < count) {
+          if (i == st.root) live = true;
+          else if (parent >= c0) live = (mask >> (parent - c0)) & 1u;
+          else if (parent >= 0) live = remap[parent] >= 0;
+        }
+        unsigned nm = simt::ballot(live);
+        if (nm == mask) break;
+        mask = nm;
+      }
+      if (i < count) remap[i] = ((mask >> lane) & 1u) ? base + simt::popc(mask & ((1u << lane) - 1u)) : -1;
+      base += simt::popc(mask);
+      simt::sync();
+    }
+    for (int i = 0; i < count; ++i) {
+      int ni = remap[i];
+      if (ni < 0) continue;  // warp-uniform
+      const size_t ro = row(i), rn = row(ni);
+#pragma unroll
+      for (int k = 0; k < KA; ++k) {
+        int a = k * 32 + lane;
+        float nn = v.N[ro + a], ww = v.W[ro + a], pp = v.P[ro + a];
+        int cc = v.child[ro + a];
+        if (cc >= 0) cc = remap[cc];
+        v.N[rn + a] = nn; v.W[rn + a] = ww; v.P[rn + a] = pp; v.child[rn + a] = cc;
+      }
+      if (ni != i) {
+        const uint32_t* bo = bits_of(i);
+        uint32_t* bn = bits_of(ni);
+        for (int k = lane; k < 3 * c.KB; k += 32) bn[k] = bo[k];
+      }
+      NodeMeta m = load_meta(i);
+      if (lane == 0) {
+        m.parent = m.parent >= 0 ? remap[m.parent] : -1;
+        v.meta[nbase + ni] = m;
+      }
+      simt::sync();
+    }
+    st.root = remap[st.root];
+    st.count = base;
+    simt::sync();
+  }
+
+  // ---- play_move!(player, c) (mcts_play.jl:26-50): record pi / q, re-root on the chosen child -----------
+  AGZ_DEV int play_move(int mv, bool record) {
+    const int root = st.root;
+    const NodeMeta rm = load_meta(root);
+    const size_t r = row(root);
+    int child = v.child[r + mv];
+    if (child < 0) {
+      child = create_child(root, rm, mv, true);
+      if (child < 0) return st.err;
+      if (lane == 0) v.child[r + mv] = child;
+      simt::sync();
+    }
+    const int t = st.n_moves;
+    if (record && t < c.max_game_length + 2) {
+      const size_t rb = ((size_t)g * (c.max_game_length + 2) + t);
+      if (c.tau_threshold >= 0) {  // searches_pi is only kept outside two_player_mode
+        float n[KA];
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+          int a = k * 32 + lane;
+          n[k] = a < c.A ? v.N[r + a] : 0.f;
+        }
+        if (rm.n <= c.tau_threshold) {  // squash: child_N .^ 0.98 in Float64 (mcts.jl:247-251)
+          double x[KA], acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < KA; ++k) {
+            int a = k * 32 + lane;
+            x[k] = 0.0;
+            if (a < c.A) { x[k] = det_pow((double)n[k], 0.98); acc = simt::dadd(acc, x[k]); }
+          }
+          double total = butterfly_sum(acc);
+#pragma unroll
+          for (int k = 0; k < KA; ++k) {
+            int a = k * 32 + lane;
+            if (a < c.A) v.rec_pi[rb * c.A + a] = (float)simt::ddiv(x[k], total);
+          }
+        } else {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < KA; ++k) acc = simt::fadd(acc, n[k]);
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) acc = simt::fadd(acc, simt::shfl_xor(acc, off));
+#pragma unroll
+          for (int k = 0; k < KA; ++k) {
+            int a = k * 32 + lane;
+            if (a < c.A) v.rec_pi[rb * c.A + a] = simt::fdiv(n[k], acc);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < KA; ++k) {
+          int a = k * 32 + lane;
+          if (a < c.A) v.rec_vis[rb * c.A + a] = n[k];
+        }
+      }
+      if (lane == 0) {
+        v.rec_q[rb] = simt::fdiv(st.root_W, simt::fadd(1.0f, st.root_N));  // Q(root) (mcts_play.jl:38)
+        v.rec_moves[rb] = (int16_t)mv;
+      }
+      st.n_moves = t + 1;
+    }
+    // the child keeps its own statistics; its siblings are dropped (mcts_play.jl:40,48)
+    st.root_N = v.N[r + mv];
+    st.root_W = v.W[r + mv];
+    uint32_t* h = v.hist + (size_t)g * (7 * 2 * c.KB);
+    const uint32_t* rbits = bits_of(root);
+    simt::sync();
+    // shift the history ring by one board through registers: 7*2*KB <= 168 words -> at most 6 per lane
+    {
+      const int W2 = 2 * c.KB, total = 7 * W2;
+      uint32_t tmp[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        int k = q * 32 + lane;
+        tmp[q] = 0;
+        if (k < total) tmp[q] = k < W2 ? rbits[k] : h[k - W2];
+      }
+      simt::sync();
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        int k = q * 32 + lane;
+        if (k < total) h[k] = tmp[q];
+      }
+    }
+    st.hist_len = st.hist_len < 7 ? st.hist_len + 1 : 7;
+    if (lane == 0) v.meta[nbase + child].parent = -1;
+    st.root = child;
+    st.sel_ctr = 0;
+    st.noise_ctr = 0;
+    simt::sync();
+    const int need = c.readouts + 2 * c.pmax + 4;
+    if (st.count + need > c.cap) {
+      compact();
+      if (st.count + need > c.cap) { st.err = E_CAPACITY; return st.err; }
+    }
+    return E_OK;
+  }
+
+  // ---- get_feats(node.position) (features.jl:3-26): the last 8 boards come from the node, its ancestors in
+  // the tree and, past the root, the per-game ring of earlier root boards; the oldest one is repeated.
+  // emit(plane_pair h, point p, mine, theirs) is called for every on-board point of every history board.
+  template <class Emit>
+  AGZ_DEV int gather_features(int node, Emit emit) {
+    const NodeMeta m = load_meta(node);
+    const int tp = m.to_play;
+    int cur = node;
+    const uint32_t* src = bits_of(cur);
+    const uint32_t* h = v.hist + (size_t)g * (7 * 2 * c.KB);
+    bool in_tree = true;
+    int ri = 0;
+    for (int hb = 0; hb < 8; ++hb) {
+      for (int k = 0; k < c.KB; ++k) {
+        int p = k * 32 + lane;
+        uint32_t b = (src[k] >> lane) & 1u, w = (src[c.KB + k] >> lane) & 1u;
+        if (p < c.N2) emit(hb, p, tp == 1 ? b : w, tp == 1 ? w : b);
+      }
+      if (in_tree) {
+        int pm = load_meta(cur).parent;
+        if (pm >= 0) { cur = pm; src = bits_of(cur); continue; }
+        in_tree = false;
+      }
+      if (ri < st.hist_len) { src = h + (size_t)ri * 2 * c.KB; ++ri; }
+    }
+    return tp;
+  }
+
+  // ---- new game in this slot (initialize_game! + selfplay.jl:9) ---------------------------------------
+  AGZ_DEV void init_root_from_scratch(int n, int ko, int to_play, int flags) {
+    st.root = 0;
+    st.count = 1;
+    st.root_N = 0.f;
+    st.root_W = 0.f;
+    st.sel_ctr = 0;
+    st.noise_ctr = 0;
+    st.n_moves = 0;
+    st.nleaf = 0;
+    st.vloss_balance = 0;
+    st.err = 0;
+    st.result = 0;
+    st.resigned = 0;
+    bool term = (flags & F_DONE) || n >= c.max_game_length;
+    if (!term) { rules_label(B, rs, 0); rules_count_liberties(B, rs); }
+    write_node(0, -1, -1, n, ko, to_play, flags, term);
+    simt::sync();
+  }
+
+  AGZ_DEV void start_game(long long game_id) {
+    st.game_id = game_id;
+    st.game_id_lo = (uint32_t)game_id;
+    st.hist_len = 0;
+    for (int k = 0; k < c.KB; ++k) rs.bd[k * 32 + lane] = 0;
+    simt::sync();
+    init_root_from_scratch(0, -1, 1, 0);
+    U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_RESIGN, 0, 0, 0);
+    st.resign_thr = u53(rr.x, rr.y) < c.resign_disable_frac ? -1.0 : c.resign_threshold;
+    st.phase = PH_SEED;
+    count(CTR_STARTED, 1);
+  }
+
+  // ---- game end: publish the record into the finished ring, then refill the slot --------------------
+  AGZ_DEV bool publish() {
+    unsigned long long t = 0;
+    int ok = 0;
+    if (lane == 0) {
+#if AGZ_CUDA
+      for (;;) {
+        t = *((volatile unsigned long long*)&v.ctr[CTR_RING_TAIL]);
+        unsigned long long h = *((volatile unsigned long long*)&v.ctr[CTR_RING_HEAD]);
+        if (t - h >= (unsigned long long)c.ring_cap) break;
+        if (atomicCAS(&v.ctr[CTR_RING_TAIL], t, t + 1) == t) { ok = 1; break; }
+      }
+#else
+      t = v.ctr[CTR_RING_TAIL];
+      if (t - v.ctr[CTR_RING_HEAD] < (unsigned long long)c.ring_cap) { v.ctr[CTR_RING_TAIL] = t + 1; ok = 1; }
+#endif
+    }
+    ok = simt::shfl(ok, 0);
+    if (!ok) return false;
+    const int rslot = simt::shfl((int)(t % (unsigned long long)c.ring_cap), 0);
+    const int L = c.max_game_length + 2;
+    const size_t src = (size_t)g * L, dst = (size_t)rslot * L;
+    const int nm = st.n_moves;
+    for (int i = lane; i < nm; i += 32) {
+      v.ring_moves[dst + i] = v.rec_moves[src + i];
+      v.ring_q[dst + i] = v.rec_q[src + i];
+    }
+    const size_t tot = (size_t)nm * c.A;
+    for (size_t i = lane; i < tot; i += 32) {
+      v.ring_pi[dst * c.A + i] = v.rec_pi[src * c.A + i];
+      v.ring_vis[dst * c.A + i] = v.rec_vis[src * c.A + i];
+    }
+    if (lane == 0) {
+      RingHeader hd;
+      hd.game_id = st.game_id; hd.n_moves = nm; hd.result = st.result; hd.resigned = st.resigned;
+      hd.final_score = st.final_score; hd.resign_threshold = st.resign_thr;
+      v.ring_hdr[rslot] = hd;
+    }
+    count(CTR_FINISHED, 1);
+    return true;
+  }
+
+  AGZ_DEV void finish_or_wait() {
+    if (!publish()) { st.phase = PH_WAIT_RING; return; }
+    long long next = st.game_id + (long long)c.n_games * c.world;
+    if (c.total_games < 0 || next < c.total_games) start_game(next);
+    else st.phase = PH_IDLE;
+  }
+
+  // ---- selfplay.jl:22-43, evaluated once per round after the leaves have been incorporated -----------
+  AGZ_DEV void after_round() {
+    if (st.err) { st.phase = PH_IDLE; return; }
+    if (st.phase == PH_WAIT_RING) { finish_or_wait(); return; }
+    if (st.phase == PH_SEED) {
+      if (st.seed_round) {
+        st.phase = PH_SEARCH;
+        if (c.inject_noise) inject_noise();
+        st.target_N = simt::fadd(st.root_N, (float)c.readouts);
+      }
+      return;
+    }
+    if (st.phase != PH_SEARCH) return;
+    if (st.root_N < st.target_N) return;  // while N(root) < current_readouts + readouts (selfplay.jl:27)
+    const NodeMeta rm = load_meta(st.root);
+    const float q = simt::fdiv(st.root_W, simt::fadd(1.0f, st.root_N));
+    const float qp = simt::fmul(q, (float)rm.to_play);
+    if ((double)qp < st.resign_thr) {  // should_resign (mcts_play.jl:124)
+      st.result = -rm.to_play;
+      st.resigned = 1;
+      st.final_score = 0.f;
+      finish_or_wait();
+      return;
+    }
+    int mv = pick_move();
+    if (mv < 0) { st.phase = PH_IDLE; return; }
+    if (play_move(mv, true) != E_OK) { st.phase = PH_IDLE; return; }
+    count(CTR_MOVES, 1);
+    const NodeMeta nm = load_meta(st.root);
+    if (terminal(nm)) {  // is_done(root) (selfplay.jl:39-42)
+      const uint32_t* lb = bits_of(st.root);
+      rules_load(B, rs, lb, lb + c.KB);
+      float sc = rules_score(B, rs, c.komi);
+      st.final_score = sc;
+      st.result = sc > 0.f ? 1 : (sc < 0.f ? -1 : 0);
+      st.resigned = 0;
+      finish_or_wait();
+      return;
+    }
+    if (c.inject_noise) inject_noise();
+    st.target_N = simt::fadd(st.root_N, (float)c.readouts);
+  }
+};
+
+}  // namespace agz

@@ -12,9 +12,12 @@ dirichlet_noise_weight = 0.25                            # mcts.jl:13
 f32 = np.float32
 
 
+MAX_GAME_LENGTH_OVERRIDE = None   # tests shorten 19x19 games; None = the reference's N^2*7/5
+
+
 class MCTSRules:                                         # mcts.jl:15-25
     def __init__(self, env):
-        self.max_game_length = (env.N ** 2 * 7) // 5
+        self.max_game_length = MAX_GAME_LENGTH_OVERRIDE or (env.N ** 2 * 7) // 5
         self.dirichlet_noise_alpha = f32(0.03 * env.max_action_space / env.action_space)
 
 

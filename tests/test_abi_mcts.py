@@ -1,0 +1,340 @@
+"""The reference's test/test_mcts.jl and test/test_mcts_player.jl driven through the C ABI (device tree code),
+plus bit-exact self-play parity against the oracle (visit counts, chosen moves, pi, q, result)."""
+import numpy as np
+import pytest
+
+from backends import BACKENDS, agz, lib_for
+from oracle import go as ogo
+from oracle import mcts as OM
+from oracle import mcts_play as OP
+from oracle import selfplay as osp
+from refboards import load_board, ALMOST_DONE_BOARD, TT_FTW_BOARD
+
+BLACK, WHITE = 1, -1
+f32 = np.float32
+
+
+class DummyNet:                                          # test_mcts_player.jl:10-32
+    def __init__(self, A=82, fake_priors=None, fake_value=0):
+        self.fake_priors = (np.ones(A) / A if fake_priors is None else np.asarray(fake_priors)).astype(f32)
+        self.fake_value = f32(fake_value)
+
+    def __call__(self, positions):
+        n = len(positions)
+        return np.repeat(self.fake_priors[:, None], n, axis=1), np.repeat(self.fake_value, n)
+
+
+@pytest.fixture(scope="module", params=BACKENDS)
+def env(request):
+    return agz.GoEnv(9, lib_path=lib_for(request.param))
+
+
+A = 82
+
+
+def root_of(env, pos=None, net=None, **kw):
+    pl = agz.MCTSPlayer(env, net or DummyNet(), **kw)
+    pl.initialize_game(pos)
+    return pl, pl.root
+
+
+def send_two_return_one(env, n=75, komi=0.5, caps=(0, 0), three=True):
+    recent = [(BLACK, (0, 1)), (WHITE, (0, 8))] + ([(BLACK, (1, 0))] if three else [])
+    return agz.GoPosition(env, board=load_board(ALMOST_DONE_BOARD, env), n=n, komi=komi, caps=caps, recent=recent,
+                          to_play=WHITE if three else BLACK)
+
+
+def test_action_flipping(env):                           # test_mcts.jl:45-59
+    rs = np.random.RandomState(1)
+    probs = (0.02 * np.ones(A) + rs.rand(A) * 0.001).astype(f32)
+    _, broot = root_of(env)
+    _, wroot = root_of(env, agz.GoPosition(env, to_play=WHITE))
+    agz.incorporate_results(agz.select_leaf(broot), probs, 0)
+    agz.incorporate_results(agz.select_leaf(wroot), probs, 0)
+    bl, wl = agz.select_leaf(broot), agz.select_leaf(wroot)
+    assert bl.fmove == wl.fmove
+    assert (broot.child_action_score() == wroot.child_action_score()).all()
+
+
+def test_select_leaf(env):                               # :61-70
+    flattened = agz.to_flat(agz.from_kgs("D9", env), env)
+    probs = (0.02 * np.ones(A)).astype(f32)
+    probs[flattened] = 0.4
+    _, root = root_of(env, send_two_return_one(env))
+    agz.incorporate_results(agz.select_leaf(root), probs, 0)
+    assert root.position.to_play == WHITE
+    assert agz.select_leaf(root) == root.children[flattened]
+
+
+def test_backup_incorporate_results(env):                # :72-114
+    probs = (0.02 * np.ones(A)).astype(f32)
+    _, root = root_of(env, send_two_return_one(env))
+    agz.incorporate_results(agz.select_leaf(root), probs, 0)
+    leaf = agz.select_leaf(root)
+    agz.incorporate_results(leaf, probs, -1)
+    assert root.N == 2
+    assert root.Q == pytest.approx(-1 / 3, rel=1e-6)
+    assert root.child_N[leaf.fmove] == 1 and leaf.N == 1
+    assert root.child_Q()[leaf.fmove] == -0.5
+    assert leaf.Q == pytest.approx(-0.5)
+    leaf2 = agz.select_leaf(root)
+    agz.incorporate_results(leaf2, probs, -0.2)
+    assert root.N == 3 and root.Q == pytest.approx(-0.3, rel=1e-6)
+    assert leaf.N == 2 and leaf2.N == 1 and leaf2.parent == leaf
+    assert leaf.Q == pytest.approx(-0.4, rel=1e-6)
+    assert leaf.child_Q()[leaf2.fmove] == pytest.approx(-0.6, rel=1e-6)
+    assert leaf2.Q == pytest.approx(-0.6, rel=1e-6)
+
+
+def test_do_not_explore_past_finish(env):                # :116-127
+    probs = (0.02 * np.ones(A)).astype(f32)
+    _, root = root_of(env)
+    agz.incorporate_results(agz.select_leaf(root), probs, 0)
+    first_pass = agz.maybe_add_child(root, 81)
+    agz.incorporate_results(first_pass, probs, 0)
+    second_pass = agz.maybe_add_child(first_pass, 81)
+    with pytest.raises(AssertionError):
+        agz.incorporate_results(second_pass, probs, 0)
+    assert agz.select_leaf(second_pass) == second_pass
+
+
+def test_add_child_and_idempotency(env):                 # :129-144
+    _, root = root_of(env)
+    child = agz.maybe_add_child(root, 16)
+    assert 16 in root.children and child.parent == root and child.fmove == 16
+    before = root.children
+    assert agz.maybe_add_child(root, 16) == child
+    assert before == root.children
+
+
+def test_never_select_illegal_moves(env):                # :146-167
+    probs = (0.02 * np.ones(A)).astype(f32)
+    probs[1] = 0.99
+    pl, root = root_of(env, send_two_return_one(env))
+    agz.incorporate_results(root, probs, 0)
+    legal = root.legal_moves().astype(bool)
+    assert not legal[1]
+    cn = root.child_N
+    cn[legal] = 10000
+    pl.engine.tree_set_stats(0, root.id, self_N=10000, child_N=cn)
+    assert agz.select_leaf(root).fmove != 1
+    for _ in range(10):
+        agz.inject_noise(root)
+        assert agz.select_leaf(root).fmove != 1
+
+
+def test_dont_pick_unexpanded_child(env):                # :169-183
+    probs = (0.02 * np.ones(A)).astype(f32)
+    probs[17] = 0.999
+    _, root = root_of(env)
+    agz.incorporate_results(root, probs, 0)
+    leaf1 = agz.select_leaf(root)
+    assert leaf1.fmove == 17
+    agz.add_virtual_loss(leaf1)
+    assert agz.select_leaf(root) == leaf1
+
+
+def test_node_features(env):                             # test_features.jl:48-79 via tree nodes
+    pl, root = root_of(env)
+    for c in ((0, 0), (0, 1), (0, 2), (0, 3), (1, 1)):
+        assert pl.play_move(c)
+    f = pl.engine.tree_node_features(0, pl.root.id).reshape(17, 9, 9)      # [c, j, i]
+    lb = lambda two_rows: load_board(two_rows + "." * 9 + "\n" + ("." * 9 + "\n") * 6, env).T
+    assert (f[0] == lb("...X.....\n.........\n")).all()
+    assert (f[1] == lb("X.X......\n.X.......\n")).all()
+    assert (f[2] == lb(".X.X.....\n.........\n")).all()
+    assert (f[3] == lb("X.X......\n.........\n")).all()
+    assert (f[4] == lb(".X.......\n.........\n")).all()
+    assert (f[5] == lb("X.X......\n.........\n")).all()
+    assert (f[10:16] == 0).all() and (f[16] == -1).all()
+
+
+# ------------------------------------------------------------ test_mcts_player.jl
+def basic_player(env):                                   # :59-66
+    pl, root = root_of(env)
+    first = agz.select_leaf(root)
+    agz.incorporate_results(first, DummyNet().fake_priors, 0)
+    return pl
+
+
+def almost_done_player(env):                             # :68-77
+    probs = np.ones(A) * 0.001
+    probs[2:5] = 0.2
+    probs[-1] = 0.2
+    pl, _ = root_of(env, send_two_return_one(env, n=70, komi=2.5, caps=(1, 4), three=False), DummyNet(fake_priors=probs))
+    return pl
+
+
+def test_inject_noise(env):                              # :93-109
+    pl = basic_player(env)
+    s = pl.root.child_prior.sum()
+    assert s == pytest.approx(1, rel=1e-5)
+    agz.inject_noise(pl.root)
+    assert pl.root.child_prior.sum() == pytest.approx(s, rel=1e-5)
+    assert pl.root.child_prior.max() > 3 / A
+
+
+def test_pick_moves(env):                                # :111-137
+    pl = basic_player(env)
+    cn = pl.root.child_N
+    cn[agz.to_flat((2, 0), env)] = 10
+    cn[agz.to_flat((1, 0), env)] = 5
+    cn[agz.to_flat((3, 0), env)] = 1
+    pl.engine.tree_set_stats(0, pl.root.id, child_N=cn, n_override=A)
+    assert pl.pick_move() == (2, 0)
+    pl.engine.tree_set_stats(0, pl.root.id, n_override=3)
+    assert pl.pick_move() in ((2, 0), (1, 0), (3, 0))
+
+
+def test_dont_pass_if_losing(env):                       # :139-165
+    pl = almost_done_player(env)
+    assert agz.score(pl.root.position) == -0.5
+    for _ in range(20):
+        pl.tree_search()
+    flattened = agz.to_flat(agz.from_kgs("D9", env), env)
+    root = pl.root
+    assert int(np.argmax(root.child_N)) == flattened
+    assert root.children[flattened].Q > 0
+    assert root.N >= 20
+    assert root.child_Q()[-1] < 0
+    assert pl.engine.tree_pending_vlosses(0) == 0
+
+
+def test_parallel_tree_search(env):                      # :167-202
+    pl = almost_done_player(env)
+    pl.tree_search(1)
+    for _ in range(6):
+        pl.tree_search(10)
+    flattened = agz.to_flat(agz.from_kgs("D9", env), env)
+    cn = pl.root.child_N
+    assert flattened in np.flatnonzero(cn == cn.max())
+    assert pl.root.children[flattened].Q > 0 and pl.root.N >= 20
+    assert pl.engine.tree_pending_vlosses(0) == 0
+    pl2 = almost_done_player(env)
+    for _ in range(10):
+        pl2.tree_search(50)
+    assert pl2.engine.tree_pending_vlosses(0) == 0
+
+
+def test_long_game_tree_search(env):                     # :204-225
+    maxlen = 81 * 7 // 5
+    endgame = agz.GoPosition(env, board=load_board(TT_FTW_BOARD, env), n=maxlen - 2, komi=2.5,
+                             recent=[(BLACK, (0, 1)), (WHITE, (0, 8))], to_play=BLACK)
+    pl, _ = root_of(env, endgame)
+    for _ in range(10):
+        pl.tree_search(8)
+    assert pl.engine.tree_pending_vlosses(0) == 0
+    assert pl.root.Q > 0
+
+
+def test_cold_start_parallel_tree_search(env):           # :227-240
+    pl, root = root_of(env, None, DummyNet(fake_value=0.17))
+    assert root.N == 0 and not root.is_expanded
+    pl.tree_search(4)
+    assert pl.engine.tree_pending_vlosses(0) == 0
+    assert pl.root.N == 1
+    assert pl.root.Q == pytest.approx(0.085, rel=1e-6)
+
+
+def test_tree_search_failsafe(env):                      # :242-252
+    probs = np.ones(A) * 0.001
+    probs[-1] = 1
+    pl, _ = root_of(env, agz.api.pass_move(agz.GoPosition(env)), DummyNet(fake_priors=probs))
+    pl.tree_search(1)
+    assert pl.engine.tree_pending_vlosses(0) == 0
+
+
+def test_only_check_game_end_once(env):                  # :254-283
+    pos = agz.GoPosition(env)
+    for c in ((3, 3), (3, 4), (4, 3), None):
+        pos = agz.play_move(pos, c)
+    pl, _ = root_of(env, pos)
+    for _ in range(15):
+        pl.tree_search()
+    assert pl.root.children[81].N == 1 and pl.root.child_N[81] == 1
+    pl.tree_search()
+    assert pl.root.child_N[81] == 1
+
+
+def test_extract_data(env):                              # :285-321
+    pl, _ = root_of(env)
+    pl.tree_search()
+    pl.play_move(None)
+    pl.tree_search()
+    pl.play_move(None)
+    assert pl.is_done()
+    pl.set_result(agz.result(pl.root.position), False)
+    positions, pis, results = pl.extract_data()
+    assert len(positions) == len(pis) == len(results) == 2
+    assert results[0] == WHITE and pl.result_string == "W+7.5"
+    pl, _ = root_of(env)
+    pl.tree_search()
+    pl.play_move((0, 0))
+    pl.tree_search()
+    pl.play_move(None)
+    pl.tree_search()
+    assert agz.result(pl.root.position) == BLACK
+    pl.set_result(WHITE, True)
+    positions, pis, results = pl.extract_data()
+    assert results[0] == WHITE and pl.result_string == "W+R"
+
+
+def test_generic_callable_network(env):
+    """`network` may be any callable positions -> (A x B, B): same tree as the on-device dummy evaluator."""
+    rs = np.random.RandomState(3)
+    pri = rs.dirichlet(np.ones(A)).astype(f32)
+
+    class HostNet:
+        def __call__(self, positions):
+            n = len(positions)
+            return np.repeat(pri[:, None], n, axis=1), np.repeat(f32(0.1), n)
+
+    p1, _ = root_of(env, None, HostNet(), seed=5)
+    p2, _ = root_of(env, None, DummyNet(fake_priors=pri, fake_value=0.1), seed=5)
+    for _ in range(6):
+        p1.tree_search()
+        p2.tree_search()
+    assert (p1.root.child_N == p2.root.child_N).all() and (p1.root.child_W == p2.root.child_W).all()
+
+
+# ------------------------------------------------------------ self-play parity with the oracle
+def check_selfplay_parity(env, N, readouts, seeds, priors_seed=None, value=0.0, n_games=1, **kw):
+    oenv = ogo.GoEnv(N)
+    A_ = N * N + 1
+    if priors_seed is None:
+        net = DummyNet(A_, fake_value=value)
+    else:
+        pri = np.random.RandomState(priors_seed).dirichlet(np.ones(A_) * 0.5).astype(f32)
+        net = DummyNet(A_, fake_priors=pri, fake_value=value)
+    OM.MAX_GAME_LENGTH_OVERRIDE = kw.get("max_game_length")
+    for seed in seeds:
+        recs = agz.selfplay(env, net, readouts, seed=seed, n_games=n_games, **kw)
+        recs = [recs] if n_games == 1 else recs
+        for gid, r in enumerate(recs):
+            op = osp.selfplay(oenv, net, readouts, seed=seed, game_id=gid)
+            om = [ogo.to_flat(m.move, oenv) for m in op.root.position.recent]
+            assert list(r.record.moves) == om, (seed, gid)
+            assert r.result == op.result and r.result_string == op.result_string
+            assert np.array_equal(np.array(op.searches_N), r.record.visits), (seed, gid)
+            assert np.array_equal(np.array(op.searches_pi, dtype=f32), r.record.searches_pi), (seed, gid)
+            assert np.array_equal(np.array(op.qs, dtype=f32), r.record.qs), (seed, gid)
+    OM.MAX_GAME_LENGTH_OVERRIDE = None
+
+
+def test_selfplay_matches_oracle(env):
+    check_selfplay_parity(env, 9, 24, seeds=[0, 1])
+    check_selfplay_parity(env, 9, 16, seeds=[2], priors_seed=7, value=-0.2)
+
+
+def test_selfplay_concurrent_games_match_oracle(env):
+    check_selfplay_parity(env, 9, 16, seeds=[3], n_games=3)
+
+
+@pytest.mark.gpu
+def test_selfplay_matches_oracle_bulk():
+    """C2-like readouts on a handful of games, and many concurrent small games (slot refill, ring, compaction)."""
+    env = agz.GoEnv(9, lib_path=lib_for("cuda"))
+    check_selfplay_parity(env, 9, 400, seeds=[0], n_games=2)
+    check_selfplay_parity(env, 9, 32, seeds=[11], priors_seed=5, value=0.1, n_games=24, concurrent=8)
+    env19 = agz.GoEnv(19, lib_path=lib_for("cuda"))
+    check_selfplay_parity(env19, 19, 16, seeds=[4], n_games=2, max_game_length=60)
