@@ -45,6 +45,12 @@ struct TCInput {
 };
 TCInput nn_tc_input(NNet* n);
 int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen);
+// feature kernels that write the tensor-core input directly (nn_tc.cu): from the leaves of the current round
+// (batch rows [0, row0+nrows)), and from caller-supplied positions.
+struct Cfg;
+struct View;
+int engine_tc_features(const Cfg& c, const View& v, NNet* n, int row0, int nrows, int smem_per_warp, cudaStream_t s);
+int engine_host_features_tc(const Cfg& c, NNet* n, const int8_t* boards_hist, const int8_t* to_play, int B, cudaStream_t s);
 // 2*MACs of one position through the network (stem + tower + heads), for the roofline
 double nn_flops_per_position(const NNShape& s);
 long long nn_tc_launches_per_forward(const NNet* n);

@@ -1,0 +1,392 @@
+// nn_f32.cu -- network state, parameter handling, and the fp32 SIMT implementation of the forward pass
+// (src/neural_net.jl:57-68; src/resnet.jl:26-32).  The fp32 path is the on-device cross-check of the
+// tcgen05 path in nn_tc.cu; it is not the fast path.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "nn_state.h"
+
+namespace agz {
+
+static size_t base_count(const NNShape& s) {
+  size_t C = s.filters;
+  return 9 * (size_t)s.planes * C + 3 * C + (size_t)s.tower * (2 * (9 * C * C + C) + 4 * C);
+}
+static size_t value_count(const NNShape& s) {
+  size_t C = s.filters, N2 = (size_t)s.N * s.N;
+  return C + 3 + 256 * N2 + 256 + 256 + 1;
+}
+static size_t policy_count(const NNShape& s) {
+  size_t C = s.filters, N2 = (size_t)s.N * s.N, A = N2 + 1;
+  return 2 * C + 6 + A * 2 * N2 + A;
+}
+
+size_t nn_param_count(const NNet* n, int chain) {
+  if (!n) return 0;
+  return chain == 0 ? base_count(n->s) : (chain == 1 ? value_count(n->s) : policy_count(n->s));
+}
+size_t nn_bn_count(const NNet* n, int chain) {
+  if (!n) return 0;
+  return chain == 0 ? (size_t)n->s.filters * (1 + 2 * n->s.tower) : (chain == 1 ? 1 : 2);
+}
+
+double nn_flops_per_position(const NNShape& s) {
+  double N2 = (double)s.N * s.N, C = s.filters, A = N2 + 1;
+  double stem = 2 * 9 * s.planes * C * N2;
+  double tower = (double)s.tower * 2 * (2 * 9 * C * C * N2);
+  double heads = 2 * (3 * C * N2) + 2 * (256 * N2 + 256) + 2 * (A * 2 * N2);
+  return stem + tower + heads;
+}
+
+#define CUDA_TRY(x)                        \
+  do {                                     \
+    cudaError_t e__ = (x);                 \
+    if (e__ != cudaSuccess) return (int)e__; \
+  } while (0)
+
+template <class T>
+static bool dmal(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)) == cudaSuccess; }
+
+NNet* nn_create(const NNShape& s, int max_batch, char* err, size_t errlen) {
+  NNet* n = new NNet();
+  n->s = s;
+  n->N2 = s.N * s.N;
+  n->A = n->N2 + 1;
+  n->C = s.filters;
+  n->max_batch = max_batch;
+  n->ready = false;
+  n->tc = nullptr;
+  for (int k = 0; k < 3; ++k) {
+    n->have[k] = false;
+    n->bn_mode[k] = 0;
+    n->hmu[k].assign(nn_bn_count(n, k), 0.f);
+    n->hsigma[k].assign(nn_bn_count(n, k), 1.f);
+  }
+  const int nconv = 1 + 2 * s.tower;
+  bool ok = true;
+  n->f_w.assign(nconv, nullptr);
+  n->f_scale.assign(nconv, nullptr);
+  n->f_shift.assign(nconv, nullptr);
+  for (int l = 0; l < nconv && ok; ++l) {
+    size_t cin = l == 0 ? s.planes : s.filters;
+    ok = ok && dmal(&n->f_w[l], (size_t)s.filters * cin * 9) && dmal(&n->f_scale[l], (size_t)s.filters) && dmal(&n->f_shift[l], (size_t)s.filters);
+  }
+  ok = ok && dmal(&n->f_vw, (size_t)s.filters) && dmal(&n->f_pw, (size_t)2 * s.filters) && dmal(&n->f_head_aff_d, (size_t)6);
+  ok = ok && dmal(&n->f_D1W, (size_t)256 * n->N2) && dmal(&n->f_D1b, (size_t)256) && dmal(&n->f_D2W, (size_t)256) && dmal(&n->f_D2b, (size_t)1);
+  ok = ok && dmal(&n->f_PW, (size_t)n->A * 2 * n->N2) && dmal(&n->f_Pb, (size_t)n->A);
+  // fp32 activations are only needed by the cross-check path; cap the batch it supports to bound memory
+  for (int i = 0; i < 3; ++i) n->f_act[i] = nullptr;
+  if (!ok) {
+    snprintf(err, errlen, "cudaMalloc failed for network parameters");
+    nn_destroy(n);
+    return nullptr;
+  }
+  if (nn_tc_create(n, err, errlen)) {
+    nn_destroy(n);
+    return nullptr;
+  }
+  return n;
+}
+
+void nn_destroy(NNet* n) {
+  if (!n) return;
+  nn_tc_destroy(n);
+  for (auto p : n->f_w) cudaFree(p);
+  for (auto p : n->f_scale) cudaFree(p);
+  for (auto p : n->f_shift) cudaFree(p);
+  cudaFree(n->f_vw); cudaFree(n->f_pw); cudaFree(n->f_head_aff_d);
+  cudaFree(n->f_D1W); cudaFree(n->f_D1b); cudaFree(n->f_D2W); cudaFree(n->f_D2b); cudaFree(n->f_PW); cudaFree(n->f_Pb);
+  for (int i = 0; i < 3; ++i) cudaFree(n->f_act[i]);
+  delete n;
+}
+
+int nn_set_params(NNet* n, int chain, const float* flat, size_t cnt) {
+  if (cnt != nn_param_count(n, chain)) return 1;
+  n->hparams[chain].assign(flat, flat + cnt);
+  n->have[chain] = true;
+  n->ready = false;
+  return 0;
+}
+
+int nn_set_bn(NNet* n, int chain, const float* mu, const float* sigma, size_t cnt, int mode) {
+  if (cnt != nn_bn_count(n, chain)) return 1;
+  n->hmu[chain].assign(mu, mu + cnt);
+  n->hsigma[chain].assign(sigma, sigma + cnt);
+  n->bn_mode[chain] = mode;
+  n->ready = false;
+  return 0;
+}
+
+bool nn_ready(const NNet* n) { return n && n->ready; }
+
+static void fold_bn(const float* beta, const float* gamma, const float* mu, const float* sigma, const float* bias, int C, int mode,
+                    float* scale, float* shift) {
+  for (int c = 0; c < C; ++c) {
+    float den = mode == 0 ? sqrtf(sigma[c] + 1e-5f) : sigma[c];
+    float sc = gamma[c] / den;
+    scale[c] = sc;
+    shift[c] = beta[c] - mu[c] * sc + sc * bias[c];
+  }
+}
+
+int nn_fold_layers(const NNet* n, std::vector<ConvLayerHost>& convs, char* err, size_t errlen) {
+  if (!n->have[0] || !n->have[1] || !n->have[2]) {
+    snprintf(err, errlen, "parameters of chain %d have not been set (agz_net_set_params)", !n->have[0] ? 0 : (!n->have[1] ? 1 : 2));
+    return 1;
+  }
+  const int C = n->C, T = n->s.tower, P = n->s.planes;
+  const float* p = n->hparams[0].data();
+  const float* mu = n->hmu[0].data();
+  const float* sg = n->hsigma[0].data();
+  convs.clear();
+  auto add = [&](const float* W, const float* b, const float* beta, const float* gamma, int cin, int bn_index) {
+    ConvLayerHost L;
+    L.cin = cin; L.cout = C;
+    L.w.assign(W, W + (size_t)9 * cin * C);
+    L.scale.resize(C); L.shift.resize(C);
+    fold_bn(beta, gamma, mu + (size_t)bn_index * C, sg + (size_t)bn_index * C, b, C, n->bn_mode[0], L.scale.data(), L.shift.data());
+    convs.push_back(std::move(L));
+  };
+  // stem: W, b, beta, gamma
+  add(p, p + (size_t)9 * P * C, p + (size_t)9 * P * C + C, p + (size_t)9 * P * C + 2 * C, P, 0);
+  p += (size_t)9 * P * C + 3 * C;
+  for (int t = 0; t < T; ++t) {  // W1, b1, W2, b2, beta1, gamma1, beta2, gamma2
+    const float* W1 = p; const float* b1 = W1 + (size_t)9 * C * C;
+    const float* W2 = b1 + C; const float* b2 = W2 + (size_t)9 * C * C;
+    const float* be1 = b2 + C; const float* ga1 = be1 + C; const float* be2 = ga1 + C; const float* ga2 = be2 + C;
+    add(W1, b1, be1, ga1, C, 1 + 2 * t);
+    add(W2, b2, be2, ga2, C, 2 + 2 * t);
+    p = ga2 + C;
+  }
+  return 0;
+}
+
+int nn_commit(NNet* n, cudaStream_t s, char* err, size_t errlen) {
+  std::vector<ConvLayerHost> convs;
+  if (nn_fold_layers(n, convs, err, errlen)) return 1;
+  const int C = n->C, N2 = n->N2, A = n->A;
+  for (size_t l = 0; l < convs.size(); ++l) {
+    const ConvLayerHost& L = convs[l];
+    // device layout w[co][ci][t], t = kj*3 + ki for the input offset (dj, di) = (kj-1, ki-1):
+    // Flux Conv is a true convolution, so tap (ki, kj) of the correlation uses W[2-ki, 2-kj]
+    std::vector<float> w((size_t)L.cout * L.cin * 9);
+    for (int co = 0; co < L.cout; ++co)
+      for (int ci = 0; ci < L.cin; ++ci)
+        for (int kj = 0; kj < 3; ++kj)
+          for (int ki = 0; ki < 3; ++ki)
+            w[((size_t)co * L.cin + ci) * 9 + kj * 3 + ki] = L.w[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)L.cin * co];
+    cudaMemcpyAsync(n->f_w[l], w.data(), w.size() * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(n->f_scale[l], L.scale.data(), (size_t)C * 4, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(n->f_shift[l], L.shift.data(), (size_t)C * 4, cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+  }
+  // value head: W(1,1,C,1), b, beta, gamma, D1W(256,N2), D1b, D2W(1,256), D2b
+  const float* v = n->hparams[1].data();
+  float aff[6];
+  fold_bn(v + C + 1, v + C + 2, n->hmu[1].data(), n->hsigma[1].data(), v + C, 1, n->bn_mode[1], &aff[0], &aff[1]);
+  cudaMemcpyAsync(n->f_vw, v, (size_t)C * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(n->f_D1W, v + C + 3, (size_t)256 * N2 * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(n->f_D1b, v + C + 3 + (size_t)256 * N2, 256 * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(n->f_D2W, v + C + 3 + (size_t)256 * N2 + 256, 256 * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(n->f_D2b, v + C + 3 + (size_t)256 * N2 + 512, 4, cudaMemcpyHostToDevice, s);
+  // policy head: W(1,1,C,2), b(2), beta(2), gamma(2), DW(A, 2*N2), Db(A)
+  const float* p = n->hparams[2].data();
+  float sc2[2], sh2[2];
+  fold_bn(p + 2 * C + 2, p + 2 * C + 4, n->hmu[2].data(), n->hsigma[2].data(), p + 2 * C, 2, n->bn_mode[2], sc2, sh2);
+  aff[2] = sc2[0]; aff[3] = sh2[0]; aff[4] = sc2[1]; aff[5] = sh2[1];
+  // 1x1 conv weight W[0,0,ci,co] at ci + C*co -> f_pw[co][ci]
+  cudaMemcpyAsync(n->f_pw, p, (size_t)2 * C * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(n->f_PW, p + 2 * C + 6, (size_t)A * 2 * N2 * 4, cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(n->f_Pb, p + 2 * C + 6 + (size_t)A * 2 * N2, (size_t)A * 4, cudaMemcpyHostToDevice, s);
+  memcpy(n->f_head_aff, aff, sizeof(aff));
+  cudaMemcpyAsync(n->f_head_aff_d, aff, sizeof(aff), cudaMemcpyHostToDevice, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) {
+    snprintf(err, errlen, "uploading network parameters failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  if (nn_tc_commit(n, convs, s, err, errlen)) return 1;
+  n->ready = true;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// fp32 kernels.  Activations: [B][C][N2] with point p = N*j + i (i fastest) = the reference's W x H x C x B.
+
+static const int COT = 16, CIT = 16;
+
+__global__ void __launch_bounds__(128) conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                          const float* __restrict__ res, float* __restrict__ out, int Cin, int Cout,
+                                                          int N, int relu) {
+  extern __shared__ float sm[];
+  const int N2 = N * N, NP = N + 2, NPP = NP * NP;
+  float* sin = sm;                      // [CIT][NPP], zero halo
+  float* sw = sm + CIT * NPP;           // [COT][CIT][9]
+  const int b = blockIdx.x, co0 = blockIdx.y * COT, tid = threadIdx.x;
+  float acc[COT][3];
+#pragma unroll
+  for (int c = 0; c < COT; ++c)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) acc[c][q] = 0.f;
+  for (int ci0 = 0; ci0 < Cin; ci0 += CIT) {
+    for (int x = tid; x < CIT * NPP; x += 128) {
+      int ci = x / NPP, r = x % NPP, jj = r / NP - 1, ii = r % NP - 1;
+      float val = 0.f;
+      if (ci0 + ci < Cin && ii >= 0 && ii < N && jj >= 0 && jj < N) val = in[((size_t)b * Cin + ci0 + ci) * N2 + jj * N + ii];
+      sin[x] = val;
+    }
+    for (int x = tid; x < COT * CIT * 9; x += 128) {
+      int co = x / (CIT * 9), r = x % (CIT * 9), ci = r / 9, t = r % 9;
+      sw[x] = (ci0 + ci < Cin && co0 + co < Cout) ? w[((size_t)(co0 + co) * Cin + ci0 + ci) * 9 + t] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int p = tid + q * 128;
+      if (p < N2) {
+        int jj = p / N, ii = p % N;
+        for (int ci = 0; ci < CIT; ++ci) {
+          float x[9];
+#pragma unroll
+          for (int kj = 0; kj < 3; ++kj)
+#pragma unroll
+            for (int ki = 0; ki < 3; ++ki) x[kj * 3 + ki] = sin[ci * NPP + (jj + kj) * NP + (ii + ki)];
+#pragma unroll
+          for (int c = 0; c < COT; ++c) {
+            const float* wp = sw + (c * CIT + ci) * 9;
+            float a = acc[c][q];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) a = fmaf(wp[t], x[t], a);
+            acc[c][q] = a;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    int p = tid + q * 128;
+    if (p < N2) {
+#pragma unroll
+      for (int c = 0; c < COT; ++c) {
+        int co = co0 + c;
+        if (co < Cout) {
+          size_t o = ((size_t)b * Cout + co) * N2 + p;
+          float y = acc[c][q] * scale[co] + shift[co];
+          if (res) y += res[o];
+          if (relu) y = fmaxf(y, 0.f);
+          out[o] = y;
+        }
+      }
+    }
+  }
+}
+
+// heads (neural_net.jl:23-30): one block per position
+__global__ void __launch_bounds__(256) heads_f32_kernel(const float* __restrict__ trunk, const float* __restrict__ vw,
+                                                        const float* __restrict__ pw, const float* __restrict__ aff,
+                                                        const float* __restrict__ D1W, const float* __restrict__ D1b,
+                                                        const float* __restrict__ D2W, const float* __restrict__ D2b,
+                                                        const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
+                                                        float* __restrict__ v, int C, int N2) {
+  extern __shared__ float sm[];
+  float* vf = sm;             // [N2]
+  float* pf = sm + N2;        // [2*N2], index p + N2*c
+  float* hid = sm + 3 * N2;   // [256]
+  float* red = hid + 256;     // [256]
+  const int b = blockIdx.x, tid = threadIdx.x, A = N2 + 1;
+  const float* x = trunk + (size_t)b * C * N2;
+  for (int p = tid; p < N2; p += 256) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float xv = x[(size_t)c * N2 + p];
+      a0 = fmaf(vw[c], xv, a0);
+      a1 = fmaf(pw[c], xv, a1);
+      a2 = fmaf(pw[C + c], xv, a2);
+    }
+    vf[p] = fmaxf(a0 * aff[0] + aff[1], 0.f);
+    pf[p] = fmaxf(a1 * aff[2] + aff[3], 0.f);
+    pf[N2 + p] = fmaxf(a2 * aff[4] + aff[5], 0.f);
+  }
+  __syncthreads();
+  {  // Dense(N2 -> 256, relu): W (256, N2) column-major
+    float a = D1b[tid];
+    for (int i = 0; i < N2; ++i) a = fmaf(D1W[tid + 256 * i], vf[i], a);
+    hid[tid] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  red[tid] = D2W[tid] * hid[tid];  // Dense(256 -> 1): W (1, 256)
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  if (tid == 0) v[b] = tanhf(red[0] + D2b[0]);
+  __syncthreads();
+  // Dense(2*N2 -> A) + softmax
+  float lg[2];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int a = tid + q * 256;
+    lg[q] = -INFINITY;
+    if (a < A) {
+      float acc = Pb[a];
+      for (int i = 0; i < 2 * N2; ++i) acc = fmaf(PW[a + (size_t)A * i], pf[i], acc);
+      lg[q] = acc;
+      mx = fmaxf(mx, acc);
+    }
+  }
+  red[tid] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  mx = red[0];
+  __syncthreads();
+  float ex[2], sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    ex[q] = lg[q] == -INFINITY ? 0.f : expf(lg[q] - mx);
+    sum += ex[q];
+  }
+  red[tid] = sum;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  sum = red[0];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int a = tid + q * 256;
+    if (a < A) pi[(size_t)b * A + a] = ex[q] / sum;
+  }
+}
+
+long long nn_f32_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower + 1; }
+
+int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cudaStream_t s) {
+  const int C = n->C, N = n->s.N, N2 = n->N2;
+  if (B > n->max_batch) return (int)cudaErrorInvalidValue;
+  for (int i = 0; i < 3; ++i)
+    if (!n->f_act[i]) CUDA_TRY(cudaMalloc((void**)&n->f_act[i], (size_t)n->max_batch * C * N2 * sizeof(float)));
+  const size_t smem = (size_t)(CIT * (N + 2) * (N + 2) + COT * CIT * 9) * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(B, (C + COT - 1) / COT);
+  conv3x3_f32_kernel<<<grid, 128, smem, s>>>(feats, n->f_w[0], n->f_scale[0], n->f_shift[0], nullptr, n->f_act[0], n->s.planes, C, N, 1);
+  float *h = n->f_act[0], *t1 = n->f_act[1], *t2 = n->f_act[2];
+  for (int t = 0; t < n->s.tower; ++t) {
+    conv3x3_f32_kernel<<<grid, 128, smem, s>>>(h, n->f_w[1 + 2 * t], n->f_scale[1 + 2 * t], n->f_shift[1 + 2 * t], nullptr, t1, C, C, N, 1);
+    conv3x3_f32_kernel<<<grid, 128, smem, s>>>(t1, n->f_w[2 + 2 * t], n->f_scale[2 + 2 * t], n->f_shift[2 + 2 * t], h, t2, C, C, N, 1);
+    float* tmp = h; h = t2; t2 = tmp;
+  }
+  const size_t hsm = (size_t)(3 * N2 + 512) * sizeof(float);
+  heads_f32_kernel<<<B, 256, hsm, s>>>(h, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb, pi, v, C, N2);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace agz

@@ -1,0 +1,218 @@
+// replay.cu -- see replay.h.
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "devrt.h"
+#include "replay.h"
+
+namespace agz {
+
+static const long long kReplayCap = 500000;  // memory_size default (src/train.jl:38)
+
+struct ReplayState {
+  ncclComm_t comm;
+  bool have_comm;
+  int world, rank;
+  size_t stride;            // bytes per packed tuple: pi (4A) | board (N2) | to_play | z | pad -> multiple of 16
+  unsigned char* ring;      // [cap][stride]
+  long long cap, total;     // tuples ever appended (ring index = total % cap)
+  unsigned long long gather_pos;  // finished-ring records already packed
+  unsigned char* send;      // packed local tuples
+  unsigned char* recv;      // world * max_count * stride
+  size_t send_cap, recv_cap;
+  long long* d_counts;      // [world]
+  int* d_rec_idx;           // per packed record: ring slot, tuple offset
+  size_t rec_cap;
+};
+
+ReplayState* replay_create(const Cfg& c, char* err, size_t errlen) {
+  ReplayState* r = new ReplayState();
+  memset(r, 0, sizeof(*r));
+  r->world = c.world;
+  r->rank = c.rank;
+  r->stride = ((size_t)4 * c.A + c.N2 + 2 + 15) / 16 * 16;
+  r->cap = kReplayCap;
+  if (cudaMalloc((void**)&r->ring, (size_t)r->cap * r->stride) != cudaSuccess || cudaMalloc((void**)&r->d_counts, sizeof(long long) * c.world) != cudaSuccess) {
+    snprintf(err, errlen, "cudaMalloc of the replay ring failed");
+    replay_destroy(r);
+    return nullptr;
+  }
+  return r;
+}
+
+void replay_destroy(ReplayState* r) {
+  if (!r) return;
+  if (r->have_comm) ncclCommDestroy(r->comm);
+  cudaFree(r->ring); cudaFree(r->send); cudaFree(r->recv); cudaFree(r->d_counts); cudaFree(r->d_rec_idx);
+  delete r;
+}
+
+int replay_unique_id(uint8_t id_out[128]) {
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (ncclGetUniqueId(&id) != ncclSuccess) return 1;
+  memcpy(id_out, &id, 128);
+  return 0;
+}
+
+int replay_nccl_init(ReplayState* r, const uint8_t idb[128], int world, int rank, char* err, size_t errlen) {
+  ncclUniqueId id;
+  memcpy(&id, idb, 128);
+  ncclResult_t rc = ncclCommInitRank(&r->comm, world, id, rank);
+  if (rc != ncclSuccess) {
+    snprintf(err, errlen, "ncclCommInitRank: %s", ncclGetErrorString(rc));
+    return 1;
+  }
+  r->have_comm = true;
+  r->world = world;
+  r->rank = rank;
+  return 0;
+}
+
+// One warp per finished game: replay its moves from the empty board (replay_position, board.jl:557-578) and emit,
+// for every ply, the packed tuple (pi | board before the move | to_play | z = final result from Black's view).
+struct PackOp {
+  Cfg c;
+  View v;
+  const int* rec;  // [n][2]: finished-ring slot, first tuple index
+  unsigned char* out;
+  size_t stride;
+  __device__ void operator()(int wi, char* smem) const {
+    const int lane = threadIdx.x & 31;
+    Board B;
+    B.N = c.N; B.N2 = c.N2; B.KB = c.KB;
+    RulesScratch rs = rules_scratch_at(smem, c.KB);
+    const int rslot = rec[2 * wi], first = rec[2 * wi + 1];
+    const RingHeader hd = v.ring_hdr[rslot];
+    const size_t L = c.max_game_length + 2;
+    for (int k = 0; k < c.KB; ++k) rs.bd[k * 32 + lane] = 0;
+    __syncwarp();
+    int to_play = 1;
+    for (int t = 0; t < hd.n_moves; ++t) {
+      unsigned char* o = out + (size_t)(first + t) * stride;
+      float* opi = reinterpret_cast<float*>(o);
+      const float* pi = v.ring_pi + ((size_t)rslot * L + t) * c.A;
+      for (int a = lane; a < c.A; a += 32) opi[a] = pi[a];
+      int8_t* ob = reinterpret_cast<int8_t*>(o + (size_t)4 * c.A);
+      for (int p = lane; p < c.N2; p += 32) ob[p] = rs.bd[p];
+      if (lane == 0) {
+        ob[c.N2] = (int8_t)to_play;
+        ob[c.N2 + 1] = (int8_t)hd.result;
+      }
+      __syncwarp();
+      const int mv = v.ring_moves[(size_t)rslot * L + t];
+      if (mv != c.N2) {
+        int ko, ncap;
+        rules_play(B, rs, mv, to_play, false, ko, ncap);
+      }
+      to_play = -to_play;
+      __syncwarp();
+    }
+  }
+};
+
+static int grow(unsigned char** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  cudaFree(*p);
+  *p = nullptr;
+  size_t n = need + need / 2 + 4096;
+  if (cudaMalloc((void**)p, n) != cudaSuccess) return 1;
+  *cap = n;
+  return 0;
+}
+
+static void ring_append(ReplayState* r, const unsigned char* src, long long n, cudaStream_t s) {
+  while (n > 0) {  // trim-oldest ring (train.jl:52,63-65)
+    long long pos = r->total % r->cap;
+    long long run = n < r->cap - pos ? n : r->cap - pos;
+    cudaMemcpyAsync(r->ring + (size_t)pos * r->stride, src, (size_t)run * r->stride, cudaMemcpyDeviceToDevice, s);
+    src += (size_t)run * r->stride;
+    r->total += run;
+    n -= run;
+  }
+}
+
+int replay_gather(ReplayState* r, const Cfg& c, const View& v, int smem_per_warp, cudaStream_t s, int64_t* n_total, long long* launches,
+                  char* err, size_t errlen) {
+  *launches = 0;
+  cudaStreamSynchronize(s);
+  unsigned long long ctr[CTR_COUNT];
+  cudaMemcpy(ctr, v.ctr, sizeof(ctr), cudaMemcpyDeviceToHost);
+  unsigned long long head = ctr[CTR_RING_HEAD], tail = ctr[CTR_RING_TAIL];
+  if (r->gather_pos < head) r->gather_pos = head;  // records released before being gathered are gone
+  std::vector<int> rec;
+  long long n_local = 0;
+  for (unsigned long long q = r->gather_pos; q < tail; ++q) {
+    int rslot = (int)(q % (unsigned long long)c.ring_cap);
+    RingHeader hd;
+    cudaMemcpy(&hd, v.ring_hdr + rslot, sizeof(hd), cudaMemcpyDeviceToHost);
+    rec.push_back(rslot);
+    rec.push_back((int)n_local);
+    n_local += hd.n_moves;
+  }
+  r->gather_pos = tail;
+  const int nrec = (int)rec.size() / 2;
+  if (grow(&r->send, &r->send_cap, (size_t)(n_local ? n_local : 1) * r->stride)) { snprintf(err, errlen, "replay send buffer allocation failed"); return 3; }
+  if (nrec) {
+    if (rec.size() * sizeof(int) > r->rec_cap) {
+      cudaFree(r->d_rec_idx);
+      r->rec_cap = rec.size() * sizeof(int) * 2;
+      if (cudaMalloc((void**)&r->d_rec_idx, r->rec_cap) != cudaSuccess) { snprintf(err, errlen, "replay index allocation failed"); return 3; }
+    }
+    cudaMemcpyAsync(r->d_rec_idx, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+    PackOp op{c, v, r->d_rec_idx, r->send, r->stride};
+    int rc = devrt::launch_warps(op, nrec, smem_per_warp, s);
+    if (rc) { snprintf(err, errlen, "pack kernel: %s", cudaGetErrorString((cudaError_t)rc)); return 3; }
+    *launches += 1;
+  }
+  if (!r->have_comm || r->world == 1) {
+    ring_append(r, r->send, n_local, s);
+  } else {
+    // ragged all-gather: counts first, then fixed-stride padded blocks
+    cudaMemcpyAsync(r->d_counts + r->rank, &n_local, sizeof(long long), cudaMemcpyHostToDevice, s);
+    ncclResult_t nr = ncclAllGather(r->d_counts + r->rank, r->d_counts, 1, ncclInt64, r->comm, s);
+    if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(counts): %s", ncclGetErrorString(nr)); return 4; }
+    std::vector<long long> counts((size_t)r->world);
+    cudaMemcpyAsync(counts.data(), r->d_counts, sizeof(long long) * r->world, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    long long mx = 0;
+    for (long long x : counts) mx = x > mx ? x : mx;
+    if (mx > 0) {
+      if (grow(&r->send, &r->send_cap, (size_t)mx * r->stride) && n_local == 0) { snprintf(err, errlen, "replay send buffer allocation failed"); return 3; }
+      if ((size_t)mx * r->stride > r->send_cap) { snprintf(err, errlen, "replay send buffer too small"); return 3; }
+      if (grow(&r->recv, &r->recv_cap, (size_t)mx * r->stride * r->world)) { snprintf(err, errlen, "replay recv buffer allocation failed"); return 3; }
+      nr = ncclAllGather(r->send, r->recv, (size_t)mx * r->stride, ncclUint8, r->comm, s);
+      if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(tuples): %s", ncclGetErrorString(nr)); return 4; }
+      for (int k = 0; k < r->world; ++k) ring_append(r, r->recv + (size_t)k * mx * r->stride, counts[(size_t)k], s);
+    }
+  }
+  if (cudaStreamSynchronize(s) != cudaSuccess) { snprintf(err, errlen, "replay gather: %s", cudaGetErrorString(cudaGetLastError())); return 3; }
+  if (n_total) *n_total = r->total;
+  return 0;
+}
+
+int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs,
+                cudaStream_t s, char* err, size_t errlen) {
+  long long oldest = r->total > r->cap ? r->total - r->cap : 0;
+  if (first < oldest || first + count > r->total || count < 0) {
+    snprintf(err, errlen, "replay tuples [%lld, %lld) not in the ring [%lld, %lld)", (long long)first, (long long)(first + count), oldest, r->total);
+    return 5;
+  }
+  std::vector<unsigned char> buf(r->stride);
+  for (int i = 0; i < count; ++i) {
+    long long pos = (first + i) % r->cap;
+    cudaMemcpyAsync(buf.data(), r->ring + (size_t)pos * r->stride, r->stride, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (pis) memcpy(pis + (size_t)i * c.A, buf.data(), (size_t)4 * c.A);
+    const int8_t* b = reinterpret_cast<const int8_t*>(buf.data() + (size_t)4 * c.A);
+    if (boards) memcpy(boards + (size_t)i * c.N2, b, (size_t)c.N2);
+    if (to_play) to_play[i] = b[c.N2];
+    if (zs) zs[i] = b[c.N2 + 1];
+  }
+  return 0;
+}
+
+}  // namespace agz

@@ -1,0 +1,26 @@
+// replay.h -- K9: finished-game tuple packing + NCCL all-gather into the device-resident replay ring.
+// Stands for extract_data (src/mcts_play.jl:126-139) -> replay_position (src/game/go/board.jl:557-578) and the
+// buffer append / trim of src/train.jl:58-65.  Games never exchange data during search; this is the only
+// collective of the path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "tree.cuh"
+
+namespace agz {
+struct ReplayState;
+ReplayState* replay_create(const Cfg& c, char* err, size_t errlen);
+void replay_destroy(ReplayState* r);
+int replay_unique_id(uint8_t id_out[128]);
+int replay_nccl_init(ReplayState* r, const uint8_t id[128], int world, int rank, char* err, size_t errlen);
+// packs the finished-ring records not gathered yet, all-gathers them, appends to the ring (trim-oldest)
+int replay_gather(ReplayState* r, const Cfg& c, const View& v, int smem_per_warp, cudaStream_t s, int64_t* n_total, long long* launches,
+                  char* err, size_t errlen);
+int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs,
+                cudaStream_t s, char* err, size_t errlen);
+
+// feature kernels over caller-supplied positions (agz_features / agz_net_forward), features.cu
+int engine_host_features(const Cfg& c, const int8_t* boards_hist, const int8_t* to_play, int B, float* out_host, float* out_dev, cudaStream_t s);
+}  // namespace agz

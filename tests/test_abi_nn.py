@@ -1,0 +1,148 @@
+"""Network + feature parity through the C ABI (GPU): agz_features / agz_net_forward against the oracle
+(oracle/net.py, torch-CPU fp32) on the shipped agz weights (golden fixture) and random-init towers, and
+NN-driven self-play checked move by move against the oracle tree fed with the same network outputs."""
+import os
+
+import numpy as np
+import pytest
+
+from backends import agz, lib_for
+from oracle import go as ogo
+from oracle import net as onet
+from oracle import selfplay as osp
+from oracle import features as ofeat
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "agz_shipped_9x9.npz")
+TOL_F32 = 2e-5      # fp32 SIMT path vs torch fp32
+TOL_TC = 1e-3       # north_star: policy/value within 1e-3 of the fp32 reference
+
+
+def test_golden_fixture_matches_oracle_feature_code():
+    """CPU: the committed fixture is self-consistent (features <-> boards_hist) -- guards the generator."""
+    g = np.load(GOLD)
+    bh, tp, feats = g["boards_hist"], g["to_play"], g["feats"]
+    for b in range(bh.shape[0]):
+        for k in range(8):
+            board = bh[b, k].reshape(9, 9, order="F")
+            assert (feats[b, :, :, 2 * k] == (board == tp[b])).all()
+            assert (feats[b, :, :, 2 * k + 1] == (board == -tp[b])).all()
+        assert (feats[b, :, :, 16] == tp[b]).all()
+    assert np.allclose(g["pi"].sum(axis=1), 1, atol=1e-5)
+
+
+def hist_stack(pos):
+    f = ofeat.stone_features(pos)
+    return np.stack([((f[:, :, 2 * k] - f[:, :, 2 * k + 1]) * pos.to_play).astype(np.int8).flatten(order="F") for k in range(8)])
+
+
+def push_oracle_net(eng, nn):
+    flat = lambda lst: np.concatenate([np.asarray(a, np.float32).flatten(order="F") for a in lst])
+    eng.net_set_params(0, flat(nn.base_params()))
+    eng.net_set_params(1, flat(nn.value_params()))
+    eng.net_set_params(2, flat(nn.policy_params()))
+    bns = nn.base_bns()
+    eng.net_set_bn_stats(0, np.concatenate([b.mu for b in bns]), np.concatenate([b.sigma for b in bns]), bns[0].mode)
+    eng.net_set_bn_stats(1, nn.v_bn.mu, nn.v_bn.sigma, nn.v_bn.mode)
+    eng.net_set_bn_stats(2, nn.p_bn.mu, nn.p_bn.sigma, nn.p_bn.mode)
+
+
+def random_positions(N, count, seed, max_plies=70):
+    env = ogo.GoEnv(N)
+    rs = np.random.RandomState(seed)
+    out = []
+    while len(out) < count:
+        pos = ogo.GoPosition(env)
+        for t in range(rs.randint(0, max_plies)):
+            legal = np.flatnonzero(ogo.all_legal_moves(pos)[:-1])
+            mv = None if len(legal) == 0 or rs.rand() < 0.05 else ogo.from_flat(int(rs.choice(legal)), env)
+            pos = ogo.play_move(pos, mv)
+            if pos.done:
+                break
+        if not pos.done:
+            out.append(pos)
+    return out
+
+
+EVALS = [pytest.param(agz.EVAL_NN_F32, TOL_F32, id="f32"), pytest.param(agz.EVAL_NN_TC, TOL_TC, id="tcgen05")]
+
+
+@pytest.mark.gpu
+def test_features_match_golden_and_oracle():
+    g = np.load(GOLD)
+    eng = agz.Engine(9, lib_path=lib_for("cuda"), n_games=4, tower_height=0)
+    out = eng.features(g["boards_hist"], g["to_play"])                      # [B][17][N2]
+    ref = np.transpose(g["feats"], (0, 3, 2, 1)).reshape(-1, 17, 81)        # [b][c][j][i] -> p = 9*j + i
+    assert np.array_equal(out, ref.astype(np.float32))
+    poss = random_positions(19, 6, 3, max_plies=200)
+    eng19 = agz.Engine(19, lib_path=lib_for("cuda"), n_games=2, tower_height=0)
+    out = eng19.features(np.stack([hist_stack(p) for p in poss]), np.array([p.to_play for p in poss], np.int8))
+    ref = np.stack([np.transpose(ofeat.get_feats(p), (2, 1, 0)).reshape(17, 361) for p in poss])
+    assert np.array_equal(out, ref.astype(np.float32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("evaluator,tol", EVALS)
+def test_shipped_agz_net_matches_golden(evaluator, tol):
+    g = np.load(GOLD)
+    eng = agz.Engine(9, lib_path=lib_for("cuda"), n_games=4, tower_height=0)
+    eng.net_set_params(0, g["base"]); eng.net_set_params(1, g["value"]); eng.net_set_params(2, g["policy"])
+    eng.net_set_bn_stats(0, g["bn_mu_base"], g["bn_sigma_base"], agz.BN_STD)
+    eng.net_set_bn_stats(1, g["bn_mu_value"], g["bn_sigma_value"], agz.BN_STD)
+    eng.net_set_bn_stats(2, g["bn_mu_policy"], g["bn_sigma_policy"], agz.BN_STD)
+    pi, v = eng.net_forward(evaluator, g["boards_hist"], g["to_play"])
+    assert np.abs(pi - g["pi"]).max() <= tol, np.abs(pi - g["pi"]).max()
+    assert np.abs(v - g["v"]).max() <= tol, np.abs(v - g["v"]).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("evaluator,tol", EVALS)
+@pytest.mark.parametrize("N,T,B", [(9, 1, 40), (9, 6, 70), (19, 2, 9)])
+def test_random_towers_match_oracle(evaluator, tol, N, T, B):
+    nn = onet.NeuralNet(N, T, seed=10 + T)
+    nn.randomize_bn(seed=T)
+    poss = random_positions(N, B, 100 + N + T, max_plies=70 if N == 9 else 250)
+    pi_ref, v_ref = nn(poss)
+    eng = agz.Engine(N, lib_path=lib_for("cuda"), n_games=8, tower_height=T)     # 64 rows per internal batch -> B=70 spans 2
+    push_oracle_net(eng, nn)
+    pi, v = eng.net_forward(evaluator, np.stack([hist_stack(p) for p in poss]), np.array([p.to_play for p in poss], np.int8))
+    assert np.abs(pi - pi_ref.T).max() <= tol, np.abs(pi - pi_ref.T).max()
+    assert np.abs(v - v_ref).max() <= tol, np.abs(v - v_ref).max()
+    # batch invariance: a position's outputs must not depend on its batch neighbours (hard part 7)
+    idx = np.arange(B)[::-1].copy()
+    pi2, v2 = eng.net_forward(evaluator, np.stack([hist_stack(poss[i]) for i in idx]), np.array([poss[i].to_play for i in idx], np.int8))
+    assert np.array_equal(pi2, pi[idx]) and np.array_equal(v2, v[idx])
+
+
+class EngineBackedNet:
+    """Oracle-side network whose numbers come from the engine's own forward pass, so the oracle tree and the
+    engine tree see bit-identical (pi, v): isolates tree/feature/batching parity from NN rounding."""
+
+    def __init__(self, eng, evaluator, tower_height):
+        self.eng, self.evaluator, self.tower_height = eng, evaluator, tower_height
+
+    def __call__(self, positions):
+        pi, v = self.eng.net_forward(self.evaluator, np.stack([hist_stack(p) for p in positions]),
+                                     np.array([p.to_play for p in positions], np.int8))
+        return pi.T.copy(), v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("evaluator", [pytest.param(agz.EVAL_NN_F32, id="f32"), pytest.param(agz.EVAL_NN_TC, id="tcgen05")])
+def test_nn_selfplay_matches_oracle_tree(evaluator):
+    N, T, R = 9, 1, 24
+    nn = onet.NeuralNet(N, T, seed=5)
+    nn.randomize_bn(seed=2)
+    helper = agz.Engine(N, lib_path=lib_for("cuda"), n_games=2, tower_height=T)
+    push_oracle_net(helper, nn)
+    eng = agz.Engine(N, lib_path=lib_for("cuda"), n_games=3, readouts=R, seed=9, tower_height=T)
+    push_oracle_net(eng, nn)
+    eng.set_evaluator(evaluator)
+    recs = eng.selfplay_run(3)
+    oenv = ogo.GoEnv(N)
+    onn = EngineBackedNet(helper, evaluator, T)
+    for gid, r in enumerate(recs):
+        op = osp.selfplay(oenv, onn, R, seed=9, game_id=gid)
+        om = [ogo.to_flat(m.move, oenv) for m in op.root.position.recent]
+        assert list(r.moves) == om, gid
+        assert np.array_equal(np.array(op.searches_N), r.visits)
+        assert r.result == op.result and r.result_string == op.result_string
