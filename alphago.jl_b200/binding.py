@@ -58,7 +58,7 @@ class GameHeader(C.Structure):
 class Progress(C.Structure):
     _fields_ = [("moves_played", C.c_int64), ("games_finished", C.c_int64), ("games_started", C.c_int64),
                 ("positions_evaluated", C.c_int64), ("readouts", C.c_int64), ("path_nodes", C.c_int64),
-                ("games_live", C.c_int32), ("error", C.c_int32)]
+                ("games_live", C.c_int32), ("error", C.c_int32), ("step_ms", C.c_float), ("reserved", C.c_int32)]
 
 
 # every symbol include/agz.h declares (the CPU test-suite checks the built library exports all of them)
@@ -72,8 +72,9 @@ SYMBOLS = [
     "agz_tree_inject_noise", "agz_tree_pick_move", "agz_tree_play_move", "agz_tree_should_resign", "agz_tree_root",
     "agz_tree_read_node", "agz_tree_set_stats", "agz_tree_pending_vlosses", "agz_tree_read_record",
     "agz_tree_node_features", "agz_pos_play_move", "agz_pos_legal_moves", "agz_pos_score", "agz_pos_liberties",
-    "agz_kernel_launches", "agz_phase_times", "agz_set_timing",
+    "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops",
 ]
+KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
 _libs = {}
 
@@ -358,10 +359,16 @@ class Engine:
         self._check(self.lib.agz_set_timing(self._h, C.c_int32(1 if on else 0)))
 
     def phase_times(self, reset=True):
-        ms = (C.c_float * 4)()
-        ln = (C.c_int64 * 4)()
+        ms = (C.c_float * 6)()
+        ln = (C.c_int64 * 6)()
         self._check(self.lib.agz_phase_times(self._h, ms, ln, C.c_int32(1 if reset else 0)))
         return list(ms), list(ln)
+
+
+    def net_flops(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.agz_net_flops(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
 
 class GameRecord:

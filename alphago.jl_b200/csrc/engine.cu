@@ -50,11 +50,12 @@ struct agz_engine {
   bool started;
   unsigned long long ring_head;
   int timing;
-  float phase_ms[4];
-  long long phase_launches[4];
+  float phase_ms[AGZ_NKERNELS];
+  long long phase_launches[AGZ_NKERNELS];
 #if AGZ_CUDA
   NNet* nn;
-  cudaEvent_t ev[5];
+  cudaEvent_t ev[8];   // 0 select | 1 features | 2 stem | 3 tower | 4 heads | 5 incorporate | 6 end
+  cudaEvent_t ev_step[2];
   ReplayState* replay;
 #endif
 };
@@ -135,7 +136,8 @@ extern "C" void agz_engine_destroy(agz_engine* e) {
   cudaStreamSynchronize(e->stream);
   if (e->replay) replay_destroy(e->replay);
   if (e->nn) nn_destroy(e->nn);
-  for (int i = 0; i < 5; ++i) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_step[i]);
 #endif
   for (void* p : e->allocs) devrt::dfree(p);
 #if AGZ_CUDA
@@ -184,7 +186,8 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
     delete e;
     return fail(nullptr, AGZ_ERR_CUDA, "cudaStreamCreate failed");
   }
-  for (int i = 0; i < 5; ++i) cudaEventCreate(&e->ev[i]);
+  for (int i = 0; i < 8; ++i) cudaEventCreate(&e->ev[i]);
+  for (int i = 0; i < 2; ++i) cudaEventCreate(&e->ev_step[i]);
 #else
   e->stream = 0;
 #endif
@@ -338,6 +341,7 @@ static int run_network(agz_engine* e, int row0, int nrows) {
     if (nn_commit(e->nn, e->stream, nerr, sizeof(nerr))) return fail(e, AGZ_ERR_ARG, "network not ready: %s", nerr);
   }
   if (e->timing) cudaEventRecord(e->ev[1], e->stream);
+  cudaEvent_t* nev = e->timing ? &e->ev[2] : nullptr;   // ev[2..5]: before stem, after stem, after tower, after heads
   if (e->evaluator == AGZ_EVAL_NN_F32) {
     float* feats = e->d_feats_f32 + (size_t)row0 * 17 * e->c.N2;
     DISPATCH_KA(e, {
@@ -347,16 +351,14 @@ static int run_network(agz_engine* e, int row0, int nrows) {
       DCHECK(e, devrt::launch_warps(op, row0 + nrows, e->smem_per_warp, e->stream));
     });
     e->launches += 1;
-    if (e->timing) cudaEventRecord(e->ev[2], e->stream);
-    int rc = nn_forward_f32(e->nn, e->d_feats_f32 + (size_t)row0 * 17 * e->c.N2, nrows, e->d_eval_pi + (size_t)row0 * e->c.A, e->d_eval_v + row0, e->stream);
+    int rc = nn_forward_f32(e->nn, e->d_feats_f32 + (size_t)row0 * 17 * e->c.N2, nrows, e->d_eval_pi + (size_t)row0 * e->c.A, e->d_eval_v + row0, e->stream, nev);
     if (rc) return fail(e, AGZ_ERR_CUDA, "nn_forward_f32: %s", cudaGetErrorString((cudaError_t)rc));
     e->launches += nn_f32_launches_per_forward(e->nn);
   } else {
     int rc = engine_tc_features(e->c, e->v, e->nn, row0, nrows, e->smem_per_warp, e->stream);
     if (rc) return fail(e, AGZ_ERR_CUDA, "tc feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
     e->launches += 1;
-    if (e->timing) cudaEventRecord(e->ev[2], e->stream);
-    rc = nn_forward_tc(e->nn, row0 + nrows, e->d_eval_pi, e->d_eval_v, e->stream, nerr, sizeof(nerr));
+    rc = nn_forward_tc(e->nn, row0 + nrows, e->d_eval_pi, e->d_eval_v, e->stream, nerr, sizeof(nerr), nev);
     if (rc) return fail(e, AGZ_ERR_CUDA, "nn_forward_tc: %s", nerr);
     e->launches += nn_tc_launches_per_forward(e->nn);
   }
@@ -415,10 +417,8 @@ static int one_round(agz_engine* e) {
     int rc = run_network(e, 0, e->c.n_games * e->c.pmax);
     if (rc) return rc;
   } else if (e->timing) {
-    cudaEventRecord(e->ev[1], e->stream);
-    cudaEventRecord(e->ev[2], e->stream);
+    for (int i = 1; i <= 5; ++i) cudaEventRecord(e->ev[i], e->stream);
   }
-  if (e->timing) cudaEventRecord(e->ev[3], e->stream);
 #endif
   DISPATCH_KA(e, {
     IncorporateOp<KA> op{e->c, e->v, -1};
@@ -427,17 +427,20 @@ static int one_round(agz_engine* e) {
   e->launches += 1;
 #if AGZ_CUDA
   if (e->timing) {
-    cudaEventRecord(e->ev[4], e->stream);
-    cudaEventSynchronize(e->ev[4]);
-    for (int i = 0; i < 4; ++i) {
+    cudaEventRecord(e->ev[6], e->stream);
+    cudaEventSynchronize(e->ev[6]);
+    for (int i = 0; i < AGZ_NKERNELS; ++i) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
       e->phase_ms[i] += ms;
     }
+    const bool net = e->evaluator != AGZ_EVAL_DUMMY;
     e->phase_launches[0] += 1;
-    e->phase_launches[1] += e->evaluator != AGZ_EVAL_DUMMY ? 1 : 0;
-    e->phase_launches[2] += e->evaluator == AGZ_EVAL_NN_TC ? nn_tc_launches_per_forward(e->nn) : (e->evaluator == AGZ_EVAL_NN_F32 ? nn_f32_launches_per_forward(e->nn) : 0);
-    e->phase_launches[3] += 1;
+    e->phase_launches[1] += net ? 1 : 0;
+    e->phase_launches[2] += net ? 1 : 0;
+    e->phase_launches[3] += net ? 2 * e->cfg.tower_height : 0;
+    e->phase_launches[4] += net ? 1 : 0;
+    e->phase_launches[5] += 1;
   }
 #endif
   return AGZ_OK;
@@ -447,13 +450,25 @@ extern "C" int32_t agz_selfplay_step(agz_engine* e, int32_t rounds, agz_progress
   if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
   if (!e->started) return fail(e, AGZ_ERR_ARG, "agz_selfplay_start has not been called");
   bind_evaluator(e);
+#if AGZ_CUDA
+  if (progress) cudaEventRecord(e->ev_step[0], e->stream);
+#endif
   for (int r = 0; r < rounds; ++r) {
     int rc = one_round(e);
     if (rc) return rc;
   }
   if (progress) {
+#if AGZ_CUDA
+    cudaEventRecord(e->ev_step[1], e->stream);
+#endif
     DCHECK(e, devrt::sync(e->stream));
-    return read_progress(e, progress);
+    int rc = read_progress(e, progress);
+    progress->step_ms = 0.f;
+    progress->reserved = 0;
+#if AGZ_CUDA
+    cudaEventElapsedTime(&progress->step_ms, e->ev_step[0], e->ev_step[1]);
+#endif
+    return rc;
   }
   return AGZ_OK;
 }
@@ -879,9 +894,9 @@ extern "C" int32_t agz_set_timing(agz_engine* e, int32_t enabled) {
   return AGZ_OK;
 }
 
-extern "C" int32_t agz_phase_times(agz_engine* e, float ms[4], int64_t launches[4], int32_t reset) {
+extern "C" int32_t agz_phase_times(agz_engine* e, float ms[AGZ_NKERNELS], int64_t launches[AGZ_NKERNELS], int32_t reset) {
   if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < AGZ_NKERNELS; ++i) {
     if (ms) ms[i] = e->phase_ms[i];
     if (launches) launches[i] = e->phase_launches[i];
   }
@@ -893,6 +908,14 @@ extern "C" int32_t agz_phase_times(agz_engine* e, float ms[4], int64_t launches[
 }
 
 // ------------------------------------------------------------------------------------------- network ABI
+extern "C" int32_t agz_net_flops(agz_engine* e, double* per_position, double* per_tower_conv_position) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  const double N2 = (double)e->c.N2, C = e->cfg.filters, A = N2 + 1;
+  const double conv = 2.0 * 9 * C * C * N2;
+  if (per_tower_conv_position) *per_tower_conv_position = conv;
+  if (per_position) *per_position = 2.0 * 9 * e->cfg.planes * C * N2 + e->cfg.tower_height * 2.0 * conv + 2.0 * (3 * C * N2) + 2.0 * (256 * N2 + 256) + 2.0 * (A * 2 * N2);
+  return AGZ_OK;
+}
 #if AGZ_CUDA
 extern "C" size_t agz_net_param_count(agz_engine* e, int32_t chain) { return e ? nn_param_count(e->nn, chain) : 0; }
 extern "C" size_t agz_net_bn_count(agz_engine* e, int32_t chain) { return e ? nn_bn_count(e->nn, chain) : 0; }

@@ -31,7 +31,7 @@ bool nn_ready(const NNet* n);
 //   feats_f32 : [B][17][N2] float, reference (W x H x C x B) order               (NN_F32)
 //   feats_tc  : see nn_tc_input_layout()                                          (NN_TC)
 // Output: pi [B][A] float (softmax over all A actions, no legality masking), v [B] float (Black's view).
-int nn_forward_f32(NNet* n, const float* feats_f32, int B, float* pi, float* v, cudaStream_t s);
+int nn_forward_f32(NNet* n, const float* feats_f32, int B, float* pi, float* v, cudaStream_t s, cudaEvent_t* ev = nullptr);
 
 // The tensor-core path consumes activations as fp16 rows of `cin_pad` channels in a zero-bordered board
 // layout: every board is (N+1) rows of (N+1) points plus one leading pad row, so a 3x3 tap is a constant
@@ -44,7 +44,8 @@ struct TCInput {
   long long rows_total;
 };
 TCInput nn_tc_input(NNet* n);
-int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen);
+// ev (optional): 4 events recorded before the stem, after the stem, after the tower, after the heads
+int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev = nullptr);
 // feature kernels that write the tensor-core input directly (nn_tc.cu): from the leaves of the current round
 // (batch rows [0, row0+nrows)), and from caller-supplied positions.
 struct Cfg;

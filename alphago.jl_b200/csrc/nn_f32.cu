@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(256) heads_f32_kernel(const float* __restrict_
 
 long long nn_f32_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower + 1; }
 
-int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cudaStream_t s) {
+int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cudaStream_t s, cudaEvent_t* ev) {
   const int C = n->C, N = n->s.N, N2 = n->N2;
   if (B > n->max_batch) return (int)cudaErrorInvalidValue;
   for (int i = 0; i < 3; ++i)
@@ -377,15 +377,19 @@ int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cuda
   const size_t smem = (size_t)(CIT * (N + 2) * (N + 2) + COT * CIT * 9) * sizeof(float);
   CUDA_TRY(cudaFuncSetAttribute(conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(B, (C + COT - 1) / COT);
+  if (ev) cudaEventRecord(ev[0], s);
   conv3x3_f32_kernel<<<grid, 128, smem, s>>>(feats, n->f_w[0], n->f_scale[0], n->f_shift[0], nullptr, n->f_act[0], n->s.planes, C, N, 1);
+  if (ev) cudaEventRecord(ev[1], s);
   float *h = n->f_act[0], *t1 = n->f_act[1], *t2 = n->f_act[2];
   for (int t = 0; t < n->s.tower; ++t) {
     conv3x3_f32_kernel<<<grid, 128, smem, s>>>(h, n->f_w[1 + 2 * t], n->f_scale[1 + 2 * t], n->f_shift[1 + 2 * t], nullptr, t1, C, C, N, 1);
     conv3x3_f32_kernel<<<grid, 128, smem, s>>>(t1, n->f_w[2 + 2 * t], n->f_scale[2 + 2 * t], n->f_shift[2 + 2 * t], h, t2, C, C, N, 1);
     float* tmp = h; h = t2; t2 = tmp;
   }
+  if (ev) cudaEventRecord(ev[2], s);
   const size_t hsm = (size_t)(3 * N2 + 512) * sizeof(float);
   heads_f32_kernel<<<B, 256, hsm, s>>>(h, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb, pi, v, C, N2);
+  if (ev) cudaEventRecord(ev[3], s);
   return (int)cudaGetLastError();
 }
 

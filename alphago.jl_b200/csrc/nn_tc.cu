@@ -1,19 +1,620 @@
-// nn_tc.cu -- placeholder until the tcgen05 path lands (next commit): every entry point reports that clearly.
+// nn_tc.cu -- the residual tower on Blackwell tensor cores (replaces the Flux Conv/BatchNorm/relu calls of
+// src/neural_net.jl:16-21 and src/resnet.jl:26-32, which the reference sends to NNlib / cuDNN).
+//
+// A 3x3 convolution is an implicit GEMM  D[M, 256] = sum over 9 taps of A_tap[M, Cin] * W_tap[Cin, 256].
+// Activations live in HBM as fp16 rows of C channels (NHWC) in a zero-bordered board layout: every board is one
+// pad row of N+1 zero points followed by N rows of N points + 1 zero point.  With that layout the input of tap
+// (dj, di) for output row m is simply row m + dj*(N+1) + di, so each tap's A tile is ONE plain 2-D TMA box at a
+// shifted row coordinate (negative / past-the-end rows are zero-filled by TMA) -- no im2col buffer, no halo logic.
+//
+// Kernel conv3x3_tc_kernel (persistent, 1 CTA per SM, 256 threads, warp-specialised):
+//   warp 0   : TMA producer -- per (tap, 64-channel chunk): A box 128 rows x 64 ch, W box 256 cout x 64 ch, both
+//              SWIZZLE_128B, 4-stage mbarrier ring (48 KB / stage)
+//   warp 1   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16  M=128, N=256, K=16 (4 per stage),
+//              fp32 accumulators in TMEM; tcgen05.commit releases the smem stage / publishes the accumulator
+//   warp 2   : allocates / frees the 512 TMEM columns (2 accumulator stages of 256 columns)
+//   warps 4-7: epilogue -- tcgen05.ld 32 lanes x 32 columns, fused (conv bias + BatchNorm) scale/shift,
+//              residual add, ReLU, fp16 pack, 16-byte global stores; overlaps the next tile's MMAs
+#include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
+#include <string.h>
 
+#include <vector>
+
+#include "devrt.h"
 #include "nn_state.h"
-#include "tree.cuh"
+#include "ops.cuh"
 
 namespace agz {
-int nn_tc_create(NNet*, char*, size_t) { return 0; }
-void nn_tc_destroy(NNet*) {}
-int nn_tc_commit(NNet*, const std::vector<ConvLayerHost>&, cudaStream_t, char*, size_t) { return 0; }
-TCInput nn_tc_input(NNet*) { TCInput t{}; return t; }
-int nn_forward_tc(NNet*, int, float*, float*, cudaStream_t, char* err, size_t errlen) {
-  snprintf(err, errlen, "the tcgen05 network path is not built yet");
-  return 1;
+
+static const int BM = 128, BN = 256, BK = 64, STAGES = 4;
+static const int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+static const int CIN0 = 64;  // stem input channels: 17 planes zero-padded to one 64-channel K chunk
+static const size_t CONV_SMEM = (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
+
+struct TCState {
+  int N, NP1, PP, C, T, max_batch;
+  long long rows_alloc;       // rows allocated per activation buffer (multiple of 128, >= max_batch*PP + N+2)
+  __half* in64;               // [rows_alloc][64]
+  __half* act[3];             // [rows_alloc][256]
+  std::vector<__half*> w;     // per conv layer: [9*256][cin] fp16, tap-major, K (cin) contiguous
+  CUtensorMap tm_in64, tm_act[3];
+  std::vector<CUtensorMap> tm_w;
+  int num_sms;
+  bool attr_set;
+};
+
+// ------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-long long nn_tc_launches_per_forward(const NNet*) { return 0; }
-int engine_tc_features(const Cfg&, const View&, NNet*, int, int, int, cudaStream_t) { return (int)cudaErrorNotSupported; }
-int engine_host_features_tc(const Cfg&, NNet*, const int8_t*, const int8_t*, int, cudaStream_t) { return (int)cudaErrorNotSupported; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t a = smem_u32(bar);
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 64 fp16 (128 B), 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major), 16 B units
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = 256
+static const uint32_t IDESC_F16_M128_N256 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct ConvArgs {
+  const float* scale;   // [256] folded BatchNorm scale
+  const float* shift;   // [256] folded BatchNorm shift (+ scale * conv bias)
+  const __half* res;    // residual input [rows][256] or nullptr
+  __half* out;          // [rows][256]
+  int n_tiles;          // ceil(rows_valid / 128)
+  long long rows_valid; // rows of real boards (B * PP)
+  int kchunks;          // Cin / 64
+  int N, NP1, PP;
+  int relu;
+};
+
+__global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                            const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  float* s_scale = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* full = bars;             // [STAGES]
+  uint64_t* empty = bars + STAGES;   // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;      // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 256; i += 256) {
+    s_scale[i] = a.scale[i];
+    s_shift[i] = a.shift[i];
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = 9 * a.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int off = (tap / 3 - 1) * a.NP1 + (tap % 3 - 1);
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], STAGE_BYTES);
+            uint8_t* sa = tiles + (size_t)stage * STAGE_BYTES;
+            tma_load_2d(sa, &tmA, &full[stage], kc * BK, m0 + off);
+            tma_load_2d(sa + A_BYTES, &tmW, &full[stage], kc * BK, tap * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int titer = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++titer) {
+        const int as = titer & 1;
+        const uint32_t aphase = (titer >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)  // advancing 16 fp16 = 32 B inside the 128 B swizzle row: +2 in 16 B units
+            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M128_N256, (it > 0 || k > 0) ? 1u : 0u);
+          tc_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;  // TMEM lane quarter of this warp (warp id % 4)
+    int titer = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++titer) {
+      const int as = titer & 1;
+      const uint32_t aphase = (titer >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const long long row = (long long)tile * BM + q * 32 + lane;
+      const bool valid = row < a.rows_valid;
+      bool pad = true;
+      if (valid) {
+        const int r = (int)(row % a.PP);
+        pad = r < a.NP1 || ((r - a.NP1) % a.NP1) == a.N;
+      }
+      __half* orow = a.out + row * 256;
+      const __half* rrow = a.res ? a.res + row * 256 : nullptr;
+#pragma unroll 1
+      for (int cc = 0; cc < 8; ++cc) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + (uint32_t)as * BN + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
+        if (valid) {
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+          uint4 rv[4];
+          if (rrow && !pad) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(rrow + cc * 32 + j * 8);
+          }
+          const __half2* rh = reinterpret_cast<const __half2*>(rv);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c0 = cc * 32 + 2 * j;
+            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
+            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
+            if (rrow && !pad) {
+              float2 rr = __half22float2(rh[j]);
+              y0 += rr.x;
+              y1 += rr.y;
+            }
+            if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            if (pad) { y0 = 0.f; y1 = 0.f; }
+            __half2 h = __floats2half2_rn(y0, y1);
+            ow[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------- heads (fp16 trunk)
+// neural_net.jl:23-30 for one position per block, reading the trunk output in the padded NHWC layout.
+__global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict__ trunk, const float* __restrict__ vw,
+                                                       const float* __restrict__ pw, const float* __restrict__ aff,
+                                                       const float* __restrict__ D1W, const float* __restrict__ D1b,
+                                                       const float* __restrict__ D2W, const float* __restrict__ D2b,
+                                                       const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
+                                                       float* __restrict__ v, int N, int PP) {
+  extern __shared__ float sm[];
+  const int N2 = N * N, NP1 = N + 1, A = N2 + 1;
+  float* vf = sm;
+  float* pf = sm + N2;
+  float* hid = sm + 3 * N2;
+  float* red = hid + 256;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __half* base = trunk + ((size_t)b * PP + NP1) * 256;
+  // 1x1 convolutions: a warp per point, 8 channels per lane (one 16-byte load)
+  float wv[8], wp0[8], wp1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    wv[j] = vw[lane * 8 + j];
+    wp0[j] = pw[lane * 8 + j];
+    wp1[j] = pw[256 + lane * 8 + j];
+  }
+  for (int p = warp; p < N2; p += 8) {
+    const int jj = p / N, ii = p % N;
+    const uint4 raw = *reinterpret_cast<const uint4*>(base + ((size_t)jj * NP1 + ii) * 256 + lane * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 x = __half22float2(h[j]);
+      a0 = fmaf(wv[2 * j], x.x, a0); a0 = fmaf(wv[2 * j + 1], x.y, a0);
+      a1 = fmaf(wp0[2 * j], x.x, a1); a1 = fmaf(wp0[2 * j + 1], x.y, a1);
+      a2 = fmaf(wp1[2 * j], x.x, a2); a2 = fmaf(wp1[2 * j + 1], x.y, a2);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (lane == 0) {
+      vf[p] = fmaxf(a0 * aff[0] + aff[1], 0.f);
+      pf[p] = fmaxf(a1 * aff[2] + aff[3], 0.f);
+      pf[N2 + p] = fmaxf(a2 * aff[4] + aff[5], 0.f);
+    }
+  }
+  __syncthreads();
+  {
+    float acc = D1b[tid];
+    for (int i = 0; i < N2; ++i) acc = fmaf(D1W[tid + 256 * i], vf[i], acc);
+    hid[tid] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  red[tid] = D2W[tid] * hid[tid];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  if (tid == 0) v[b] = tanhf(red[0] + D2b[0]);
+  __syncthreads();
+  float lg[2];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int a = tid + q * 256;
+    lg[q] = -INFINITY;
+    if (a < A) {
+      float acc = Pb[a];
+      for (int i = 0; i < 2 * N2; ++i) acc = fmaf(PW[a + (size_t)A * i], pf[i], acc);
+      lg[q] = acc;
+      mx = fmaxf(mx, acc);
+    }
+  }
+  red[tid] = mx;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]);
+    __syncthreads();
+  }
+  mx = red[0];
+  __syncthreads();
+  float ex[2], sum = 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    ex[q] = lg[q] == -INFINITY ? 0.f : expf(lg[q] - mx);
+    sum += ex[q];
+  }
+  red[tid] = sum;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  sum = red[0];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int a = tid + q * 256;
+    if (a < A) pi[(size_t)b * A + a] = ex[q] / sum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- feature kernels
+// get_feats (features.jl:3-26) written straight into the stem's input rows: channels 0..15 stone planes,
+// 16 = colour (+-1), 17..23 zero (24..63 stay zero from initialisation).
+template <int KA>
+struct LeafFeaturesTCOp {
+  Cfg c;
+  View v;
+  __half* in64;
+  int PP;
+  __device__ void operator()(int b, char* smem) const {
+    const int g = b / c.pmax, k = b % c.pmax;
+    Warp<KA> w(c, v, g, smem);
+    if (k >= w.st.nleaf) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t planes[KA];
+#pragma unroll
+    for (int q = 0; q < KA; ++q) planes[q] = 0;
+    const int tp = w.gather_features(v.leaf_node[b], [&](int hb, int p, uint32_t mine, uint32_t theirs) {
+#pragma unroll
+      for (int q = 0; q < KA; ++q)
+        if (q == (p >> 5)) planes[q] |= (mine << (2 * hb)) | (theirs << (2 * hb + 1));
+    });
+    const __half one = __float2half(1.f), zero = __float2half(0.f), tph = __float2half((float)tp);
+#pragma unroll
+    for (int q = 0; q < KA; ++q) {
+      const int p = q * 32 + lane;
+      if (p < c.N2) {
+        const int jj = p / c.N, ii = p % c.N;
+        __half* row = in64 + ((size_t)b * PP + (c.N + 1) + (size_t)jj * (c.N + 1) + ii) * CIN0;
+        __align__(16) __half h[24];
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) h[ch] = ((planes[q] >> ch) & 1u) ? one : zero;
+        h[16] = tph;
+#pragma unroll
+        for (int ch = 17; ch < 24; ++ch) h[ch] = zero;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) reinterpret_cast<uint4*>(row)[j] = reinterpret_cast<const uint4*>(h)[j];
+      }
+    }
+  }
+};
+
+__global__ void host_features_tc_kernel(const int8_t* __restrict__ bh, const int8_t* __restrict__ tp, __half* __restrict__ in64, int B, int N,
+                                        int PP) {
+  const int N2 = N * N;
+  const size_t total = (size_t)B * N2;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int p = (int)(idx % N2), b = (int)(idx / N2);
+    const int t = tp[b];
+    const int jj = p / N, ii = p % N;
+    __half* row = in64 + ((size_t)b * PP + (N + 1) + (size_t)jj * (N + 1) + ii) * CIN0;
+    __align__(16) __half h[24];
+#pragma unroll
+    for (int kq = 0; kq < 8; ++kq) {
+      const int s = bh[((size_t)b * 8 + kq) * N2 + p];
+      h[2 * kq] = __float2half(s == t ? 1.f : 0.f);
+      h[2 * kq + 1] = __float2half(s == -t ? 1.f : 0.f);
+    }
+    h[16] = __float2half((float)t);
+#pragma unroll
+    for (int ch = 17; ch < 24; ++ch) h[ch] = __float2half(0.f);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) reinterpret_cast<uint4*>(row)[j] = reinterpret_cast<const uint4*>(h)[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp16 tensor [rows][cols] row-major, box = box_rows x 64 columns, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* tm, void* base, long long rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 1;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+int nn_tc_create(NNet* n, char* err, size_t errlen) {
+  TCState* t = new TCState();
+  n->tc = t;
+  t->N = n->s.N;
+  t->NP1 = t->N + 1;
+  t->PP = t->NP1 * t->NP1;
+  t->C = n->C;
+  t->T = n->s.tower;
+  t->max_batch = n->max_batch;
+  t->attr_set = false;
+  t->in64 = nullptr;
+  for (int i = 0; i < 3; ++i) t->act[i] = nullptr;
+  if (n->C != 256) {
+    snprintf(err, errlen, "the tensor-core path is built for 256 filters");
+    return 1;
+  }
+  long long rows = (long long)t->max_batch * t->PP + t->N + 2;
+  t->rows_alloc = (rows + 127) / 128 * 128 + 128;
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  t->num_sms = prop.multiProcessorCount;
+  bool ok = cudaMalloc((void**)&t->in64, (size_t)t->rows_alloc * CIN0 * 2) == cudaSuccess;
+  for (int i = 0; i < 3 && ok; ++i) ok = cudaMalloc((void**)&t->act[i], (size_t)t->rows_alloc * 256 * 2) == cudaSuccess;
+  const int nconv = 1 + 2 * t->T;
+  t->w.assign(nconv, nullptr);
+  t->tm_w.resize(nconv);
+  for (int l = 0; l < nconv && ok; ++l) ok = cudaMalloc((void**)&t->w[l], (size_t)9 * 256 * (l == 0 ? CIN0 : 256) * 2) == cudaSuccess;
+  if (!ok) {
+    snprintf(err, errlen, "cudaMalloc failed for the tensor-core activations (%lld rows)", t->rows_alloc);
+    return 1;
+  }
+  cudaMemset(t->in64, 0, (size_t)t->rows_alloc * CIN0 * 2);
+  for (int i = 0; i < 3; ++i) cudaMemset(t->act[i], 0, (size_t)t->rows_alloc * 256 * 2);
+  int rc = make_map(&t->tm_in64, t->in64, t->rows_alloc, CIN0, BM);
+  for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm_act[i], t->act[i], t->rows_alloc, 256, BM);
+  for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm_w[l], t->w[l], 9 * 256, l == 0 ? CIN0 : 256, BN);
+  if (rc) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d)", rc);
+    return 1;
+  }
+  return 0;
+}
+
+void nn_tc_destroy(NNet* n) {
+  TCState* t = (TCState*)n->tc;
+  if (!t) return;
+  cudaFree(t->in64);
+  for (int i = 0; i < 3; ++i) cudaFree(t->act[i]);
+  for (auto p : t->w) cudaFree(p);
+  delete t;
+  n->tc = nullptr;
+}
+
+int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t s, char* err, size_t errlen) {
+  TCState* t = (TCState*)n->tc;
+  for (size_t l = 0; l < convs.size(); ++l) {
+    const ConvLayerHost& L = convs[l];
+    const int cin_pad = l == 0 ? CIN0 : 256;
+    std::vector<__half> w((size_t)9 * 256 * cin_pad, __float2half(0.f));
+    // Wt[tap][co][ci], tap = kj*3 + ki for input offset (dj, di) = (kj-1, ki-1); true convolution => W[2-ki, 2-kj]
+    for (int kj = 0; kj < 3; ++kj)
+      for (int ki = 0; ki < 3; ++ki)
+        for (int co = 0; co < 256; ++co)
+          for (int ci = 0; ci < L.cin; ++ci)
+            w[((size_t)(kj * 3 + ki) * 256 + co) * cin_pad + ci] =
+                __float2half(L.w[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)L.cin * co]);
+    cudaMemcpyAsync(t->w[l], w.data(), w.size() * 2, cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+  }
+  if (cudaGetLastError() != cudaSuccess) {
+    snprintf(err, errlen, "uploading fp16 weights failed");
+    return 1;
+  }
+  return 0;
+}
+
+TCInput nn_tc_input(NNet* n) {
+  TCState* t = (TCState*)n->tc;
+  TCInput r;
+  r.act = t->in64; r.rows_per_board = t->PP; r.row_stride_pts = t->NP1; r.cin_pad = CIN0; r.rows_total = t->rows_alloc;
+  return r;
+}
+
+long long nn_tc_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower + 1; }
+
+static int launch_conv(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
+                       __half* out, int B, int kchunks, cudaStream_t s) {
+  ConvArgs a;
+  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
+  a.rows_valid = (long long)B * t->PP;
+  a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
+  a.kchunks = kchunks;
+  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
+  a.relu = 1;
+  int grid = a.n_tiles < t->num_sms ? a.n_tiles : t->num_sms;
+  conv3x3_tc_kernel<<<grid, 256, CONV_SMEM, s>>>(tmA, tmW, a);
+  return (int)cudaGetLastError();
+}
+
+int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev) {
+  TCState* t = (TCState*)n->tc;
+  if (B > t->max_batch) { snprintf(err, errlen, "batch %d exceeds max_batch %d", B, t->max_batch); return 1; }
+  if (!t->attr_set) {
+    cudaError_t rc = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM);
+    if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
+    t->attr_set = true;
+  }
+  if (ev) cudaEventRecord(ev[0], s);
+  int rc = launch_conv(t, t->tm_in64, t->tm_w[0], n->f_scale[0], n->f_shift[0], nullptr, t->act[0], B, CIN0 / BK, s);
+  if (ev) cudaEventRecord(ev[1], s);
+  int h = 0, t1 = 1, t2 = 2;
+  for (int blk = 0; blk < t->T && !rc; ++blk) {
+    rc = launch_conv(t, t->tm_act[h], t->tm_w[1 + 2 * blk], n->f_scale[1 + 2 * blk], n->f_shift[1 + 2 * blk], nullptr, t->act[t1], B, 4, s);
+    if (!rc) rc = launch_conv(t, t->tm_act[t1], t->tm_w[2 + 2 * blk], n->f_scale[2 + 2 * blk], n->f_shift[2 + 2 * blk], t->act[h], t->act[t2], B, 4, s);
+    int tmp = h; h = t2; t2 = tmp;
+  }
+  if (rc) { snprintf(err, errlen, "conv launch: %s", cudaGetErrorString((cudaError_t)rc)); return 1; }
+  if (ev) cudaEventRecord(ev[2], s);
+  const size_t hsm = (size_t)(3 * n->N2 + 512) * sizeof(float);
+  heads_tc_kernel<<<B, 256, hsm, s>>>(t->act[h], n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb,
+                                       pi, v, t->N, t->PP);
+  if (ev) cudaEventRecord(ev[3], s);
+  cudaError_t e2 = cudaGetLastError();
+  if (e2 != cudaSuccess) { snprintf(err, errlen, "heads launch: %s", cudaGetErrorString(e2)); return 1; }
+  return 0;
+}
+
+int engine_tc_features(const Cfg& c, const View& v, NNet* n, int row0, int nrows, int smem_per_warp, cudaStream_t s) {
+  TCState* t = (TCState*)n->tc;
+  int rc = 0;
+  switch (c.KA) {
+    case 3: { LeafFeaturesTCOp<3> op{c, v, t->in64, t->PP}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
+    case 6: { LeafFeaturesTCOp<6> op{c, v, t->in64, t->PP}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
+    default: { LeafFeaturesTCOp<12> op{c, v, t->in64, t->PP}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
+  }
+  return rc;
+}
+
+int engine_host_features_tc(const Cfg& c, NNet* n, const int8_t* boards_hist, const int8_t* to_play, int B, cudaStream_t s) {
+  TCState* t = (TCState*)n->tc;
+  int8_t *dbh = nullptr, *dtp = nullptr;
+  const size_t nb = (size_t)B * 8 * c.N2;
+  cudaError_t rc = cudaMalloc((void**)&dbh, nb);
+  if (rc == cudaSuccess) rc = cudaMalloc((void**)&dtp, (size_t)B);
+  if (rc == cudaSuccess) rc = cudaMemcpyAsync(dbh, boards_hist, nb, cudaMemcpyHostToDevice, s);
+  if (rc == cudaSuccess) rc = cudaMemcpyAsync(dtp, to_play, (size_t)B, cudaMemcpyHostToDevice, s);
+  if (rc == cudaSuccess) {
+    int blocks = (int)(((size_t)B * c.N2 + 255) / 256);
+    host_features_tc_kernel<<<blocks, 256, 0, s>>>(dbh, dtp, t->in64, B, c.N, t->PP);
+    rc = cudaGetLastError();
+  }
+  cudaError_t rs = cudaStreamSynchronize(s);
+  if (rc == cudaSuccess) rc = rs;
+  cudaFree(dbh);
+  cudaFree(dtp);
+  return (int)rc;
+}
+
 }  // namespace agz

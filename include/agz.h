@@ -127,6 +127,8 @@ typedef struct agz_progress {
   int64_t path_nodes;         /* sum of path lengths (for the tree-traffic roofline) */
   int32_t games_live;
   int32_t error;              /* first per-game error seen (AGZ_ERR_*) or 0 */
+  float step_ms;              /* device time of this agz_selfplay_step call (CUDA events on the engine's stream) */
+  int32_t reserved;
 } agz_progress;
 
 /* ---- lifecycle ----------------------------------------------------------------------------- */
@@ -207,10 +209,14 @@ int32_t agz_pos_liberties(agz_engine* e, const agz_position* in, uint8_t* libert
 
 /* ---- introspection for bench/roofline ---------------------------------------------------------- */
 int32_t agz_kernel_launches(agz_engine* e, int64_t* n);  /* kernels of this library launched since create */
-/* Device time (ms, CUDA events on the engine's stream) spent in each phase since the last call with reset != 0:
- * [0] select, [1] features, [2] network, [3] incorporate+move. */
-int32_t agz_phase_times(agz_engine* e, float ms[4], int64_t launches[4], int32_t reset);
+/* Per-kernel device time (ms, CUDA events on the engine's stream, accumulated while timing is enabled) and launch
+ * counts since the last call with reset != 0: [0] select (tree descent + expansion), [1] leaf features,
+ * [2] stem conv, [3] tower 3x3 conv (tcgen05), [4] heads, [5] incorporate + move logic. */
+#define AGZ_NKERNELS 6
+int32_t agz_phase_times(agz_engine* e, float ms[AGZ_NKERNELS], int64_t launches[AGZ_NKERNELS], int32_t reset);
 int32_t agz_set_timing(agz_engine* e, int32_t enabled);
+/* FLOPs (2*MAC) of one position through the whole network / through one tower 3x3 convolution. */
+int32_t agz_net_flops(agz_engine* e, double* per_position, double* per_tower_conv_position);
 
 #ifdef __cplusplus
 }
