@@ -214,6 +214,12 @@ class Engine:
                                                   _ptr(pi, C.c_float), _ptr(vis, C.c_float), C.byref(n)))
         return [GameRecord(hd[i], mv[i], q[i], pi[i], vis[i]) for i in range(n.value)]
 
+    def selfplay_harvest_discard(self, max_records=1 << 20):
+        """Release finished-game records without copying them to the host."""
+        n = C.c_int32()
+        self._check(self.lib.agz_selfplay_harvest(self._h, C.c_int32(max_records), None, None, None, None, None, C.byref(n)))
+        return n.value
+
     def selfplay_run(self, total_games):
         mine = (total_games - self.cfg.rank + self.cfg.world_size - 1) // self.cfg.world_size
         hd, mv, q, pi, vis = self._record_buffers(max(mine, 1))

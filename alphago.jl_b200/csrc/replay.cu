@@ -1,5 +1,6 @@
 // replay.cu -- see replay.h.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: libnccl is resolved at run time (see nccl_api) so that the library loads without it
 #include <stdio.h>
 #include <string.h>
 
@@ -11,6 +12,38 @@
 namespace agz {
 
 static const long long kReplayCap = 500000;  // memory_size default (src/train.jl:38)
+
+// NCCL is bound lazily with dlopen: a process that also runs torch.distributed must share torch's bundled
+// libnccl.so.2 (a second, older copy in the same process breaks torch), so an already-loaded copy is preferred.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    api.ok = false;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+    }
+  }
+  return api.ok ? &api : nullptr;
+}
 
 struct ReplayState {
   ncclComm_t comm;
@@ -45,7 +78,7 @@ ReplayState* replay_create(const Cfg& c, char* err, size_t errlen) {
 
 void replay_destroy(ReplayState* r) {
   if (!r) return;
-  if (r->have_comm) ncclCommDestroy(r->comm);
+  if (r->have_comm && nccl_api()) nccl_api()->CommDestroy(r->comm);
   cudaFree(r->ring); cudaFree(r->send); cudaFree(r->recv); cudaFree(r->d_counts); cudaFree(r->d_rec_idx);
   delete r;
 }
@@ -53,7 +86,7 @@ void replay_destroy(ReplayState* r) {
 int replay_unique_id(uint8_t id_out[128]) {
   ncclUniqueId id;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-  if (ncclGetUniqueId(&id) != ncclSuccess) return 1;
+  if (!nccl_api() || nccl_api()->GetUniqueId(&id) != ncclSuccess) return 1;
   memcpy(id_out, &id, 128);
   return 0;
 }
@@ -61,9 +94,13 @@ int replay_unique_id(uint8_t id_out[128]) {
 int replay_nccl_init(ReplayState* r, const uint8_t idb[128], int world, int rank, char* err, size_t errlen) {
   ncclUniqueId id;
   memcpy(&id, idb, 128);
-  ncclResult_t rc = ncclCommInitRank(&r->comm, world, id, rank);
+  if (!nccl_api()) {
+    snprintf(err, errlen, "libnccl.so.2 could not be loaded");
+    return 1;
+  }
+  ncclResult_t rc = nccl_api()->CommInitRank(&r->comm, world, id, rank);
   if (rc != ncclSuccess) {
-    snprintf(err, errlen, "ncclCommInitRank: %s", ncclGetErrorString(rc));
+    snprintf(err, errlen, "ncclCommInitRank: %s", nccl_api()->GetErrorString(rc));
     return 1;
   }
   r->have_comm = true;
@@ -173,8 +210,8 @@ int replay_gather(ReplayState* r, const Cfg& c, const View& v, int smem_per_warp
   } else {
     // ragged all-gather: counts first, then fixed-stride padded blocks
     cudaMemcpyAsync(r->d_counts + r->rank, &n_local, sizeof(long long), cudaMemcpyHostToDevice, s);
-    ncclResult_t nr = ncclAllGather(r->d_counts + r->rank, r->d_counts, 1, ncclInt64, r->comm, s);
-    if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(counts): %s", ncclGetErrorString(nr)); return 4; }
+    ncclResult_t nr = nccl_api()->AllGather(r->d_counts + r->rank, r->d_counts, 1, ncclInt64, r->comm, s);
+    if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(counts): %s", nccl_api()->GetErrorString(nr)); return 4; }
     std::vector<long long> counts((size_t)r->world);
     cudaMemcpyAsync(counts.data(), r->d_counts, sizeof(long long) * r->world, cudaMemcpyDeviceToHost, s);
     cudaStreamSynchronize(s);
@@ -184,8 +221,8 @@ int replay_gather(ReplayState* r, const Cfg& c, const View& v, int smem_per_warp
       if (grow(&r->send, &r->send_cap, (size_t)mx * r->stride) && n_local == 0) { snprintf(err, errlen, "replay send buffer allocation failed"); return 3; }
       if ((size_t)mx * r->stride > r->send_cap) { snprintf(err, errlen, "replay send buffer too small"); return 3; }
       if (grow(&r->recv, &r->recv_cap, (size_t)mx * r->stride * r->world)) { snprintf(err, errlen, "replay recv buffer allocation failed"); return 3; }
-      nr = ncclAllGather(r->send, r->recv, (size_t)mx * r->stride, ncclUint8, r->comm, s);
-      if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(tuples): %s", ncclGetErrorString(nr)); return 4; }
+      nr = nccl_api()->AllGather(r->send, r->recv, (size_t)mx * r->stride, ncclUint8, r->comm, s);
+      if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(tuples): %s", nccl_api()->GetErrorString(nr)); return 4; }
       for (int k = 0; k < r->world; ++k) ring_append(r, r->recv + (size_t)k * mx * r->stride, counts[(size_t)k], s);
     }
   }

@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py -- self-play moves/sec of the B200 engine (BASELINE.json metric) and of the CPU reference arm.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU path (oracle port), rank 0 only
+
+Workload (config C2 of BASELINE.json): 9x9 Go, 1024 concurrent self-play games per GPU, 400 readouts per move,
+tower_height 6, random-init weights (Flux default init restated, seed 0), all games from empty boards.
+One "step" = 50 batched tree_search! rounds = 400 readouts for every live game = one move-step of the whole
+job; moves are counted from the device counter, so `value` = moves actually played / device time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BOARD, GAMES, READOUTS, TOWER, ROUNDS_PER_STEP = 9, 1024, 400, 6, 50
+METRIC = "self-play moves/sec (9x9, 400 readouts)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
+
+
+def oracle_moves_per_sec(max_moves, budget_s, torch_threads=None):
+    """The reference's CPU path (oracle port): one game at a time, <= 8 leaves per network call, fp32 torch-CPU net."""
+    import torch
+    from oracle import go as ogo, net as onet, selfplay as osp
+    if torch_threads:
+        torch.set_num_threads(torch_threads)
+    env = ogo.GoEnv(BOARD)
+    nn = onet.NeuralNet(BOARD, TOWER, seed=0)
+    state = {"moves": 0, "t0": time.perf_counter(), "elapsed": 0.0}
+
+    class Stop(Exception):
+        pass
+
+    def on_move(player, move):
+        state["moves"] += 1
+        state["elapsed"] = time.perf_counter() - state["t0"]
+        if state["moves"] >= max_moves or state["elapsed"] > budget_s:
+            raise Stop()
+
+    gid = 0
+    try:
+        while True:
+            osp.selfplay(env, nn, READOUTS, seed=0, game_id=gid, on_move=on_move)
+            gid += 1
+    except Stop:
+        pass
+    return state["moves"] / state["elapsed"], state["moves"], state["elapsed"], torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step_moves = 2
+    t0 = time.perf_counter()
+    for _ in range(max(0, min(args.warmup, 1))):
+        oracle_moves_per_sec(1, 30)
+    vals = []
+    for _ in range(args.steps):
+        v, m, el, cores = oracle_moves_per_sec(per_step_moves, 60)
+        vals.append((m, el))
+        if time.perf_counter() - t0 > 240:
+            break
+    moves = sum(m for m, _ in vals)
+    el = sum(e for _, e in vals)
+    value = moves / el
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "moves/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / max(1, len(vals)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "C2 sample: 9x9 Go, 1 game at a time, 400 readouts/move, tower_height 6, random-init weights, %d moves per step" % per_step_moves},
+        "cpu_baseline": {"value": value, "unit": "moves/s", "cores": cores, "kind": "port",
+                         "sample": "%d moves of sequential self-play (oracle port of src/selfplay.jl: python tree, torch-CPU fp32 net, <=8 leaves per call)" % moves},
+        "e2e": {"value": value, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="agz")
+    ap.add_argument("--games", type=int, default=GAMES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import pkg
+    agz = pkg.load()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(3, args.warmup)
+
+    env = agz.GoEnv(BOARD, device=local)
+    nn = agz.NeuralNet(env, tower_height=TOWER, seed=0)
+    eng = agz.Engine(BOARD, n_games=args.games, readouts=READOUTS, tower_height=TOWER, seed=0, device=local, world_size=world, rank=rank,
+                     evaluator=agz.EVAL_NN_TC)
+    nn.push(eng)
+    if world > 1:  # NCCL communicator of the replay all-gather: rank 0's unique id goes round through torch.distributed
+        ids = [eng.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.nccl_init(ids[0])
+    flat_params = [np.concatenate([np.asarray(a, np.float32).flatten(order="F") for a in nn.params[k]]) for k in range(3)]
+    param_bytes = int(sum(p.nbytes for p in flat_params))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        """one step, inputs resident: 50 rounds + replay all-gather of the games that finished"""
+        pr = eng.selfplay_step(ROUNDS_PER_STEP)
+        eng.replay_gather()
+        eng.selfplay_harvest_discard()
+        return pr
+
+    eng.selfplay_start(-1)
+    for _ in range(warmup):
+        pr = device_step()
+    # ---- timed region 1: device-resident throughput (`value`) ---------------------------------------------------
+    eng.set_timing(True)
+    eng.phase_times(reset=True)
+    l0 = eng.kernel_launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    m0 = pr.moves_played
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        pr = device_step()
+        dev_ms += pr.step_ms
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    kms, kln = eng.phase_times(reset=True)
+    launches = eng.kernel_launches() - l0
+    moves = pr.moves_played - m0
+    # device time of the steps (CUDA events on the engine stream) plus the gather/harvest tail measured by wall clock
+    t_rank = max(wall, dev_ms / 1e3)
+    eng.set_timing(False)
+    # ---- timed region 2: end to end through the public API with host buffers (`e2e`) ----------------------------
+    barrier()
+    m1 = pr.moves_played
+    d2h = 0
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        for k in range(3):                      # H2D: the caller's current network parameters (train.jl hands selfplay cur_nn)
+            eng.net_set_params(k, flat_params[k])
+        pr = eng.selfplay_step(ROUNDS_PER_STEP)
+        eng.replay_gather()
+        recs = eng.selfplay_harvest(4 * args.games)   # D2H: finished games (moves, pi, q, result)
+        d2h += sum(r.searches_pi.nbytes + r.visits.nbytes + r.moves.nbytes + r.qs.nbytes + 40 for r in recs) + 80
+    barrier()
+    t_e2e = time.perf_counter() - t1
+    moves_e2e = pr.moves_played - m1
+
+    tot = torch.tensor([float(moves), float(moves_e2e), float(launches)], device="cuda", dtype=torch.float64)
+    tmx = torch.tensor([t_rank, t_e2e], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+    tot, tmx = tot.cpu().numpy(), tmx.cpu().numpy()
+    if rank == 0:
+        hbm, tf_sus, tf_burst, src = peaks()
+        _, conv_flops_pos = eng.net_flops()
+        flops_pos, _ = eng.net_flops()
+        rows = args.games * 8
+        conv_ms = kms[3] / max(1, kln[3])
+        achieved = conv_flops_pos * rows / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": tot[0] / tmx[0], "unit": "moves/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": 1e3 * tmx[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": "C2: 9x9 Go, %d concurrent self-play games per GPU, 400 readouts/move (50 rounds x 8 leaves per step), tower_height 6, 256 filters, random-init weights seed 0, empty-board starts, finished games refilled" % args.games,
+                       "step": "50 tree_search rounds over all games + replay all-gather of finished games",
+                       "l2": "inputs larger than L2: tree arenas %.1f GB and %.0f MB per activation buffer vs 126 MB L2" % (args.games * eng.cfg.nodes_per_game * 1.5e-6 if eng.cfg.nodes_per_game else args.games * 1680 * 1.5e-6, rows * 100 * 512 / 1e6)},
+            "e2e": {"value": tot[1] / tmx[1], "unit": "moves/s", "h2d_bytes_per_step": param_bytes, "d2h_bytes_per_step": int(d2h / args.steps)},
+            "gpu_launches": int(tot[2]),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tower 3x3 conv, fp16 tcgen05)", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
+                         "frac": achieved / tf_sus, "traffic": None, "peak_source": src + " bf16 sustained",
+                         "flops_per_launch": conv_flops_pos * rows, "ms_per_launch": conv_ms},
+            "kernel_ms_per_round": {n: kms[i] / max(1, kln[0]) for i, n in enumerate(agz.binding.KERNEL_NAMES)},
+            "network_tflops": flops_pos * rows / ((kms[2] + kms[3] + kms[4]) / max(1, kln[0]) * 1e-3) / 1e12 if kln[0] else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, m, el, cores = oracle_moves_per_sec(3, 25)
+            line["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d moves of one 9x9 game, 400 readouts, tower_height 6 (oracle port of src/selfplay.jl, %.1f s)" % (m, el)}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
