@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -34,6 +35,11 @@ static const int CIN0 = 64;  // stem input channels: 17 planes zero-padded to on
 static const size_t CONV_SMEM = (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 
 struct TCState {
+  int version;                // 2 = slab kernel (default), 1 = per-tap kernel (AGZ_CONV_KERNEL=1)
+  int base_offset_mode;       // debug knob (AGZ_CONV_BASEOFF): measured on B200 -- the swizzle is a function of the absolute smem address, so 0 is correct
+  int H8, arows;              // v2: halo rows rounded up to 8, slab rows = 256 + 2*H8
+  CUtensorMap tm2_in64, tm2_act[3];
+  std::vector<CUtensorMap> tm2_w;
   int N, NP1, PP, C, T, max_batch;
   long long rows_alloc;       // rows allocated per activation buffer (multiple of 128, >= max_batch*PP + N+2)
   __half* in64;               // [rows_alloc][64]
@@ -87,6 +93,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 64 fp16 (128 B), 8-row atoms 1024 B apart
@@ -257,6 +269,216 @@ __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constan
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+}
+
+
+// ------------------------------------------------------------------------------------------- v2: slab kernel
+// Work item = 256 output rows x 128 output channels.  Per 64-channel chunk the producer loads ONE activation slab of
+// (256 + 2*H8) rows (H8 = halo N+2 rounded up to 8) and the 9 taps are taken as row-shifted views of it by moving the
+// start address of the A descriptor by whole 128-byte rows (measured on B200: the SWIZZLE_128B XOR is a function of the
+// absolute shared-memory address, exactly like the TMA write side, so any 128-byte-aligned start is valid and the
+// descriptor's base-offset field stays 0).  Each 16 KB weight stage (128 cout x 64 ch) feeds two M = 128 MMAs.
+// L2 -> SM operand traffic per (128 rows x 256 cout): 737 KB instead of 1770 KB for the per-tap kernel above.
+static const int V2_BM = 256, V2_BN = 128, V2_SA = 2, V2_SB = 6;
+static const int V2_B_BYTES = V2_BN * BK * 2;
+static const uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((uint32_t)(V2_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+struct Conv2Args {
+  const float* scale;
+  const float* shift;
+  const __half* res;
+  __half* out;
+  int n_work;           // 2 * ceil(rows_valid / 256): (m tile, cout half)
+  long long rows_valid;
+  int kchunks;
+  int N, NP1, PP;
+  int H8, arows;        // slab geometry
+  int slab_bytes;       // arows * 128
+  int base_offset_mode;
+  int relu;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_desc_shifted(uint32_t saddr, int mode) {
+  uint64_t d = make_sw128_desc(saddr);
+  if (mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;   // debug only: setting the base-offset field gives WRONG results on B200
+  return d;
+}
+
+__global__ void __launch_bounds__(256, 1) conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                             const Conv2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* slabs = smem;                                        // [V2_SA][slab_bytes]
+  uint8_t* wst = smem + (size_t)V2_SA * a.slab_bytes;           // [V2_SB][16 KB]
+  float* s_scale = reinterpret_cast<float*>(wst + (size_t)V2_SB * V2_B_BYTES);
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + V2_SA;
+  uint64_t* b_full = a_empty + V2_SA;
+  uint64_t* b_empty = b_full + V2_SB;
+  uint64_t* tfull = b_empty + V2_SB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  s_scale[threadIdx.x] = a.scale[threadIdx.x];
+  s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < V2_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < V2_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int half_rows = a.arows / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+        const int m0 = (w >> 1) * V2_BM, nh = w & 1;
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], (uint32_t)a.slab_bytes);
+          uint8_t* sl = slabs + (size_t)sa * a.slab_bytes;
+          tma_load_2d(sl, &tmA, &a_full[sa], kc * BK, m0 - a.H8);
+          tma_load_2d(sl + (size_t)half_rows * 128, &tmA, &a_full[sa], kc * BK, m0 - a.H8 + half_rows);
+          if (++sa == V2_SA) { sa = 0; pa ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], V2_B_BYTES);
+            tma_load_2d(wst + (size_t)sb * V2_B_BYTES, &tmW, &b_full[sb], kc * BK, tap * 256 + nh * V2_BN);
+            if (++sb == V2_SB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int titer = 0;
+      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++titer) {
+        const int as = titer & 1;
+        const uint32_t aphase = (titer >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t slab = smem_u32(slabs + (size_t)sa * a.slab_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int off = (tap / 3 - 1) * a.NP1 + (tap % 3 - 1);
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t bdesc = make_sw128_desc(smem_u32(wst + (size_t)sb * V2_B_BYTES));
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint64_t adesc = make_sw128_desc_shifted(slab + (uint32_t)(a.H8 + sub * 128 + off) * 128u, a.base_offset_mode);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                tc_mma_f16(d_tmem + (uint32_t)sub * V2_BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M128_N128,
+                           (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&b_empty[sb]);
+            if (++sb == V2_SB) { sb = 0; pb ^= 1; }
+          }
+          tc_commit(&a_empty[sa]);
+          if (++sa == V2_SA) { sa = 0; pa ^= 1; }
+        }
+        tc_commit(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int titer = 0;
+    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++titer) {
+      const int as = titer & 1;
+      const uint32_t aphase = (titer >> 1) & 1;
+      const int m0 = (w >> 1) * V2_BM, nh = w & 1;
+      // the residual rows do not depend on the MMAs: fetch them while the accumulator is still being produced
+      uint4 rbuf[2][16];
+      bool valid[2], pad[2];
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const long long row = (long long)m0 + sub * 128 + q * 32 + lane;
+        valid[sub] = row < a.rows_valid;
+        pad[sub] = true;
+        if (valid[sub]) {
+          const int r = (int)(row % a.PP);
+          pad[sub] = r < a.NP1 || ((r - a.NP1) % a.NP1) == a.N;
+        }
+        if (a.res && !pad[sub]) {
+          const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256 + nh * V2_BN);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rbuf[sub][j] = ld_nc_v4(rrow + j);
+        }
+      }
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const long long row = (long long)m0 + sub * 128 + q * 32 + lane;
+        __half* orow = a.out + row * 256 + nh * V2_BN;
+        const bool addres = a.res && !pad[sub];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)sub * V2_BN + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
+          if (valid[sub]) {
+            uint4 o[4];
+            uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c0 = nh * V2_BN + cc * 32 + 2 * j;
+              float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
+              float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
+              if (addres) {
+                const uint4& rq = rbuf[sub][cc * 4 + (j >> 2)];
+                const uint32_t rw = (j & 3) == 0 ? rq.x : ((j & 3) == 1 ? rq.y : ((j & 3) == 2 ? rq.z : rq.w));
+                float2 rr = __half22float2(*reinterpret_cast<const __half2*>(&rw));
+                y0 += rr.x;
+                y1 += rr.y;
+              }
+              if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+              if (pad[sub]) { y0 = 0.f; y1 = 0.f; }
+              __half2 h = __floats2half2_rn(y0, y1);
+              ow[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+static size_t conv2_smem(int arows) {
+  return (size_t)V2_SA * arows * 128 + (size_t)V2_SB * V2_B_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 }
 
 // ------------------------------------------------------------------------------------------- heads (fp16 trunk)
@@ -474,7 +696,7 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
     return 1;
   }
   long long rows = (long long)t->max_batch * t->PP + t->N + 2;
-  t->rows_alloc = (rows + 127) / 128 * 128 + 128;
+  t->rows_alloc = (rows + 255) / 256 * 256 + 256;
   cudaDeviceProp prop;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -495,6 +717,17 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   int rc = make_map(&t->tm_in64, t->in64, t->rows_alloc, CIN0, BM);
   for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm_act[i], t->act[i], t->rows_alloc, 256, BM);
   for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm_w[l], t->w[l], 9 * 256, l == 0 ? CIN0 : 256, BN);
+  // v2 maps: activation boxes of half a slab, weight boxes of 128 output channels
+  t->H8 = (t->N + 2 + 7) / 8 * 8;
+  t->arows = V2_BM + 2 * t->H8;
+  t->tm2_w.resize(nconv);
+  if (!rc) rc = make_map(&t->tm2_in64, t->in64, t->rows_alloc, CIN0, t->arows / 2);
+  for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm2_act[i], t->act[i], t->rows_alloc, 256, t->arows / 2);
+  for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm2_w[l], t->w[l], 9 * 256, l == 0 ? CIN0 : 256, V2_BN);
+  const char* ev = getenv("AGZ_CONV_KERNEL");
+  t->version = (ev && atoi(ev) == 1) ? 1 : 2;
+  const char* eb = getenv("AGZ_CONV_BASEOFF");
+  t->base_offset_mode = eb ? atoi(eb) : 0;
   if (rc) {
     snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d)", rc);
     return 1;
@@ -544,6 +777,22 @@ TCInput nn_tc_input(NNet* n) {
 
 long long nn_tc_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower + 1; }
 
+static int launch_conv2(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
+                        __half* out, int B, int kchunks, cudaStream_t s) {
+  Conv2Args a;
+  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
+  a.rows_valid = (long long)B * t->PP;
+  a.n_work = 2 * (int)((a.rows_valid + V2_BM - 1) / V2_BM);
+  a.kchunks = kchunks;
+  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
+  a.H8 = t->H8; a.arows = t->arows; a.slab_bytes = t->arows * 128;
+  a.base_offset_mode = t->base_offset_mode;
+  a.relu = 1;
+  int grid = a.n_work < t->num_sms ? a.n_work : t->num_sms;
+  conv3x3_tc2_kernel<<<grid, 256, conv2_smem(t->arows), s>>>(tmA, tmW, a);
+  return (int)cudaGetLastError();
+}
+
 static int launch_conv(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
                        __half* out, int B, int kchunks, cudaStream_t s) {
   ConvArgs a;
@@ -563,16 +812,24 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   if (B > t->max_batch) { snprintf(err, errlen, "batch %d exceeds max_batch %d", B, t->max_batch); return 1; }
   if (!t->attr_set) {
     cudaError_t rc = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv2_smem(t->arows));
     if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
     t->attr_set = true;
   }
   if (ev) cudaEventRecord(ev[0], s);
-  int rc = launch_conv(t, t->tm_in64, t->tm_w[0], n->f_scale[0], n->f_shift[0], nullptr, t->act[0], B, CIN0 / BK, s);
+  const bool v2 = t->version == 2;
+  auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
+    const int kch = in_buf < 0 ? CIN0 / BK : 4;
+    const __half* res = res_buf >= 0 ? t->act[res_buf] : nullptr;
+    if (v2) return launch_conv2(t, in_buf < 0 ? t->tm2_in64 : t->tm2_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
+    return launch_conv(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
+  };
+  int rc = conv(-1, 0, -1, 0);
   if (ev) cudaEventRecord(ev[1], s);
   int h = 0, t1 = 1, t2 = 2;
   for (int blk = 0; blk < t->T && !rc; ++blk) {
-    rc = launch_conv(t, t->tm_act[h], t->tm_w[1 + 2 * blk], n->f_scale[1 + 2 * blk], n->f_shift[1 + 2 * blk], nullptr, t->act[t1], B, 4, s);
-    if (!rc) rc = launch_conv(t, t->tm_act[t1], t->tm_w[2 + 2 * blk], n->f_scale[2 + 2 * blk], n->f_shift[2 + 2 * blk], t->act[h], t->act[t2], B, 4, s);
+    rc = conv(h, 1 + 2 * blk, -1, t1);
+    if (!rc) rc = conv(t1, 2 + 2 * blk, h, t2);
     int tmp = h; h = t2; t2 = tmp;
   }
   if (rc) { snprintf(err, errlen, "conv launch: %s", cudaGetErrorString((cudaError_t)rc)); return 1; }

@@ -182,7 +182,7 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    m0 = pr.moves_played
+    m0, p0, r0, f0 = pr.moves_played, pr.positions_evaluated, pr.readouts, pr.games_finished
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
@@ -194,6 +194,8 @@ def main():
     kms, kln = eng.phase_times(reset=True)
     launches = eng.kernel_launches() - l0
     moves = pr.moves_played - m0
+    fill = (pr.positions_evaluated - p0) / float(args.steps * ROUNDS_PER_STEP * args.games * 8)
+    readouts_done, finished = pr.readouts - r0, pr.games_finished - f0
     # device time of the steps (CUDA events on the engine stream) plus the gather/harvest tail measured by wall clock
     t_rank = max(wall, dev_ms / 1e3)
     eng.set_timing(False)
@@ -240,6 +242,7 @@ def main():
                          "frac": achieved / tf_sus, "traffic": None, "peak_source": src + " bf16 sustained",
                          "flops_per_launch": conv_flops_pos * rows, "ms_per_launch": conv_ms},
             "kernel_ms_per_round": {n: kms[i] / max(1, kln[0]) for i, n in enumerate(agz.binding.KERNEL_NAMES)},
+            "leaf_fill": fill, "readouts_per_s": readouts_done / tmx[0], "games_finished_rank0": int(finished),
             "network_tflops": flops_pos * rows / ((kms[2] + kms[3] + kms[4]) / max(1, kln[0]) * 1e-3) / 1e12 if kln[0] else None,
         }
         if world == 1 and not args.no_cpu_baseline:
