@@ -35,10 +35,11 @@ static const int CIN0 = 64;  // stem input channels: 17 planes zero-padded to on
 static const size_t CONV_SMEM = (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 
 struct TCState {
-  int version;                // 2 = slab kernel (default), 1 = per-tap kernel (AGZ_CONV_KERNEL=1)
+  int version;                // AGZ_CONV_KERNEL: 1 per-tap, 2 slab, 3 CTA pair (default), 4 CTA pair + slab
   int base_offset_mode;       // debug knob (AGZ_CONV_BASEOFF): measured on B200 -- the swizzle is a function of the absolute smem address, so 0 is correct
   int H8, arows;              // v2: halo rows rounded up to 8, slab rows = 256 + 2*H8
   CUtensorMap tm2_in64, tm2_act[3];
+  CUtensorMap tm4_in64, tm4_act[3];   // v4: box = one CTA's slab (128 + 2*H8 rows)
   std::vector<CUtensorMap> tm2_w;
   int N, NP1, PP, C, T, max_batch;
   long long rows_alloc;       // rows allocated per activation buffer (multiple of 128, >= max_batch*PP + N+2)
@@ -481,6 +482,388 @@ static size_t conv2_smem(int arows) {
   return (size_t)V2_SA * arows * 128 + (size_t)V2_SB * V2_B_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 }
 
+
+// ------------------------------------------------------------------------------------------- v3: CTA-pair kernel
+// cta_group::2: two CTAs of a cluster (one TPC) work on one 256-row x 256-channel tile.  Each CTA stages only ITS
+// 128 activation rows and HALF of the weight tile (128 of the 256 output channels); one tcgen05.mma issued by the
+// leader CTA consumes both halves, so per-SM shared-memory operand traffic per FLOP drops by a third versus
+// cta_group::1 (A 4 KB + B 4 KB per 128-cycle MMA instead of 4 + 8).  TMA completions of both CTAs land on the
+// leader's mbarrier; tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs.
+static const int V3_STAGES = 6;
+static const int V3_STAGE_BYTES = A_BYTES + A_BYTES;   // A 128x64 + B-half 128x64
+static const size_t CONV3_SMEM = (size_t)V3_STAGES * V3_STAGE_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
+static const uint32_t IDESC_F16_M256_N256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t a = smem_u32(bar);
+  uint32_t spins = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (!done && ++spins > 40000000u) asm volatile("trap;");   // a broken pipeline aborts the launch instead of hanging the GPU
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  float* s_scale = reinterpret_cast<float*>(smem + (size_t)V3_STAGES * V3_STAGE_BYTES);
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* full = bars;                       // [V3_STAGES]  (the leader's copy is the one in use)
+  uint64_t* empty = bars + V3_STAGES;          // [V3_STAGES]  local, fed by the multicast commit
+  uint64_t* tfull = bars + 2 * V3_STAGES;      // [2] local, fed by the multicast commit
+  uint64_t* tempty = bars + 2 * V3_STAGES + 2; // [2] the leader's copy collects 8 arrivals (4 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V3_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_ptiles = (a.n_tiles + 1) >> 1;   // 256-row tiles
+  s_scale[threadIdx.x] = a.scale[threadIdx.x];
+  s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < V3_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = 9 * a.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < n_ptiles; t += n_pairs) {
+        const int m0 = t * 256 + (int)rank * 128;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int off = (tap / 3 - 1) * a.NP1 + (tap % 3 - 1);
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait_guard(&empty[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * V3_STAGE_BYTES);
+            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+            uint8_t* sa = tiles + (size_t)stage * V3_STAGE_BYTES;
+            tma_load_2d_2sm(sa, &tmA, lbar, kc * BK, m0 + off);
+            tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, kc * BK, tap * 256 + (int)rank * 128);
+            if (++stage == V3_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int titer = 0;
+      for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
+        const int as = titer & 1;
+        const uint32_t aphase = (titer >> 1) & 1;
+        mbar_wait_guard(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait_guard(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * V3_STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M256_N256, (it > 0 || k > 0) ? 1u : 0u);
+          tc_commit_2sm(&empty[stage]);
+          if (++stage == V3_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int titer = 0;
+    for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
+      const int as = titer & 1;
+      const uint32_t aphase = (titer >> 1) & 1;
+      const long long row = (long long)t * 256 + rank * 128 + q * 32 + lane;
+      const bool valid = row < a.rows_valid;
+      bool pad = true;
+      if (valid) {
+        const int r = (int)(row % a.PP);
+        pad = r < a.NP1 || ((r - a.NP1) % a.NP1) == a.N;
+      }
+      __half* orow = a.out + row * 256;
+      const bool addres = a.res != nullptr && !pad;
+      mbar_wait_guard(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll 2
+      for (int cc = 0; cc < 8; ++cc) {
+        uint4 rv[4];
+        if (addres) {
+          const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256 + cc * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rv[j] = ld_nc_v4(rrow + j);
+        }
+        uint32_t v[32];
+        tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
+        if (valid) {
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+          const __half2* rh = reinterpret_cast<const __half2*>(rv);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c0 = cc * 32 + 2 * j;
+            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
+            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
+            if (addres) {
+              float2 rr = __half22float2(rh[j]);
+              y0 += rr.x;
+              y1 += rr.y;
+            }
+            if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            if (pad) { y0 = 0.f; y1 = 0.f; }
+            __half2 h = __floats2half2_rn(y0, y1);
+            ow[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t lb = mapa_u32(smem_u32(&tempty[as]), 0);
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lb) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------- v4: CTA pair + slab
+// v3's operand sharing across the CTA pair combined with v2's resident activation slab: per 64-channel chunk each CTA
+// loads ONE slab of 128 + 2*H8 rows and takes the 9 taps as row-shifted descriptor views; only the 16 KB half weight
+// tile is streamed per (tap, chunk).  L2 -> SM traffic per 256x256 tile: 2*(4*slab) + 1.18 MB instead of 2*1.77 MB.
+static const int V4_SA = 3, V4_SB = 7;
+
+struct Conv4Args {
+  ConvArgs c;
+  int H8, slab_rows, slab_bytes;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Conv4Args g) {
+  const ConvArgs& a = g.c;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* slabs = smem;                                          // [V4_SA][slab_bytes]
+  uint8_t* wst = smem + (size_t)V4_SA * g.slab_bytes;             // [V4_SB][16 KB]
+  float* s_scale = reinterpret_cast<float*>(wst + (size_t)V4_SB * A_BYTES);
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* a_full = bars;               // leader's copy in use
+  uint64_t* a_empty = a_full + V4_SA;    // local
+  uint64_t* b_full = a_empty + V4_SA;    // leader's copy in use
+  uint64_t* b_empty = b_full + V4_SB;    // local
+  uint64_t* tfull = b_empty + V4_SB;     // local
+  uint64_t* tempty = tfull + 2;          // leader's copy: 8 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_ptiles = (a.n_tiles + 1) >> 1;
+  s_scale[threadIdx.x] = a.scale[threadIdx.x];
+  s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < V4_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < V4_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int t = pair; t < n_ptiles; t += n_pairs) {
+        const int m0 = t * 256 + (int)rank * 128;
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait_guard(&a_empty[sa], pa ^ 1);
+          if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * (uint32_t)g.slab_bytes);
+          tma_load_2d_2sm(slabs + (size_t)sa * g.slab_bytes, &tmA, mapa_u32(smem_u32(&a_full[sa]), 0), kc * BK, m0 - g.H8);
+          if (++sa == V4_SA) { sa = 0; pa ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait_guard(&b_empty[sb], pb ^ 1);
+            if (rank == 0) mbar_expect_tx(&b_full[sb], 2u * A_BYTES);
+            tma_load_2d_2sm(wst + (size_t)sb * A_BYTES, &tmW, mapa_u32(smem_u32(&b_full[sb]), 0), kc * BK, tap * 256 + (int)rank * 128);
+            if (++sb == V4_SB) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int titer = 0;
+      for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
+        const int as = titer & 1;
+        const uint32_t aphase = (titer >> 1) & 1;
+        mbar_wait_guard(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait_guard(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t slab = smem_u32(slabs + (size_t)sa * g.slab_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int off = (tap / 3 - 1) * a.NP1 + (tap % 3 - 1);
+            mbar_wait_guard(&b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_desc(slab + (uint32_t)(g.H8 + off) * 128u);
+            const uint64_t bdesc = make_sw128_desc(smem_u32(wst + (size_t)sb * A_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M256_N256, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            tc_commit_2sm(&b_empty[sb]);
+            if (++sb == V4_SB) { sb = 0; pb ^= 1; }
+          }
+          tc_commit_2sm(&a_empty[sa]);
+          if (++sa == V4_SA) { sa = 0; pa ^= 1; }
+        }
+        tc_commit_2sm(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int titer = 0;
+    for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
+      const int as = titer & 1;
+      const uint32_t aphase = (titer >> 1) & 1;
+      const long long row = (long long)t * 256 + rank * 128 + q * 32 + lane;
+      const bool valid = row < a.rows_valid;
+      bool pad = true;
+      if (valid) {
+        const int r = (int)(row % a.PP);
+        pad = r < a.NP1 || ((r - a.NP1) % a.NP1) == a.N;
+      }
+      __half* orow = a.out + row * 256;
+      const bool addres = a.res != nullptr && !pad;
+      mbar_wait_guard(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll 2
+      for (int cc = 0; cc < 8; ++cc) {
+        uint4 rv[4];
+        if (addres) {
+          const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256 + cc * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rv[j] = ld_nc_v4(rrow + j);
+        }
+        uint32_t v[32];
+        tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
+        if (valid) {
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+          const __half2* rh = reinterpret_cast<const __half2*>(rv);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c0 = cc * 32 + 2 * j;
+            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
+            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
+            if (addres) {
+              float2 rr = __half22float2(rh[j]);
+              y0 += rr.x;
+              y1 += rr.y;
+            }
+            if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            if (pad) { y0 = 0.f; y1 = 0.f; }
+            __half2 h = __floats2half2_rn(y0, y1);
+            ow[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t lb = mapa_u32(smem_u32(&tempty[as]), 0);
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lb) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+static size_t conv4_smem(int slab_rows) {
+  return (size_t)V4_SA * slab_rows * 128 + (size_t)V4_SB * A_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
+}
+
 // ------------------------------------------------------------------------------------------- heads (fp16 trunk)
 // neural_net.jl:23-30 for one position per block, reading the trunk output in the padded NHWC layout.
 __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict__ trunk, const float* __restrict__ vw,
@@ -724,8 +1107,11 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   if (!rc) rc = make_map(&t->tm2_in64, t->in64, t->rows_alloc, CIN0, t->arows / 2);
   for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm2_act[i], t->act[i], t->rows_alloc, 256, t->arows / 2);
   for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm2_w[l], t->w[l], 9 * 256, l == 0 ? CIN0 : 256, V2_BN);
+  if (!rc) rc = make_map(&t->tm4_in64, t->in64, t->rows_alloc, CIN0, 128 + 2 * t->H8);
+  for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm4_act[i], t->act[i], t->rows_alloc, 256, 128 + 2 * t->H8);
   const char* ev = getenv("AGZ_CONV_KERNEL");
-  t->version = (ev && atoi(ev) == 1) ? 1 : 2;
+  t->version = ev ? atoi(ev) : 3;
+  if (t->version < 1 || t->version > 4) t->version = 3;
   const char* eb = getenv("AGZ_CONV_BASEOFF");
   t->base_offset_mode = eb ? atoi(eb) : 0;
   if (rc) {
@@ -793,6 +1179,38 @@ static int launch_conv2(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   return (int)cudaGetLastError();
 }
 
+static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
+                        __half* out, int B, int kchunks, cudaStream_t s) {
+  ConvArgs a;
+  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
+  a.rows_valid = (long long)B * t->PP;
+  a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
+  a.kchunks = kchunks;
+  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
+  a.relu = 1;
+  const int n_ptiles = (a.n_tiles + 1) / 2;
+  int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
+  conv3x3_tc3_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
+  return (int)cudaGetLastError();
+}
+
+static int launch_conv4(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
+                        __half* out, int B, int kchunks, cudaStream_t s) {
+  Conv4Args g;
+  ConvArgs& a = g.c;
+  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
+  a.rows_valid = (long long)B * t->PP;
+  a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
+  a.kchunks = kchunks;
+  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
+  a.relu = 1;
+  g.H8 = t->H8; g.slab_rows = 128 + 2 * t->H8; g.slab_bytes = g.slab_rows * 128;
+  const int n_ptiles = (a.n_tiles + 1) / 2;
+  int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
+  conv3x3_tc4_kernel<<<2 * pairs, 256, conv4_smem(g.slab_rows), s>>>(tmA, tmW, g);
+  return (int)cudaGetLastError();
+}
+
 static int launch_conv(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
                        __half* out, int B, int kchunks, cudaStream_t s) {
   ConvArgs a;
@@ -813,6 +1231,8 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   if (!t->attr_set) {
     cudaError_t rc = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv2_smem(t->arows));
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv4_smem(128 + 2 * t->H8));
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
     t->attr_set = true;
   }
@@ -821,6 +1241,8 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
     const int kch = in_buf < 0 ? CIN0 / BK : 4;
     const __half* res = res_buf >= 0 ? t->act[res_buf] : nullptr;
+    if (t->version == 4) return launch_conv4(t, in_buf < 0 ? t->tm4_in64 : t->tm4_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
+    if (t->version == 3) return launch_conv3(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (v2) return launch_conv2(t, in_buf < 0 ? t->tm2_in64 : t->tm2_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     return launch_conv(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
   };
