@@ -35,13 +35,16 @@ static const int CIN0 = 64;  // stem input channels: 17 planes zero-padded to on
 static const size_t CONV_SMEM = (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 
 struct TCState {
-  int version;                // AGZ_CONV_KERNEL: 1 per-tap, 2 slab, 3 CTA pair (default), 4 CTA pair + slab
+  int version;                // AGZ_CONV_KERNEL: 1 per-tap, 2 slab, 3 CTA pair, 4 CTA pair + slab (zero-bordered layout); 5 CTA pair + im2col (dense, default)
   int base_offset_mode;       // debug knob (AGZ_CONV_BASEOFF): measured on B200 -- the swizzle is a function of the absolute smem address, so 0 is correct
   int H8, arows;              // v2: halo rows rounded up to 8, slab rows = 256 + 2*H8
   CUtensorMap tm2_in64, tm2_act[3];
   CUtensorMap tm4_in64, tm4_act[3];   // v4: box = one CTA's slab (128 + 2*H8 rows)
   std::vector<CUtensorMap> tm2_w;
   int N, NP1, PP, C, T, max_batch;
+  int dense;                  // 1: dense NHWC rows (b*N^2 + p), im2col TMA (v5); 0: zero-bordered boards (v1-v4)
+  int rowbase, pitch;         // row of point (j, i) of board b = b*PP + rowbase + j*pitch + i
+  CUtensorMap tm5_in64, tm5_act[3];
   long long rows_alloc;       // rows allocated per activation buffer (multiple of 128, >= max_batch*PP + N+2)
   __half* in64;               // [rows_alloc][64]
   __half* act[3];             // [rows_alloc][256]
@@ -864,6 +867,166 @@ static size_t conv4_smem(int slab_rows) {
   return (size_t)V4_SA * slab_rows * 128 + (size_t)V4_SB * A_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 }
 
+
+// ------------------------------------------------------------------------------------------- v5: CTA pair + TMA im2col
+// Dense NHWC activations (row = b*N^2 + N*j + i, no border rows): the A tile of tap (kj, ki) is ONE TMA im2col load --
+// 128 consecutive output pixels starting at (w, h, n) = (i0 - 1, j0 - 1, b0) with filter offsets {ki, kj}; the TMA unit
+// walks pixels across rows and boards and zero-fills the halo (pixelBoxLowerCorner = upperCorner = -1, i.e. pad 1,
+// 3x3).  No MMA work is spent on border rows: M = B*N^2 exactly (v1-v4 issue (N+1)^2/N^2 = 1.235x the MMAs on 9x9).
+__device__ __forceinline__ void tma_load_im2col_2sm(void* dst, const CUtensorMap* tm, uint32_t leader_bar, int c, int w, int h, int n,
+                                                    uint16_t ow, uint16_t oh) {
+  asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  float* s_scale = reinterpret_cast<float*>(smem + (size_t)V3_STAGES * V3_STAGE_BYTES);
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + V3_STAGES;
+  uint64_t* tfull = bars + 2 * V3_STAGES;
+  uint64_t* tempty = bars + 2 * V3_STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V3_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_ptiles = (a.n_tiles + 1) >> 1;
+  s_scale[threadIdx.x] = a.scale[threadIdx.x];
+  s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < V3_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = 9 * a.kchunks;
+  const int N2 = a.N * a.N;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < n_ptiles; t += n_pairs) {
+        const int m0 = t * 256 + (int)rank * 128;
+        const int b0 = m0 / N2, rem = m0 - b0 * N2, j0 = rem / a.N, i0 = rem - j0 * a.N;
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint16_t oh = (uint16_t)(tap / 3), ow = (uint16_t)(tap % 3);
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait_guard(&empty[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * V3_STAGE_BYTES);
+            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+            uint8_t* sa = tiles + (size_t)stage * V3_STAGE_BYTES;
+            tma_load_im2col_2sm(sa, &tmA, lbar, kc * BK, i0 - 1, j0 - 1, b0, ow, oh);
+            tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, kc * BK, tap * 256 + (int)rank * 128);
+            if (++stage == V3_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int titer = 0;
+      for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
+        const int as = titer & 1;
+        const uint32_t aphase = (titer >> 1) & 1;
+        mbar_wait_guard(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait_guard(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * V3_STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M256_N256, (it > 0 || k > 0) ? 1u : 0u);
+          tc_commit_2sm(&empty[stage]);
+          if (++stage == V3_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    int titer = 0;
+    for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
+      const int as = titer & 1;
+      const uint32_t aphase = (titer >> 1) & 1;
+      const long long row = (long long)t * 256 + rank * 128 + q * 32 + lane;
+      const bool valid = row < a.rows_valid;
+      __half* orow = a.out + row * 256;
+      const bool addres = a.res != nullptr && valid;
+      mbar_wait_guard(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll 2
+      for (int cc = 0; cc < 8; ++cc) {
+        uint4 rv[4];
+        if (addres) {
+          const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256 + cc * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rv[j] = ld_nc_v4(rrow + j);
+        }
+        uint32_t v[32];
+        tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
+        if (valid) {
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+          const __half2* rh = reinterpret_cast<const __half2*>(rv);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c0 = cc * 32 + 2 * j;
+            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
+            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
+            if (addres) {
+              float2 rr = __half22float2(rh[j]);
+              y0 += rr.x;
+              y1 += rr.y;
+            }
+            if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            __half2 h = __floats2half2_rn(y0, y1);
+            ow[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t lb = mapa_u32(smem_u32(&tempty[as]), 0);
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lb) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------------------- heads (fp16 trunk)
 // neural_net.jl:23-30 for one position per block, reading the trunk output in the padded NHWC layout.
 __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict__ trunk, const float* __restrict__ vw,
@@ -871,15 +1034,15 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
                                                        const float* __restrict__ D1W, const float* __restrict__ D1b,
                                                        const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                        const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
-                                                       float* __restrict__ v, int N, int PP) {
+                                                       float* __restrict__ v, int N, int PP, int rowbase, int pitch) {
   extern __shared__ float sm[];
-  const int N2 = N * N, NP1 = N + 1, A = N2 + 1;
+  const int N2 = N * N, A = N2 + 1;
   float* vf = sm;
   float* pf = sm + N2;
   float* hid = sm + 3 * N2;
   float* red = hid + 256;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __half* base = trunk + ((size_t)b * PP + NP1) * 256;
+  const __half* base = trunk + ((size_t)b * PP + rowbase) * 256;
   // 1x1 convolutions: a warp per point, 8 channels per lane (one 16-byte load)
   float wv[8], wp0[8], wp1[8];
 #pragma unroll
@@ -890,7 +1053,7 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
   }
   for (int p = warp; p < N2; p += 8) {
     const int jj = p / N, ii = p % N;
-    const uint4 raw = *reinterpret_cast<const uint4*>(base + ((size_t)jj * NP1 + ii) * 256 + lane * 8);
+    const uint4 raw = *reinterpret_cast<const uint4*>(base + ((size_t)jj * pitch + ii) * 256 + lane * 8);
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
@@ -976,7 +1139,7 @@ struct LeafFeaturesTCOp {
   Cfg c;
   View v;
   __half* in64;
-  int PP;
+  int PP, rowbase, pitch;
   __device__ void operator()(int b, char* smem) const {
     const int g = b / c.pmax, k = b % c.pmax;
     Warp<KA> w(c, v, g, smem);
@@ -996,7 +1159,7 @@ struct LeafFeaturesTCOp {
       const int p = q * 32 + lane;
       if (p < c.N2) {
         const int jj = p / c.N, ii = p % c.N;
-        __half* row = in64 + ((size_t)b * PP + (c.N + 1) + (size_t)jj * (c.N + 1) + ii) * CIN0;
+        __half* row = in64 + ((size_t)b * PP + rowbase + (size_t)jj * pitch + ii) * CIN0;
         __align__(16) __half h[24];
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) h[ch] = ((planes[q] >> ch) & 1u) ? one : zero;
@@ -1011,14 +1174,14 @@ struct LeafFeaturesTCOp {
 };
 
 __global__ void host_features_tc_kernel(const int8_t* __restrict__ bh, const int8_t* __restrict__ tp, __half* __restrict__ in64, int B, int N,
-                                        int PP) {
+                                        int PP, int rowbase, int pitch) {
   const int N2 = N * N;
   const size_t total = (size_t)B * N2;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int p = (int)(idx % N2), b = (int)(idx / N2);
     const int t = tp[b];
     const int jj = p / N, ii = p % N;
-    __half* row = in64 + ((size_t)b * PP + (N + 1) + (size_t)jj * (N + 1) + ii) * CIN0;
+    __half* row = in64 + ((size_t)b * PP + rowbase + (size_t)jj * pitch + ii) * CIN0;
     __align__(16) __half h[24];
 #pragma unroll
     for (int kq = 0; kq < 8; ++kq) {
@@ -1037,6 +1200,40 @@ __global__ void host_features_tc_kernel(const int8_t* __restrict__ bh, const int
 // ------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeIm2colFn)p;
+  }
+  return fn;
+}
+
+// NHWC fp16 tensor (C, W = N, H = N, boards) for a 3x3 / pad 1 convolution: 128 pixels x 64 channels per load
+static int make_map_im2col(CUtensorMap* tm, void* base, int N, long long boards, int C) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc) return 1;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)boards};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * N, (cuuint64_t)C * 2 * N * N};
+  int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, lower, upper, (cuuint32_t)BK, (cuuint32_t)BM, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 2;
+  // driver quirk mirrored from CUTLASS (copy_traits_sm90_im2col.hpp): small tensors need bit 21 of word 1 cleared on drivers <= 13.1
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (unsigned long long)C * 2ull * N * N * (unsigned long long)boards < 131072ull)
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return 0;
+}
 
 static EncodeTiledFn get_encode() {
   static EncodeTiledFn fn = nullptr;
@@ -1067,7 +1264,15 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   n->tc = t;
   t->N = n->s.N;
   t->NP1 = t->N + 1;
-  t->PP = t->NP1 * t->NP1;
+  {
+    const char* ev0 = getenv("AGZ_CONV_KERNEL");
+    t->version = ev0 ? atoi(ev0) : 5;
+    if (t->version < 1 || t->version > 5) t->version = 5;
+  }
+  t->dense = t->version == 5;
+  t->PP = t->dense ? t->N * t->N : t->NP1 * t->NP1;
+  t->rowbase = t->dense ? 0 : t->NP1;
+  t->pitch = t->dense ? t->N : t->NP1;
   t->C = n->C;
   t->T = n->s.tower;
   t->max_batch = n->max_batch;
@@ -1080,6 +1285,10 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   }
   long long rows = (long long)t->max_batch * t->PP + t->N + 2;
   t->rows_alloc = (rows + 255) / 256 * 256 + 256;
+  if (t->dense) {  // whole boards, with enough spare boards for the last 256-row tile
+    const long long n2 = (long long)t->N * t->N;
+    t->rows_alloc = ((long long)t->max_batch + (256 + n2 - 1) / n2 + 1) * n2;
+  }
   cudaDeviceProp prop;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1109,9 +1318,12 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm2_w[l], t->w[l], 9 * 256, l == 0 ? CIN0 : 256, V2_BN);
   if (!rc) rc = make_map(&t->tm4_in64, t->in64, t->rows_alloc, CIN0, 128 + 2 * t->H8);
   for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm4_act[i], t->act[i], t->rows_alloc, 256, 128 + 2 * t->H8);
-  const char* ev = getenv("AGZ_CONV_KERNEL");
-  t->version = ev ? atoi(ev) : 3;
-  if (t->version < 1 || t->version > 4) t->version = 3;
+  if (t->dense) {
+    // boards dimension covers the whole allocation so that tiles running past the batch read zero-initialised rows
+    const long long boards = t->rows_alloc / (t->N * t->N);
+    if (!rc) rc = make_map_im2col(&t->tm5_in64, t->in64, t->N, boards, CIN0);
+    for (int i = 0; i < 3 && !rc; ++i) rc = make_map_im2col(&t->tm5_act[i], t->act[i], t->N, boards, 256);
+  }
   const char* eb = getenv("AGZ_CONV_BASEOFF");
   t->base_offset_mode = eb ? atoi(eb) : 0;
   if (rc) {
@@ -1194,6 +1406,21 @@ static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   return (int)cudaGetLastError();
 }
 
+static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
+                        __half* out, int B, int kchunks, cudaStream_t s) {
+  ConvArgs a;
+  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
+  a.rows_valid = (long long)B * t->PP;
+  a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
+  a.kchunks = kchunks;
+  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
+  a.relu = 1;
+  const int n_ptiles = (a.n_tiles + 1) / 2;
+  int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
+  conv3x3_tc5_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
+  return (int)cudaGetLastError();
+}
+
 static int launch_conv4(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
                         __half* out, int B, int kchunks, cudaStream_t s) {
   Conv4Args g;
@@ -1232,6 +1459,7 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
     cudaError_t rc = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv2_smem(t->arows));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv4_smem(128 + 2 * t->H8));
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
     t->attr_set = true;
@@ -1241,6 +1469,7 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
     const int kch = in_buf < 0 ? CIN0 / BK : 4;
     const __half* res = res_buf >= 0 ? t->act[res_buf] : nullptr;
+    if (t->version == 5) return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (t->version == 4) return launch_conv4(t, in_buf < 0 ? t->tm4_in64 : t->tm4_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (t->version == 3) return launch_conv3(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (v2) return launch_conv2(t, in_buf < 0 ? t->tm2_in64 : t->tm2_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
@@ -1258,7 +1487,7 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   if (ev) cudaEventRecord(ev[2], s);
   const size_t hsm = (size_t)(3 * n->N2 + 512) * sizeof(float);
   heads_tc_kernel<<<B, 256, hsm, s>>>(t->act[h], n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb,
-                                       pi, v, t->N, t->PP);
+                                       pi, v, t->N, t->PP, t->rowbase, t->pitch);
   if (ev) cudaEventRecord(ev[3], s);
   cudaError_t e2 = cudaGetLastError();
   if (e2 != cudaSuccess) { snprintf(err, errlen, "heads launch: %s", cudaGetErrorString(e2)); return 1; }
@@ -1269,9 +1498,9 @@ int engine_tc_features(const Cfg& c, const View& v, NNet* n, int row0, int nrows
   TCState* t = (TCState*)n->tc;
   int rc = 0;
   switch (c.KA) {
-    case 3: { LeafFeaturesTCOp<3> op{c, v, t->in64, t->PP}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
-    case 6: { LeafFeaturesTCOp<6> op{c, v, t->in64, t->PP}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
-    default: { LeafFeaturesTCOp<12> op{c, v, t->in64, t->PP}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
+    case 3: { LeafFeaturesTCOp<3> op{c, v, t->in64, t->PP, t->rowbase, t->pitch}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
+    case 6: { LeafFeaturesTCOp<6> op{c, v, t->in64, t->PP, t->rowbase, t->pitch}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
+    default: { LeafFeaturesTCOp<12> op{c, v, t->in64, t->PP, t->rowbase, t->pitch}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
   }
   return rc;
 }
@@ -1286,7 +1515,7 @@ int engine_host_features_tc(const Cfg& c, NNet* n, const int8_t* boards_hist, co
   if (rc == cudaSuccess) rc = cudaMemcpyAsync(dtp, to_play, (size_t)B, cudaMemcpyHostToDevice, s);
   if (rc == cudaSuccess) {
     int blocks = (int)(((size_t)B * c.N2 + 255) / 256);
-    host_features_tc_kernel<<<blocks, 256, 0, s>>>(dbh, dtp, t->in64, B, c.N, t->PP);
+    host_features_tc_kernel<<<blocks, 256, 0, s>>>(dbh, dtp, t->in64, B, c.N, t->PP, t->rowbase, t->pitch);
     rc = cudaGetLastError();
   }
   cudaError_t rs = cudaStreamSynchronize(s);
