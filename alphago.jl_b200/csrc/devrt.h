@@ -38,6 +38,13 @@ __global__ void __launch_bounds__(128) k_warps(const Op op, int n_warps, int sme
 template <class Op>
 inline int launch_warps(const Op& op, int n_warps, int smem_per_warp, stream_t s) {
   if (n_warps <= 0) return 0;
+  // same shared-memory carveout as the persistent conv kernel: an SM cannot host CTAs of kernels that ask for
+  // different L1/shared splits at the same time, and these kernels are meant to run underneath the conv kernel
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    cudaFuncSetAttribute(k_warps<Op>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
   k_warps<Op><<<(n_warps + 3) / 4, 128, 4 * smem_per_warp, s>>>(op, n_warps, smem_per_warp);
   return (int)cudaGetLastError();
 }

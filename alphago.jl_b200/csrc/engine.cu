@@ -56,6 +56,10 @@ struct agz_engine {
   NNet* nn;
   cudaEvent_t ev[8];   // 0 select | 1 features | 2 stem | 3 tower | 4 heads | 5 incorporate | 6 end
   cudaEvent_t ev_step[2];
+  cudaStream_t gstream[2];   // half-batch pipelining: group g's select -> features -> network -> incorporate chain
+  cudaEvent_t ev_join[3];
+  cudaEvent_t ev_tok[2];
+  int pipeline;              // 1: two half batches on two streams (tree work of one hides under the network of the other)
   ReplayState* replay;
 #endif
 };
@@ -138,6 +142,9 @@ extern "C" void agz_engine_destroy(agz_engine* e) {
   if (e->nn) nn_destroy(e->nn);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
   for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_step[i]);
+  for (int i = 0; i < 3; ++i) cudaEventDestroy(e->ev_join[i]);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_tok[i]);
+  for (int i = 0; i < 2; ++i) cudaStreamDestroy(e->gstream[i]);
 #endif
   for (void* p : e->allocs) devrt::dfree(p);
 #if AGZ_CUDA
@@ -188,6 +195,13 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   }
   for (int i = 0; i < 8; ++i) cudaEventCreate(&e->ev[i]);
   for (int i = 0; i < 2; ++i) cudaEventCreate(&e->ev_step[i]);
+  for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&e->ev_tok[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&e->gstream[i], cudaStreamNonBlocking);
+  {
+    const char* pe = getenv("AGZ_PIPELINE");
+    e->pipeline = pe ? atoi(pe) : 1;
+  }
 #else
   e->stream = 0;
 #endif
@@ -218,7 +232,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   c.seed = cfg->seed;
   c.total_games = 0;
   const int need = cfg->readouts + 2 * c.pmax + 4;
-  c.cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : std::max(256, 4 * need);
+  c.cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : std::max(256, 6 * need);
   if (c.cap < need + 2) c.cap = need + 2;
   c.ring_cap = cfg->record_ring > 0 ? cfg->record_ring : 2 * cfg->n_games;
   e->smem_per_warp = (int)((c.KB * 32 * 7 + 15) / 16 * 16);
@@ -408,7 +422,7 @@ static int one_round(agz_engine* e) {
   if (e->timing) cudaEventRecord(e->ev[0], e->stream);
 #endif
   DISPATCH_KA(e, {
-    SelectOp<KA> op{e->c, e->v, -1, e->c.parallel};
+    SelectOp<KA> op{e->c, e->v, -1, e->c.parallel, 0};
     DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
   });
   e->launches += 1;
@@ -421,7 +435,7 @@ static int one_round(agz_engine* e) {
   }
 #endif
   DISPATCH_KA(e, {
-    IncorporateOp<KA> op{e->c, e->v, -1};
+    IncorporateOp<KA> op{e->c, e->v, -1, 0};
     DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
   });
   e->launches += 1;
@@ -446,12 +460,64 @@ static int one_round(agz_engine* e) {
   return AGZ_OK;
 }
 
+#if AGZ_CUDA
+// Half-batch pipelining: slots [0, G/2) and [G/2, G) run their own select -> features -> network -> incorporate chains
+// on two streams.  A token (events ev_tok[g], recorded after a group's last convolution) makes the two towers strictly
+// alternate on the tensor cores, so the latency-bound tree kernels, the feature kernel and the heads of one group
+// execute underneath the tower of the other.  (Without the token the hardware round-robins the two streams' conv
+// kernels and the chains stay in phase -- measured: no gain.)  Results are identical to the sequential schedule: games
+// never interact.
+static bool can_pipeline(agz_engine* e) {
+  return e->pipeline && !e->timing && e->evaluator == AGZ_EVAL_NN_TC && e->c.n_games >= 2 && e->c.n_games % 2 == 0 && nn_tc_groups(e->nn) == 2;
+}
+
+static int pipelined_rounds(agz_engine* e, int rounds) {
+  char nerr[256] = "";
+  if (!nn_ready(e->nn) && nn_commit(e->nn, e->stream, nerr, sizeof(nerr))) return fail(e, AGZ_ERR_ARG, "network not ready: %s", nerr);
+  const int half = e->c.n_games / 2, rows = half * e->c.pmax;
+  cudaEventRecord(e->ev_join[2], e->stream);
+  for (int g = 0; g < 2; ++g) cudaStreamWaitEvent(e->gstream[g], e->ev_join[2], 0);
+  for (int r = 0; r < rounds; ++r) {
+    for (int g = 0; g < 2; ++g) {
+      cudaStream_t st = e->gstream[g];
+      DISPATCH_KA(e, {
+        SelectOp<KA> op{e->c, e->v, -1, e->c.parallel, g * half};
+        DCHECK(e, devrt::launch_warps(op, half, e->smem_per_warp, st));
+      });
+      int rc = engine_tc_features(e->c, e->v, e->nn, g * rows, rows, e->smem_per_warp, st);
+      if (rc) return fail(e, AGZ_ERR_CUDA, "tc feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
+      if (r > 0 || g > 0) cudaStreamWaitEvent(st, e->ev_tok[1 - g], 0);   // the other group's tower must have drained
+      rc = nn_forward_tc(e->nn, rows, e->d_eval_pi + (size_t)g * rows * e->c.A, e->d_eval_v + (size_t)g * rows, st, nerr, sizeof(nerr), nullptr, g,
+                         e->ev_tok[g]);
+      if (rc) return fail(e, AGZ_ERR_CUDA, "nn_forward_tc: %s", nerr);
+      DISPATCH_KA(e, {
+        IncorporateOp<KA> op{e->c, e->v, -1, g * half};
+        DCHECK(e, devrt::launch_warps(op, half, e->smem_per_warp, st));
+      });
+      e->launches += 3 + nn_tc_launches_per_forward(e->nn);
+    }
+  }
+  for (int g = 0; g < 2; ++g) {
+    cudaEventRecord(e->ev_join[g], e->gstream[g]);
+    cudaStreamWaitEvent(e->stream, e->ev_join[g], 0);
+  }
+  return AGZ_OK;
+}
+#endif
+
 extern "C" int32_t agz_selfplay_step(agz_engine* e, int32_t rounds, agz_progress* progress) {
   if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
   if (!e->started) return fail(e, AGZ_ERR_ARG, "agz_selfplay_start has not been called");
   bind_evaluator(e);
 #if AGZ_CUDA
   if (progress) cudaEventRecord(e->ev_step[0], e->stream);
+#endif
+#if AGZ_CUDA
+  if (can_pipeline(e)) {
+    int rc = pipelined_rounds(e, rounds);
+    if (rc) return rc;
+    rounds = 0;
+  }
 #endif
   for (int r = 0; r < rounds; ++r) {
     int rc = one_round(e);
@@ -483,21 +549,31 @@ extern "C" int32_t agz_selfplay_harvest(agz_engine* e, int32_t max_records, agz_
   const unsigned long long tail = ctr[CTR_RING_TAIL];
   const size_t L = e->c.max_game_length + 2, A = e->c.A;
   int n = 0;
+  // the ring is fixed-stride, so a run of finished records is at most two contiguous device ranges: copy each array
+  // of a range with ONE transfer straight into the caller's buffers, then blank what lies past each game's length
   while (e->ring_head < tail && n < max_records) {
     const size_t rs = (size_t)(e->ring_head % (unsigned long long)e->c.ring_cap);
-    RingHeader hd;
-    DCHECK(e, devrt::d2h(&hd, e->v.ring_hdr + rs, sizeof(hd), e->stream));
-    if (headers) {
-      headers[n].game_id = hd.game_id; headers[n].n_moves = hd.n_moves; headers[n].result = hd.result;
-      headers[n].resigned = hd.resigned; headers[n].final_score = hd.final_score; headers[n].resign_threshold = hd.resign_threshold;
+    size_t run = std::min<unsigned long long>(tail - e->ring_head, (unsigned long long)(max_records - n));
+    run = std::min(run, (size_t)e->c.ring_cap - rs);
+    std::vector<RingHeader> hd(run);
+    DCHECK(e, devrt::d2h(hd.data(), e->v.ring_hdr + rs, run * sizeof(RingHeader), e->stream));
+    if (moves) DCHECK(e, devrt::d2h(moves + n * L, e->v.ring_moves + rs * L, run * L * sizeof(int16_t), e->stream));
+    if (qs) DCHECK(e, devrt::d2h(qs + n * L, e->v.ring_q + rs * L, run * L * sizeof(float), e->stream));
+    if (pis) DCHECK(e, devrt::d2h(pis + n * L * A, e->v.ring_pi + rs * L * A, run * L * A * sizeof(float), e->stream));
+    if (visits) DCHECK(e, devrt::d2h(visits + n * L * A, e->v.ring_vis + rs * L * A, run * L * A * sizeof(float), e->stream));
+    for (size_t r = 0; r < run; ++r) {
+      const size_t k = (size_t)n + r, nm = (size_t)hd[r].n_moves;
+      if (headers) {
+        headers[k].game_id = hd[r].game_id; headers[k].n_moves = hd[r].n_moves; headers[k].result = hd[r].result;
+        headers[k].resigned = hd[r].resigned; headers[k].final_score = hd[r].final_score; headers[k].resign_threshold = hd[r].resign_threshold;
+      }
+      if (moves) memset(moves + k * L + nm, 0, (L - nm) * sizeof(int16_t));
+      if (qs) memset(qs + k * L + nm, 0, (L - nm) * sizeof(float));
+      if (pis) memset(pis + (k * L + nm) * A, 0, (L - nm) * A * sizeof(float));
+      if (visits) memset(visits + (k * L + nm) * A, 0, (L - nm) * A * sizeof(float));
     }
-    const size_t nm = (size_t)hd.n_moves;
-    if (moves) { memset(moves + n * L, 0, L * sizeof(int16_t)); if (nm) DCHECK(e, devrt::d2h(moves + n * L, e->v.ring_moves + rs * L, nm * sizeof(int16_t), e->stream)); }
-    if (qs) { memset(qs + n * L, 0, L * sizeof(float)); if (nm) DCHECK(e, devrt::d2h(qs + n * L, e->v.ring_q + rs * L, nm * sizeof(float), e->stream)); }
-    if (pis) { memset(pis + n * L * A, 0, L * A * sizeof(float)); if (nm) DCHECK(e, devrt::d2h(pis + n * L * A, e->v.ring_pi + rs * L * A, nm * A * sizeof(float), e->stream)); }
-    if (visits) { memset(visits + n * L * A, 0, L * A * sizeof(float)); if (nm) DCHECK(e, devrt::d2h(visits + n * L * A, e->v.ring_vis + rs * L * A, nm * A * sizeof(float), e->stream)); }
-    ++n;
-    ++e->ring_head;
+    n += (int)run;
+    e->ring_head += run;
   }
   unsigned long long h = e->ring_head;
   DCHECK(e, devrt::h2d(e->v.ctr + CTR_RING_HEAD, &h, sizeof(h), e->stream));
@@ -656,7 +732,7 @@ extern "C" int32_t agz_tree_search(agz_engine* e, int32_t slot, int32_t parallel
   if (parallel_readouts < 1 || parallel_readouts > e->c.pmax) return fail(e, AGZ_ERR_ARG, "parallel_readouts must be in [1, max_parallel=%d]", e->c.pmax);
   bind_evaluator(e);
   DISPATCH_KA(e, {
-    SelectOp<KA> op{e->c, e->v, slot, parallel_readouts};
+    SelectOp<KA> op{e->c, e->v, slot, parallel_readouts, 0};
     DCHECK(e, devrt::launch_warps(op, 1, e->smem_per_warp, e->stream));
   });
   e->launches += 1;
@@ -671,7 +747,7 @@ extern "C" int32_t agz_tree_search(agz_engine* e, int32_t slot, int32_t parallel
   }
 #endif
   DISPATCH_KA(e, {
-    IncorporateOp<KA> op{e->c, e->v, slot};
+    IncorporateOp<KA> op{e->c, e->v, slot, 0};
     DCHECK(e, devrt::launch_warps(op, 1, e->smem_per_warp, e->stream));
   });
   e->launches += 1;

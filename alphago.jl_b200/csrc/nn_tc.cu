@@ -45,6 +45,9 @@ struct TCState {
   int dense;                  // 1: dense NHWC rows (b*N^2 + p), im2col TMA (v5); 0: zero-bordered boards (v1-v4)
   int rowbase, pitch;         // row of point (j, i) of board b = b*PP + rowbase + j*pitch + i
   CUtensorMap tm5_in64, tm5_act[3];
+  int groups;                 // 2 when the batch can be split into two half batches (dense layout, even max_batch)
+  long long grp_rows;         // rows per group
+  CUtensorMap tm5g_in64[2], tm5g_act[2][3];
   long long rows_alloc;       // rows allocated per activation buffer (multiple of 128, >= max_batch*PP + N+2)
   __half* in64;               // [rows_alloc][64]
   __half* act[3];             // [rows_alloc][256]
@@ -976,15 +979,15 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool valid = row < a.rows_valid;
       __half* orow = a.out + row * 256;
       const bool addres = a.res != nullptr && valid;
-      // residual rows do not depend on the MMAs: chunks 0-3 are fetched before waiting for the accumulator, chunks
-      // 4-7 are fetched while chunks 0-3 are being processed (4 register buffers of 64 bytes)
-      uint4 rv[4][4];
+      // residual rows do not depend on the MMAs: chunks 0-1 are fetched before waiting for the accumulator and chunk
+      // cc+2 while chunk cc is processed (2 register buffers; keeps the CTA small enough for tree CTAs to co-reside)
+      uint4 rv[2][4];
       const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256);
       if (addres) {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
+        for (int c2 = 0; c2 < 2; ++c2)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rv[c4][j] = ld_nc_v4(rrow + c4 * 4 + j);
+          for (int j = 0; j < 4; ++j) rv[c2][j] = ld_nc_v4(rrow + c2 * 4 + j);
       }
       mbar_wait_guard(&tfull[as], aphase);
       tc_fence_after();
@@ -995,7 +998,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (valid) {
           uint4 o[4];
           uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-          const __half2* rh = reinterpret_cast<const __half2*>(rv[cc & 3]);
+          const __half2* rh = reinterpret_cast<const __half2*>(rv[cc & 1]);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int c0 = cc * 32 + 2 * j;
@@ -1010,9 +1013,9 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             __half2 h = __floats2half2_rn(y0, y1);
             ow[j] = *reinterpret_cast<uint32_t*>(&h);
           }
-          if (addres && cc < 4) {
+          if (addres && cc < 6) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rv[cc][j] = ld_nc_v4(rrow + (cc + 4) * 4 + j);
+            for (int j = 0; j < 4; ++j) rv[cc & 1][j] = ld_nc_v4(rrow + (cc + 2) * 4 + j);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
@@ -1036,22 +1039,25 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------- heads (fp16 trunk)
-// neural_net.jl:23-30 for one position per block, reading the trunk output in the padded NHWC layout.
+// neural_net.jl:23-30.  HPB positions per CTA so that the dense-layer weights (83 KB + 53 KB on 9x9, 370 KB + 1 MB on
+// 19x19) are read from L2 once per 8 positions instead of once per position.
+static const int HPB = 8;
+
 __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict__ trunk, const float* __restrict__ vw,
                                                        const float* __restrict__ pw, const float* __restrict__ aff,
                                                        const float* __restrict__ D1W, const float* __restrict__ D1b,
                                                        const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                        const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
-                                                       float* __restrict__ v, int N, int PP, int rowbase, int pitch) {
+                                                       float* __restrict__ v, int B, int N, int PP, int rowbase, int pitch) {
   extern __shared__ float sm[];
   const int N2 = N * N, A = N2 + 1;
-  float* vf = sm;
-  float* pf = sm + N2;
-  float* hid = sm + 3 * N2;
-  float* red = hid + 256;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const __half* base = trunk + ((size_t)b * PP + rowbase) * 256;
-  // 1x1 convolutions: a warp per point, 8 channels per lane (one 16-byte load)
+  float* vf = sm;                       // [HPB][N2]
+  float* pf = vf + HPB * N2;            // [HPB][2*N2], index p + N2*c
+  float* hid = pf + HPB * 2 * N2;       // [HPB][256]
+  float* lg = hid + HPB * 256;          // [HPB][A]
+  const int b0 = blockIdx.x * HPB, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb = min(HPB, B - b0);
+  // 1x1 convolutions + BatchNorm + relu: a warp per (position, point), 8 channels per lane (one 16-byte load)
   float wv[8], wp0[8], wp1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -1059,9 +1065,10 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
     wp0[j] = pw[lane * 8 + j];
     wp1[j] = pw[256 + lane * 8 + j];
   }
-  for (int p = warp; p < N2; p += 8) {
-    const int jj = p / N, ii = p % N;
-    const uint4 raw = *reinterpret_cast<const uint4*>(base + ((size_t)jj * pitch + ii) * 256 + lane * 8);
+  for (int it = warp; it < nb * N2; it += 8) {
+    const int pb = it / N2, p = it - pb * N2;
+    const int jj = p / N, ii = p - jj * N;
+    const uint4 raw = *reinterpret_cast<const uint4*>(trunk + ((size_t)(b0 + pb) * PP + rowbase + (size_t)jj * pitch + ii) * 256 + lane * 8);
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
@@ -1078,64 +1085,60 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
       a2 += __shfl_xor_sync(0xffffffffu, a2, off);
     }
     if (lane == 0) {
-      vf[p] = fmaxf(a0 * aff[0] + aff[1], 0.f);
-      pf[p] = fmaxf(a1 * aff[2] + aff[3], 0.f);
-      pf[N2 + p] = fmaxf(a2 * aff[4] + aff[5], 0.f);
+      vf[pb * N2 + p] = fmaxf(a0 * aff[0] + aff[1], 0.f);
+      pf[pb * 2 * N2 + p] = fmaxf(a1 * aff[2] + aff[3], 0.f);
+      pf[pb * 2 * N2 + N2 + p] = fmaxf(a2 * aff[4] + aff[5], 0.f);
     }
   }
   __syncthreads();
-  {
-    float acc = D1b[tid];
-    for (int i = 0; i < N2; ++i) acc = fmaf(D1W[tid + 256 * i], vf[i], acc);
-    hid[tid] = fmaxf(acc, 0.f);
-  }
-  __syncthreads();
-  red[tid] = D2W[tid] * hid[tid];
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s) red[tid] += red[tid + s];
-    __syncthreads();
-  }
-  if (tid == 0) v[b] = tanhf(red[0] + D2b[0]);
-  __syncthreads();
-  float lg[2];
-  float mx = -INFINITY;
+  {  // Dense(N2 -> 256, relu): thread o, weights streamed once for all HPB positions
+    float acc[HPB];
+    const float bias = D1b[tid];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    int a = tid + q * 256;
-    lg[q] = -INFINITY;
-    if (a < A) {
-      float acc = Pb[a];
-      for (int i = 0; i < 2 * N2; ++i) acc = fmaf(PW[a + (size_t)A * i], pf[i], acc);
-      lg[q] = acc;
-      mx = fmaxf(mx, acc);
+    for (int pb = 0; pb < HPB; ++pb) acc[pb] = bias;
+    for (int i = 0; i < N2; ++i) {
+      const float w = D1W[tid + 256 * i];
+#pragma unroll
+      for (int pb = 0; pb < HPB; ++pb) acc[pb] = fmaf(w, vf[pb * N2 + i], acc[pb]);
     }
-  }
-  red[tid] = mx;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]);
-    __syncthreads();
-  }
-  mx = red[0];
-  __syncthreads();
-  float ex[2], sum = 0.f;
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    ex[q] = lg[q] == -INFINITY ? 0.f : expf(lg[q] - mx);
-    sum += ex[q];
+    for (int pb = 0; pb < HPB; ++pb) hid[pb * 256 + tid] = fmaxf(acc[pb], 0.f);
   }
-  red[tid] = sum;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s) red[tid] += red[tid + s];
-    __syncthreads();
-  }
-  sum = red[0];
+  if (warp < nb) {  // Dense(256 -> 1, tanh): one warp per position
+    float acc = 0.f;
+    for (int o = lane; o < 256; o += 32) acc = fmaf(D2W[o], hid[warp * 256 + o], acc);
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    int a = tid + q * 256;
-    if (a < A) pi[(size_t)b * A + a] = ex[q] / sum;
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) v[b0 + warp] = tanhf(acc + D2b[0]);
+  }
+  // Dense(2*N2 -> A): thread a (and a + 256)
+  for (int a0i = tid; a0i < A; a0i += 256) {
+    float acc[HPB];
+    const float bias = Pb[a0i];
+#pragma unroll
+    for (int pb = 0; pb < HPB; ++pb) acc[pb] = bias;
+    for (int i = 0; i < 2 * N2; ++i) {
+      const float w = PW[a0i + (size_t)A * i];
+#pragma unroll
+      for (int pb = 0; pb < HPB; ++pb) acc[pb] = fmaf(w, pf[pb * 2 * N2 + i], acc[pb]);
+    }
+#pragma unroll
+    for (int pb = 0; pb < HPB; ++pb) lg[pb * A + a0i] = acc[pb];
+  }
+  __syncthreads();
+  if (warp < nb) {  // softmax over all A actions (no legality masking, as the reference): one warp per position
+    const float* l = lg + warp * A;
+    float mx = -INFINITY;
+    for (int a0i = lane; a0i < A; a0i += 32) mx = fmaxf(mx, l[a0i]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.f;
+    for (int a0i = lane; a0i < A; a0i += 32) sum += expf(l[a0i] - mx);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    float* out = pi + (size_t)(b0 + warp) * A;
+    for (int a0i = lane; a0i < A; a0i += 32) out[a0i] = expf(l[a0i] - mx) / sum;
   }
 }
 
@@ -1148,7 +1151,9 @@ struct LeafFeaturesTCOp {
   View v;
   __half* in64;
   int PP, rowbase, pitch;
-  __device__ void operator()(int b, char* smem) const {
+  int row0;  // first batch row handled by this launch
+  __device__ void operator()(int wi, char* smem) const {
+    const int b = row0 + wi;
     const int g = b / c.pmax, k = b % c.pmax;
     Warp<KA> w(c, v, g, smem);
     if (k >= w.st.nleaf) return;
@@ -1331,6 +1336,18 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
     const long long boards = t->rows_alloc / (t->N * t->N);
     if (!rc) rc = make_map_im2col(&t->tm5_in64, t->in64, t->N, boards, CIN0);
     for (int i = 0; i < 3 && !rc; ++i) rc = make_map_im2col(&t->tm5_act[i], t->act[i], t->N, boards, 256);
+    t->groups = (t->max_batch % 2 == 0 && t->max_batch >= 2) ? 2 : 1;
+    t->grp_rows = (long long)(t->max_batch / 2) * t->PP;
+    if (t->groups == 2) {
+      for (int g = 0; g < 2 && !rc; ++g) {  // same buffers, base shifted by one group; the boards dimension ends where the allocation ends
+        const long long gb = boards - (long long)g * (t->max_batch / 2);
+        rc = make_map_im2col(&t->tm5g_in64[g], t->in64 + (size_t)g * t->grp_rows * CIN0, t->N, gb, CIN0);
+        for (int i = 0; i < 3 && !rc; ++i) rc = make_map_im2col(&t->tm5g_act[g][i], t->act[i] + (size_t)g * t->grp_rows * 256, t->N, gb, 256);
+      }
+    }
+  } else {
+    t->groups = 1;
+    t->grp_rows = 0;
   }
   const char* eb = getenv("AGZ_CONV_BASEOFF");
   t->base_offset_mode = eb ? atoi(eb) : 0;
@@ -1460,13 +1477,17 @@ static int launch_conv(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tm
   return (int)cudaGetLastError();
 }
 
-int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev) {
+int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev, int group, cudaEvent_t convs_done) {
   TCState* t = (TCState*)n->tc;
+  if (group >= 0 && (t->groups != 2 || group > 1 || B > t->max_batch / 2)) { snprintf(err, errlen, "bad group"); return 1; }
+  const size_t roff = group > 0 ? (size_t)t->grp_rows : 0;   // row offset of this group inside the shared buffers
   if (B > t->max_batch) { snprintf(err, errlen, "batch %d exceeds max_batch %d", B, t->max_batch); return 1; }
   if (!t->attr_set) {
     cudaError_t rc = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv2_smem(t->arows));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv4_smem(128 + 2 * t->H8));
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)HPB * (3 * n->N2 + 256 + n->A) * sizeof(float)));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
@@ -1476,7 +1497,10 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   const bool v2 = t->version == 2;
   auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
     const int kch = in_buf < 0 ? CIN0 / BK : 4;
-    const __half* res = res_buf >= 0 ? t->act[res_buf] : nullptr;
+    const __half* res = res_buf >= 0 ? t->act[res_buf] + roff * 256 : nullptr;
+    if (t->version == 5 && group >= 0)
+      return launch_conv5(t, in_buf < 0 ? t->tm5g_in64[group] : t->tm5g_act[group][in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res,
+                          t->act[out_buf] + roff * 256, B, kch, s);
     if (t->version == 5) return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (t->version == 4) return launch_conv4(t, in_buf < 0 ? t->tm4_in64 : t->tm4_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (t->version == 3) return launch_conv3(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
@@ -1493,9 +1517,10 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   }
   if (rc) { snprintf(err, errlen, "conv launch: %s", cudaGetErrorString((cudaError_t)rc)); return 1; }
   if (ev) cudaEventRecord(ev[2], s);
-  const size_t hsm = (size_t)(3 * n->N2 + 512) * sizeof(float);
-  heads_tc_kernel<<<B, 256, hsm, s>>>(t->act[h], n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb,
-                                       pi, v, t->N, t->PP, t->rowbase, t->pitch);
+  if (convs_done) cudaEventRecord(convs_done, s);
+  const size_t hsm = (size_t)HPB * (3 * n->N2 + 256 + n->A) * sizeof(float);
+  heads_tc_kernel<<<(B + HPB - 1) / HPB, 256, hsm, s>>>(t->act[h] + roff * 256, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW,
+                                                        n->f_Pb, pi, v, B, t->N, t->PP, t->rowbase, t->pitch);
   if (ev) cudaEventRecord(ev[3], s);
   cudaError_t e2 = cudaGetLastError();
   if (e2 != cudaSuccess) { snprintf(err, errlen, "heads launch: %s", cudaGetErrorString(e2)); return 1; }
@@ -1506,12 +1531,14 @@ int engine_tc_features(const Cfg& c, const View& v, NNet* n, int row0, int nrows
   TCState* t = (TCState*)n->tc;
   int rc = 0;
   switch (c.KA) {
-    case 3: { LeafFeaturesTCOp<3> op{c, v, t->in64, t->PP, t->rowbase, t->pitch}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
-    case 6: { LeafFeaturesTCOp<6> op{c, v, t->in64, t->PP, t->rowbase, t->pitch}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
-    default: { LeafFeaturesTCOp<12> op{c, v, t->in64, t->PP, t->rowbase, t->pitch}; rc = devrt::launch_warps(op, row0 + nrows, smem_per_warp, s); } break;
+    case 3: { LeafFeaturesTCOp<3> op{c, v, t->in64, t->PP, t->rowbase, t->pitch, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
+    case 6: { LeafFeaturesTCOp<6> op{c, v, t->in64, t->PP, t->rowbase, t->pitch, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
+    default: { LeafFeaturesTCOp<12> op{c, v, t->in64, t->PP, t->rowbase, t->pitch, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
   }
   return rc;
 }
+
+int nn_tc_groups(const NNet* n) { return ((TCState*)n->tc)->groups; }
 
 int engine_host_features_tc(const Cfg& c, NNet* n, const int8_t* boards_hist, const int8_t* to_play, int B, cudaStream_t s) {
   TCState* t = (TCState*)n->tc;

@@ -28,8 +28,9 @@ struct SelectOp {
   View v;
   int only_slot;  // >= 0: hook mode, run this slot with `parallel` leaves regardless of phase
   int parallel;
+  int slot0;      // first slot of this launch (half-batch pipelining)
   AGZ_DEV void operator()(int wi, char* smem) const {
-    const int g = only_slot >= 0 ? only_slot : wi;
+    const int g = only_slot >= 0 ? only_slot : slot0 + wi;
     Warp<KA> w(c, v, g, smem);
     if (only_slot >= 0) {
       w.search_select(parallel, false);
@@ -51,8 +52,9 @@ struct IncorporateOp {
   Cfg c;
   View v;
   int only_slot;
+  int slot0;
   AGZ_DEV void operator()(int wi, char* smem) const {
-    const int g = only_slot >= 0 ? only_slot : wi;
+    const int g = only_slot >= 0 ? only_slot : slot0 + wi;
     Warp<KA> w(c, v, g, smem);
     w.search_incorporate();
     if (only_slot < 0) w.after_round();

@@ -176,8 +176,6 @@ def main():
     for _ in range(warmup):
         pr = device_step()
     # ---- timed region 1: device-resident throughput (`value`) ---------------------------------------------------
-    eng.set_timing(True)
-    eng.phase_times(reset=True)
     l0 = eng.kernel_launches()
     sampler = ClockSampler(local)
     sampler.start()
@@ -191,18 +189,26 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
-    kms, kln = eng.phase_times(reset=True)
     launches = eng.kernel_launches() - l0
     moves = pr.moves_played - m0
     fill = (pr.positions_evaluated - p0) / float(args.steps * ROUNDS_PER_STEP * args.games * 8)
     readouts_done, finished = pr.readouts - r0, pr.games_finished - f0
     # device time of the steps (CUDA events on the engine stream) plus the gather/harvest tail measured by wall clock
     t_rank = max(wall, dev_ms / 1e3)
+    # ---- per-kernel CUDA-event timing on the same workload, sequential schedule (with the two half batches
+    #      overlapped, a kernel's event interval would include the other group's kernels) -----------------------------
+    eng.set_timing(True)
+    eng.phase_times(reset=True)
+    for _ in range(min(2, args.steps)):
+        device_step()
+    kms, kln = eng.phase_times(reset=True)
     eng.set_timing(False)
+    pr = eng.selfplay_step(1)
     # ---- timed region 2: end to end through the public API with host buffers (`e2e`) ----------------------------
     barrier()
     m1 = pr.moves_played
     d2h = 0
+    glen = []
     t1 = time.perf_counter()
     for _ in range(args.steps):
         for k in range(3):                      # H2D: the caller's current network parameters (train.jl hands selfplay cur_nn)
@@ -210,6 +216,7 @@ def main():
         pr = eng.selfplay_step(ROUNDS_PER_STEP)
         eng.replay_gather()
         recs = eng.selfplay_harvest(4 * args.games)   # D2H: finished games (moves, pi, q, result)
+        glen += [r.n_moves for r in recs]
         d2h += sum(r.searches_pi.nbytes + r.visits.nbytes + r.moves.nbytes + r.qs.nbytes + 40 for r in recs) + 80
     barrier()
     t_e2e = time.perf_counter() - t1
@@ -233,15 +240,17 @@ def main():
             "ms_per_step": 1e3 * tmx[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
             "config": {"workload": "C2: 9x9 Go, %d concurrent self-play games per GPU, 400 readouts/move (50 rounds x 8 leaves per step), tower_height 6, 256 filters, random-init weights seed 0, empty-board starts, finished games refilled" % args.games,
-                       "step": "50 tree_search rounds over all games + replay all-gather of finished games",
+                       "step": "50 tree_search rounds over all games (two half batches pipelined on two streams) + replay all-gather of finished games",
                        "l2": "inputs larger than L2: tree arenas %.1f GB and %.0f MB per activation buffer vs 126 MB L2" % (args.games * eng.cfg.nodes_per_game * 1.5e-6 if eng.cfg.nodes_per_game else args.games * 1680 * 1.5e-6, rows * 100 * 512 / 1e6)},
             "e2e": {"value": tot[1] / tmx[1], "unit": "moves/s", "h2d_bytes_per_step": param_bytes, "d2h_bytes_per_step": int(d2h / args.steps)},
             "gpu_launches": int(tot[2]),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (tower 3x3 conv, fp16 tcgen05)", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc5_kernel (tower 3x3 conv 256->256, fp16 tcgen05 cta_group::2 + TMA im2col)",
+                         "measured_in": "CUDA events around every kernel, sequential schedule, %d steps of the same workload right after the timed region" % min(2, args.steps), "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
                          "frac": achieved / tf_sus, "traffic": None, "peak_source": src + " bf16 sustained",
                          "flops_per_launch": conv_flops_pos * rows, "ms_per_launch": conv_ms},
             "kernel_ms_per_round": {n: kms[i] / max(1, kln[0]) for i, n in enumerate(agz.binding.KERNEL_NAMES)},
+            "harvested_games_e2e": len(glen), "mean_game_length_e2e": (sum(glen) / len(glen)) if glen else None,
             "leaf_fill": fill, "readouts_per_s": readouts_done / tmx[0], "games_finished_rank0": int(finished),
             "network_tflops": flops_pos * rows / ((kms[2] + kms[3] + kms[4]) / max(1, kln[0]) * 1e-3) / 1e12 if kln[0] else None,
         }

@@ -134,10 +134,11 @@ def test_nn_selfplay_matches_oracle_tree(evaluator):
     nn.randomize_bn(seed=2)
     helper = agz.Engine(N, lib_path=lib_for("cuda"), n_games=2, tower_height=T)
     push_oracle_net(helper, nn)
-    eng = agz.Engine(N, lib_path=lib_for("cuda"), n_games=3, readouts=R, seed=9, tower_height=T)
+    # 4 slots: the tcgen05 evaluator then runs the two-stream half-batch pipeline, the fp32 one the sequential schedule
+    eng = agz.Engine(N, lib_path=lib_for("cuda"), n_games=4, readouts=R, seed=9, tower_height=T)
     push_oracle_net(eng, nn)
     eng.set_evaluator(evaluator)
-    recs = eng.selfplay_run(3)
+    recs = eng.selfplay_run(6)
     oenv = ogo.GoEnv(N)
     onn = EngineBackedNet(helper, evaluator, T)
     for gid, r in enumerate(recs):
