@@ -66,7 +66,7 @@ SYMBOLS = [
     "agz_config_default", "agz_engine_create", "agz_engine_destroy", "agz_last_error", "agz_version",
     "agz_net_set_params", "agz_net_set_bn_stats", "agz_net_param_count", "agz_net_bn_count", "agz_net_forward",
     "agz_features", "agz_set_dummy_evaluator", "agz_set_evaluator", "agz_selfplay_start", "agz_selfplay_step",
-    "agz_selfplay_harvest", "agz_selfplay_run", "agz_replay_gather", "agz_replay_read", "agz_nccl_unique_id",
+    "agz_selfplay_harvest", "agz_selfplay_run", "agz_replay_gather", "agz_replay_read", "agz_replay_sample", "agz_nccl_unique_id",
     "agz_nccl_init", "agz_tree_init", "agz_tree_select_leaf", "agz_tree_incorporate", "agz_tree_backup_value",
     "agz_tree_add_virtual_loss", "agz_tree_revert_virtual_loss", "agz_tree_maybe_add_child", "agz_tree_search",
     "agz_tree_inject_noise", "agz_tree_pick_move", "agz_tree_play_move", "agz_tree_should_resign", "agz_tree_root",
@@ -240,6 +240,17 @@ class Engine:
         self._check(self.lib.agz_replay_read(self._h, C.c_int64(first), C.c_int32(count), _ptr(boards, C.c_int8), _ptr(tp, C.c_int8),
                                              _ptr(pis, C.c_float), _ptr(zs, C.c_int8)))
         return boards, tp, pis, zs
+
+    def replay_sample(self, batch, seed=0):
+        """get_replay_batch (src/train.jl:4-12): uniform, without replacement."""
+        boards = np.zeros((batch, self.N2), np.int8)
+        tp = np.zeros(batch, np.int8)
+        pis = np.zeros((batch, self.A), np.float32)
+        zs = np.zeros(batch, np.int8)
+        idx = np.zeros(batch, np.int64)
+        self._check(self.lib.agz_replay_sample(self._h, C.c_int32(batch), C.c_uint64(seed), _ptr(boards, C.c_int8), _ptr(tp, C.c_int8),
+                                               _ptr(pis, C.c_float), _ptr(zs, C.c_int8), _ptr(idx, C.c_int64)))
+        return boards, tp, pis, zs, idx
 
     def nccl_unique_id(self):
         buf = (C.c_uint8 * 128)()

@@ -232,7 +232,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   c.seed = cfg->seed;
   c.total_games = 0;
   const int need = cfg->readouts + 2 * c.pmax + 4;
-  c.cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : std::max(256, 6 * need);
+  c.cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : std::max(256, 10 * need);
   if (c.cap < need + 2) c.cap = need + 2;
   c.ring_cap = cfg->record_ring > 0 ? cfg->record_ring : 2 * cfg->n_games;
   e->smem_per_warp = (int)((c.KB * 32 * 7 + 15) / 16 * 16);
@@ -421,10 +421,17 @@ static int one_round(agz_engine* e) {
 #if AGZ_CUDA
   if (e->timing) cudaEventRecord(e->ev[0], e->stream);
 #endif
-  DISPATCH_KA(e, {
-    SelectOp<KA> op{e->c, e->v, -1, e->c.parallel, 0};
-    DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
-  });
+  if (e->c.n_games >= 2048) {
+    DISPATCH_KA(e, {
+      SelectOp<KA, 1> op{e->c, e->v, -1, e->c.parallel, 0};
+      DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+    });
+  } else {
+    DISPATCH_KA(e, {
+      SelectOp<KA> op{e->c, e->v, -1, e->c.parallel, 0};
+      DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+    });
+  }
   e->launches += 1;
 #if AGZ_CUDA
   if (e->evaluator != AGZ_EVAL_DUMMY) {
@@ -473,6 +480,7 @@ static bool can_pipeline(agz_engine* e) {
 
 static int pipelined_rounds(agz_engine* e, int rounds) {
   char nerr[256] = "";
+  devrt::prefer_max_smem() = 1;
   if (!nn_ready(e->nn) && nn_commit(e->nn, e->stream, nerr, sizeof(nerr))) return fail(e, AGZ_ERR_ARG, "network not ready: %s", nerr);
   const int half = e->c.n_games / 2, rows = half * e->c.pmax;
   cudaEventRecord(e->ev_join[2], e->stream);
@@ -501,6 +509,7 @@ static int pipelined_rounds(agz_engine* e, int rounds) {
     cudaEventRecord(e->ev_join[g], e->gstream[g]);
     cudaStreamWaitEvent(e->stream, e->ev_join[g], 0);
   }
+  devrt::prefer_max_smem() = 0;
   return AGZ_OK;
 }
 #endif
@@ -1084,6 +1093,15 @@ extern "C" int32_t agz_replay_read(agz_engine* e, int64_t first, int32_t count, 
   if (rc) return fail(e, rc, "%s", rerr);
   return AGZ_OK;
 }
+
+extern "C" int32_t agz_replay_sample(agz_engine* e, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices) {
+  if (!e || !e->replay) return fail(e, AGZ_ERR_ARG, "no replay ring (call agz_replay_gather first)");
+  cudaSetDevice(e->cfg.device);
+  char rerr[256] = "";
+  int rc = replay_sample(e->replay, e->c, batch, seed, boards, to_play, pis, zs, indices, e->stream, rerr, sizeof(rerr));
+  if (rc) return fail(e, rc, "%s", rerr);
+  return AGZ_OK;
+}
 #else
 extern "C" size_t agz_net_param_count(agz_engine*, int32_t) { return 0; }
 extern "C" size_t agz_net_bn_count(agz_engine*, int32_t) { return 0; }
@@ -1095,4 +1113,5 @@ extern "C" int32_t agz_nccl_unique_id(uint8_t*) { return AGZ_ERR_NCCL; }
 extern "C" int32_t agz_nccl_init(agz_engine* e, const uint8_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
 extern "C" int32_t agz_replay_gather(agz_engine* e, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
 extern "C" int32_t agz_replay_read(agz_engine* e, int64_t, int32_t, int8_t*, int8_t*, float*, int8_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
+extern "C" int32_t agz_replay_sample(agz_engine* e, int32_t, uint64_t, int8_t*, int8_t*, float*, int8_t*, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
 #endif

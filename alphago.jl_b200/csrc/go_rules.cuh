@@ -24,7 +24,24 @@ struct RulesScratch {
 
 struct Board {
   int N, N2, KB;  // KB = ceil(N2 / 32) words per bitplane
+  // per-lane neighbour masks of the points this lane owns (point k*32 + lane -> bits [4k, 4k+4):
+  // 1 = has row-1, 2 = has row+1, 4 = has column-1, 8 = has column+1); saves a div/mod per point per sweep
+  unsigned long long nbm;
 };
+
+AGZ_DEV void board_init_masks(Board& B) {
+  const int lane = simt::lane();
+  unsigned long long m = 0;
+  for (int k = 0; k < B.KB; ++k) {
+    const int p = k * 32 + lane;
+    if (p < B.N2) {
+      const int i = p % B.N, j = p / B.N;
+      unsigned long long b = (i > 0 ? 1u : 0u) | (i < B.N - 1 ? 2u : 0u) | (j > 0 ? 4u : 0u) | (j < B.N - 1 ? 8u : 0u);
+      m |= b << (4 * k);
+    }
+  }
+  B.nbm = m;
+}
 
 AGZ_DEV size_t rules_scratch_bytes(int KB) { return (size_t)KB * 32 * (1 + 2 + 4); }
 
@@ -46,6 +63,17 @@ AGZ_DEV RulesScratch rules_scratch_at(char* smem, int KB) {
     if (i__ < (B).N - 1) { q = (p) + 1; BODY }      \
     if (j__ > 0) { q = (p) - (B).N; BODY }          \
     if (j__ < (B).N - 1) { q = (p) + (B).N; BODY }  \
+  }
+
+// same, for a point owned by this lane: k-th point of the lane, neighbour mask from B.nbm
+#define AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, BODY)               \
+  {                                                           \
+    const unsigned m__ = (unsigned)((B).nbm >> (4 * (k))) & 15u; \
+    int q;                                                    \
+    if (m__ & 1u) { q = (p)-1; BODY }                         \
+    if (m__ & 2u) { q = (p) + 1; BODY }                       \
+    if (m__ & 4u) { q = (p) - (B).N; BODY }                   \
+    if (m__ & 8u) { q = (p) + (B).N; BODY }                   \
   }
 
 AGZ_DEV void rules_load(const Board& B, RulesScratch& s, const uint32_t* black, const uint32_t* white) {
@@ -100,7 +128,7 @@ AGZ_DEV void rules_label(const Board& B, RulesScratch& s, int mode) {
       if (m0 >= 0) {
         int v = s.bd[p];
         int m = m0;
-        AGZ_FOR_NEIGHBORS(B, p, q, {
+        AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, {
           int lq = s.lab[q];
           if (lq >= 0 && s.bd[q] == v && lq < m) m = lq;
         })
@@ -127,7 +155,7 @@ AGZ_DEV void rules_count_liberties(const Board& B, RulesScratch& s) {
     if (p < B.N2 && s.bd[p] == 0) {
       int r[4];
       int nr = 0;
-      AGZ_FOR_NEIGHBORS(B, p, q, {
+      AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, {
         if (s.bd[q] != 0) {
           int l = s.lab[q];
           bool dup = false;
@@ -211,7 +239,7 @@ AGZ_DEV void rules_legal_mask(const Board& B, const RulesScratch& s, int to_play
     int p = k * 32 + lane;
     bool ok = false;
     if (p < B.N2 && s.bd[p] == 0 && p != ko) {
-      AGZ_FOR_NEIGHBORS(B, p, q, {
+      AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, {
         int v = s.bd[q];
         if (v == 0) {
           ok = true;
@@ -235,7 +263,7 @@ AGZ_DEV float rules_score(const Board& B, RulesScratch& s, float komi) {
     int p = k * 32 + lane;
     if (p < B.N2 && s.bd[p] == 0) {
       int f = 0;
-      AGZ_FOR_NEIGHBORS(B, p, q, {
+      AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, {
         int v = s.bd[q];
         if (v == 1) f |= 1;
         if (v == -1) f |= 2;

@@ -131,7 +131,7 @@ static void fold_bn(const float* beta, const float* gamma, const float* mu, cons
   }
 }
 
-int nn_fold_layers(const NNet* n, std::vector<ConvLayerHost>& convs, char* err, size_t errlen) {
+int nn_fold_layers(const NNet* n, std::vector<ConvLayerHost>& convs, char* err, size_t errlen, bool with_weights) {
   if (!n->have[0] || !n->have[1] || !n->have[2]) {
     snprintf(err, errlen, "parameters of chain %d have not been set (agz_net_set_params)", !n->have[0] ? 0 : (!n->have[1] ? 1 : 2));
     return 1;
@@ -144,7 +144,7 @@ int nn_fold_layers(const NNet* n, std::vector<ConvLayerHost>& convs, char* err, 
   auto add = [&](const float* W, const float* b, const float* beta, const float* gamma, int cin, int bn_index) {
     ConvLayerHost L;
     L.cin = cin; L.cout = C;
-    L.w.assign(W, W + (size_t)9 * cin * C);
+    if (with_weights) L.w.assign(W, W + (size_t)9 * cin * C);
     L.scale.resize(C); L.shift.resize(C);
     fold_bn(beta, gamma, mu + (size_t)bn_index * C, sg + (size_t)bn_index * C, b, C, n->bn_mode[0], L.scale.data(), L.shift.data());
     convs.push_back(std::move(L));
@@ -165,7 +165,7 @@ int nn_fold_layers(const NNet* n, std::vector<ConvLayerHost>& convs, char* err, 
 
 int nn_commit(NNet* n, cudaStream_t s, char* err, size_t errlen) {
   std::vector<ConvLayerHost> convs;
-  if (nn_fold_layers(n, convs, err, errlen)) return 1;
+  if (nn_fold_layers(n, convs, err, errlen, false)) return 1;
   const int C = n->C, N2 = n->N2, A = n->A;
   n->f32_weights_ready = false;
   for (size_t l = 0; l < convs.size(); ++l) {
@@ -366,7 +366,7 @@ long long nn_f32_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower
 static int upload_f32_weights(NNet* n, cudaStream_t s) {
   std::vector<ConvLayerHost> convs;
   char err[128];
-  if (nn_fold_layers(n, convs, err, sizeof(err))) return (int)cudaErrorInvalidValue;
+  if (nn_fold_layers(n, convs, err, sizeof(err), true)) return (int)cudaErrorInvalidValue;
   for (size_t l = 0; l < convs.size(); ++l) {
     const ConvLayerHost& L = convs[l];
     // device layout w[co][ci][t], t = kj*3 + ki for the input offset (dj, di) = (kj-1, ki-1):

@@ -41,7 +41,7 @@ struct NNet {
 };
 
 // shared helpers (nn_f32.cu)
-int nn_fold_layers(const NNet* n, std::vector<ConvLayerHost>& convs, char* err, size_t errlen);
+int nn_fold_layers(const NNet* n, std::vector<ConvLayerHost>& convs, char* err, size_t errlen, bool with_weights);
 int nn_tc_create(NNet* n, char* err, size_t errlen);
 void nn_tc_destroy(NNet* n);
 int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t s, char* err, size_t errlen);

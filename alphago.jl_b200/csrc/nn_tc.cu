@@ -56,6 +56,8 @@ struct TCState {
   std::vector<CUtensorMap> tm_w;
   int num_sms;
   bool attr_set;
+  float* stage;               // device staging copy of the raw Flux parameter list (base chain)
+  size_t stage_cap;
 };
 
 // ------------------------------------------------------------------------------------------- PTX helpers
@@ -1290,6 +1292,8 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   t->T = n->s.tower;
   t->max_batch = n->max_batch;
   t->attr_set = false;
+  t->stage = nullptr;
+  t->stage_cap = 0;
   t->in64 = nullptr;
   for (int i = 0; i < 3; ++i) t->act[i] = nullptr;
   if (n->C != 256) {
@@ -1362,30 +1366,52 @@ void nn_tc_destroy(NNet* n) {
   TCState* t = (TCState*)n->tc;
   if (!t) return;
   cudaFree(t->in64);
+  cudaFree(t->stage);
   for (int i = 0; i < 3; ++i) cudaFree(t->act[i]);
   for (auto p : t->w) cudaFree(p);
   delete t;
   n->tc = nullptr;
 }
 
+// Flux (3, 3, Cin, Cout) fp32, column-major -> Wt[tap][co][ci] fp16 with tap = kj*3 + ki for input offset (dj, di) =
+// (kj-1, ki-1); Flux Conv is a true convolution, so tap (ki, kj) uses W[2-ki, 2-kj].  Done on the device: the host only
+// ships the raw parameter list (what train hands selfplay every iteration).
+__global__ void reorder_weights_kernel(const float* __restrict__ flux, __half* __restrict__ out, int cin, int cin_pad) {
+  const size_t total = (size_t)9 * 256 * cin_pad;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % cin_pad);
+    const int co = (int)((idx / cin_pad) % 256);
+    const int tap = (int)(idx / ((size_t)cin_pad * 256));
+    const int kj = tap / 3, ki = tap % 3;
+    float w = 0.f;
+    if (ci < cin) w = flux[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)cin * co];
+    out[idx] = __float2half(w);
+  }
+}
+
 int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t s, char* err, size_t errlen) {
   TCState* t = (TCState*)n->tc;
-  for (size_t l = 0; l < convs.size(); ++l) {
-    const ConvLayerHost& L = convs[l];
-    const int cin_pad = l == 0 ? CIN0 : 256;
-    std::vector<__half> w((size_t)9 * 256 * cin_pad, __float2half(0.f));
-    // Wt[tap][co][ci], tap = kj*3 + ki for input offset (dj, di) = (kj-1, ki-1); true convolution => W[2-ki, 2-kj]
-    for (int kj = 0; kj < 3; ++kj)
-      for (int ki = 0; ki < 3; ++ki)
-        for (int co = 0; co < 256; ++co)
-          for (int ci = 0; ci < L.cin; ++ci)
-            w[((size_t)(kj * 3 + ki) * 256 + co) * cin_pad + ci] =
-                __float2half(L.w[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)L.cin * co]);
-    cudaMemcpyAsync(t->w[l], w.data(), w.size() * 2, cudaMemcpyHostToDevice, s);
-    cudaStreamSynchronize(s);
+  // raw base-chain parameters (Flux order) go up in one transfer; conv weights are located inside it
+  const size_t nbase = n->hparams[0].size();
+  if (t->stage_cap < nbase) {
+    cudaFree(t->stage);
+    t->stage = nullptr;
+    if (cudaMalloc((void**)&t->stage, nbase * sizeof(float)) != cudaSuccess) { snprintf(err, errlen, "staging buffer allocation failed"); return 1; }
+    t->stage_cap = nbase;
   }
-  if (cudaGetLastError() != cudaSuccess) {
-    snprintf(err, errlen, "uploading fp16 weights failed");
+  cudaMemcpyAsync(t->stage, n->hparams[0].data(), nbase * sizeof(float), cudaMemcpyHostToDevice, s);
+  const size_t C = 256, P = (size_t)n->s.planes;
+  size_t off = 0;
+  for (size_t l = 0; l < convs.size(); ++l) {
+    const int cin = l == 0 ? (int)P : 256, cin_pad = l == 0 ? CIN0 : 256;
+    reorder_weights_kernel<<<296, 256, 0, s>>>(t->stage + off, t->w[l], cin, cin_pad);
+    // next conv weight inside the Flux list: stem = W,b,beta,gamma; block = W1,b1,W2,b2,beta1,gamma1,beta2,gamma2
+    if (l == 0) off += 9 * P * C + 3 * C;
+    else if (l % 2 == 1) off += 9 * C * C + C;          // W1, b1 -> W2
+    else off += 9 * C * C + C + 4 * C;                   // W2, b2, beta1, gamma1, beta2, gamma2 -> next block
+  }
+  if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+    snprintf(err, errlen, "uploading / reordering the conv weights failed");
     return 1;
   }
   return 0;

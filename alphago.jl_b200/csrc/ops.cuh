@@ -22,7 +22,9 @@ struct StartOp {
 };
 
 // tree_search! part 1 (mcts_play.jl:74-87) / the seed selection of selfplay.jl:18
-template <int KA>
+// OCC = 1: compiled for high occupancy (64 registers, 8 CTAs/SM) -- used when there are thousands of trees per GPU
+// (MCTS-only config: +17 % readouts/s); OCC = 0: more registers, no spills -- better when a few warps per SM suffice.
+template <int KA, int OCC = 0>
 struct SelectOp {
   Cfg c;
   View v;
@@ -87,6 +89,16 @@ struct LeafFeaturesF32Op {
     for (int p = lane; p < N2; p += 32) o[16 * N2 + p] = (float)tp;
   }
 };
+
+}  // namespace agz
+#if AGZ_CUDA
+namespace devrt {
+template <class Op> struct MinBlocks;
+template <> struct MinBlocks<agz::SelectOp<3, 1>> { static const int v = 8; };
+template <> struct MinBlocks<agz::SelectOp<6, 1>> { static const int v = 6; };
+}  // namespace devrt
+#endif
+namespace agz {
 
 // ------------------------------------------------------------------------------------------------ hooks
 enum {

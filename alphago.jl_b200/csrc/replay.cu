@@ -121,6 +121,7 @@ struct PackOp {
     const int lane = threadIdx.x & 31;
     Board B;
     B.N = c.N; B.N2 = c.N2; B.KB = c.KB;
+    board_init_masks(B);
     RulesScratch rs = rules_scratch_at(smem, c.KB);
     const int rslot = rec[2 * wi], first = rec[2 * wi + 1];
     const RingHeader hd = v.ring_hdr[rslot];
@@ -248,6 +249,34 @@ int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8
     if (boards) memcpy(boards + (size_t)i * c.N2, b, (size_t)c.N2);
     if (to_play) to_play[i] = b[c.N2];
     if (zs) zs[i] = b[c.N2 + 1];
+  }
+  return 0;
+}
+
+// uniform sample without replacement (src/train.jl:5): partial Fisher-Yates over the ring's index range, splitmix64 stream
+int replay_sample(ReplayState* r, const Cfg& c, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices,
+                  cudaStream_t s, char* err, size_t errlen) {
+  const long long oldest = r->total > r->cap ? r->total - r->cap : 0, n = r->total - oldest;
+  if (batch < 0 || batch > n) {
+    snprintf(err, errlen, "cannot sample %d tuples without replacement from %lld", batch, n);
+    return 5;
+  }
+  std::vector<long long> pool((size_t)n);
+  for (long long i = 0; i < n; ++i) pool[(size_t)i] = oldest + i;
+  uint64_t x = seed;
+  auto next = [&x]() {
+    uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  for (int k = 0; k < batch; ++k) {
+    const size_t j = (size_t)k + (size_t)(next() % (uint64_t)(n - k));
+    std::swap(pool[(size_t)k], pool[j]);
+    if (indices) indices[k] = pool[(size_t)k];
+    int rc = replay_read(r, c, pool[(size_t)k], 1, boards ? boards + (size_t)k * c.N2 : nullptr, to_play ? to_play + k : nullptr,
+                         pis ? pis + (size_t)k * c.A : nullptr, zs ? zs + k : nullptr, s, err, errlen);
+    if (rc) return rc;
   }
   return 0;
 }

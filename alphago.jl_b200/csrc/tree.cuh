@@ -116,6 +116,7 @@ struct Warp {
 
   AGZ_DEV Warp(const Cfg& c_, const View& v_, int g_, char* smem) : c(c_), v(v_), g(g_), lane(simt::lane()) {
     B.N = c.N; B.N2 = c.N2; B.KB = c.KB;
+    board_init_masks(B);
     rs = rules_scratch_at(smem, c.KB);
     st = v.gs[g];
     nbase = (size_t)g * c.cap;

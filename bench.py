@@ -222,6 +222,9 @@ def main():
     t_e2e = time.perf_counter() - t1
     moves_e2e = pr.moves_played - m1
 
+    if pr.error:
+        print(json.dumps({"metric": METRIC, "error": "a game stopped on the device with status %d (6 = node arena full)" % pr.error}), flush=True)
+        sys.exit(2)
     tot = torch.tensor([float(moves), float(moves_e2e), float(launches)], device="cuda", dtype=torch.float64)
     tmx = torch.tensor([t_rank, t_e2e], device="cuda", dtype=torch.float64)
     if dist is not None:

@@ -177,6 +177,9 @@ int32_t agz_replay_gather(agz_engine* e, int64_t* n_tuples_total);
 /* Read tuples [first, first+count) of the replay ring: boards count x N*N int8 (position before the move),
  * to_play count, pis count x A, zs count (result from Black's view, board.jl:574). */
 int32_t agz_replay_read(agz_engine* e, int64_t first, int32_t count, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs);
+/* get_replay_batch (src/train.jl:4-12): `batch` distinct tuples drawn uniformly without replacement from the ring
+ * (deterministic in `seed`); same output arrays as agz_replay_read. */
+int32_t agz_replay_sample(agz_engine* e, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices);
 /* NCCL bootstrap for world_size > 1: rank 0 fills a 128-byte id, every rank passes the same bytes. */
 int32_t agz_nccl_unique_id(uint8_t id_out[128]);
 int32_t agz_nccl_init(agz_engine* e, const uint8_t id[128]);

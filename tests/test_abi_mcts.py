@@ -384,3 +384,47 @@ def test_c2_full_size_properties():
             assert n3 == n1 and np.array_equal(mv3, mv1) and np.array_equal(pi3, pi1)
     for e in (e1, e2, e3):
         e.close()
+
+
+# ------------------------------------------------------------ replay ring (extract_data / replay_position / get_replay_batch)
+@pytest.mark.gpu
+def test_replay_gather_read_sample():
+    """agz_replay_gather packs (position before the move, pi, z) for every ply of every finished game -- the same tuples the
+    oracle's extract_data / replay_position produce -- and agz_replay_sample draws distinct tuples from the ring."""
+    eng = agz.Engine(9, lib_path=lib_for("cuda"), n_games=4, readouts=16, seed=77)
+    eng.set_dummy_evaluator(None, 0.0)
+    eng.selfplay_start(6)
+    for _ in range(400):
+        pr = eng.selfplay_step(16)
+        if pr.games_finished == 6:
+            break
+    assert pr.games_finished == 6 and pr.error == 0
+    total = eng.replay_gather()
+    recs = sorted(eng.selfplay_harvest(16), key=lambda r: r.game_id)
+    assert total == sum(r.n_moves for r in recs) and total > 0
+    boards, tp, pis, zs = eng.replay_read(0, total)
+    # tuples are appended game by game in ring order; rebuild the expected stream from the harvested records + oracle rules
+    oenv = ogo.GoEnv(9)
+    expected = {}
+    for r in recs:
+        pos = ogo.GoPosition(oenv)
+        for t, m in enumerate(r.moves):
+            expected[(r.game_id, t)] = (pos.board.flatten(order="F").copy(), pos.to_play, r.searches_pi[t], r.result)
+            pos = ogo.play_move(pos, ogo.from_flat(int(m), oenv))
+    # match every ring tuple to exactly one expected tuple
+    used = set()
+    for k in range(total):
+        hit = None
+        for key, (b, p, pi, z) in expected.items():
+            if key not in used and p == tp[k] and z == zs[k] and np.array_equal(b, boards[k]) and np.array_equal(pi, pis[k]):
+                hit = key
+                break
+        assert hit is not None, k
+        used.add(hit)
+    assert len(used) == total
+    sb, stp, spi, sz, idx = eng.replay_sample(8, seed=3)
+    assert len(set(idx.tolist())) == 8 and idx.min() >= 0 and idx.max() < total
+    for j, i in enumerate(idx):
+        assert np.array_equal(sb[j], boards[i]) and np.array_equal(spi[j], pis[i]) and sz[j] == zs[i] and stp[j] == tp[i]
+    with pytest.raises(agz.AgzError):
+        eng.replay_sample(total + 1)
