@@ -42,6 +42,7 @@ struct TCState {
   CUtensorMap tm4_in64, tm4_act[3];   // v4: box = one CTA's slab (128 + 2*H8 rows)
   std::vector<CUtensorMap> tm2_w;
   int N, NP1, PP, C, T, max_batch;
+  int res_tma;                // AGZ_CONV_RES_TMA (default 1): residual convs use conv3x3_tc6_kernel (shortcut tile by TMA)
   int dense;                  // 1: dense NHWC rows (b*N^2 + p), im2col TMA (v5); 0: zero-bordered boards (v1-v4)
   int rowbase, pitch;         // row of point (j, i) of board b = b*PP + rowbase + j*pitch + i
   CUtensorMap tm5_in64, tm5_act[3];
@@ -1040,10 +1041,181 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------- v6: v5 + residual tile by TMA
+// For the second convolution of a residual block the shortcut rows (128 x 256 fp16 = 64 KB per CTA and tile) are
+// fetched by TMA into shared memory half way through the tile's K loop -- long before the epilogue needs them -- instead
+// of by per-thread global loads inside the epilogue (ncu on v5: the residual-carrying launches were 19 % slower, the
+// epilogue waiting on 64-byte global loads).  4 operand stages (128 KB) + 64 KB residual tile.
+static const int V6_STAGES = 4;
+static const int V6_RES_BYTES = BM * 256 * 2;
+static const size_t CONV6_SMEM = (size_t)V6_STAGES * V3_STAGE_BYTES + V6_RES_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR,
+                   const ConvArgs a, const int res_row0) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  uint8_t* resbuf = smem + (size_t)V6_STAGES * V3_STAGE_BYTES;      // 4 boxes of 128 rows x 64 channels, SWIZZLE_128B
+  float* s_scale = reinterpret_cast<float*>(resbuf + V6_RES_BYTES);
+  float* s_shift = s_scale + 256;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + V6_STAGES;
+  uint64_t* tfull = bars + 2 * V6_STAGES;
+  uint64_t* tempty = bars + 2 * V6_STAGES + 2;
+  uint64_t* rfull = bars + 2 * V6_STAGES + 4;    // local: residual tile landed
+  uint64_t* rempty = bars + 2 * V6_STAGES + 5;   // local: 4 epilogue warps are done with it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V6_STAGES + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_ptiles = (a.n_tiles + 1) >> 1;
+  s_scale[threadIdx.x] = a.scale[threadIdx.x];
+  s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < V6_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    mbar_init(rfull, 1);
+    mbar_init(rempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = 9 * a.kchunks;
+  const int N2 = a.N * a.N;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, rphase = 0;
+      for (int t = pair; t < n_ptiles; t += n_pairs) {
+        const int m0 = t * 256 + (int)rank * 128;
+        const int b0 = m0 / N2, rem = m0 - b0 * N2, j0 = rem / a.N, i0 = rem - j0 * a.N;
+        int it = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint16_t oh = (uint16_t)(tap / 3), ow = (uint16_t)(tap % 3);
+          for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
+            mbar_wait_guard(&empty[stage], phase ^ 1);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * V3_STAGE_BYTES);
+            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+            uint8_t* sa = tiles + (size_t)stage * V3_STAGE_BYTES;
+            tma_load_im2col_2sm(sa, &tmA, lbar, kc * BK, i0 - 1, j0 - 1, b0, ow, oh);
+            tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, kc * BK, tap * 256 + (int)rank * 128);
+            if (++stage == V6_STAGES) { stage = 0; phase ^= 1; }
+            if (it == iters / 2) {  // the previous tile's epilogue is long done by now: fetch this tile's shortcut rows
+              mbar_wait_guard(rempty, rphase ^ 1);
+              mbar_expect_tx(rfull, V6_RES_BYTES);
+#pragma unroll
+              for (int bx = 0; bx < 4; ++bx) tma_load_2d(resbuf + (size_t)bx * A_BYTES, &tmR, rfull, bx * BK, res_row0 + m0);
+              rphase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int titer = 0;
+      for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
+        const int as = titer & 1;
+        const uint32_t aphase = (titer >> 1) & 1;
+        mbar_wait_guard(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait_guard(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * V3_STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M256_N256, (it > 0 || k > 0) ? 1u : 0u);
+          tc_commit_2sm(&empty[stage]);
+          if (++stage == V6_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tfull[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int r = q * 32 + lane;   // row of this thread inside the CTA's 128-row tile
+    int titer = 0;
+    for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
+      const int as = titer & 1;
+      const uint32_t aphase = (titer >> 1) & 1;
+      const long long row = (long long)t * 256 + rank * 128 + r;
+      const bool valid = row < a.rows_valid;
+      __half* orow = a.out + row * 256;
+      mbar_wait_guard(&tfull[as], aphase);
+      mbar_wait_guard(rfull, (uint32_t)(titer & 1));
+      tc_fence_after();
+#pragma unroll 2
+      for (int cc = 0; cc < 8; ++cc) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
+        // shortcut values of columns cc*32 .. +31: box cc/2, 16-byte chunks (cc%2)*4 + j, swizzled with the row
+        uint4 rv[4];
+        const uint8_t* rb = resbuf + (size_t)(cc >> 1) * A_BYTES + (size_t)r * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(rb + ((((cc & 1) * 4 + j) ^ (r & 7)) << 4));
+        if (valid) {
+          uint4 o[4];
+          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+          const __half2* rh = reinterpret_cast<const __half2*>(rv);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c0 = cc * 32 + 2 * j;
+            float2 rr = __half22float2(rh[j]);
+            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]) + rr.x;
+            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]) + rr.y;
+            if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            __half2 h = __floats2half2_rn(y0, y1);
+            ow[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(rempty);
+        const uint32_t lb = mapa_u32(smem_u32(&tempty[as]), 0);
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lb) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------------------- heads (fp16 trunk)
 // neural_net.jl:23-30.  HPB positions per CTA so that the dense-layer weights (83 KB + 53 KB on 9x9, 370 KB + 1 MB on
 // 19x19) are read from L2 once per 8 positions instead of once per position.
 static const int HPB = 8;
+static size_t heads_smem(int N2, int A) { return (size_t)HPB * (3 * N2 + 256 + A + (A <= 128 ? (256 / A) * A : 0)) * sizeof(float); }
 
 __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict__ trunk, const float* __restrict__ vw,
                                                        const float* __restrict__ pw, const float* __restrict__ aff,
@@ -1098,7 +1270,8 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
     const float bias = D1b[tid];
 #pragma unroll
     for (int pb = 0; pb < HPB; ++pb) acc[pb] = bias;
-    for (int i = 0; i < N2; ++i) {
+#pragma unroll 4
+    for (int i = 0; i < N2; ++i) {   // 4 independent L2 loads in flight per thread
       const float w = D1W[tid + 256 * i];
 #pragma unroll
       for (int pb = 0; pb < HPB; ++pb) acc[pb] = fmaf(w, vf[pb * N2 + i], acc[pb]);
@@ -1114,19 +1287,48 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) v[b0 + warp] = tanhf(acc + D2b[0]);
   }
-  // Dense(2*N2 -> A): thread a (and a + 256)
-  for (int a0i = tid; a0i < A; a0i += 256) {
-    float acc[HPB];
-    const float bias = Pb[a0i];
+  // Dense(2*N2 -> A).  Small boards (A <= 128): the K range is split over S = 256 / A thread groups so that all 256
+  // threads stream weights (partials are summed through shared memory in a fixed order); otherwise thread a, a + 256.
+  const int S = A <= 128 ? 256 / A : 1;
+  if (S > 1) {
+    float* part = lg + HPB * A;                 // [S][HPB][A]
+    const int slice = tid / A, a0i = tid - slice * A;
+    if (slice < S) {
+      const int chunk = (2 * N2 + S - 1) / S, i0 = slice * chunk, i1 = min(2 * N2, i0 + chunk);
+      float acc[HPB];
 #pragma unroll
-    for (int pb = 0; pb < HPB; ++pb) acc[pb] = bias;
-    for (int i = 0; i < 2 * N2; ++i) {
-      const float w = PW[a0i + (size_t)A * i];
+      for (int pb = 0; pb < HPB; ++pb) acc[pb] = 0.f;
+#pragma unroll 6
+      for (int i = i0; i < i1; ++i) {
+        const float w = PW[a0i + (size_t)A * i];
 #pragma unroll
-      for (int pb = 0; pb < HPB; ++pb) acc[pb] = fmaf(w, pf[pb * 2 * N2 + i], acc[pb]);
+        for (int pb = 0; pb < HPB; ++pb) acc[pb] = fmaf(w, pf[pb * 2 * N2 + i], acc[pb]);
+      }
+#pragma unroll
+      for (int pb = 0; pb < HPB; ++pb) part[(slice * HPB + pb) * A + a0i] = acc[pb];
     }
+    __syncthreads();
+    for (int idx = tid; idx < HPB * A; idx += 256) {
+      const int a1 = idx % A;
+      float acc = Pb[a1];
+      for (int sl = 0; sl < S; ++sl) acc += part[sl * HPB * A + idx];
+      lg[idx] = acc;
+    }
+  } else {
+    for (int a0i = tid; a0i < A; a0i += 256) {
+      float acc[HPB];
+      const float bias = Pb[a0i];
 #pragma unroll
-    for (int pb = 0; pb < HPB; ++pb) lg[pb * A + a0i] = acc[pb];
+      for (int pb = 0; pb < HPB; ++pb) acc[pb] = bias;
+#pragma unroll 6
+      for (int i = 0; i < 2 * N2; ++i) {
+        const float w = PW[a0i + (size_t)A * i];
+#pragma unroll
+        for (int pb = 0; pb < HPB; ++pb) acc[pb] = fmaf(w, pf[pb * 2 * N2 + i], acc[pb]);
+      }
+#pragma unroll
+      for (int pb = 0; pb < HPB; ++pb) lg[pb * A + a0i] = acc[pb];
+    }
   }
   __syncthreads();
   if (warp < nb) {  // softmax over all A actions (no legality masking, as the reference): one warp per position
@@ -1285,6 +1487,10 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
     if (t->version < 1 || t->version > 5) t->version = 5;
   }
   t->dense = t->version == 5;
+  {
+    const char* er = getenv("AGZ_CONV_RES_TMA");
+    t->res_tma = er ? atoi(er) : 1;
+  }
   t->PP = t->dense ? t->N * t->N : t->NP1 * t->NP1;
   t->rowbase = t->dense ? 0 : t->NP1;
   t->pitch = t->dense ? t->N : t->NP1;
@@ -1458,7 +1664,7 @@ static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
 }
 
 static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
-                        __half* out, int B, int kchunks, cudaStream_t s) {
+                        __half* out, int B, int kchunks, cudaStream_t s, const CUtensorMap* res_map = nullptr, int res_row0 = 0) {
   ConvArgs a;
   a.scale = scale; a.shift = shift; a.res = res; a.out = out;
   a.rows_valid = (long long)B * t->PP;
@@ -1468,7 +1674,8 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.relu = 1;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
-  conv3x3_tc5_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
+  if (res_map && t->res_tma) conv3x3_tc6_kernel<<<2 * pairs, 256, CONV6_SMEM, s>>>(tmA, tmW, *res_map, a, res_row0);
+  else conv3x3_tc5_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
   return (int)cudaGetLastError();
 }
 
@@ -1513,8 +1720,9 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv2_smem(t->arows));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv4_smem(128 + 2 * t->H8));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)HPB * (3 * n->N2 + 256 + n->A) * sizeof(float)));
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem(n->N2, n->A));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
     t->attr_set = true;
@@ -1524,10 +1732,13 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
     const int kch = in_buf < 0 ? CIN0 / BK : 4;
     const __half* res = res_buf >= 0 ? t->act[res_buf] + roff * 256 : nullptr;
+    const CUtensorMap* rmap = res_buf >= 0 ? &t->tm_act[res_buf] : nullptr;   // plain 2-D map (128 rows x 64 ch boxes) over the shortcut buffer
     if (t->version == 5 && group >= 0)
       return launch_conv5(t, in_buf < 0 ? t->tm5g_in64[group] : t->tm5g_act[group][in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res,
-                          t->act[out_buf] + roff * 256, B, kch, s);
-    if (t->version == 5) return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
+                          t->act[out_buf] + roff * 256, B, kch, s, rmap, (int)roff);
+    if (t->version == 5)
+      return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s,
+                          rmap, 0);
     if (t->version == 4) return launch_conv4(t, in_buf < 0 ? t->tm4_in64 : t->tm4_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (t->version == 3) return launch_conv3(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (v2) return launch_conv2(t, in_buf < 0 ? t->tm2_in64 : t->tm2_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
@@ -1544,7 +1755,7 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   if (rc) { snprintf(err, errlen, "conv launch: %s", cudaGetErrorString((cudaError_t)rc)); return 1; }
   if (ev) cudaEventRecord(ev[2], s);
   if (convs_done) cudaEventRecord(convs_done, s);
-  const size_t hsm = (size_t)HPB * (3 * n->N2 + 256 + n->A) * sizeof(float);
+  const size_t hsm = heads_smem(n->N2, n->A);
   heads_tc_kernel<<<(B + HPB - 1) / HPB, 256, hsm, s>>>(t->act[h] + roff * 256, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW,
                                                         n->f_Pb, pi, v, B, t->N, t->PP, t->rowbase, t->pitch);
   if (ev) cudaEventRecord(ev[3], s);

@@ -244,7 +244,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "C2: 9x9 Go, %d concurrent self-play games per GPU, 400 readouts/move (50 rounds x 8 leaves per step), tower_height 6, 256 filters, random-init weights seed 0, empty-board starts, finished games refilled" % args.games,
                        "step": "50 tree_search rounds over all games (two half batches pipelined on two streams) + replay all-gather of finished games",
-                       "l2": "inputs larger than L2: tree arenas %.1f GB and %.0f MB per activation buffer vs 126 MB L2" % (args.games * eng.cfg.nodes_per_game * 1.5e-6 if eng.cfg.nodes_per_game else args.games * 1680 * 1.5e-6, rows * 100 * 512 / 1e6)},
+                       "l2": "inputs larger than L2: tree arenas %.1f GB and %.0f MB per activation buffer vs 126 MB L2" % (args.games * (eng.cfg.nodes_per_game or 10 * (READOUTS + 20)) * 1.5e-6, rows * 81 * 512 / 1e6)},
             "e2e": {"value": tot[1] / tmx[1], "unit": "moves/s", "h2d_bytes_per_step": param_bytes, "d2h_bytes_per_step": int(d2h / args.steps)},
             "gpu_launches": int(tot[2]),
             "clocks": sampler.summary(),
@@ -258,7 +258,7 @@ def main():
             "network_tflops": flops_pos * rows / ((kms[2] + kms[3] + kms[4]) / max(1, kln[0]) * 1e-3) / 1e12 if kln[0] else None,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, m, el, cores = oracle_moves_per_sec(3, 25)
+            v, m, el, cores = oracle_moves_per_sec(8, 25)
             line["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
                                     "sample": "first %d moves of one 9x9 game, 400 readouts, tower_height 6 (oracle port of src/selfplay.jl, %.1f s)" % (m, el)}
         print(json.dumps(line), flush=True)
