@@ -253,6 +253,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   rc |= dalloc(e, &v.leaf_node, rows);
   rc |= dalloc(e, &v.leaf_plen, rows);
   rc |= dalloc(e, &v.remap, nodes);
+  rc |= dalloc(e, &v.order, nodes);
   rc |= dalloc(e, &v.rec_moves, G * L);
   rc |= dalloc(e, &v.rec_q, G * L);
   rc |= dalloc(e, &v.rec_pi, G * L * c.A);

@@ -90,7 +90,8 @@ struct View {
   uint32_t* hist;  // [slot][7][2*KB]
   PathEnt* path;   // [slot][pmax][maxd]
   int32_t *leaf_node, *leaf_plen;  // [slot][pmax]
-  int32_t* remap;  // [slot][cap]
+  int32_t* remap;  // [slot][cap] old id -> new id (compaction)
+  int32_t* order;  // [slot][cap] new id -> old id
   const float* eval_pi;  // row b at eval_pi + b*pi_stride
   const float* eval_v;   // eval_v[b*v_stride]
   long long pi_stride;
@@ -561,8 +562,12 @@ struct Warp {
   }
 
   // ---- arena compaction: keep the subtree of the root, slide it to the front (stable) -------------------
+  // Pass 1 marks live nodes (a parent always has a smaller id than its child) and builds remap (old -> new) and order
+  // (new -> old).  Pass 2 walks only the live nodes, U at a time: all loads of a group are issued before its stores, so the
+  // dependent-load chains of U nodes overlap (new id <= old id and ascending order make the in-place move safe).
   AGZ_DEV void compact() {
     int32_t* remap = v.remap + (size_t)g * c.cap;
+    int32_t* order = v.order + (size_t)g * c.cap;
     const int count = st.count;
     int base = 0;
     for (int c0 = 0; c0 < count; c0 += 32) {
@@ -570,7 +575,7 @@ struct Warp {
       int parent = -2;
       if (i < count) parent = load_meta(i).parent;
       unsigned mask = 0;
-      for (;;) {  // a parent always has a smaller id than its child; resolve same-chunk parents by iteration
+      for (;;) {  // resolve same-chunk parents by iteration
         bool live = false;
         if (i < count) {
           if (i == st.root) live = true;
@@ -581,36 +586,76 @@ struct Warp {
         if (nm == mask) break;
         mask = nm;
       }
-      if (i < count) remap[i] = ((mask >> lane) & 1u) ? base + simt::popc(mask & ((1u << lane) - 1u)) : -1;
+      if (i < count) {
+        const bool live = (mask >> lane) & 1u;
+        const int ni = base + simt::popc(mask & ((1u << lane) - 1u));
+        remap[i] = live ? ni : -1;
+        if (live) order[ni] = i;
+      }
       base += simt::popc(mask);
       simt::sync();
     }
-    for (int i = 0; i < count; ++i) {
-      int ni = remap[i];
-      if (ni < 0) continue;  // warp-uniform
-      const size_t ro = row(i), rn = row(ni);
+    const int nlive = base;
+    constexpr int U = KA <= 3 ? 4 : (KA <= 6 ? 2 : 1);
+    for (int n0 = 0; n0 < nlive; n0 += U) {
+      float nn[U][KA], ww[U][KA], pp[U][KA];
+      int cc[U][KA];
+      NodeMeta mm[U];
+      uint32_t bb[U][(3 * KA + 31) / 32 + 3];
+      int src[U];
 #pragma unroll
-      for (int k = 0; k < KA; ++k) {
-        int a = k * 32 + lane;
-        float nn = v.N[ro + a], ww = v.W[ro + a], pp = v.P[ro + a];
-        int cc = v.child[ro + a];
-        if (cc >= 0) cc = remap[cc];
-        v.N[rn + a] = nn; v.W[rn + a] = ww; v.P[rn + a] = pp; v.child[rn + a] = cc;
+      for (int u = 0; u < U; ++u) {
+        src[u] = n0 + u < nlive ? order[n0 + u] : -1;
+        if (src[u] >= 0) {
+          const size_t ro = row(src[u]);
+#pragma unroll
+          for (int k = 0; k < KA; ++k) {
+            int a = k * 32 + lane;
+            nn[u][k] = v.N[ro + a]; ww[u][k] = v.W[ro + a]; pp[u][k] = v.P[ro + a]; cc[u][k] = v.child[ro + a];
+          }
+          mm[u] = load_meta(src[u]);
+          const uint32_t* bo = bits_of(src[u]);
+#pragma unroll
+          for (int q = 0; q < (3 * KA + 31) / 32 + 3; ++q) {
+            int k = q * 32 + lane;
+            bb[u][q] = k < 3 * c.KB ? bo[k] : 0u;
+          }
+        }
       }
-      if (ni != i) {
-        const uint32_t* bo = bits_of(i);
-        uint32_t* bn = bits_of(ni);
-        for (int k = lane; k < 3 * c.KB; k += 32) bn[k] = bo[k];
-      }
-      NodeMeta m = load_meta(i);
-      if (lane == 0) {
-        m.parent = m.parent >= 0 ? remap[m.parent] : -1;
-        v.meta[nbase + ni] = m;
-      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (src[u] >= 0) {
+#pragma unroll
+          for (int k = 0; k < KA; ++k)
+            if (cc[u][k] >= 0) cc[u][k] = remap[cc[u][k]];
+        }
+      simt::sync();  // every lane has loaded its part of the U sources before any destination is written
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (src[u] >= 0) {
+          const int ni = n0 + u;
+          const size_t rn = row(ni);
+#pragma unroll
+          for (int k = 0; k < KA; ++k) {
+            int a = k * 32 + lane;
+            v.N[rn + a] = nn[u][k]; v.W[rn + a] = ww[u][k]; v.P[rn + a] = pp[u][k]; v.child[rn + a] = cc[u][k];
+          }
+          uint32_t* bn = bits_of(ni);
+#pragma unroll
+          for (int q = 0; q < (3 * KA + 31) / 32 + 3; ++q) {
+            int k = q * 32 + lane;
+            if (k < 3 * c.KB) bn[k] = bb[u][q];
+          }
+          if (lane == 0) {
+            NodeMeta m = mm[u];
+            m.parent = m.parent >= 0 ? remap[m.parent] : -1;
+            v.meta[nbase + ni] = m;
+          }
+        }
       simt::sync();
     }
     st.root = remap[st.root];
-    st.count = base;
+    st.count = nlive;
     simt::sync();
   }
 

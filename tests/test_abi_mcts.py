@@ -330,6 +330,11 @@ def test_selfplay_concurrent_games_match_oracle(env):
     check_selfplay_parity(env, 9, 16, seeds=[3], n_games=3)
 
 
+def test_selfplay_with_tiny_arena_compacts_every_move(env):
+    """An arena barely larger than one move's worth of nodes forces the in-place compaction at (almost) every re-root."""
+    check_selfplay_parity(env, 9, 16, seeds=[5], priors_seed=2, value=0.05, n_games=2, nodes_per_game=96)
+
+
 @pytest.mark.gpu
 def test_selfplay_matches_oracle_bulk():
     """C2-like readouts on a handful of games, and many concurrent small games (slot refill, ring, compaction)."""
