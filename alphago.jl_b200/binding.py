@@ -72,7 +72,7 @@ SYMBOLS = [
     "agz_tree_inject_noise", "agz_tree_pick_move", "agz_tree_play_move", "agz_tree_should_resign", "agz_tree_root",
     "agz_tree_read_node", "agz_tree_set_stats", "agz_tree_pending_vlosses", "agz_tree_read_record",
     "agz_tree_node_features", "agz_pos_play_move", "agz_pos_legal_moves", "agz_pos_score", "agz_pos_liberties",
-    "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops",
+    "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -381,6 +381,15 @@ class Engine:
         self._check(self.lib.agz_phase_times(self._h, ms, ln, C.c_int32(1 if reset else 0)))
         return list(ms), list(ln)
 
+
+    def trace_read(self, max_records=1 << 16, reset=True):
+        """Kernel timeline trace (AGZ_TRACE=<records> at engine creation): array of (tag, block, grid, start_ns, end_ns, sm)."""
+        buf = np.zeros((max_records, 4), np.uint64)
+        n = C.c_int32()
+        self._check(self.lib.agz_trace_read(self._h, _ptr(buf, C.c_uint64), C.c_int32(max_records), C.byref(n), C.c_int32(1 if reset else 0)))
+        b = buf[:n.value]
+        w0 = b[:, 0]
+        return np.stack([w0 & np.uint64(0xFF), (w0 >> np.uint64(8)) & np.uint64(0xFFFFFF), w0 >> np.uint64(32), b[:, 1], b[:, 2], b[:, 3]], axis=1).astype(np.int64)
 
     def net_flops(self):
         a, b = C.c_double(), C.c_double()

@@ -35,11 +35,22 @@ struct MinBlocks {
 };
 
 template <class Op>
+struct TraceTag {
+  static const int v = 9;
+};
+
+template <class Op>
 __global__ void __launch_bounds__(128, MinBlocks<Op>::v) k_warps(const Op op, int n_warps, int smem_per_warp) {
   extern __shared__ __align__(16) char smem[];
   const int wib = threadIdx.x >> 5;
   const int w = blockIdx.x * 4 + wib;
+  unsigned long long t0 = 0;
+  if (op.v.trace) t0 = simt::gtimer();
   if (w < n_warps) op(w, smem + (size_t)wib * smem_per_warp);
+  if (op.v.trace) {
+    __syncthreads();
+    if (simt::trace_cta()) simt::trace_rec(op.v.trace, TraceTag<Op>::v, t0);
+  }
 }
 
 // When the tree kernels are meant to run underneath the persistent conv kernel (half-batch pipelining) they must ask for

@@ -47,6 +47,8 @@ struct agz_engine {
   uint8_t* d_hook_libs;
   float* d_hook_feats;
   long long launches;
+  unsigned long long* d_trace;   // AGZ_TRACE=<records>: kernel timeline trace (simt.h), read back with agz_trace_read
+  int trace_cap;
   bool started;
   unsigned long long ring_head;
   int timing;
@@ -56,9 +58,11 @@ struct agz_engine {
   NNet* nn;
   cudaEvent_t ev[8];   // 0 select | 1 features | 2 stem | 3 tower | 4 heads | 5 incorporate | 6 end
   cudaEvent_t ev_step[2];
-  cudaStream_t gstream[2];   // half-batch pipelining: group g's select -> features -> network -> incorporate chain
+  cudaStream_t gstream[2];   // half-batch pipelining: group g's heads -> incorporate -> select -> features chain (low priority)
+  cudaStream_t cstream;      // ... and the convolutions of both groups, alternating (high priority)
   cudaEvent_t ev_join[3];
-  cudaEvent_t ev_tok[2];
+  cudaEvent_t ev_feat[2];    // group g's leaf features are written: its stem may start
+  cudaEvent_t ev_conv[2];    // group g's last convolution is done: its heads may start
   int pipeline;              // 1: two half batches on two streams (tree work of one hides under the network of the other)
   ReplayState* replay;
 #endif
@@ -143,8 +147,10 @@ extern "C" void agz_engine_destroy(agz_engine* e) {
   for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
   for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_step[i]);
   for (int i = 0; i < 3; ++i) cudaEventDestroy(e->ev_join[i]);
-  for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_tok[i]);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_feat[i]);
+  for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_conv[i]);
   for (int i = 0; i < 2; ++i) cudaStreamDestroy(e->gstream[i]);
+  cudaStreamDestroy(e->cstream);
 #endif
   for (void* p : e->allocs) devrt::dfree(p);
 #if AGZ_CUDA
@@ -196,11 +202,20 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   for (int i = 0; i < 8; ++i) cudaEventCreate(&e->ev[i]);
   for (int i = 0; i < 2; ++i) cudaEventCreate(&e->ev_step[i]);
   for (int i = 0; i < 3; ++i) cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming);
-  for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&e->ev_tok[i], cudaEventDisableTiming);
-  for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&e->gstream[i], cudaStreamNonBlocking);
+  for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&e->ev_feat[i], cudaEventDisableTiming);
+  for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&e->ev_conv[i], cudaEventDisableTiming);
   {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&e->gstream[i], cudaStreamNonBlocking, least);
+    cudaStreamCreateWithPriority(&e->cstream, cudaStreamNonBlocking, greatest);
+  }
+  {
+    // 0 (default): one batch per round on one stream.  1: two half batches, convolutions on a high-priority stream and the
+    // tree / heads kernels of the other half underneath (pipelined_rounds).  On a power-capped B200 the overlap does not pay:
+    // measured back to back on one box, 2551 / 2545 moves/s sequential vs 2522 / 2516 pipelined (profiles/r01_schedule_ab.md).
     const char* pe = getenv("AGZ_PIPELINE");
-    e->pipeline = pe ? atoi(pe) : 1;
+    e->pipeline = pe ? atoi(pe) : 0;
   }
 #else
   e->stream = 0;
@@ -276,6 +291,21 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   rc |= dalloc(e, &e->d_hook_libs, (size_t)AGZ_MAX_POINTS);
   rc |= dalloc(e, &e->d_hook_feats, (size_t)17 * c.N2);
   e->d_feats_f32 = nullptr;
+  e->d_trace = nullptr;
+  e->trace_cap = 0;
+#if AGZ_CUDA
+  if (const char* et = getenv("AGZ_TRACE")) {
+    e->trace_cap = atoi(et) > 0 ? atoi(et) : 0;
+    if (e->trace_cap) {
+      rc |= dalloc(e, &e->d_trace, (size_t)2 + 4 * (size_t)e->trace_cap);
+      if (!rc) {
+        unsigned long long cap = (unsigned long long)e->trace_cap;
+        rc |= devrt::h2d(e->d_trace + 1, &cap, sizeof(cap), e->stream);
+        v.trace = e->d_trace;
+      }
+    }
+  }
+#endif
   if (rc) {
     int code = fail(nullptr, AGZ_ERR_CUDA, "device allocation failed (n_games=%d, nodes_per_game=%d)", c.n_games, c.cap);
     agz_engine_destroy(e);
@@ -298,6 +328,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
       agz_engine_destroy(e);
       return code;
     }
+    nn_tc_set_trace(e->nn, e->d_trace);
     int r2 = dalloc(e, &e->d_feats_f32, rows * 17 * c.N2);
     if (r2) {
       agz_engine_destroy(e);
@@ -469,41 +500,58 @@ static int one_round(agz_engine* e) {
 }
 
 #if AGZ_CUDA
-// Half-batch pipelining: slots [0, G/2) and [G/2, G) run their own select -> features -> network -> incorporate chains
-// on two streams.  A token (events ev_tok[g], recorded after a group's last convolution) makes the two towers strictly
-// alternate on the tensor cores, so the latency-bound tree kernels, the feature kernel and the heads of one group
-// execute underneath the tower of the other.  (Without the token the hardware round-robins the two streams' conv
-// kernels and the chains stay in phase -- measured: no gain.)  Results are identical to the sequential schedule: games
-// never interact.
+// Half-batch pipelining: slots [0, G/2) and [G/2, G) are two groups.  The convolutions of both groups run back to back on
+// one high-priority stream (group 0's tower, group 1's tower, group 0's next tower, ...), so the tensor cores never wait;
+// each group's heads -> incorporate -> select -> leaf-features chain runs on its own low-priority stream underneath the
+// other group's tower (events ev_conv[g] / ev_feat[g] hand a group from one stream to the other).  The priorities matter:
+// the heads kernel (27 KB of shared memory per CTA, 8 CTAs per SM) would otherwise grab the SMs the moment a tower ends and
+// hold the next stem back for its whole duration (measured with the AGZ_TRACE timeline: a 135 us bubble per half round).
+// Results are identical to the sequential schedule: games never interact.
 static bool can_pipeline(agz_engine* e) {
   return e->pipeline && !e->timing && e->evaluator == AGZ_EVAL_NN_TC && e->c.n_games >= 2 && e->c.n_games % 2 == 0 && nn_tc_groups(e->nn) == 2;
 }
 
 static int pipelined_rounds(agz_engine* e, int rounds) {
   char nerr[256] = "";
+  if (rounds <= 0) return AGZ_OK;
   devrt::prefer_max_smem() = 1;
   if (!nn_ready(e->nn) && nn_commit(e->nn, e->stream, nerr, sizeof(nerr))) return fail(e, AGZ_ERR_ARG, "network not ready: %s", nerr);
   const int half = e->c.n_games / 2, rows = half * e->c.pmax;
   cudaEventRecord(e->ev_join[2], e->stream);
+  cudaStreamWaitEvent(e->cstream, e->ev_join[2], 0);
   for (int g = 0; g < 2; ++g) cudaStreamWaitEvent(e->gstream[g], e->ev_join[2], 0);
+  auto select_and_features = [&](int g) -> int {
+    cudaStream_t st = e->gstream[g];
+    DISPATCH_KA(e, {
+      SelectOp<KA> op{e->c, e->v, -1, e->c.parallel, g * half};
+      DCHECK(e, devrt::launch_warps(op, half, e->smem_per_warp, st));
+    });
+    int rc = engine_tc_features(e->c, e->v, e->nn, g * rows, rows, e->smem_per_warp, st);
+    if (rc) return fail(e, AGZ_ERR_CUDA, "tc feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
+    cudaEventRecord(e->ev_feat[g], st);
+    e->launches += 2;
+    return AGZ_OK;
+  };
+  for (int g = 0; g < 2; ++g) {
+    int rc = select_and_features(g);
+    if (rc) return rc;
+  }
   for (int r = 0; r < rounds; ++r) {
     for (int g = 0; g < 2; ++g) {
       cudaStream_t st = e->gstream[g];
-      DISPATCH_KA(e, {
-        SelectOp<KA> op{e->c, e->v, -1, e->c.parallel, g * half};
-        DCHECK(e, devrt::launch_warps(op, half, e->smem_per_warp, st));
-      });
-      int rc = engine_tc_features(e->c, e->v, e->nn, g * rows, rows, e->smem_per_warp, st);
-      if (rc) return fail(e, AGZ_ERR_CUDA, "tc feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
-      if (r > 0 || g > 0) cudaStreamWaitEvent(st, e->ev_tok[1 - g], 0);   // the other group's tower must have drained
-      rc = nn_forward_tc(e->nn, rows, e->d_eval_pi + (size_t)g * rows * e->c.A, e->d_eval_v + (size_t)g * rows, st, nerr, sizeof(nerr), nullptr, g,
-                         e->ev_tok[g]);
+      cudaStreamWaitEvent(e->cstream, e->ev_feat[g], 0);
+      int rc = nn_forward_tc(e->nn, rows, e->d_eval_pi + (size_t)g * rows * e->c.A, e->d_eval_v + (size_t)g * rows, e->cstream, nerr, sizeof(nerr), nullptr, g,
+                             e->ev_conv[g], st);
       if (rc) return fail(e, AGZ_ERR_CUDA, "nn_forward_tc: %s", nerr);
       DISPATCH_KA(e, {
         IncorporateOp<KA> op{e->c, e->v, -1, g * half};
         DCHECK(e, devrt::launch_warps(op, half, e->smem_per_warp, st));
       });
-      e->launches += 3 + nn_tc_launches_per_forward(e->nn);
+      e->launches += 1 + nn_tc_launches_per_forward(e->nn);
+      if (r + 1 < rounds) {
+        rc = select_and_features(g);
+        if (rc) return rc;
+      }
     }
   }
   for (int g = 0; g < 2; ++g) {
@@ -1061,6 +1109,22 @@ extern "C" int32_t agz_net_forward(agz_engine* e, int32_t evaluator, const int8_
   return AGZ_OK;
 }
 
+extern "C" int32_t agz_trace_read(agz_engine* e, uint64_t* out, int32_t max_records, int32_t* n_out, int32_t reset) {
+  if (!e || !n_out) return fail(e, AGZ_ERR_ARG, "null argument");
+  *n_out = 0;
+  if (!e->d_trace) return AGZ_OK;
+  cudaSetDevice(e->cfg.device);
+  DCHECK(e, (int)cudaDeviceSynchronize());
+  unsigned long long n = 0;
+  DCHECK(e, devrt::d2h(&n, e->d_trace, sizeof(n), e->stream));
+  if (n > (unsigned long long)e->trace_cap) n = (unsigned long long)e->trace_cap;
+  if (n > (unsigned long long)max_records) n = (unsigned long long)(max_records < 0 ? 0 : max_records);
+  if (out && n) DCHECK(e, devrt::d2h(out, e->d_trace + 2, (size_t)n * 4 * sizeof(unsigned long long), e->stream));
+  *n_out = (int32_t)n;
+  if (reset) DCHECK(e, devrt::dmemset(e->d_trace, 0, sizeof(unsigned long long), e->stream));
+  return AGZ_OK;
+}
+
 extern "C" int32_t agz_nccl_unique_id(uint8_t id_out[128]) { return replay_unique_id(id_out) ? fail(nullptr, AGZ_ERR_NCCL, "ncclGetUniqueId failed") : AGZ_OK; }
 
 extern "C" int32_t agz_nccl_init(agz_engine* e, const uint8_t id[128]) {
@@ -1110,6 +1174,7 @@ extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t, const float*, size
 extern "C" int32_t agz_net_set_bn_stats(agz_engine* e, int32_t, const float*, const float*, size_t, int32_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_features(agz_engine* e, const int8_t*, const int8_t*, int32_t, float*) { return fail(e, AGZ_ERR_CUDA, "not in the emulation build"); }
 extern "C" int32_t agz_net_forward(agz_engine* e, int32_t, const int8_t*, const int8_t*, int32_t, float*, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
+extern "C" int32_t agz_trace_read(agz_engine*, uint64_t*, int32_t, int32_t* n_out, int32_t) { if (n_out) *n_out = 0; return AGZ_OK; }
 extern "C" int32_t agz_nccl_unique_id(uint8_t*) { return AGZ_ERR_NCCL; }
 extern "C" int32_t agz_nccl_init(agz_engine* e, const uint8_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
 extern "C" int32_t agz_replay_gather(agz_engine* e, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }

@@ -47,8 +47,10 @@ TCInput nn_tc_input(NNet* n);
 // ev (optional): 4 events recorded before the stem, after the stem, after the tower, after the heads
 // group >= 0: evaluate only half batch `group` (rows [group*max_batch/2, ...)); pi / v point at that half's first row
 int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev = nullptr, int group = -1,
-                  cudaEvent_t convs_done = nullptr /* recorded after the last convolution, before the heads */);
+                  cudaEvent_t convs_done = nullptr /* recorded after the last convolution, before the heads */,
+                  cudaStream_t heads_stream = nullptr /* with convs_done: launch the heads there instead of on s */);
 int nn_tc_groups(const NNet* n);
+void nn_tc_set_trace(NNet* n, unsigned long long* trace);   // kernel timeline trace buffer (simt.h), nullptr = off
 // feature kernels that write the tensor-core input directly (nn_tc.cu): from the leaves of the current round
 // (batch rows [0, row0+nrows)), and from caller-supplied positions.
 struct Cfg;

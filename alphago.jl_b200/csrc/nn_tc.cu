@@ -35,6 +35,9 @@ static const int CIN0 = 64;  // stem input channels: 17 planes zero-padded to on
 static const size_t CONV_SMEM = (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 
 struct TCState {
+  unsigned long long* trace;  // kernel timeline trace buffer or nullptr (nn_tc_set_trace)
+  int pdl;                    // AGZ_CONV_PDL (default 1): tower convolutions use programmatic dependent launch
+  int max_pairs;              // AGZ_CONV_PAIRS
   int version;                // AGZ_CONV_KERNEL: 1 per-tap, 2 slab, 3 CTA pair, 4 CTA pair + slab (zero-bordered layout); 5 CTA pair + im2col (dense, default)
   int base_offset_mode;       // debug knob (AGZ_CONV_BASEOFF): measured on B200 -- the swizzle is a function of the absolute smem address, so 0 is correct
   int H8, arows;              // v2: halo rows rounded up to 8, slab rows = 256 + 2*H8
@@ -135,6 +138,7 @@ struct ConvArgs {
   int kchunks;          // Cin / 64
   int N, NP1, PP;
   int relu;
+  unsigned long long* trace;   // kernel timeline trace (simt.h) or nullptr
 };
 
 __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -887,6 +891,8 @@ __device__ __forceinline__ void tma_load_im2col_2sm(void* dst, const CUtensorMap
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs a) {
+  const unsigned long long trace_t0 = a.trace ? simt::gtimer() : 0ULL;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next convolution may start its prologue as SMs free up
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;
@@ -922,6 +928,9 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  // programmatic dependent launch: everything above overlapped the previous convolution's tail; its output (this kernel's
+  // input / shortcut) and the buffer this kernel overwrites are only touched after the wait (no-op for a normal launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const int iters = 9 * a.kchunks;
   const int N2 = a.N * a.N;
@@ -1039,6 +1048,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+  if (a.trace && simt::trace_cta()) simt::trace_rec(a.trace, a.kchunks == 1 ? 4 : 5, trace_t0);
 }
 
 
@@ -1054,6 +1064,8 @@ static const size_t CONV6_SMEM = (size_t)V6_STAGES * V3_STAGE_BYTES + V6_RES_BYT
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR,
                    const ConvArgs a, const int res_row0) {
+  const unsigned long long trace_t0 = a.trace ? simt::gtimer() : 0ULL;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next convolution may start its prologue as SMs free up
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;
@@ -1095,6 +1107,9 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
+  // programmatic dependent launch: everything above overlapped the previous convolution's tail; its output (this kernel's
+  // input / shortcut) and the buffer this kernel overwrites are only touched after the wait (no-op for a normal launch)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const int iters = 9 * a.kchunks;
   const int N2 = a.N * a.N;
@@ -1209,6 +1224,7 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
+  if (a.trace && simt::trace_cta()) simt::trace_rec(a.trace, 6, trace_t0);
 }
 
 // ------------------------------------------------------------------------------------------- heads (fp16 trunk)
@@ -1222,7 +1238,9 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
                                                        const float* __restrict__ D1W, const float* __restrict__ D1b,
                                                        const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                        const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
-                                                       float* __restrict__ v, int B, int N, int PP, int rowbase, int pitch) {
+                                                       float* __restrict__ v, int B, int N, int PP, int rowbase, int pitch,
+                                                       unsigned long long* trace) {
+  const unsigned long long trace_t0 = trace ? simt::gtimer() : 0ULL;
   extern __shared__ float sm[];
   const int N2 = N * N, A = N2 + 1;
   float* vf = sm;                       // [HPB][N2]
@@ -1344,6 +1362,10 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
     float* out = pi + (size_t)(b0 + warp) * A;
     for (int a0i = lane; a0i < A; a0i += 32) out[a0i] = expf(l[a0i] - mx) / sum;
   }
+  if (trace) {
+    __syncthreads();
+    if (simt::trace_cta()) simt::trace_rec(trace, 7, trace_t0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------- feature kernels
@@ -1389,6 +1411,12 @@ struct LeafFeaturesTCOp {
     }
   }
 };
+
+}  // namespace agz
+namespace devrt {
+template <int KA> struct TraceTag<agz::LeafFeaturesTCOp<KA>> { static const int v = 3; };
+}
+namespace agz {
 
 __global__ void host_features_tc_kernel(const int8_t* __restrict__ bh, const int8_t* __restrict__ tp, __half* __restrict__ in64, int B, int N,
                                         int PP, int rowbase, int pitch) {
@@ -1498,6 +1526,7 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   t->T = n->s.tower;
   t->max_batch = n->max_batch;
   t->attr_set = false;
+  t->trace = nullptr;
   t->stage = nullptr;
   t->stage_cap = 0;
   t->in64 = nullptr;
@@ -1558,6 +1587,14 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   } else {
     t->groups = 1;
     t->grp_rows = 0;
+  }
+  {
+    const char* ed = getenv("AGZ_CONV_PDL");
+    t->pdl = ed ? atoi(ed) : 1;
+  }
+  {
+    const char* ep = getenv("AGZ_CONV_PAIRS");   // cap on the CTA pairs of the persistent conv kernels (0 = all SMs)
+    t->max_pairs = ep ? atoi(ep) : 0;
   }
   const char* eb = getenv("AGZ_CONV_BASEOFF");
   t->base_offset_mode = eb ? atoi(eb) : 0;
@@ -1657,6 +1694,7 @@ static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.kchunks = kchunks;
   a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
   a.relu = 1;
+  a.trace = t->trace;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
   conv3x3_tc3_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
@@ -1664,7 +1702,7 @@ static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
 }
 
 static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
-                        __half* out, int B, int kchunks, cudaStream_t s, const CUtensorMap* res_map = nullptr, int res_row0 = 0) {
+                        __half* out, int B, int kchunks, cudaStream_t s, const CUtensorMap* res_map = nullptr, int res_row0 = 0, bool pdl = false) {
   ConvArgs a;
   a.scale = scale; a.shift = shift; a.res = res; a.out = out;
   a.rows_valid = (long long)B * t->PP;
@@ -1672,11 +1710,33 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.kchunks = kchunks;
   a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
   a.relu = 1;
+  a.trace = t->trace;
   const int n_ptiles = (a.n_tiles + 1) / 2;
-  int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
-  if (res_map && t->res_tma) conv3x3_tc6_kernel<<<2 * pairs, 256, CONV6_SMEM, s>>>(tmA, tmW, *res_map, a, res_row0);
-  else conv3x3_tc5_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
-  return (int)cudaGetLastError();
+  // Same number of waves on as few CTA pairs as possible: 9x9 with 8192 (4096) positions is 2592 (1296) pair tiles =
+  // 36 (18) waves on 72 pairs exactly, where 74 pairs would idle through a 37th (19th) wave's worth of tail.  The SMs
+  // left over run the tree / feature / heads kernels of the other half batch.
+  const int max_pairs = t->max_pairs > 0 && t->max_pairs < t->num_sms / 2 ? t->max_pairs : t->num_sms / 2;
+  const int waves = (n_ptiles + max_pairs - 1) / max_pairs;
+  int pairs = (n_ptiles + waves - 1) / waves;
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(2 * pairs);
+  lc.blockDim = dim3(256);
+  lc.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = (pdl && t->pdl) ? 1 : 0;
+  cudaError_t rc;
+  if (res_map && t->res_tma) {
+    lc.dynamicSmemBytes = CONV6_SMEM;
+    rc = cudaLaunchKernelEx(&lc, conv3x3_tc6_kernel, tmA, tmW, *res_map, a, res_row0);
+  } else {
+    lc.dynamicSmemBytes = CONV3_SMEM;
+    rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel, tmA, tmW, a);
+  }
+  return rc != cudaSuccess ? (int)rc : (int)cudaGetLastError();
 }
 
 static int launch_conv4(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
@@ -1689,6 +1749,7 @@ static int launch_conv4(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.kchunks = kchunks;
   a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
   a.relu = 1;
+  a.trace = t->trace;
   g.H8 = t->H8; g.slab_rows = 128 + 2 * t->H8; g.slab_bytes = g.slab_rows * 128;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
@@ -1705,12 +1766,14 @@ static int launch_conv(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tm
   a.kchunks = kchunks;
   a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
   a.relu = 1;
+  a.trace = t->trace;
   int grid = a.n_tiles < t->num_sms ? a.n_tiles : t->num_sms;
   conv3x3_tc_kernel<<<grid, 256, CONV_SMEM, s>>>(tmA, tmW, a);
   return (int)cudaGetLastError();
 }
 
-int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev, int group, cudaEvent_t convs_done) {
+int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev, int group, cudaEvent_t convs_done,
+                  cudaStream_t heads_stream) {
   TCState* t = (TCState*)n->tc;
   if (group >= 0 && (t->groups != 2 || group > 1 || B > t->max_batch / 2)) { snprintf(err, errlen, "bad group"); return 1; }
   const size_t roff = group > 0 ? (size_t)t->grp_rows : 0;   // row offset of this group inside the shared buffers
@@ -1730,15 +1793,16 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   if (ev) cudaEventRecord(ev[0], s);
   const bool v2 = t->version == 2;
   auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
+    const bool pdl = in_buf >= 0;   // tower convolutions directly follow another convolution on the same stream
     const int kch = in_buf < 0 ? CIN0 / BK : 4;
     const __half* res = res_buf >= 0 ? t->act[res_buf] + roff * 256 : nullptr;
     const CUtensorMap* rmap = res_buf >= 0 ? &t->tm_act[res_buf] : nullptr;   // plain 2-D map (128 rows x 64 ch boxes) over the shortcut buffer
     if (t->version == 5 && group >= 0)
       return launch_conv5(t, in_buf < 0 ? t->tm5g_in64[group] : t->tm5g_act[group][in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res,
-                          t->act[out_buf] + roff * 256, B, kch, s, rmap, (int)roff);
+                          t->act[out_buf] + roff * 256, B, kch, s, rmap, (int)roff, pdl);
     if (t->version == 5)
       return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s,
-                          rmap, 0);
+                          rmap, 0, pdl);
     if (t->version == 4) return launch_conv4(t, in_buf < 0 ? t->tm4_in64 : t->tm4_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (t->version == 3) return launch_conv3(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (v2) return launch_conv2(t, in_buf < 0 ? t->tm2_in64 : t->tm2_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
@@ -1755,9 +1819,13 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   if (rc) { snprintf(err, errlen, "conv launch: %s", cudaGetErrorString((cudaError_t)rc)); return 1; }
   if (ev) cudaEventRecord(ev[2], s);
   if (convs_done) cudaEventRecord(convs_done, s);
+  if (heads_stream && convs_done) {   // the heads run on another stream, after this group's last convolution
+    cudaStreamWaitEvent(heads_stream, convs_done, 0);
+    s = heads_stream;
+  }
   const size_t hsm = heads_smem(n->N2, n->A);
   heads_tc_kernel<<<(B + HPB - 1) / HPB, 256, hsm, s>>>(t->act[h] + roff * 256, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW,
-                                                        n->f_Pb, pi, v, B, t->N, t->PP, t->rowbase, t->pitch);
+                                                        n->f_Pb, pi, v, B, t->N, t->PP, t->rowbase, t->pitch, t->trace);
   if (ev) cudaEventRecord(ev[3], s);
   cudaError_t e2 = cudaGetLastError();
   if (e2 != cudaSuccess) { snprintf(err, errlen, "heads launch: %s", cudaGetErrorString(e2)); return 1; }
@@ -1776,6 +1844,7 @@ int engine_tc_features(const Cfg& c, const View& v, NNet* n, int row0, int nrows
 }
 
 int nn_tc_groups(const NNet* n) { return ((TCState*)n->tc)->groups; }
+void nn_tc_set_trace(NNet* n, unsigned long long* trace) { ((TCState*)n->tc)->trace = trace; }
 
 int engine_host_features_tc(const Cfg& c, NNet* n, const int8_t* boards_hist, const int8_t* to_play, int B, cudaStream_t s) {
   TCState* t = (TCState*)n->tc;

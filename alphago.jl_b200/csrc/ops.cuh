@@ -96,6 +96,9 @@ namespace devrt {
 template <class Op> struct MinBlocks;
 template <> struct MinBlocks<agz::SelectOp<3, 1>> { static const int v = 8; };
 template <> struct MinBlocks<agz::SelectOp<6, 1>> { static const int v = 6; };
+template <class Op> struct TraceTag;
+template <int KA, int OCC> struct TraceTag<agz::SelectOp<KA, OCC>> { static const int v = 1; };
+template <int KA> struct TraceTag<agz::IncorporateOp<KA>> { static const int v = 2; };
 }  // namespace devrt
 #endif
 namespace agz {
@@ -151,8 +154,8 @@ struct HookOp {
         w.st.target_N = 0.f;
         if (p == nullptr) {
           w.st.hist_len = 0;
-          for (int k = 0; k < c.KB; ++k) w.rs.bd[k * 32 + lane] = 0;
-          simt::sync();
+          w.pos.b = 0;
+          w.pos.w = 0;
           w.init_root_from_scratch(0, -1, 1, 0);
         } else {
           uint32_t* hh = v.hist + (size_t)h.slot * (7 * 2 * c.KB);
@@ -169,7 +172,7 @@ struct HookOp {
             }
           }
           w.st.hist_len = nh;
-          rules_load_bytes(w.B, w.rs, p->board);
+          w.pos = bits_from_bytes(w.B, p->board);
           int flags = (p->last_move_pass ? F_LASTPASS : 0) | (p->done ? F_DONE : 0);
           w.init_root_from_scratch(p->n, p->ko, p->to_play, flags);
         }
@@ -243,18 +246,18 @@ struct HookOp {
       case HK_POS_PLAY: {  // play_move!(pos, c) (board.jl:451-509) on a caller-supplied position
         const agz_position* p = h.pos_in;
         agz_position* o = h.pos_out;
-        rules_load_bytes(w.B, w.rs, p->board);
+        w.pos = bits_from_bytes(w.B, p->board);
         int status = 0, ko = -1, ncap = 0;
         const int mv = h.fmove;
         if (mv != c.N2) {
           if (mv == p->ko) status = E_ILLEGAL;
-          else if (rules_play(w.B, w.rs, mv, p->to_play, true, ko, ncap)) status = E_ILLEGAL;
+          else if (bits_play(w.B, w.pos, mv, p->to_play, true, ko, ncap)) status = E_ILLEGAL;
         }
         if (status == 0) {
+          bits_to_bytes(w.B, w.pos, o->board);
           for (int k = 0; k < c.KB; ++k) {
             int pt = k * 32 + lane;
             if (pt < c.N2) {
-              o->board[pt] = w.rs.bd[pt];
               o->hist[0][pt] = p->board[pt];
               for (int r = 1; r < 7; ++r) o->hist[r][pt] = p->hist[r - 1][pt];
             }
@@ -276,35 +279,32 @@ struct HookOp {
       }
       case HK_POS_LEGAL: {  // all_legal_moves (board.jl:393-424)
         const agz_position* p = h.pos_in;
-        rules_load_bytes(w.B, w.rs, p->board);
-        rules_label(w.B, w.rs, 0);
-        rules_count_liberties(w.B, w.rs);
-        uint32_t lw[KA];
-        rules_legal_mask<KA>(w.B, w.rs, p->to_play, p->ko, lw);
-#pragma unroll
-        for (int k = 0; k < KA; ++k) {
-          int pt = k * 32 + lane;
-          if (pt < c.N2) h.legal_out[pt] = (int8_t)((lw[k] >> lane) & 1u);
-        }
+        w.pos = bits_from_bytes(w.B, p->board);
+        const uint32_t legal = bits_legal(w.B, w.pos, p->to_play, p->ko);
+        if (lane < c.N)
+          for (int i = 0; i < c.N; ++i) h.legal_out[c.N * lane + i] = (int8_t)((legal >> i) & 1u);
         if (lane == 0) h.legal_out[c.N2] = 1;
         finish(w, 0, 0, 0.f);
         return;
       }
       case HK_POS_SCORE: {
         const agz_position* p = h.pos_in;
-        rules_load_bytes(w.B, w.rs, p->board);
-        float sc = rules_score(w.B, w.rs, p->komi);
+        float sc = bits_score(w.B, bits_from_bytes(w.B, p->board), p->komi);
         finish(w, 0, 0, sc);
         return;
       }
-      case HK_POS_LIBS: {  // liberty_cache
+      case HK_POS_LIBS: {  // liberty_cache: the shared-memory label / liberty-count code of go_rules.cuh
         const agz_position* p = h.pos_in;
-        rules_load_bytes(w.B, w.rs, p->board);
-        rules_label(w.B, w.rs, 0);
-        rules_count_liberties(w.B, w.rs);
+        Board OB;
+        OB.N = c.N; OB.N2 = c.N2; OB.KB = c.KB;
+        board_init_masks(OB);
+        RulesScratch rs = rules_scratch_at(w.smem, c.KB);
+        rules_load_bytes(OB, rs, p->board);
+        rules_label(OB, rs, 0);
+        rules_count_liberties(OB, rs);
         for (int k = 0; k < c.KB; ++k) {
           int pt = k * 32 + lane;
-          if (pt < c.N2) h.libs_out[pt] = (uint8_t)(w.rs.bd[pt] != 0 ? w.rs.cnt[w.rs.lab[pt]] : 0);
+          if (pt < c.N2) h.libs_out[pt] = (uint8_t)(rs.bd[pt] != 0 ? rs.cnt[rs.lab[pt]] : 0);
         }
         finish(w, 0, 0, 0.f);
         return;

@@ -27,6 +27,8 @@ AGZ_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v
 AGZ_DEV int atomic_add(int* p, int v) { return atomicAdd(p, v); }
 AGZ_DEV int atomic_or(int* p, int v) { return atomicOr(p, v); }
 AGZ_DEV unsigned long long atomic_add(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+AGZ_DEV unsigned reduce_or(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
+AGZ_DEV int reduce_add(int v) { return __reduce_add_sync(0xffffffffu, v); }
 AGZ_DEV int popc(unsigned x) { return __popc(x); }
 AGZ_DEV int ffs(unsigned x) { return __ffs(x); }
 // correctly-rounded ops that can never be contracted into an FMA
@@ -43,6 +45,25 @@ AGZ_DEV double dfloor(double a) { return floor(a); }
 AGZ_DEV long long dbits(double a) { return __double_as_longlong(a); }
 AGZ_DEV double bitsd(long long a) { return __longlong_as_double(a); }
 AGZ_DEV uint32_t mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+// ---- kernel timeline trace (debug aid, AGZ_TRACE=<records>): tr[0] = records written, tr[1] = capacity, then 4 words per
+// record: tag | block << 8 | grid << 32, start, end (%globaltimer ns), SM id.  Written by the first and last CTA of a launch.
+AGZ_DEV unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+AGZ_DEV void trace_rec(unsigned long long* tr, int tag, unsigned long long t0) {
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const unsigned long long i = atomicAdd(tr, 1ULL);
+  if (i < tr[1]) {
+    tr[2 + 4 * i] = (unsigned long long)tag | ((unsigned long long)blockIdx.x << 8) | ((unsigned long long)gridDim.x << 32);
+    tr[3 + 4 * i] = t0;
+    tr[4 + 4 * i] = gtimer();
+    tr[5 + 4 * i] = smid;
+  }
+}
+AGZ_DEV bool trace_cta() { return threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1); }
 }  // namespace simt
 
 #else  // ------------------------------------------------------------------ host emulation (tests only)
@@ -100,6 +121,26 @@ inline unsigned ballot(bool p) {
   return m;
 }
 inline bool any(bool p) { return ballot(p) != 0; }
+inline unsigned reduce_or(unsigned v) {
+  EmuWarp* w = g_warp;
+  int me = w->cur;
+  int par = w->ncoll[me]++ & 1;
+  w->slot[par][me] = v;
+  barrier();
+  unsigned m = 0;
+  for (int i = 0; i < 32; ++i) m |= (unsigned)w->slot[par][i];
+  return m;
+}
+inline int reduce_add(int v) {
+  EmuWarp* w = g_warp;
+  int me = w->cur;
+  int par = w->ncoll[me]++ & 1;
+  w->slot[par][me] = (uint64_t)(uint32_t)v;
+  barrier();
+  int m = 0;
+  for (int i = 0; i < 32; ++i) m += (int)(uint32_t)w->slot[par][i];
+  return m;
+}
 inline int shfl(int v, int src) { return exchange_(v, src); }
 inline unsigned shfl(unsigned v, int src) { return exchange_(v, src); }
 inline float shfl(float v, int src) { return exchange_(v, src); }

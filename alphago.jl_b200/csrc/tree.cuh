@@ -15,6 +15,7 @@
 // per-game state.  One warp owns one game: the 8 selections of a tree_search! round are serial inside the
 // warp (they are order dependent through virtual loss), parallelism comes from thousands of games.
 #pragma once
+#include "go_bits.cuh"
 #include "go_rules.cuh"
 #include "rng.cuh"
 #include "simt.h"
@@ -102,6 +103,7 @@ struct View {
   int16_t* ring_moves;
   float *ring_q, *ring_pi, *ring_vis;
   unsigned long long* ctr;
+  unsigned long long* trace;  // kernel timeline trace buffer (simt.h) or nullptr
 };
 
 template <int KA>
@@ -110,15 +112,16 @@ struct Warp {
   const View& v;
   const int g;
   const int lane;
-  Board B;
-  RulesScratch rs;
+  BitsCtx B;
+  Lines pos;     // the position being worked on: this lane's board line of black / white stones (go_bits.cuh)
+  char* smem;    // per-warp scratch of the shared-memory rules code (go_rules.cuh; liberty-cache hook only)
   GameState st;  // register copy (warp-uniform); written back by store_state()
   size_t nbase;
 
-  AGZ_DEV Warp(const Cfg& c_, const View& v_, int g_, char* smem) : c(c_), v(v_), g(g_), lane(simt::lane()) {
-    B.N = c.N; B.N2 = c.N2; B.KB = c.KB;
-    board_init_masks(B);
-    rs = rules_scratch_at(smem, c.KB);
+  AGZ_DEV Warp(const Cfg& c_, const View& v_, int g_, char* smem_) : c(c_), v(v_), g(g_), lane(simt::lane()), smem(smem_) {
+    B = bits_ctx(c.N, c.KB);
+    pos.b = 0;
+    pos.w = 0;
     st = v.gs[g];
     nbase = (size_t)g * c.cap;
   }
@@ -148,17 +151,18 @@ struct Warp {
     }
   }
 
-  // Write a node whose position is on the rules scratch (labels/liberties valid unless `skip_legal`).
+  // Write a node whose position is `pos` (terminal nodes carry no legal-move mask: `skip_legal`).
   AGZ_DEV void write_node(int node, int parent, int fmove, int n, int ko, int to_play, int flags, bool skip_legal) {
     uint32_t bw[KA], ww[KA], lw[KA];
-    rules_pack<KA>(B, rs, bw, ww);
-#pragma unroll
-    for (int k = 0; k < KA; ++k) lw[k] = 0;
-    if (!skip_legal) rules_legal_mask<KA>(B, rs, to_play, ko, lw);
+    bits_pack<KA>(B, pos.b, bw);
+    bits_pack<KA>(B, pos.w, ww);
+    uint32_t legal = 0;
+    if (!skip_legal) legal = bits_legal(B, pos, to_play, ko);
+    bits_pack<KA>(B, legal, lw);
     uint32_t* bp = bits_of(node);
 #pragma unroll
     for (int k = 0; k < KA; ++k) {
-      if (k < c.KB && lane == 0) {
+      if (k < c.KB && lane == k) {
         bp[k] = bw[k];
         bp[c.KB + k] = ww[k];
         bp[2 * c.KB + k] = lw[k];
@@ -183,7 +187,7 @@ struct Warp {
       if (!((lw >> (move & 31)) & 1u)) { st.err = E_ILLEGAL; return -1; }
     }
     int idx = st.count++;
-    rules_load(B, rs, pb, pb + c.KB);
+    pos = bits_load(B, pb, pb + c.KB);
     int color = pm.to_play;
     int n = pm.n + 1;
     int ko = -1, flags = 0, ncap = 0;
@@ -191,9 +195,8 @@ struct Warp {
     if (move == c.N2) {  // pass_move! (board.jl:426-440)
       flags = F_LASTPASS | ((pm.flags & F_LASTPASS) ? F_DONE : 0);
       term = (flags & F_DONE) || n >= c.max_game_length;
-      if (!term) { rules_label(B, rs, 0); rules_count_liberties(B, rs); }
     } else {
-      rules_play(B, rs, move, color, false, ko, ncap);
+      bits_play(B, pos, move, color, false, ko, ncap);
       term = n >= c.max_game_length;
     }
     write_node(idx, parent, move, n, ko, -color, flags, term);
@@ -334,8 +337,11 @@ struct Warp {
           tm[k] = simt::ballot(s[k] == mx);
           total += simt::popc(tm[k]);
         }
-        U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_SELECT, move_no, sel_idx, (uint32_t)depth);
-        int pick = (int)simt::mulhi(rr.x, (uint32_t)total);
+        int pick = 0;   // mulhi(r, 1) = 0: the draw only matters when several children tie (warp-uniform branch)
+        if (total > 1) {
+          U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_SELECT, move_no, sel_idx, (uint32_t)depth);
+          pick = (int)simt::mulhi(rr.x, (uint32_t)total);
+        }
         best = pass;
         bool found = false;
 #pragma unroll
@@ -393,8 +399,7 @@ struct Warp {
       NodeMeta lm = load_meta(leaf);
       if (terminal(lm)) {  // game over: back up the true result, do not evaluate (mcts_play.jl:80-84)
         const uint32_t* lb = bits_of(leaf);
-        rules_load(B, rs, lb, lb + c.KB);
-        float sc = rules_score(B, rs, c.komi);
+        float sc = bits_score(B, bits_load(B, lb, lb + c.KB), c.komi);
         float value = sc > 0.f ? 1.f : (sc < 0.f ? -1.f : 0.f);
         apply_path(path, plen, OP_BACKUP, value);
         continue;
@@ -784,7 +789,7 @@ struct Warp {
     return tp;
   }
 
-  // ---- new game in this slot (initialize_game! + selfplay.jl:9) ---------------------------------------
+  // ---- new game in this slot (initialize_game! + selfplay.jl:9); the root position is `pos` ----------------
   AGZ_DEV void init_root_from_scratch(int n, int ko, int to_play, int flags) {
     st.root = 0;
     st.count = 1;
@@ -799,7 +804,6 @@ struct Warp {
     st.result = 0;
     st.resigned = 0;
     bool term = (flags & F_DONE) || n >= c.max_game_length;
-    if (!term) { rules_label(B, rs, 0); rules_count_liberties(B, rs); }
     write_node(0, -1, -1, n, ko, to_play, flags, term);
     simt::sync();
   }
@@ -808,8 +812,8 @@ struct Warp {
     st.game_id = game_id;
     st.game_id_lo = (uint32_t)game_id;
     st.hist_len = 0;
-    for (int k = 0; k < c.KB; ++k) rs.bd[k * 32 + lane] = 0;
-    simt::sync();
+    pos.b = 0;
+    pos.w = 0;
     init_root_from_scratch(0, -1, 1, 0);
     U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_RESIGN, 0, 0, 0);
     st.resign_thr = u53(rr.x, rr.y) < c.resign_disable_frac ? -1.0 : c.resign_threshold;
@@ -897,8 +901,7 @@ struct Warp {
     const NodeMeta nm = load_meta(st.root);
     if (terminal(nm)) {  // is_done(root) (selfplay.jl:39-42)
       const uint32_t* lb = bits_of(st.root);
-      rules_load(B, rs, lb, lb + c.KB);
-      float sc = rules_score(B, rs, c.komi);
+      float sc = bits_score(B, bits_load(B, lb, lb + c.KB), c.komi);
       st.final_score = sc;
       st.result = sc > 0.f ? 1 : (sc < 0.f ? -1 : 0);
       st.resigned = 0;

@@ -218,6 +218,10 @@ int32_t agz_kernel_launches(agz_engine* e, int64_t* n);  /* kernels of this libr
 #define AGZ_NKERNELS 6
 int32_t agz_phase_times(agz_engine* e, float ms[AGZ_NKERNELS], int64_t launches[AGZ_NKERNELS], int32_t reset);
 int32_t agz_set_timing(agz_engine* e, int32_t enabled);
+/* Kernel timeline trace (debug aid; enabled by the environment variable AGZ_TRACE=<records> at engine creation): every
+ * kernel's first and last CTA append {tag | block << 8 | grid << 32, start ns, end ns, SM id} (%globaltimer).  Tags:
+ * 1 select, 2 incorporate, 3 leaf features, 4 stem conv, 5 tower conv, 6 tower conv with shortcut, 7 heads, 9 other. */
+int32_t agz_trace_read(agz_engine* e, uint64_t* out, int32_t max_records, int32_t* n_out, int32_t reset);
 /* FLOPs (2*MAC) of one position through the whole network / through one tower 3x3 convolution. */
 int32_t agz_net_flops(agz_engine* e, double* per_position, double* per_tower_conv_position);
 

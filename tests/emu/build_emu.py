@@ -16,7 +16,7 @@ OUT = os.path.join(HERE, "libagz_emu.so")
 
 def build(force=False):
     srcs = [os.path.join(ROOT, "alphago.jl_b200", "csrc", f) for f in
-            ("engine.cu", "ops.cuh", "tree.cuh", "go_rules.cuh", "rng.cuh", "simt.h", "devrt.h")]
+            ("engine.cu", "ops.cuh", "tree.cuh", "go_bits.cuh", "go_rules.cuh", "rng.cuh", "simt.h", "devrt.h")]
     srcs += [os.path.join(HERE, "emu_runtime.cpp"), os.path.join(ROOT, "include", "agz.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in srcs):
         return OUT
