@@ -409,6 +409,80 @@ class MCTSPlayer:
         return self.pick_move()
 
 
+# ------------------------------------------------------------------ evaluate (neural_net.jl:103-158)
+class MatchGame:
+    """What evaluate leaves in its two players per game: the moves, `result` / `result_string` (set_result!) and whether the
+    final position scores as a Black win (what the win counter reads, neural_net.jl:150)."""
+
+    def __init__(self):
+        self.moves, self.result, self.result_string, self.black_won = [], 0, "", False
+
+
+def _bind(eng, net):
+    if isinstance(net, NeuralNet):
+        net.push(eng)
+        eng.set_evaluator(net.evaluator)
+    else:
+        eng.set_dummy_evaluator(getattr(net, "fake_priors", None), float(getattr(net, "fake_value", 0.0)))
+        eng.set_evaluator(B.EVAL_DUMMY)
+
+
+def _score_string(s):
+    return "B+%.1f" % s if s > 0 else ("W+%.1f" % abs(s) if s < 0 else "DRAW")
+
+
+def evaluate(env, black_net, white_net, num_games=400, ro=800, verbose=False, seed=0, resign_threshold=-0.9, details=None,
+             **engine_overrides):
+    """evaluate(env, black_net, white_net; num_games, ro) -> Bool: all `num_games` gating games run concurrently, one engine
+    per player (two_player_mode: tau_threshold = -1, no noise), alternating exactly like the reference's two MCTSPlayers.
+    `details`, if a list, receives one MatchGame per game."""
+    G = num_games
+    engines = []
+    try:
+        for k, net in enumerate((black_net, white_net)):
+            eng = B.Engine(env.N, lib_path=env.lib_path, n_games=G, readouts=ro, tau_threshold=-1, inject_noise=0,
+                           resign_threshold=resign_threshold, seed=seed + k, device=env.device,
+                           tower_height=getattr(net, "tower_height", 1), **engine_overrides)
+            engines.append(eng)
+            _bind(eng, net)
+            eng.match_start()
+        games = [MatchGame() for _ in range(G)]
+        alive = np.ones(G, bool)
+        black_score = np.zeros(G, np.float32)
+        num_move = 0
+        while alive.any():
+            active, inactive = (engines[1], engines[0]) if num_move % 2 == 1 else (engines[0], engines[1])
+            to_play = WHITE if num_move % 2 == 1 else BLACK
+            moves, resigned, rscore = active.match_search(alive)
+            for g in np.flatnonzero(alive & resigned):              # forced resignation (:129-133)
+                games[g].result = -to_play
+                games[g].result_string = "B+R" if -to_play == BLACK else "W+R"
+                black_score[g] = rscore[g]
+                alive[g] = False
+            mv = np.where(alive, moves, -1).astype(np.int32)
+            done, sc = active.match_play(mv)
+            inactive.match_play(mv)
+            for g in np.flatnonzero(alive):
+                games[g].moves.append(int(mv[g]))
+            for g in np.flatnonzero(alive & done):                  # is_done(active) (:140-146)
+                games[g].result = 1 if sc[g] > 0 else (-1 if sc[g] < 0 else 0)
+                games[g].result_string = _score_string(float(sc[g]))
+                black_score[g] = sc[g]
+                alive[g] = False
+            num_move += 1
+        for g in range(G):
+            games[g].black_won = bool(black_score[g] > 0)           # result(black.root.position) == BLACK (:150)
+        games_won = int(sum(gm.black_won for gm in games))
+    finally:
+        for eng in engines:
+            eng.close()
+    if details is not None:
+        details.extend(games)
+    if verbose:
+        print("Won %d / %d. Win rate: %s. " % (games_won, G, games_won / G), end="")
+    return games_won / G >= 0.55
+
+
 # free-function spellings used by the reference and its tests
 def initialize_game(player, pos=None): return player.initialize_game(pos)
 def tree_search(player, parallel_readouts=8): return player.tree_search(parallel_readouts)

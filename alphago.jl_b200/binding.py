@@ -73,6 +73,7 @@ SYMBOLS = [
     "agz_tree_read_node", "agz_tree_set_stats", "agz_tree_pending_vlosses", "agz_tree_read_record",
     "agz_tree_node_features", "agz_pos_play_move", "agz_pos_legal_moves", "agz_pos_score", "agz_pos_liberties",
     "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read",
+    "agz_match_start", "agz_match_search", "agz_match_play",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -381,6 +382,27 @@ class Engine:
         self._check(self.lib.agz_phase_times(self._h, ms, ln, C.c_int32(1 if reset else 0)))
         return list(ms), list(ln)
 
+
+    # ---- two-player matches (evaluate / play)
+    def match_start(self, game_ids=None):
+        ids = None if game_ids is None else np.ascontiguousarray(game_ids, np.int64)
+        self._check(self.lib.agz_match_start(self._h, _ptr(ids, C.c_int64)))
+
+    def match_search(self, active):
+        G = self.cfg.n_games
+        act = np.ascontiguousarray(active, np.uint8)
+        assert act.size == G
+        moves, res, sc = np.zeros(G, np.int32), np.zeros(G, np.int32), np.zeros(G, np.float32)
+        self._check(self.lib.agz_match_search(self._h, _ptr(act, C.c_uint8), _ptr(moves, C.c_int32), _ptr(res, C.c_int32), _ptr(sc, C.c_float)))
+        return moves, res.astype(bool), sc
+
+    def match_play(self, moves):
+        G = self.cfg.n_games
+        mv = np.ascontiguousarray(moves, np.int32)
+        assert mv.size == G
+        done, sc = np.zeros(G, np.int32), np.zeros(G, np.float32)
+        self._check(self.lib.agz_match_play(self._h, _ptr(mv, C.c_int32), _ptr(done, C.c_int32), _ptr(sc, C.c_float)))
+        return done.astype(bool), sc
 
     def trace_read(self, max_records=1 << 16, reset=True):
         """Kernel timeline trace (AGZ_TRACE=<records> at engine creation): array of (tag, block, grid, start_ns, end_ns, sm)."""

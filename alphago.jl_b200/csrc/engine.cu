@@ -47,6 +47,10 @@ struct agz_engine {
   uint8_t* d_hook_libs;
   float* d_hook_feats;
   long long launches;
+  int32_t *d_match_i, *d_match_j, *d_match_in;   // two-player match scratch (agz_match_*), allocated on first use
+  float* d_match_f;
+  uint8_t* d_match_active;
+  long long* d_match_ids;
   unsigned long long* d_trace;   // AGZ_TRACE=<records>: kernel timeline trace (simt.h), read back with agz_trace_read
   int trace_cap;
   bool started;
@@ -293,6 +297,10 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   e->d_feats_f32 = nullptr;
   e->d_trace = nullptr;
   e->trace_cap = 0;
+  e->d_match_i = e->d_match_j = e->d_match_in = nullptr;
+  e->d_match_f = nullptr;
+  e->d_match_active = nullptr;
+  e->d_match_ids = nullptr;
 #if AGZ_CUDA
   if (const char* et = getenv("AGZ_TRACE")) {
     e->trace_cap = atoi(et) > 0 ? atoi(et) : 0;
@@ -679,6 +687,104 @@ extern "C" int32_t agz_selfplay_run(agz_engine* e, int32_t total_games, agz_game
     if (pr.games_live == 0 && got < mine && n == 0) return fail(e, AGZ_ERR_ASSERT, "self-play stalled with %d of %d games", got, mine);
     if (++guard > 100000000LL) return fail(e, AGZ_ERR_ASSERT, "self-play did not terminate");
   }
+  return AGZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ matches
+// evaluate (neural_net.jl:103-158) / play (play.jl:25-77): every slot is one game seen by ONE player (this engine's network);
+// the host keeps a second engine for the opponent and alternates them, exactly as the reference alternates two MCTSPlayers.
+static int match_scratch(agz_engine* e) {
+  if (e->d_match_i) return AGZ_OK;
+  const size_t G = (size_t)e->c.n_games;
+  int rc = 0;
+  rc |= dalloc(e, &e->d_match_i, G);
+  rc |= dalloc(e, &e->d_match_j, G);
+  rc |= dalloc(e, &e->d_match_f, G);
+  rc |= dalloc(e, &e->d_match_in, G);
+  rc |= dalloc(e, &e->d_match_active, G);
+  rc |= dalloc(e, &e->d_match_ids, G);
+  if (rc) return fail(e, AGZ_ERR_CUDA, "match scratch allocation failed");
+  return AGZ_OK;
+}
+
+template <class F>
+static int launch_match(agz_engine* e, F fill) {
+  bind_evaluator(e);
+  DISPATCH_KA(e, {
+    MatchOp<KA> op{e->c, e->v, 0, nullptr, nullptr, nullptr, e->d_match_i, e->d_match_j, e->d_match_f};
+    fill(op);
+    DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+  });
+  e->launches += 1;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_match_start(agz_engine* e, const int64_t* game_ids) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  int rc = match_scratch(e);
+  if (rc) return rc;
+  DCHECK(e, devrt::dmemset(e->v.ctr, 0, sizeof(unsigned long long) * CTR_COUNT, e->stream));
+  if (game_ids) DCHECK(e, devrt::h2d(e->d_match_ids, game_ids, sizeof(long long) * e->c.n_games, e->stream));
+  const long long* ids = game_ids ? e->d_match_ids : nullptr;
+  rc = launch_match(e, [&](auto& op) { op.kind = MK_BEGIN; op.game_ids = ids; });
+  if (rc) return rc;
+  e->started = true;
+  DCHECK(e, devrt::sync(e->stream));
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_match_search(agz_engine* e, const uint8_t* active, int32_t* moves, int32_t* resigned, float* scores) {
+  if (!e || !active || !moves || !resigned) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (!e->d_match_i) return fail(e, AGZ_ERR_ARG, "agz_match_start has not been called");
+  const size_t G = (size_t)e->c.n_games;
+  DCHECK(e, devrt::h2d(e->d_match_active, active, G, e->stream));
+  int rc = launch_match(e, [&](auto& op) { op.kind = MK_ARM; op.active = e->d_match_active; });
+  if (rc) return rc;
+  // every tree_search! adds at least one visit to a searching root, so the loop ends; poll the busy counter after the
+  // minimum number of rounds a search can take and then every few rounds
+  const int first = (e->c.readouts + 2 * e->c.parallel - 1) / (2 * e->c.parallel);
+  long long guard = 0;
+  for (int chunk = first > 0 ? first : 1;; chunk = 4) {
+    unsigned long long busy = 0;
+    DCHECK(e, devrt::d2h(&busy, e->v.ctr + CTR_MATCH_BUSY, sizeof(busy), e->stream));
+    if (busy == 0) break;
+    for (int r = 0; r < chunk; ++r) {
+      rc = one_round(e);
+      if (rc) return rc;
+    }
+    if ((guard += chunk) > 100000000LL) return fail(e, AGZ_ERR_ASSERT, "match search did not terminate");
+  }
+  rc = launch_match(e, [&](auto& op) { op.kind = MK_PICK; op.active = e->d_match_active; });
+  if (rc) return rc;
+  DCHECK(e, devrt::d2h(moves, e->d_match_i, sizeof(int32_t) * G, e->stream));
+  DCHECK(e, devrt::d2h(resigned, e->d_match_j, sizeof(int32_t) * G, e->stream));
+  if (scores) DCHECK(e, devrt::d2h(scores, e->d_match_f, sizeof(float) * G, e->stream));
+  std::vector<GameState> gs(G);
+  DCHECK(e, devrt::d2h(gs.data(), e->v.gs, G * sizeof(GameState), e->stream));
+  for (size_t g = 0; g < G; ++g)
+    if (gs[g].err) return fail(e, gs[g].err == E_CAPACITY ? AGZ_ERR_CAPACITY : AGZ_ERR_ASSERT, "match slot %d stopped with device status %d", (int)g, gs[g].err);
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_match_play(agz_engine* e, const int32_t* moves, int32_t* done, float* scores) {
+  if (!e || !moves) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (!e->d_match_i) return fail(e, AGZ_ERR_ARG, "agz_match_start has not been called");
+  const size_t G = (size_t)e->c.n_games;
+  for (size_t g = 0; g < G; ++g)
+    if (moves[g] >= e->c.A) return fail(e, AGZ_ERR_ARG, "move out of range");
+  DCHECK(e, devrt::h2d(e->d_match_in, moves, sizeof(int32_t) * G, e->stream));
+  int rc = launch_match(e, [&](auto& op) { op.kind = MK_PLAY; op.moves_in = e->d_match_in; });
+  if (rc) return rc;
+  std::vector<int32_t> dn(G);
+  DCHECK(e, devrt::d2h(dn.data(), e->d_match_i, sizeof(int32_t) * G, e->stream));
+  if (done) memcpy(done, dn.data(), sizeof(int32_t) * G);
+  if (scores) DCHECK(e, devrt::d2h(scores, e->d_match_f, sizeof(float) * G, e->stream));
+  std::vector<GameState> gs(G);
+  DCHECK(e, devrt::d2h(gs.data(), e->v.gs, G * sizeof(GameState), e->stream));
+  for (size_t g = 0; g < G; ++g)
+    if (gs[g].err) return fail(e, gs[g].err == E_CAPACITY ? AGZ_ERR_CAPACITY : AGZ_ERR_ASSERT, "match slot %d stopped with device status %d", (int)g, gs[g].err);
+  for (size_t g = 0; g < G; ++g)
+    if (dn[g] < 0) return fail(e, AGZ_ERR_ILLEGAL_MOVE, "illegal move in slot %d", (int)g);
   return AGZ_OK;
 }
 

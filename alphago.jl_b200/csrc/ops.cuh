@@ -38,7 +38,7 @@ struct SelectOp {
       w.search_select(parallel, false);
     } else if (w.st.phase == PH_SEED) {
       w.search_select(1, true);
-    } else if (w.st.phase == PH_SEARCH) {
+    } else if (w.st.phase == PH_SEARCH || w.st.phase == PH_MATCH_SEARCH) {
       w.search_select(c.parallel, false);
     } else {
       w.st.nleaf = 0;
@@ -61,6 +61,90 @@ struct IncorporateOp {
     w.search_incorporate();
     if (only_slot < 0) w.after_round();
     w.st.seed_round = 0;
+    w.store_state();
+  }
+};
+
+// Two-player matches (evaluate, neural_net.jl:103-158; play, play.jl:25-77) over all slots at once: one slot = one game of
+// one player's tree; the host alternates the two players' engines.
+enum { MK_BEGIN = 1, MK_ARM, MK_PICK, MK_PLAY };
+
+template <int KA>
+struct MatchOp {
+  Cfg c;
+  View v;
+  int kind;
+  const long long* game_ids;    // BEGIN: game id of every slot (RNG key) or nullptr = slot index
+  const unsigned char* active;  // ARM / PICK: slots whose player is to move
+  const int* moves_in;          // PLAY: flat move per slot, < 0 = leave the slot alone
+  int* out_i;                   // PICK: move (or -1); PLAY: is_done
+  int* out_j;                   // PICK: should_resign
+  float* out_f;                 // PICK (resigned slots) / PLAY (finished slots): score(root position)
+  AGZ_DEV void operator()(int g, char* smem) const {
+    Warp<KA> w(c, v, g, smem);
+    const int lane = simt::lane();
+    switch (kind) {
+      case MK_BEGIN: {  // initialize_game!(player) (mcts_play.jl:110-118)
+        const long long id = game_ids ? game_ids[g] : (long long)g;
+        w.st.game_id = id;
+        w.st.game_id_lo = (uint32_t)id;
+        w.st.resign_thr = c.resign_threshold;
+        w.st.hist_len = 0;
+        w.st.target_N = 0.f;
+        w.pos.b = 0;
+        w.pos.w = 0;
+        w.init_root_from_scratch(0, -1, 1, 0);
+        w.st.phase = PH_MATCH_WAIT;
+        break;
+      }
+      case MK_ARM:  // current_readouts = N(root); search until N(root) >= current_readouts + readouts
+        if (active[g] && w.st.phase == PH_MATCH_WAIT && !w.st.err) {
+          w.st.target_N = simt::fadd(w.st.root_N, (float)c.readouts);
+          w.st.phase = PH_MATCH_SEARCH;
+          if (lane == 0) simt::atomic_add(&v.ctr[CTR_MATCH_BUSY], 1ULL);
+        }
+        break;
+      case MK_PICK: {  // should_resign (mcts_play.jl:124), else pick_move (mcts_play.jl:52-71)
+        int mv = -1, resign = 0;
+        float sc = 0.f;
+        if (active[g] && w.st.phase == PH_MATCH_WAIT && !w.st.err) {
+          const NodeMeta rm = w.load_meta(w.st.root);
+          const float q = simt::fdiv(w.st.root_W, simt::fadd(1.0f, w.st.root_N));
+          const float qp = simt::fmul(q, (float)rm.to_play);
+          if ((double)qp < w.st.resign_thr) {
+            resign = 1;
+            const uint32_t* lb = w.bits_of(w.st.root);
+            sc = bits_score(w.B, bits_load(w.B, lb, lb + c.KB), c.komi);
+          } else {
+            mv = w.pick_move();
+          }
+        }
+        if (lane == 0) { out_i[g] = mv; out_j[g] = resign; out_f[g] = sc; }
+        break;
+      }
+      case MK_PLAY: {  // play_move!(player, move) (mcts_play.jl:26-50), then is_done (mcts.jl:230-231) / score
+        int done = 0;
+        float sc = 0.f;
+        const int mv = moves_in[g];
+        if (mv >= 0 && w.st.phase == PH_MATCH_WAIT && !w.st.err) {
+          const int prc = w.play_move(mv, true);
+          if (prc == E_ILLEGAL) {  // IllegalMove is caught by play_move!(player, c): the tree is unchanged (mcts_play.jl:41-47)
+            done = -1;
+            w.st.err = 0;
+          } else if (prc == E_OK) {
+            const NodeMeta nm = w.load_meta(w.st.root);
+            if (w.terminal(nm)) {
+              done = 1;
+              const uint32_t* lb = w.bits_of(w.st.root);
+              sc = bits_score(w.B, bits_load(w.B, lb, lb + c.KB), c.komi);
+            }
+          }
+        }
+        if (lane == 0) { out_i[g] = done; out_f[g] = sc; }
+        break;
+      }
+      default: break;
+    }
     w.store_state();
   }
 };
@@ -96,6 +180,7 @@ namespace devrt {
 template <class Op> struct MinBlocks;
 template <> struct MinBlocks<agz::SelectOp<3, 1>> { static const int v = 8; };
 template <> struct MinBlocks<agz::SelectOp<6, 1>> { static const int v = 6; };
+template <> struct MinBlocks<agz::IncorporateOp<3>> { static const int v = 8; };
 template <class Op> struct TraceTag;
 template <int KA, int OCC> struct TraceTag<agz::SelectOp<KA, OCC>> { static const int v = 1; };
 template <int KA> struct TraceTag<agz::IncorporateOp<KA>> { static const int v = 2; };

@@ -22,7 +22,9 @@
 
 namespace agz {
 
-enum { PH_IDLE = 0, PH_SEED = 1, PH_SEARCH = 2, PH_WAIT_RING = 3, PH_MANUAL = 4 };
+enum { PH_IDLE = 0, PH_SEED = 1, PH_SEARCH = 2, PH_WAIT_RING = 3, PH_MANUAL = 4,
+       PH_MATCH_WAIT = 5,      // two-player match slot (evaluate / play): waiting for the host to arm a search or play a move
+       PH_MATCH_SEARCH = 6 };  // ... searching until N(root) >= target_N
 enum { F_EXPANDED = 1, F_DONE = 2, F_LASTPASS = 4 };
 enum { E_OK = 0, E_ILLEGAL = 1, E_ASSERT = 2, E_CAPACITY = 6 };
 enum { OP_VLOSS_ADD = 0, OP_VLOSS_REVERT = 1, OP_BACKUP = 2, OP_REVERT_VISITS = 3 };
@@ -73,7 +75,9 @@ struct Cfg {
   long long total_games;
 };
 
-enum { CTR_MOVES = 0, CTR_FINISHED, CTR_STARTED, CTR_POSITIONS, CTR_READOUTS, CTR_PATHNODES, CTR_RING_TAIL, CTR_RING_HEAD, CTR_COUNT };
+enum { CTR_MOVES = 0, CTR_FINISHED, CTR_STARTED, CTR_POSITIONS, CTR_READOUTS, CTR_PATHNODES, CTR_RING_TAIL, CTR_RING_HEAD,
+       CTR_MATCH_BUSY,  // match slots still searching
+       CTR_COUNT };
 
 struct RingHeader {  // mirrors agz_game_header
   int64_t game_id;
@@ -872,13 +876,24 @@ struct Warp {
 
   // ---- selfplay.jl:22-43, evaluated once per round after the leaves have been incorporated -----------
   AGZ_DEV void after_round() {
-    if (st.err) { st.phase = PH_IDLE; return; }
+    if (st.err) {
+      if (st.phase == PH_MATCH_SEARCH && lane == 0) simt::atomic_add(&v.ctr[CTR_MATCH_BUSY], ~0ULL);
+      st.phase = PH_IDLE;
+      return;
+    }
     if (st.phase == PH_WAIT_RING) { finish_or_wait(); return; }
     if (st.phase == PH_SEED) {
       if (st.seed_round) {
         st.phase = PH_SEARCH;
         if (c.inject_noise) inject_noise();
         st.target_N = simt::fadd(st.root_N, (float)c.readouts);
+      }
+      return;
+    }
+    if (st.phase == PH_MATCH_SEARCH) {  // evaluate / play: `while N(root) < current + readouts` (neural_net.jl:124-126); the host picks
+      if (!(st.root_N < st.target_N)) {
+        st.phase = PH_MATCH_WAIT;
+        if (lane == 0) simt::atomic_add(&v.ctr[CTR_MATCH_BUSY], ~0ULL);
       }
       return;
     }

@@ -25,6 +25,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 BOARD, GAMES, READOUTS, TOWER, ROUNDS_PER_STEP = 9, 1024, 400, 6, 50
 METRIC = "self-play moves/sec (9x9, 400 readouts)"
+# DRAM bytes per tower-conv launch (8192 positions) from the committed ncu --set full capture of this workload
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 0.5 * ((341.04 + 292.74) + (680.74 + 306.91)) * 1e6
 
 
 def peaks():
@@ -243,14 +245,16 @@ def main():
             "ms_per_step": 1e3 * tmx[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
             "config": {"workload": "C2: 9x9 Go, %d concurrent self-play games per GPU, 400 readouts/move (50 rounds x 8 leaves per step), tower_height 6, 256 filters, random-init weights seed 0, empty-board starts, finished games refilled" % args.games,
-                       "step": "50 tree_search rounds over all games (two half batches pipelined on two streams) + replay all-gather of finished games",
+                       "step": "50 tree_search rounds over all games (select -> leaf features -> stem + 12 tower convs -> heads -> incorporate/move logic, one stream) + replay all-gather of finished games",
                        "l2": "inputs larger than L2: tree arenas %.1f GB and %.0f MB per activation buffer vs 126 MB L2" % (args.games * (eng.cfg.nodes_per_game or 10 * (READOUTS + 20)) * 1.5e-6, rows * 81 * 512 / 1e6)},
             "e2e": {"value": tot[1] / tmx[1], "unit": "moves/s", "h2d_bytes_per_step": param_bytes, "d2h_bytes_per_step": int(d2h / args.steps)},
             "gpu_launches": int(tot[2]),
             "clocks": sampler.summary(),
-            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc5_kernel (tower 3x3 conv 256->256, fp16 tcgen05 cta_group::2 + TMA im2col)",
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc5_kernel / conv3x3_tc6_kernel (tower 3x3 conv 256->256, fp16 tcgen05 cta_group::2 + TMA im2col; tc6 = second conv of a block, shortcut tile by TMA)",
                          "measured_in": "CUDA events around every kernel, sequential schedule, %d steps of the same workload right after the timed region" % min(2, args.steps), "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
-                         "frac": achieved / tf_sus, "traffic": None, "peak_source": src + " bf16 sustained",
+                         "frac": achieved / tf_sus, "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if args.games == GAMES else None,
+                         "traffic_detail": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full on this workload (profiles/r01_conv3x3_tc_ncu_full.md): tc5 341.0 + 292.7 MB, tc6 680.7 + 306.9 MB, mean of the two; algorithmic 680 / 1020 MB",
+                         "peak_source": src + " bf16 sustained",
                          "flops_per_launch": conv_flops_pos * rows, "ms_per_launch": conv_ms},
             "kernel_ms_per_round": {n: kms[i] / max(1, kln[0]) for i, n in enumerate(agz.binding.KERNEL_NAMES)},
             "harvested_games_e2e": len(glen), "mean_game_length_e2e": (sum(glen) / len(glen)) if glen else None,

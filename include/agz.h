@@ -184,6 +184,19 @@ int32_t agz_replay_sample(agz_engine* e, int32_t batch, uint64_t seed, int8_t* b
 int32_t agz_nccl_unique_id(uint8_t id_out[128]);
 int32_t agz_nccl_init(agz_engine* e, const uint8_t id[128]);
 
+/* ---- two-player matches: evaluate (src/neural_net.jl:103-158) and play (src/play.jl:25-77) over all slots at once --------- */
+/* One engine = one player (its network, two_player_mode: create it with tau_threshold = -1 and inject_noise = 0); slot s is
+ * that player's tree of game s.  The host keeps one engine per player and alternates them like the reference alternates its
+ * two MCTSPlayers.  agz_match_start = initialize_game! on every slot (game_ids key the RNG; NULL = slot index). */
+int32_t agz_match_start(agz_engine* e, const int64_t* game_ids);
+/* For every slot with active[s] != 0: `while N(root) < current + readouts: tree_search!` (neural_net.jl:121-126), then
+ * should_resign -> resigned[s] (scores[s] = score of the root position, what evaluate reads at :150), else pick_move ->
+ * moves[s].  Inactive slots get moves[s] = -1.  scores may be NULL. */
+int32_t agz_match_search(agz_engine* e, const uint8_t* active, int32_t* moves, int32_t* resigned, float* scores);
+/* play_move!(player, move) (mcts_play.jl:26-50) on every slot with moves[s] >= 0; done[s] = is_done(root) (mcts.jl:230-231)
+ * with scores[s] = score(root position).  An illegal move leaves its tree unchanged and returns AGZ_ERR_ILLEGAL_MOVE. */
+int32_t agz_match_play(agz_engine* e, const int32_t* moves, int32_t* done, float* scores);
+
 /* ---- single-tree hooks: the reference's unit-test surface, one tree per slot ------------------ */
 int32_t agz_tree_init(agz_engine* e, int32_t slot, const agz_position* pos, int64_t game_id); /* initialize_game! (mcts_play.jl:110-118) */
 int32_t agz_tree_select_leaf(agz_engine* e, int32_t slot, int32_t from_node, int32_t* leaf);  /* select_leaf (mcts.jl:108-138) */
