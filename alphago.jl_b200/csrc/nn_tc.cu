@@ -36,6 +36,8 @@ static const size_t CONV_SMEM = (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(
 
 struct TCState {
   unsigned long long* trace;  // kernel timeline trace buffer or nullptr (nn_tc_set_trace)
+  int fuse_heads;             // AGZ_FUSE_HEADS (default 1): head 1x1 convs in the last tower conv's epilogue, trunk not stored
+  float4* head_pre;           // [rows_alloc] (value plane, policy plane 0, policy plane 1, 0) written by that epilogue
   int pdl;                    // AGZ_CONV_PDL (default 1): tower convolutions use programmatic dependent launch
   int max_pairs;              // AGZ_CONV_PAIRS
   int version;                // AGZ_CONV_KERNEL: 1 per-tap, 2 slab, 3 CTA pair, 4 CTA pair + slab (zero-bordered layout); 5 CTA pair + im2col (dense, default)
@@ -139,6 +141,12 @@ struct ConvArgs {
   int N, NP1, PP;
   int relu;
   unsigned long long* trace;   // kernel timeline trace (simt.h) or nullptr
+  // last convolution of the tower (conv3x3_tc6_kernel only): the 1x1 convolutions + BatchNorm + relu of the value and policy
+  // heads (neural_net.jl:23-24,28-29) are evaluated in the epilogue from the fp32 trunk values and the trunk is not stored
+  const float* head_vw;        // [256] value 1x1 conv weights, or nullptr
+  const float* head_pw;        // [2][256] policy 1x1 conv weights
+  const float* head_aff;       // [6] folded conv bias + BatchNorm: v scale, v shift, p0 scale, p0 shift, p1 scale, p1 shift
+  float4* head_out;            // [rows] (value plane, policy plane 0, policy plane 1, 0)
 };
 
 __global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -1059,8 +1067,9 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // epilogue waiting on 64-byte global loads).  4 operand stages (128 KB) + 64 KB residual tile.
 static const int V6_STAGES = 4;
 static const int V6_RES_BYTES = BM * 256 * 2;
-static const size_t CONV6_SMEM = (size_t)V6_STAGES * V3_STAGE_BYTES + V6_RES_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
+static const size_t CONV6_SMEM = (size_t)V6_STAGES * V3_STAGE_BYTES + V6_RES_BYTES + 2 * 256 * sizeof(float) + 256 * sizeof(float4) + 256 + 1024;
 
+template <bool HEADS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmR,
                    const ConvArgs a, const int res_row0) {
@@ -1072,7 +1081,8 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint8_t* resbuf = smem + (size_t)V6_STAGES * V3_STAGE_BYTES;      // 4 boxes of 128 rows x 64 channels, SWIZZLE_128B
   float* s_scale = reinterpret_cast<float*>(resbuf + V6_RES_BYTES);
   float* s_shift = s_scale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
+  float4* s_hw = reinterpret_cast<float4*>(s_shift + 256);   // per channel: (value w, policy-0 w, policy-1 w, 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_hw + 256);
   uint64_t* full = bars;
   uint64_t* empty = bars + V6_STAGES;
   uint64_t* tfull = bars + 2 * V6_STAGES;
@@ -1087,6 +1097,8 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int n_ptiles = (a.n_tiles + 1) >> 1;
   s_scale[threadIdx.x] = a.scale[threadIdx.x];
   s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  constexpr bool heads = HEADS;
+  if (heads) s_hw[threadIdx.x] = make_float4(a.head_vw[threadIdx.x], a.head_pw[threadIdx.x], a.head_pw[256 + threadIdx.x], 0.f);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -1181,6 +1193,7 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait_guard(&tfull[as], aphase);
       mbar_wait_guard(rfull, (uint32_t)(titer & 1));
       tc_fence_after();
+      float h0 = 0.f, h1 = 0.f, h2 = 0.f;   // this row's value / policy 1x1 convolutions (fixed channel order: batch invariant)
 #pragma unroll 2
       for (int cc = 0; cc < 8; ++cc) {
         uint32_t v[32];
@@ -1201,12 +1214,24 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]) + rr.x;
             float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]) + rr.y;
             if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-            __half2 h = __floats2half2_rn(y0, y1);
-            ow[j] = *reinterpret_cast<uint32_t*>(&h);
+            if (heads) {
+              const float4 w0 = s_hw[c0], w1 = s_hw[c0 + 1];
+              h0 = fmaf(y0, w0.x, h0); h1 = fmaf(y0, w0.y, h1); h2 = fmaf(y0, w0.z, h2);
+              h0 = fmaf(y1, w1.x, h0); h1 = fmaf(y1, w1.y, h1); h2 = fmaf(y1, w1.z, h2);
+            } else {
+              __half2 h = __floats2half2_rn(y0, y1);
+              ow[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
           }
+          if (!heads) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+          }
         }
+      }
+      if (heads && valid) {
+        const float* af = a.head_aff;
+        a.head_out[row] = make_float4(fmaxf(fmaf(h0, af[0], af[1]), 0.f), fmaxf(fmaf(h1, af[2], af[3]), 0.f), fmaxf(fmaf(h2, af[4], af[5]), 0.f), 0.f);
       }
       tc_fence_before();
       __syncwarp();
@@ -1239,7 +1264,7 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
                                                        const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                        const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
                                                        float* __restrict__ v, int B, int N, int PP, int rowbase, int pitch,
-                                                       unsigned long long* trace) {
+                                                       unsigned long long* trace, const float4* __restrict__ pre) {
   const unsigned long long trace_t0 = trace ? simt::gtimer() : 0ULL;
   extern __shared__ float sm[];
   const int N2 = N * N, A = N2 + 1;
@@ -1249,6 +1274,16 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
   float* lg = hid + HPB * 256;          // [HPB][A]
   const int b0 = blockIdx.x * HPB, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = min(HPB, B - b0);
+  if (pre != nullptr) {
+    // the last tower convolution already evaluated the 1x1 convolutions + BatchNorm + relu in its epilogue (dense layout)
+    for (int it = tid; it < nb * N2; it += 256) {
+      const int pb = it / N2, p = it - pb * N2;
+      const float4 h = pre[(size_t)(b0 + pb) * N2 + p];
+      vf[pb * N2 + p] = h.x;
+      pf[pb * 2 * N2 + p] = h.y;
+      pf[pb * 2 * N2 + N2 + p] = h.z;
+    }
+  } else {
   // 1x1 convolutions + BatchNorm + relu: a warp per (position, point), 8 channels per lane (one 16-byte load)
   float wv[8], wp0[8], wp1[8];
 #pragma unroll
@@ -1281,6 +1316,7 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
       pf[pb * 2 * N2 + p] = fmaxf(a1 * aff[2] + aff[3], 0.f);
       pf[pb * 2 * N2 + N2 + p] = fmaxf(a2 * aff[4] + aff[5], 0.f);
     }
+  }
   }
   __syncthreads();
   {  // Dense(N2 -> 256, relu): thread o, weights streamed once for all HPB positions
@@ -1526,6 +1562,7 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   t->T = n->s.tower;
   t->max_batch = n->max_batch;
   t->attr_set = false;
+  t->head_pre = nullptr;
   t->trace = nullptr;
   t->stage = nullptr;
   t->stage_cap = 0;
@@ -1547,6 +1584,7 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   cudaGetDeviceProperties(&prop, dev);
   t->num_sms = prop.multiProcessorCount;
   bool ok = cudaMalloc((void**)&t->in64, (size_t)t->rows_alloc * CIN0 * 2) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&t->head_pre, (size_t)t->rows_alloc * sizeof(float4)) == cudaSuccess;
   for (int i = 0; i < 3 && ok; ++i) ok = cudaMalloc((void**)&t->act[i], (size_t)t->rows_alloc * 256 * 2) == cudaSuccess;
   const int nconv = 1 + 2 * t->T;
   t->w.assign(nconv, nullptr);
@@ -1589,6 +1627,10 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
     t->grp_rows = 0;
   }
   {
+    const char* ef = getenv("AGZ_FUSE_HEADS");
+    t->fuse_heads = ef ? atoi(ef) : 1;
+  }
+  {
     const char* ed = getenv("AGZ_CONV_PDL");
     t->pdl = ed ? atoi(ed) : 1;
   }
@@ -1609,6 +1651,7 @@ void nn_tc_destroy(NNet* n) {
   TCState* t = (TCState*)n->tc;
   if (!t) return;
   cudaFree(t->in64);
+  cudaFree(t->head_pre);
   cudaFree(t->stage);
   for (int i = 0; i < 3; ++i) cudaFree(t->act[i]);
   for (auto p : t->w) cudaFree(p);
@@ -1695,6 +1738,7 @@ static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
   a.relu = 1;
   a.trace = t->trace;
+  a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
   conv3x3_tc3_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
@@ -1702,7 +1746,8 @@ static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
 }
 
 static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
-                        __half* out, int B, int kchunks, cudaStream_t s, const CUtensorMap* res_map = nullptr, int res_row0 = 0, bool pdl = false) {
+                        __half* out, int B, int kchunks, cudaStream_t s, const CUtensorMap* res_map = nullptr, int res_row0 = 0, bool pdl = false,
+                        const NNet* heads_of = nullptr /* fuse this network's head 1x1 convs into the epilogue */) {
   ConvArgs a;
   a.scale = scale; a.shift = shift; a.res = res; a.out = out;
   a.rows_valid = (long long)B * t->PP;
@@ -1711,6 +1756,7 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
   a.relu = 1;
   a.trace = t->trace;
+  a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   // Same number of waves on as few CTA pairs as possible: 9x9 with 8192 (4096) positions is 2592 (1296) pair tiles =
   // 36 (18) waves on 72 pairs exactly, where 74 pairs would idle through a 37th (19th) wave's worth of tail.  The SMs
@@ -1718,6 +1764,10 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   const int max_pairs = t->max_pairs > 0 && t->max_pairs < t->num_sms / 2 ? t->max_pairs : t->num_sms / 2;
   const int waves = (n_ptiles + max_pairs - 1) / max_pairs;
   int pairs = (n_ptiles + waves - 1) / waves;
+  if (heads_of && res_map && t->res_tma) {
+    a.head_vw = heads_of->f_vw; a.head_pw = heads_of->f_pw; a.head_aff = heads_of->f_head_aff_d;
+    a.head_out = t->head_pre + res_row0;
+  }
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = dim3(2 * pairs);
@@ -1731,7 +1781,8 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   cudaError_t rc;
   if (res_map && t->res_tma) {
     lc.dynamicSmemBytes = CONV6_SMEM;
-    rc = cudaLaunchKernelEx(&lc, conv3x3_tc6_kernel, tmA, tmW, *res_map, a, res_row0);
+    if (a.head_vw) rc = cudaLaunchKernelEx(&lc, conv3x3_tc6_kernel<true>, tmA, tmW, *res_map, a, res_row0);
+    else rc = cudaLaunchKernelEx(&lc, conv3x3_tc6_kernel<false>, tmA, tmW, *res_map, a, res_row0);
   } else {
     lc.dynamicSmemBytes = CONV3_SMEM;
     rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel, tmA, tmW, a);
@@ -1750,6 +1801,7 @@ static int launch_conv4(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
   a.relu = 1;
   a.trace = t->trace;
+  a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
   g.H8 = t->H8; g.slab_rows = 128 + 2 * t->H8; g.slab_bytes = g.slab_rows * 128;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
@@ -1767,6 +1819,7 @@ static int launch_conv(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tm
   a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
   a.relu = 1;
   a.trace = t->trace;
+  a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
   int grid = a.n_tiles < t->num_sms ? a.n_tiles : t->num_sms;
   conv3x3_tc_kernel<<<grid, 256, CONV_SMEM, s>>>(tmA, tmW, a);
   return (int)cudaGetLastError();
@@ -1785,24 +1838,27 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem(n->N2, n->A));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
     t->attr_set = true;
   }
   if (ev) cudaEventRecord(ev[0], s);
   const bool v2 = t->version == 2;
+  const bool fuse = t->fuse_heads && t->version == 5 && t->res_tma && t->T >= 1;
   auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
     const bool pdl = in_buf >= 0;   // tower convolutions directly follow another convolution on the same stream
+    const NNet* hf = (fuse && layer == 2 * t->T) ? n : nullptr;   // the last convolution feeds the heads directly
     const int kch = in_buf < 0 ? CIN0 / BK : 4;
     const __half* res = res_buf >= 0 ? t->act[res_buf] + roff * 256 : nullptr;
     const CUtensorMap* rmap = res_buf >= 0 ? &t->tm_act[res_buf] : nullptr;   // plain 2-D map (128 rows x 64 ch boxes) over the shortcut buffer
     if (t->version == 5 && group >= 0)
       return launch_conv5(t, in_buf < 0 ? t->tm5g_in64[group] : t->tm5g_act[group][in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res,
-                          t->act[out_buf] + roff * 256, B, kch, s, rmap, (int)roff, pdl);
+                          t->act[out_buf] + roff * 256, B, kch, s, rmap, (int)roff, pdl, hf);
     if (t->version == 5)
       return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s,
-                          rmap, 0, pdl);
+                          rmap, 0, pdl, hf);
     if (t->version == 4) return launch_conv4(t, in_buf < 0 ? t->tm4_in64 : t->tm4_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (t->version == 3) return launch_conv3(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
     if (v2) return launch_conv2(t, in_buf < 0 ? t->tm2_in64 : t->tm2_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
@@ -1825,7 +1881,7 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   }
   const size_t hsm = heads_smem(n->N2, n->A);
   heads_tc_kernel<<<(B + HPB - 1) / HPB, 256, hsm, s>>>(t->act[h] + roff * 256, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW,
-                                                        n->f_Pb, pi, v, B, t->N, t->PP, t->rowbase, t->pitch, t->trace);
+                                                        n->f_Pb, pi, v, B, t->N, t->PP, t->rowbase, t->pitch, t->trace, fuse ? t->head_pre + roff : nullptr);
   if (ev) cudaEventRecord(ev[3], s);
   cudaError_t e2 = cudaGetLastError();
   if (e2 != cudaSuccess) { snprintf(err, errlen, "heads launch: %s", cudaGetErrorString(e2)); return 1; }
