@@ -74,6 +74,7 @@ SYMBOLS = [
     "agz_tree_node_features", "agz_pos_play_move", "agz_pos_legal_moves", "agz_pos_score", "agz_pos_liberties",
     "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read",
     "agz_match_start", "agz_match_search", "agz_match_play",
+    "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -168,6 +169,35 @@ class Engine:
         mu, sigma = _f32(mu), _f32(sigma)
         self._check(self.lib.agz_net_set_bn_stats(self._h, C.c_int32(chain), _ptr(mu, C.c_float), _ptr(sigma, C.c_float),
                                                   C.c_size_t(mu.size), C.c_int32(mode)))
+
+    def train_step(self, boards_hist, to_play, pis, zs, lr=0.02, momentum=0.9):
+        bh = np.ascontiguousarray(boards_hist, dtype=np.int8)
+        tp = np.ascontiguousarray(to_play, dtype=np.int8)
+        pi = _f32(pis)
+        z = np.ascontiguousarray(zs, dtype=np.int8)
+        B = tp.shape[0]
+        assert bh.shape == (B, 8, self.N2) and pi.shape == (B, self.A) and z.shape == (B,)
+        loss = C.c_float()
+        self._check(self.lib.agz_train_step(self._h, _ptr(bh, C.c_int8), _ptr(tp, C.c_int8), _ptr(pi, C.c_float), _ptr(z, C.c_int8),
+                                            C.c_int32(B), C.c_float(lr), C.c_float(momentum), C.byref(loss)))
+        return loss.value
+
+    def train_read_grads(self, chain):
+        g = np.zeros(self.net_param_count(chain), np.float32)
+        self._check(self.lib.agz_train_read_grads(self._h, C.c_int32(chain), _ptr(g, C.c_float), C.c_size_t(g.size)))
+        return g
+
+    def net_get_params(self, chain):
+        p = np.zeros(self.net_param_count(chain), np.float32)
+        self._check(self.lib.agz_net_get_params(self._h, C.c_int32(chain), _ptr(p, C.c_float), C.c_size_t(p.size)))
+        return p
+
+    def net_get_bn_stats(self, chain):
+        n = self.net_bn_count(chain)
+        mu, sg = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        mode = C.c_int32()
+        self._check(self.lib.agz_net_get_bn_stats(self._h, C.c_int32(chain), _ptr(mu, C.c_float), _ptr(sg, C.c_float), C.c_size_t(n), C.byref(mode)))
+        return mu, sg, mode.value
 
     def net_forward(self, evaluator, boards_hist, to_play):
         bh = np.ascontiguousarray(boards_hist, dtype=np.int8)

@@ -17,7 +17,9 @@
 #include "ops.cuh"
 #if AGZ_CUDA
 #include "nn.h"
+#include "nn_state.h"
 #include "replay.h"
+#include "train.h"
 #endif
 
 using namespace agz;
@@ -51,6 +53,7 @@ struct agz_engine {
   float* d_match_f;
   uint8_t* d_match_active;
   long long* d_match_ids;
+  bool train_loaded;
   unsigned long long* d_trace;   // AGZ_TRACE=<records>: kernel timeline trace (simt.h), read back with agz_trace_read
   int trace_cap;
   bool started;
@@ -60,6 +63,7 @@ struct agz_engine {
   long long phase_launches[AGZ_NKERNELS];
 #if AGZ_CUDA
   NNet* nn;
+  TrainState* train;         // fp32 master parameters + momentum on the device, created by the first agz_train_step
   cudaEvent_t ev[8];   // 0 select | 1 features | 2 stem | 3 tower | 4 heads | 5 incorporate | 6 end
   cudaEvent_t ev_step[2];
   cudaStream_t gstream[2];   // half-batch pipelining: group g's heads -> incorporate -> select -> features chain (low priority)
@@ -147,6 +151,7 @@ extern "C" void agz_engine_destroy(agz_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->stream);
   if (e->replay) replay_destroy(e->replay);
+  if (e->train) train_destroy(e->train);
   if (e->nn) nn_destroy(e->nn);
   for (int i = 0; i < 8; ++i) cudaEventDestroy(e->ev[i]);
   for (int i = 0; i < 2; ++i) cudaEventDestroy(e->ev_step[i]);
@@ -198,6 +203,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   memset(e->phase_launches, 0, sizeof(e->phase_launches));
 #if AGZ_CUDA
   e->nn = nullptr;
+  e->train = nullptr;
   e->replay = nullptr;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
@@ -297,6 +303,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   e->d_feats_f32 = nullptr;
   e->d_trace = nullptr;
   e->trace_cap = 0;
+  e->train_loaded = false;
   e->d_match_i = e->d_match_j = e->d_match_in = nullptr;
   e->d_match_f = nullptr;
   e->d_match_active = nullptr;
@@ -1165,7 +1172,67 @@ extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t chain, const float*
   if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
   if (n != nn_param_count(e->nn, chain)) return fail(e, AGZ_ERR_ARG, "chain %d expects %zu parameters, got %zu", chain, nn_param_count(e->nn, chain), n);
   cudaSetDevice(e->cfg.device);
+  e->train_loaded = false;   // the device master copy of the training path is stale now
   return nn_set_params(e->nn, chain, flat, n) ? fail(e, AGZ_ERR_ARG, "nn_set_params failed") : AGZ_OK;
+}
+
+// ---- training step: _train / losses (neural_net.jl:75-101), Momentum (train.jl:54)
+extern "C" int32_t agz_train_step(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, const float* pis, const int8_t* zs, int32_t B,
+                                  float lr, float momentum, float* loss_out) {
+  if (!e || !boards_hist || !to_play || !pis || !zs) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (B < 1 || B > 4096) return fail(e, AGZ_ERR_ARG, "batch must be in [1, 4096]");
+  cudaSetDevice(e->cfg.device);
+  char terr[256] = "";
+  if (e->train && train_max_batch(e->train) < B) {   // grow: keep the momentum by going through the host copy is not possible; refuse instead
+    return fail(e, AGZ_ERR_ARG, "batch %d exceeds the training state's batch %d (the first agz_train_step fixes it)", B, train_max_batch(e->train));
+  }
+  if (!e->train) {
+    e->train = train_create(e->nn, B < 32 ? 32 : B, terr, sizeof(terr));
+    if (!e->train) return fail(e, AGZ_ERR_CUDA, "%s", terr);
+    e->train_loaded = false;
+  }
+  if (!e->train_loaded) {
+    if (train_load(e->train, e->nn, e->stream, terr, sizeof(terr))) return fail(e, AGZ_ERR_ARG, "%s", terr);
+    e->train_loaded = true;
+  }
+  float* d_feats = nullptr;
+  if (cudaMalloc((void**)&d_feats, (size_t)B * 17 * e->c.N2 * sizeof(float)) != cudaSuccess) return fail(e, AGZ_ERR_CUDA, "feature buffer allocation failed");
+  int rc = engine_host_features(e->c, boards_hist, to_play, B, nullptr, d_feats, e->stream);
+  if (rc) { cudaFree(d_feats); return fail(e, AGZ_ERR_CUDA, "feature kernel: %s", cudaGetErrorString((cudaError_t)rc)); }
+  std::vector<float> z((size_t)B);
+  for (int b = 0; b < B; ++b) z[b] = (float)zs[b];
+  rc = train_step(e->train, d_feats, pis, z.data(), B, lr, momentum, loss_out, e->stream, terr, sizeof(terr));
+  cudaFree(d_feats);
+  e->launches += 60 + 40 * (long long)e->cfg.tower_height;
+  if (rc) return fail(e, AGZ_ERR_CUDA, "%s", terr);
+  // the inference paths read the host copy: hand the new parameters and running statistics over (re-committed lazily)
+  if (train_store(e->train, e->nn, e->stream, terr, sizeof(terr))) return fail(e, AGZ_ERR_CUDA, "%s", terr);
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_train_read_grads(agz_engine* e, int32_t chain, float* grads, size_t n) {
+  if (!e || !grads || !e->train) return fail(e, AGZ_ERR_ARG, "no training step has run");
+  cudaSetDevice(e->cfg.device);
+  if (train_read_grads(e->train, chain, grads, n, e->stream)) return fail(e, AGZ_ERR_ARG, "bad chain / size");
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_net_get_params(agz_engine* e, int32_t chain, float* flat, size_t n) {
+  if (!e || !flat) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
+  if (n != nn_param_count(e->nn, chain) || e->nn->hparams[chain].size() != n) return fail(e, AGZ_ERR_ARG, "chain %d has %zu parameters set, asked for %zu", chain, e->nn->hparams[chain].size(), n);
+  memcpy(flat, e->nn->hparams[chain].data(), n * sizeof(float));
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_net_get_bn_stats(agz_engine* e, int32_t chain, float* mu, float* sigma, size_t n_each, int32_t* bn_mode) {
+  if (!e || !mu || !sigma) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
+  if (n_each != nn_bn_count(e->nn, chain)) return fail(e, AGZ_ERR_ARG, "chain %d has %zu BatchNorm channels, got %zu", chain, nn_bn_count(e->nn, chain), n_each);
+  memcpy(mu, e->nn->hmu[chain].data(), n_each * sizeof(float));
+  memcpy(sigma, e->nn->hsigma[chain].data(), n_each * sizeof(float));
+  if (bn_mode) *bn_mode = e->nn->bn_mode[chain];
+  return AGZ_OK;
 }
 
 extern "C" int32_t agz_net_set_bn_stats(agz_engine* e, int32_t chain, const float* mu, const float* sigma, size_t n_each, int32_t bn_mode) {
@@ -1279,6 +1346,10 @@ extern "C" size_t agz_net_bn_count(agz_engine*, int32_t) { return 0; }
 extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t, const float*, size_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_net_set_bn_stats(agz_engine* e, int32_t, const float*, const float*, size_t, int32_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_features(agz_engine* e, const int8_t*, const int8_t*, int32_t, float*) { return fail(e, AGZ_ERR_CUDA, "not in the emulation build"); }
+extern "C" int32_t agz_train_step(agz_engine* e, const int8_t*, const int8_t*, const float*, const int8_t*, int32_t, float, float, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
+extern "C" int32_t agz_train_read_grads(agz_engine* e, int32_t, float*, size_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
+extern "C" int32_t agz_net_get_params(agz_engine* e, int32_t, float*, size_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
+extern "C" int32_t agz_net_get_bn_stats(agz_engine* e, int32_t, float*, float*, size_t, int32_t*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_net_forward(agz_engine* e, int32_t, const int8_t*, const int8_t*, int32_t, float*, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_trace_read(agz_engine*, uint64_t*, int32_t, int32_t* n_out, int32_t) { if (n_out) *n_out = 0; return AGZ_OK; }
 extern "C" int32_t agz_nccl_unique_id(uint8_t*) { return AGZ_ERR_NCCL; }

@@ -362,6 +362,19 @@ __global__ void __launch_bounds__(256) heads_f32_kernel(const float* __restrict_
 
 long long nn_f32_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower + 1; }
 
+// plain launch of the fp32 convolution for other translation units (train.cu: forward and data-gradient convolutions)
+int conv3x3_f32_launch(const float* in, const float* w, const float* scale, const float* shift, const float* res, float* out, int B, int Cin,
+                       int Cout, int N, int relu, cudaStream_t s) {
+  const size_t smem = (size_t)(CIT * (N + 2) * (N + 2) + COT * CIT * 9) * sizeof(float);
+  static int attr_n = -1;
+  if (attr_n != N) {
+    if (cudaFuncSetAttribute(conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    attr_n = N;
+  }
+  conv3x3_f32_kernel<<<dim3(B, (Cout + COT - 1) / COT), 128, smem, s>>>(in, w, scale, shift, res, out, Cin, Cout, N, relu);
+  return (int)cudaGetLastError();
+}
+
 // fp32 conv weights are reordered and uploaded the first time the cross-check path is used after a commit
 static int upload_f32_weights(NNet* n, cudaStream_t s) {
   std::vector<ConvLayerHost> convs;

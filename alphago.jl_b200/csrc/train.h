@@ -1,0 +1,24 @@
+// train.h -- one optimisation step of the network on the device (train.cu): _train / losses / Momentum of
+// src/neural_net.jl:75-101 and src/train.jl:54.
+#pragma once
+#include <stddef.h>
+
+#include <cuda_runtime.h>
+
+namespace agz {
+
+struct NNet;
+struct TrainState;
+
+TrainState* train_create(const NNet* n, int max_batch, char* err, size_t errlen);
+void train_destroy(TrainState* t);
+int train_max_batch(const TrainState* t);
+int train_load(TrainState* t, const NNet* n, cudaStream_t s, char* err, size_t errlen);   // host parameters -> device master copy
+int train_store(TrainState* t, NNet* n, cudaStream_t s, char* err, size_t errlen);        // device master copy -> host parameters (marks the net for re-commit)
+bool train_dirty(const TrainState* t);
+// feats: [B][17][N2] fp32 on the device; pi [B][A], z [B] on the host.  Returns the loss of the batch before the update.
+int train_step(TrainState* t, const float* d_feats, const float* h_pi, const float* h_z, int B, float eta, float rho, float* loss_out,
+               cudaStream_t s, char* err, size_t errlen);
+int train_read_grads(TrainState* t, int chain, float* out, size_t n, cudaStream_t s);      // gradients of the last step (data loss only)
+
+}  // namespace agz

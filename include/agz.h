@@ -153,6 +153,19 @@ int32_t agz_net_forward(agz_engine* e, int32_t evaluator, const int8_t* boards_h
 /* get_feats (src/features.jl:24-26): out is N x N x 17 x B column-major (row fastest), values in {-1,0,1}. */
 int32_t agz_features(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, int32_t B, float* out);
 
+/* One optimisation step on a minibatch (the body of _train, src/neural_net.jl:91-97, with the optimiser of src/train.jl:54):
+ * train-mode forward (BatchNorm on batch statistics, running statistics moved with momentum 0.1), loss = 0.01 * crossentropy(p, pi)
+ * + 0.01 * mse(z, v) + 1e-4 * sum(theta^2) (:75-83), back-propagation, Momentum(lr, momentum): v = momentum * v - lr * grad;
+ * theta += v.  Inputs as agz_net_forward / agz_replay_sample: boards_hist B x 8 x N*N, to_play B, pis B x A, zs B.  The updated
+ * parameters are what every later forward / self-play call of this engine uses; *loss_out = the loss before the update. */
+int32_t agz_train_step(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, const float* pis, const int8_t* zs, int32_t B,
+                       float lr, float momentum, float* loss_out);
+/* gradients of the data loss of the last agz_train_step, chain's Flux params order (test hook) */
+int32_t agz_train_read_grads(agz_engine* e, int32_t chain, float* grads, size_t n);
+/* current parameters / BatchNorm running statistics of a chain (what save_model writes, src/train.jl:14-35) */
+int32_t agz_net_get_params(agz_engine* e, int32_t chain, float* flat, size_t n);
+int32_t agz_net_get_bn_stats(agz_engine* e, int32_t chain, float* mu, float* sigma, size_t n_each, int32_t* bn_mode);
+
 /* DummyNet (test/test_mcts_player.jl:10-32): priors NULL = uniform 1/A. */
 int32_t agz_set_dummy_evaluator(agz_engine* e, const float* priors, float value);
 int32_t agz_set_evaluator(agz_engine* e, int32_t evaluator);

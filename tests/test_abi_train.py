@@ -1,0 +1,103 @@
+"""agz_train_step against the oracle restatement of _train / losses / Momentum (oracle/train.py, torch autograd fp32):
+loss, gradients, updated parameters, running statistics, and the network the engine then plays with."""
+import numpy as np
+import pytest
+
+from backends import agz, lib_for
+from oracle import go as ogo
+from oracle import net as onet
+from oracle import train as otrain
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(N, B, seed):
+    """Positions from random legal playouts (boards + 7-board history), visit-count-like policy targets, results."""
+    rs = np.random.RandomState(seed)
+    env = ogo.GoEnv(N)
+    positions = []
+    while len(positions) < B:
+        pos = ogo.GoPosition(env)
+        for _ in range(rs.randint(1, 3 * N)):
+            legal = np.flatnonzero(ogo.all_legal_moves(pos)[:-1])
+            if len(legal) == 0:
+                break
+            pos = ogo.play_move(pos, ogo.from_flat(int(rs.choice(legal)), env))
+        positions.append(pos)
+    A = N * N + 1
+    pis = rs.dirichlet(np.full(A, 0.3), size=B).astype(np.float32)
+    zs = rs.choice([-1, 1], size=B).astype(np.int8)
+    return positions, pis, zs
+
+
+def _hist(positions, N):
+    from oracle import features as ofe
+    out = np.zeros((len(positions), 8, N * N), np.int8)
+    for b, p in enumerate(positions):
+        boards = ofe.history_boards(p) if hasattr(ofe, "history_boards") else None
+        if boards is None:
+            f = ofe.get_feats(p)                                  # (i, j, 17): planes 2k = mine, 2k+1 = theirs
+            for k in range(8):
+                mine, theirs = f[:, :, 2 * k], f[:, :, 2 * k + 1]
+                out[b, k] = ((mine - theirs) * p.to_play).astype(np.int8).flatten(order="F")
+        else:
+            for k in range(8):
+                out[b, k] = np.asarray(boards[k], np.int8).flatten(order="F")
+    return out, np.array([p.to_play for p in positions], np.int8)
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-12))
+
+
+@pytest.mark.parametrize("N,T,B", [(5, 1, 6), (9, 2, 8)])
+def test_train_step_matches_oracle(N, T, B):
+    lib_for("cuda")
+    onn = onet.NeuralNet(N, T, seed=3)
+    onn.randomize_bn(seed=4)
+    eng = agz.Engine(N, n_games=8, readouts=8, tower_height=T, evaluator=agz.EVAL_NN_TC)
+    flat = otrain.flat_params(onn)
+    for k in range(3):
+        eng.net_set_params(k, flat[k])
+    bns = [onn.base_bns(), [onn.v_bn], [onn.p_bn]]
+    for k in range(3):
+        eng.net_set_bn_stats(k, np.concatenate([b.mu for b in bns[k]]), np.concatenate([b.sigma for b in bns[k]]), agz.BN_VAR_EPS)
+    tr = otrain.Trainer(onn)
+    for step in range(2):
+        positions, pis, zs = _batch(N, B, 10 + step)
+        bh, tp = _hist(positions, N)
+        loss_o = tr.step(positions, pis, zs, lr=0.02, rho=0.9)
+        loss_e = eng.train_step(bh, tp, pis, zs, lr=0.02, momentum=0.9)
+        assert abs(loss_e - loss_o) <= 2e-4 * abs(loss_o), (step, loss_e, loss_o)
+        for k in range(3):
+            assert _rel(eng.train_read_grads(k), tr.last_grads[k]) < 2e-3, "chain %d gradients (step %d)" % (k, step)
+        want = otrain.flat_params(onn)
+        for k in range(3):
+            got = eng.net_get_params(k)
+            assert np.max(np.abs(got - want[k])) < 2e-5, "chain %d parameters after step %d" % (k, step)
+        for k in range(3):
+            mu, var, mode = eng.net_get_bn_stats(k)
+            assert mode == agz.BN_VAR_EPS
+            assert np.allclose(mu, np.concatenate([b.mu for b in bns[k]]), atol=2e-5, rtol=1e-4)
+            assert np.allclose(var, np.concatenate([b.sigma for b in bns[k]]), atol=2e-5, rtol=1e-4)
+    # the engine now evaluates (test mode, tensor-core path) with the trained parameters and the moved running statistics
+    positions, _, _ = _batch(N, 4, 99)
+    bh, tp = _hist(positions, N)
+    pi_e, v_e = eng.net_forward(agz.EVAL_NN_TC, bh, tp)
+    pi_o, v_o = onn(positions)
+    assert np.max(np.abs(pi_e.T - pi_o)) < 1e-3 and np.max(np.abs(v_e - v_o)) < 1e-3
+    eng.close()
+
+
+def test_training_reduces_the_loss_on_a_fixed_batch():
+    lib_for("cuda")
+    N, T, B = 9, 1, 32
+    env = agz.GoEnv(N)
+    nn = agz.NeuralNet(env, tower_height=T, seed=0)
+    eng = agz.Engine(N, n_games=8, readouts=8, tower_height=T, evaluator=agz.EVAL_NN_TC)
+    nn.push(eng)
+    positions, pis, zs = _batch(N, B, 5)
+    bh, tp = _hist(positions, N)
+    losses = [eng.train_step(bh, tp, pis, zs) for _ in range(12)]
+    assert losses[-1] < losses[0] and all(np.isfinite(losses))
+    eng.close()
