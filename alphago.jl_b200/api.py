@@ -483,6 +483,57 @@ def evaluate(env, black_net, white_net, num_games=400, ro=800, verbose=False, se
     return games_won / G >= 0.55
 
 
+# ------------------------------------------------------------------ train (train.jl:38-92)
+def train(env, num_games=25000, memory_size=500000, batch_size=32, epochs=1, ckp_freq=1000, readouts=800, tower_height=19,
+          model=None, start_training_after=50000, concurrent=None, seed=0, model_dir=None, verbose=True, lr=0.02, momentum=0.9,
+          **engine_overrides):
+    """train(env; num_games, memory_size, batch_size, epochs, ckp_freq, readouts, tower_height, model, start_training_after) -> NeuralNet.
+    The reference plays one game, appends its (position, pi, z) tuples to the buffers, and -- once `start_training_after` tuples
+    are there -- takes `epochs` optimisation steps on one uniform batch per finished game (train.jl:56-73).  Here `concurrent` games
+    run at once on the GPU with the current network; every harvested game triggers the same per-game step, so the ratio of
+    optimisation steps to games is the reference's.  The replay ring is the engine's (500 000 deep, trim-oldest)."""
+    from . import weights_io
+    assert memory_size == 500000, "the device replay ring is fixed at the reference's default memory_size"
+    cur_nn = model if model is not None else NeuralNet(env, tower_height=tower_height, seed=seed)
+    conc = concurrent or min(num_games, 1024)
+    eng = B.Engine(env.N, lib_path=env.lib_path, n_games=conc, readouts=readouts, seed=seed, device=env.device,
+                   tower_height=cur_nn.tower_height, evaluator=cur_nn.evaluator, **engine_overrides)
+    losses = []
+    try:
+        cur_nn.push(eng)
+        eng.selfplay_start(num_games)
+        done, last_ckp, stalls = 0, 0, 0
+        while done < num_games:
+            pr = eng.selfplay_step(8)
+            if pr.error:
+                raise B.AgzError(pr.error, "a game stopped on the device")
+            n_tuples = eng.replay_gather()
+            recs = eng.selfplay_harvest(conc)
+            stalls = 0 if (recs or pr.games_live) else stalls + 1
+            if stalls > 4:
+                break
+            for r in recs:
+                done += 1
+                if n_tuples >= start_training_after and n_tuples >= batch_size:
+                    bh, tp, pis, zs, _ = eng.replay_sample_hist(batch_size, seed=seed * 1000003 + done)
+                    loss = 0.0
+                    for _ in range(epochs):
+                        loss += eng.train_step(bh, tp, pis, zs, lr=lr, momentum=momentum)
+                    losses.append(loss / epochs)
+                    if verbose:
+                        print("Episode %d over. Loss: %s. Winner: %s. Moves: %d." % (done, losses[-1], r.result_string, r.n_moves))
+                if model_dir is not None and done // ckp_freq > last_ckp:
+                    last_ckp = done // ckp_freq
+                    weights_io.save_model(cur_nn, model_dir, engine=eng)
+                    if verbose:
+                        print("Model saved. ", end="")
+        weights_io.pull_from_engine(cur_nn, eng)
+    finally:
+        eng.close()
+    cur_nn.train_losses = losses
+    return cur_nn
+
+
 # free-function spellings used by the reference and its tests
 def initialize_game(player, pos=None): return player.initialize_game(pos)
 def tree_search(player, parallel_readouts=8): return player.tree_search(parallel_readouts)

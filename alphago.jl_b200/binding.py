@@ -74,7 +74,7 @@ SYMBOLS = [
     "agz_tree_node_features", "agz_pos_play_move", "agz_pos_legal_moves", "agz_pos_score", "agz_pos_liberties",
     "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read",
     "agz_match_start", "agz_match_search", "agz_match_play",
-    "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
+    "agz_replay_sample_hist", "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -282,6 +282,17 @@ class Engine:
         self._check(self.lib.agz_replay_sample(self._h, C.c_int32(batch), C.c_uint64(seed), _ptr(boards, C.c_int8), _ptr(tp, C.c_int8),
                                                _ptr(pis, C.c_float), _ptr(zs, C.c_int8), _ptr(idx, C.c_int64)))
         return boards, tp, pis, zs, idx
+
+    def replay_sample_hist(self, batch, seed=0):
+        """get_replay_batch with the 8-board history the network trains on: (boards_hist, to_play, pis, zs, indices)."""
+        bh = np.zeros((batch, 8, self.N2), np.int8)
+        tp = np.zeros(batch, np.int8)
+        pis = np.zeros((batch, self.A), np.float32)
+        zs = np.zeros(batch, np.int8)
+        idx = np.zeros(batch, np.int64)
+        self._check(self.lib.agz_replay_sample_hist(self._h, C.c_int32(batch), C.c_uint64(seed), _ptr(bh, C.c_int8), _ptr(tp, C.c_int8),
+                                                    _ptr(pis, C.c_float), _ptr(zs, C.c_int8), _ptr(idx, C.c_int64)))
+        return bh, tp, pis, zs, idx
 
     def nccl_unique_id(self):
         buf = (C.c_uint8 * 128)()

@@ -1340,7 +1340,17 @@ extern "C" int32_t agz_replay_sample(agz_engine* e, int32_t batch, uint64_t seed
   if (rc) return fail(e, rc, "%s", rerr);
   return AGZ_OK;
 }
+
+extern "C" int32_t agz_replay_sample_hist(agz_engine* e, int32_t batch, uint64_t seed, int8_t* boards_hist, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices) {
+  if (!e || !e->replay) return fail(e, AGZ_ERR_ARG, "no replay ring (call agz_replay_gather first)");
+  cudaSetDevice(e->cfg.device);
+  char rerr[256] = "";
+  int rc = replay_sample(e->replay, e->c, batch, seed, nullptr, to_play, pis, zs, indices, e->stream, rerr, sizeof(rerr), boards_hist);
+  if (rc) return fail(e, rc, "%s", rerr);
+  return AGZ_OK;
+}
 #else
+extern "C" int32_t agz_replay_sample_hist(agz_engine* e, int32_t, uint64_t, int8_t*, int8_t*, float*, int8_t*, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
 extern "C" size_t agz_net_param_count(agz_engine*, int32_t) { return 0; }
 extern "C" size_t agz_net_bn_count(agz_engine*, int32_t) { return 0; }
 extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t, const float*, size_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }

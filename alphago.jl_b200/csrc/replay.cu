@@ -49,7 +49,7 @@ struct ReplayState {
   ncclComm_t comm;
   bool have_comm;
   int world, rank;
-  size_t stride;            // bytes per packed tuple: pi (4A) | board (N2) | to_play | z | pad -> multiple of 16
+  size_t stride;            // bytes per packed tuple: pi (4A) | boards[8] (8*N2: the position and the 7 before it) | to_play | z | pad -> multiple of 16
   unsigned char* ring;      // [cap][stride]
   long long cap, total;     // tuples ever appended (ring index = total % cap)
   unsigned long long gather_pos;  // finished-ring records already packed
@@ -66,7 +66,7 @@ ReplayState* replay_create(const Cfg& c, char* err, size_t errlen) {
   memset(r, 0, sizeof(*r));
   r->world = c.world;
   r->rank = c.rank;
-  r->stride = ((size_t)4 * c.A + c.N2 + 2 + 15) / 16 * 16;
+  r->stride = ((size_t)4 * c.A + 8 * (size_t)c.N2 + 2 + 15) / 16 * 16;
   r->cap = kReplayCap;
   if (cudaMalloc((void**)&r->ring, (size_t)r->cap * r->stride) != cudaSuccess || cudaMalloc((void**)&r->d_counts, sizeof(long long) * c.world) != cudaSuccess) {
     snprintf(err, errlen, "cudaMalloc of the replay ring failed");
@@ -110,7 +110,8 @@ int replay_nccl_init(ReplayState* r, const uint8_t idb[128], int world, int rank
 }
 
 // One warp per finished game: replay its moves from the empty board (replay_position, board.jl:557-578) and emit,
-// for every ply, the packed tuple (pi | board before the move | to_play | z = final result from Black's view).
+// for every ply, the packed tuple (pi | board before the move and the 7 boards before that, oldest repeated = what get_feats
+// rebuilds from board_deltas, features.jl:7-14 | to_play | z = final result from Black's view).
 struct PackOp {
   Cfg c;
   View v;
@@ -136,9 +137,12 @@ struct PackOp {
       for (int a = lane; a < c.A; a += 32) opi[a] = pi[a];
       int8_t* ob = reinterpret_cast<int8_t*>(o + (size_t)4 * c.A);
       for (int p = lane; p < c.N2; p += 32) ob[p] = rs.bd[p];
+      // boards 1..7 = the previous tuple's boards 0..6 (all empty before the first move)
+      const int8_t* prev = t > 0 ? reinterpret_cast<const int8_t*>(o - stride + (size_t)4 * c.A) : nullptr;
+      for (int p = lane; p < 7 * c.N2; p += 32) ob[c.N2 + p] = prev ? prev[p] : (int8_t)0;
       if (lane == 0) {
-        ob[c.N2] = (int8_t)to_play;
-        ob[c.N2 + 1] = (int8_t)hd.result;
+        ob[8 * c.N2] = (int8_t)to_play;
+        ob[8 * c.N2 + 1] = (int8_t)hd.result;
       }
       __syncwarp();
       const int mv = v.ring_moves[(size_t)rslot * L + t];
@@ -233,7 +237,7 @@ int replay_gather(ReplayState* r, const Cfg& c, const View& v, int smem_per_warp
 }
 
 int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs,
-                cudaStream_t s, char* err, size_t errlen) {
+                cudaStream_t s, char* err, size_t errlen, int8_t* boards_hist) {
   long long oldest = r->total > r->cap ? r->total - r->cap : 0;
   if (first < oldest || first + count > r->total || count < 0) {
     snprintf(err, errlen, "replay tuples [%lld, %lld) not in the ring [%lld, %lld)", (long long)first, (long long)(first + count), oldest, r->total);
@@ -247,15 +251,16 @@ int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8
     if (pis) memcpy(pis + (size_t)i * c.A, buf.data(), (size_t)4 * c.A);
     const int8_t* b = reinterpret_cast<const int8_t*>(buf.data() + (size_t)4 * c.A);
     if (boards) memcpy(boards + (size_t)i * c.N2, b, (size_t)c.N2);
-    if (to_play) to_play[i] = b[c.N2];
-    if (zs) zs[i] = b[c.N2 + 1];
+    if (boards_hist) memcpy(boards_hist + (size_t)i * 8 * c.N2, b, (size_t)8 * c.N2);
+    if (to_play) to_play[i] = b[8 * c.N2];
+    if (zs) zs[i] = b[8 * c.N2 + 1];
   }
   return 0;
 }
 
 // uniform sample without replacement (src/train.jl:5): partial Fisher-Yates over the ring's index range, splitmix64 stream
 int replay_sample(ReplayState* r, const Cfg& c, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices,
-                  cudaStream_t s, char* err, size_t errlen) {
+                  cudaStream_t s, char* err, size_t errlen, int8_t* boards_hist) {
   const long long oldest = r->total > r->cap ? r->total - r->cap : 0, n = r->total - oldest;
   if (batch < 0 || batch > n) {
     snprintf(err, errlen, "cannot sample %d tuples without replacement from %lld", batch, n);
@@ -275,7 +280,8 @@ int replay_sample(ReplayState* r, const Cfg& c, int32_t batch, uint64_t seed, in
     std::swap(pool[(size_t)k], pool[j]);
     if (indices) indices[k] = pool[(size_t)k];
     int rc = replay_read(r, c, pool[(size_t)k], 1, boards ? boards + (size_t)k * c.N2 : nullptr, to_play ? to_play + k : nullptr,
-                         pis ? pis + (size_t)k * c.A : nullptr, zs ? zs + k : nullptr, s, err, errlen);
+                         pis ? pis + (size_t)k * c.A : nullptr, zs ? zs + k : nullptr, s, err, errlen,
+                         boards_hist ? boards_hist + (size_t)k * 8 * c.N2 : nullptr);
     if (rc) return rc;
   }
   return 0;

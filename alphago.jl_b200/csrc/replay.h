@@ -19,10 +19,10 @@ int replay_nccl_init(ReplayState* r, const uint8_t id[128], int world, int rank,
 int replay_gather(ReplayState* r, const Cfg& c, const View& v, int smem_per_warp, cudaStream_t s, int64_t* n_total, long long* launches,
                   char* err, size_t errlen);
 int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs,
-                cudaStream_t s, char* err, size_t errlen);
+                cudaStream_t s, char* err, size_t errlen, int8_t* boards_hist = nullptr /* count x 8 x N2: the position and the 7 before it */);
 
 int replay_sample(ReplayState* r, const Cfg& c, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices,
-                  cudaStream_t s, char* err, size_t errlen);
+                  cudaStream_t s, char* err, size_t errlen, int8_t* boards_hist = nullptr);
 
 // feature kernels over caller-supplied positions (agz_features / agz_net_forward), features.cu
 int engine_host_features(const Cfg& c, const int8_t* boards_hist, const int8_t* to_play, int B, float* out_host, float* out_dev, cudaStream_t s);

@@ -86,3 +86,92 @@ def load_reference_model(models_dir, nn):
         sigmas.append(np.concatenate([full[2 * k + 1].ravel() for k in range(nbn)]))
     nn.load_params(base=lists[0], value=lists[1], policy=lists[2], bn_mu=mus, bn_sigma=sigmas, bn_mode=B.BN_STD)
     return nn
+
+
+# ------------------------------------------------------------------ writing (save_model, src/train.jl:14-35)
+def _cstr_b(name):
+    return name.encode("utf8") + b"\x00"
+
+
+def _enc(value):
+    """BSON element (type byte, payload) for the few value kinds BSON.jl's array documents use."""
+    if isinstance(value, dict):
+        return 0x03, _enc_doc(value)
+    if isinstance(value, list):
+        return 0x04, _enc_doc({str(i): v for i, v in enumerate(value)})
+    if isinstance(value, (bytes, bytearray)):
+        return 0x05, struct.pack("<i", len(value)) + b"\x00" + bytes(value)
+    if isinstance(value, str):
+        b = value.encode("utf8") + b"\x00"
+        return 0x02, struct.pack("<i", len(b)) + b
+    if isinstance(value, (int, np.integer)):
+        return 0x12, struct.pack("<q", int(value))
+    raise TypeError("unsupported value %r" % type(value))
+
+
+def _enc_doc(d):
+    body = b""
+    for k, v in d.items():
+        t, payload = _enc(v)
+        body += bytes([t]) + _cstr_b(k) + payload
+    return struct.pack("<i", len(body) + 5) + body + b"\x00"
+
+
+def _array_doc(a):
+    a = np.asarray(a, np.float32)
+    return {"tag": "array", "type": {"tag": "datatype", "params": [], "name": ["Core", "Float32"]},
+            "size": [int(x) for x in a.shape], "data": a.flatten(order="F").tobytes()}
+
+
+def save_weight_list(path, name, arrays):
+    """One `@save path name` of save_model: a top-level document {name: [array documents]} in BSON.jl's array encoding."""
+    with open(path, "wb") as f:
+        f.write(_enc_doc({name: [_array_doc(a) for a in arrays]}))
+
+
+def save_model(nn, models_dir, engine=None):
+    """save_model(nn) (src/train.jl:14-35): weights/agz_{base,value,policy}.bson hold the three Flux `params` lists.  The reference
+    also dumps the whole structs (agz_*.bson); here those files carry what this engine needs from them -- the BatchNorm running
+    statistics (mean, variance) per chain.  With `engine`, the current (trained) parameters are read back from it first."""
+    import os
+    if engine is not None:
+        pull_from_engine(nn, engine)
+    os.makedirs(os.path.join(models_dir, "weights"), exist_ok=True)
+    for k, (chain, var) in enumerate((("base", "bn_weights"), ("value", "val_weights"), ("policy", "pol_weights"))):
+        save_weight_list(os.path.join(models_dir, "weights", "agz_%s.bson" % chain), var, nn.params[k])
+        save_weight_list(os.path.join(models_dir, "agz_%s.bson" % chain), chain + "_bn_stats", [nn.bn_mu[k], nn.bn_sigma[k]])
+
+
+def load_saved_model(models_dir, nn):
+    """Inverse of save_model above."""
+    lists, mus, sigmas = [], [], []
+    for chain in ("base", "value", "policy"):
+        lists.append(bson_arrays(os_join(models_dir, "weights", "agz_%s.bson" % chain)))
+        st = bson_arrays(os_join(models_dir, "agz_%s.bson" % chain))
+        mus.append(st[0].ravel())
+        sigmas.append(st[1].ravel())
+    nn.load_params(base=lists[0], value=lists[1], policy=lists[2], bn_mu=mus, bn_sigma=sigmas, bn_mode=B.BN_VAR_EPS)
+    return nn
+
+
+def os_join(*parts):
+    import os
+    return os.path.join(*parts)
+
+
+def pull_from_engine(nn, engine):
+    """Copy the engine's current parameters / running statistics (after agz_train_step) into an api.NeuralNet."""
+    for k in range(3):
+        flat = engine.net_get_params(k)
+        out, o = [], 0
+        for a in nn.params[k]:
+            n = int(np.prod(a.shape))
+            out.append(flat[o:o + n].reshape(a.shape, order="F").copy())
+            o += n
+        nn.params[k] = out
+        mu, sg, mode = engine.net_get_bn_stats(k)
+        nn.bn_mu[k], nn.bn_sigma[k] = mu, sg
+        nn.bn_mode = mode
+    nn._version += 1
+    engine._nn_token = (id(nn), nn._version)
+    return nn

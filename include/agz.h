@@ -193,6 +193,9 @@ int32_t agz_replay_read(agz_engine* e, int64_t first, int32_t count, int8_t* boa
 /* get_replay_batch (src/train.jl:4-12): `batch` distinct tuples drawn uniformly without replacement from the ring
  * (deterministic in `seed`); same output arrays as agz_replay_read. */
 int32_t agz_replay_sample(agz_engine* e, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices);
+/* Same draw as agz_replay_sample, returning what the network trains on: boards_hist batch x 8 x N*N = the position before the
+ * move and the 7 positions before it (oldest repeated), i.e. what get_feats rebuilds from board_deltas (features.jl:7-14). */
+int32_t agz_replay_sample_hist(agz_engine* e, int32_t batch, uint64_t seed, int8_t* boards_hist, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices);
 /* NCCL bootstrap for world_size > 1: rank 0 fills a 128-byte id, every rank passes the same bytes. */
 int32_t agz_nccl_unique_id(uint8_t id_out[128]);
 int32_t agz_nccl_init(agz_engine* e, const uint8_t id[128]);

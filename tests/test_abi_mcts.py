@@ -431,5 +431,22 @@ def test_replay_gather_read_sample():
     assert len(set(idx.tolist())) == 8 and idx.min() >= 0 and idx.max() < total
     for j, i in enumerate(idx):
         assert np.array_equal(sb[j], boards[i]) and np.array_equal(spi[j], pis[i]) and sz[j] == zs[i] and stp[j] == tp[i]
+    # the history variant returns the same draw with the 8 boards get_feats needs: board k = the position k plies earlier in the
+    # same game (empty before the first move)
+    hb, htp, hpi, hz, hidx = eng.replay_sample_hist(8, seed=3)
+    assert np.array_equal(hidx, idx) and np.array_equal(hb[:, 0], sb) and np.array_equal(hpi, spi)
+    by_board = {}
+    for r in recs:
+        pos, hist = ogo.GoPosition(oenv), []
+        for t, m in enumerate(r.moves):
+            cur = pos.board.flatten(order="F").copy()
+            stack = [cur] + hist[::-1][:7]
+            while len(stack) < 8:
+                stack.append(stack[-1] if t > 7 else np.zeros_like(cur))
+            by_board[(r.game_id, t)] = np.stack(stack[:8])
+            hist.append(cur)
+            pos = ogo.play_move(pos, ogo.from_flat(int(m), oenv))
+    for j in range(8):
+        assert any(np.array_equal(hb[j], want) for want in by_board.values()), j
     with pytest.raises(agz.AgzError):
         eng.replay_sample(total + 1)

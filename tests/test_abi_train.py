@@ -101,3 +101,25 @@ def test_training_reduces_the_loss_on_a_fixed_batch():
     losses = [eng.train_step(bh, tp, pis, zs) for _ in range(12)]
     assert losses[-1] < losses[0] and all(np.isfinite(losses))
     eng.close()
+
+
+def test_train_loop_selfplay_replay_train(tmp_path):
+    """train(env; ...) (src/train.jl:38-92): self-play fills the replay ring, every finished game triggers one optimisation step on
+    a uniform batch once `start_training_after` tuples are there, checkpoints go through save_model."""
+    lib_for("cuda")
+    from alphago_jl_b200 import weights_io
+    env = agz.GoEnv(5)
+    nn0 = agz.NeuralNet(env, tower_height=1, seed=2)
+    before = [np.concatenate([a.flatten(order="F") for a in lst]) for lst in nn0.params]
+    nn = agz.train(env, num_games=24, batch_size=16, readouts=16, tower_height=1, model=nn0, start_training_after=40, concurrent=8,
+                   ckp_freq=8, model_dir=str(tmp_path), verbose=False)
+    assert len(nn.train_losses) >= 8 and all(np.isfinite(nn.train_losses))
+    after = [np.concatenate([a.flatten(order="F") for a in lst]) for lst in nn.params]
+    assert all(np.max(np.abs(a - b)) > 0 for a, b in zip(before, after))
+    assert nn.bn_mode == agz.BN_VAR_EPS and np.max(np.abs(nn.bn_mu[0])) > 0
+    saved = weights_io.load_saved_model(str(tmp_path), agz.NeuralNet(env, tower_height=1, seed=9))
+    assert saved.params[0][0].shape == nn.params[0][0].shape
+    # the trained network plays: a short gating match against the initial one runs to completion
+    games = []
+    agz.evaluate(env, nn, agz.NeuralNet(env, tower_height=1, seed=2), num_games=4, ro=16, details=games)
+    assert len(games) == 4 and all(g.result_string for g in games)

@@ -25,3 +25,24 @@ def test_shipped_weights_load_and_match_golden():
         assert np.array_equal(nn.bn_mu[k], g["bn_mu_" + name].ravel())
         assert np.array_equal(nn.bn_sigma[k], g["bn_sigma_" + name].ravel())
     assert nn.bn_mode == agz.BN_STD
+
+
+def test_save_model_round_trip(tmp_path):
+    """save_model (src/train.jl:14-35) writes BSON.jl array documents that both readers (product and oracle) parse back bit for bit."""
+    from alphago_jl_b200 import weights_io
+    from oracle import bson as obson
+    env = agz.GoEnv(5, lib_path="unused")
+    nn = agz.NeuralNet(env, tower_height=1, seed=7)
+    rs = np.random.RandomState(1)
+    nn.bn_mu = [rs.randn(*m.shape).astype(np.float32) for m in nn.bn_mu]
+    nn.bn_sigma = [(0.5 + rs.rand(*m.shape)).astype(np.float32) for m in nn.bn_sigma]
+    weights_io.save_model(nn, str(tmp_path))
+    back = weights_io.load_saved_model(str(tmp_path), agz.NeuralNet(env, tower_height=1, seed=8))
+    for k in range(3):
+        assert len(back.params[k]) == len(nn.params[k])
+        for a, b in zip(nn.params[k], back.params[k]):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        assert np.array_equal(back.bn_mu[k], nn.bn_mu[k]) and np.array_equal(back.bn_sigma[k], nn.bn_sigma[k])
+    # the oracle's independent reader sees the same tensors in the same order
+    arrs = obson.find_arrays(obson.load(os.path.join(str(tmp_path), "weights", "agz_base.bson")))
+    assert len(arrs) == len(nn.params[0]) and all(np.array_equal(a, b) for a, b in zip(arrs, nn.params[0]))
