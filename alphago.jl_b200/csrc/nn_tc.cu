@@ -110,6 +110,29 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Split form for a software-pipelined epilogue: issue the load of the next 32 accumulator columns, work on the current ones, and
+// wait before the first use.  tcgen05.wait::ld covers every outstanding load of the thread; the registers are in/out operands of
+// the wait so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
 __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -917,8 +940,8 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_ptiles = (a.n_tiles + 1) >> 1;
-  s_scale[threadIdx.x] = a.scale[threadIdx.x];
-  s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  s_scale[2 * threadIdx.x] = a.scale[threadIdx.x];       // interleaved (scale, shift) pairs: one 16-byte read per two channels
+  s_scale[2 * threadIdx.x + 1] = a.shift[threadIdx.x];
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -1011,10 +1034,14 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       mbar_wait_guard(&tfull[as], aphase);
       tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)as * 256 + ((uint32_t)(q * 32) << 16);
+      uint32_t vv[2][32];   // the load of columns cc+1 is in flight while columns cc are scaled, packed and stored
+      tc_ld32_issue(tacc, vv[0]);
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
+        uint32_t (&v)[32] = vv[cc & 1];
+        tc_ld_wait(v);
+        if (cc < 7) tc_ld32_issue(tacc + (uint32_t)(cc + 1) * 32, vv[(cc + 1) & 1]);
         if (valid) {
           uint4 o[4];
           uint32_t* ow = reinterpret_cast<uint32_t*>(o);
@@ -1022,8 +1049,9 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int c0 = cc * 32 + 2 * j;
-            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
-            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
+            const float4 ss = *reinterpret_cast<const float4*>(s_scale + 2 * c0);
+            float y0 = fmaf(__uint_as_float(v[2 * j]), ss.x, ss.y);
+            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), ss.z, ss.w);
             if (addres) {
               float2 rr = __half22float2(rh[j]);
               y0 += rr.x;
@@ -1095,8 +1123,8 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_ptiles = (a.n_tiles + 1) >> 1;
-  s_scale[threadIdx.x] = a.scale[threadIdx.x];
-  s_shift[threadIdx.x] = a.shift[threadIdx.x];
+  s_scale[2 * threadIdx.x] = a.scale[threadIdx.x];       // interleaved (scale, shift) pairs
+  s_scale[2 * threadIdx.x + 1] = a.shift[threadIdx.x];
   constexpr bool heads = HEADS;
   if (heads) s_hw[threadIdx.x] = make_float4(a.head_vw[threadIdx.x], a.head_pw[threadIdx.x], a.head_pw[256 + threadIdx.x], 0.f);
   if (warp == 0 && lane == 0) {
@@ -1194,10 +1222,18 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait_guard(rfull, (uint32_t)(titer & 1));
       tc_fence_after();
       float h0 = 0.f, h1 = 0.f, h2 = 0.f;   // this row's value / policy 1x1 convolutions (fixed channel order: batch invariant)
-#pragma unroll 2
+      const uint32_t tacc = tmem_base + (uint32_t)as * 256 + ((uint32_t)(q * 32) << 16);
+      uint32_t vv[2][32];   // without the heads: the load of columns cc+1 is in flight while columns cc are processed
+      if (!heads) tc_ld32_issue(tacc, vv[0]);
+#pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
+        uint32_t (&v)[32] = vv[heads ? 0 : (cc & 1)];
+        if (heads) {
+          tc_ld32(tacc + (uint32_t)cc * 32, v);
+        } else {
+          tc_ld_wait(v);
+          if (cc < 7) tc_ld32_issue(tacc + (uint32_t)(cc + 1) * 32, vv[(cc + 1) & 1]);
+        }
         // shortcut values of columns cc*32 .. +31: box cc/2, 16-byte chunks (cc%2)*4 + j, swizzled with the row
         uint4 rv[4];
         const uint8_t* rb = resbuf + (size_t)(cc >> 1) * A_BYTES + (size_t)r * 128;
@@ -1211,8 +1247,9 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int j = 0; j < 16; ++j) {
             const int c0 = cc * 32 + 2 * j;
             float2 rr = __half22float2(rh[j]);
-            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]) + rr.x;
-            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]) + rr.y;
+            const float4 ss = *reinterpret_cast<const float4*>(s_scale + 2 * c0);
+            float y0 = fmaf(__uint_as_float(v[2 * j]), ss.x, ss.y) + rr.x;
+            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), ss.z, ss.w) + rr.y;
             if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
             if (heads) {
               const float4 w0 = s_hw[c0], w1 = s_hw[c0 + 1];

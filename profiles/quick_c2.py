@@ -28,7 +28,13 @@ for _ in range(steps):
     pr = eng.selfplay_step(50)
     dev += pr.step_ms
 wall = time.perf_counter() - t0
+eng.set_timing(True)
+eng.phase_times(reset=True)
+eng.selfplay_step(50)
+kms, kln = eng.phase_times(reset=True)
+eng.set_timing(False)
 knobs = {k: v for k, v in os.environ.items() if k.startswith("AGZ_")}
 print(json.dumps({"knobs": knobs, "moves_per_s": (pr.moves_played - m0) / wall, "ms_per_round_wall": 1e3 * wall / (50 * steps),
-                  "ms_per_round_device": dev / (50 * steps), "error": pr.error}), flush=True)
+                  "ms_per_round_device": dev / (50 * steps), "error": pr.error,
+                  "kernel_ms_per_round": {n: round(kms[i] / max(1, kln[0]), 4) for i, n in enumerate(agz.binding.KERNEL_NAMES)}}), flush=True)
 eng.close()
