@@ -1,0 +1,79 @@
+"""The one collective of the path on real GPUs: agz_replay_gather over NCCL.  Two ranks, one B200 each, play disjoint
+games (global slot = rank + world * slot); after the gather BOTH replay rings must hold the tuples of ALL games -- ragged counts,
+padded ncclAllGather -- and equal what the oracle's extract_data produces.  Skipped with fewer than two GPUs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _run(total_games=6, readouts=16, seed=5):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker_lockstep, args=(r, 2, total_games, readouts, seed, uid_q, out_q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    msgs = [out_q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return msgs
+
+
+def _worker_lockstep(rank, world, total_games, readouts, seed, uid_q, out_q):
+    """Fixed number of (step, gather) iterations on both ranks, so the collectives pair up."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import pkg
+    agz = pkg.load()
+    eng = agz.Engine(9, n_games=2, readouts=readouts, seed=seed, device=rank, world_size=world, rank=rank)
+    eng.set_dummy_evaluator(None, 0.0)
+    if rank == 0:
+        uid = eng.nccl_unique_id()
+        uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=120)
+    eng.nccl_init(uid)
+    eng.selfplay_start(total_games)
+    recs, total = [], 0
+    for _ in range(60):                       # 60 x 64 rounds: far more than 3 games of <= 113 moves x 2 rounds need
+        pr = eng.selfplay_step(64)
+        assert pr.error == 0
+        total = eng.replay_gather()
+        recs += eng.selfplay_harvest(16)
+    boards, tp, pis, zs = eng.replay_read(0, total)
+    out_q.put({"rank": rank, "total": int(total), "boards": boards, "tp": tp, "pis": pis, "zs": zs,
+               "recs": [(int(r.game_id), r.moves.tolist(), r.searches_pi.copy(), int(r.result)) for r in recs]})
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_nccl_replay_all_gather_two_gpus():
+    from oracle import go as ogo
+    msgs = _run()
+    by_rank = {m["rank"]: m for m in msgs}
+    games = sorted(by_rank[0]["recs"] + by_rank[1]["recs"])
+    assert [g[0] for g in games] == list(range(6))
+    assert {g[0] % 2 for g in by_rank[0]["recs"]} == {0} and {g[0] % 2 for g in by_rank[1]["recs"]} == {1}
+    n_all = sum(len(g[1]) for g in games)
+    oenv = ogo.GoEnv(9)
+    expected = []
+    for gid, moves, pis, result in games:
+        pos = ogo.GoPosition(oenv)
+        for t, m in enumerate(moves):
+            expected.append((pos.board.flatten(order="F").tobytes(), int(pos.to_play), pis[t].tobytes(), result))
+            pos = ogo.play_move(pos, ogo.from_flat(int(m), oenv))
+    want = sorted(expected)
+    for r in (0, 1):                                      # every rank's ring holds every rank's tuples
+        m = by_rank[r]
+        assert m["total"] == n_all
+        got = sorted((m["boards"][k].tobytes(), int(m["tp"][k]), m["pis"][k].tobytes(), int(m["zs"][k])) for k in range(n_all))
+        assert got == want, "rank %d ring differs from the oracle's tuples" % r
