@@ -1201,7 +1201,11 @@ extern "C" int32_t agz_train_step(agz_engine* e, const int8_t* boards_hist, cons
   if (rc) { cudaFree(d_feats); return fail(e, AGZ_ERR_CUDA, "feature kernel: %s", cudaGetErrorString((cudaError_t)rc)); }
   std::vector<float> z((size_t)B);
   for (int b = 0; b < B; ++b) z[b] = (float)zs[b];
-  rc = train_step(e->train, d_feats, pis, z.data(), B, lr, momentum, loss_out, e->stream, terr, sizeof(terr));
+  // with an initialised NCCL communicator (agz_nccl_init) the step is data parallel: every rank calls it with its own minibatch
+  const int world = replay_world(e->replay);
+  rc = train_step(e->train, d_feats, pis, z.data(), B, lr, momentum, loss_out, e->stream, terr, sizeof(terr), world,
+                  world > 1 ? [](void* ctx, float* buf, size_t n, cudaStream_t st) { return replay_allreduce_sum((ReplayState*)ctx, buf, n, st); } : (train_allreduce_fn) nullptr,
+                  e->replay);
   cudaFree(d_feats);
   e->launches += 60 + 40 * (long long)e->cfg.tower_height;
   if (rc) return fail(e, AGZ_ERR_CUDA, "%s", terr);

@@ -19,6 +19,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*CommDestroy)(ncclComm_t);
   const char* (*GetErrorString)(ncclResult_t);
   bool ok;
@@ -37,9 +38,10 @@ static NcclApi* nccl_api() {
       api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
       api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
       api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+      api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
       api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
       api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-      api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+      api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.AllReduce && api.CommDestroy && api.GetErrorString;
     }
   }
   return api.ok ? &api : nullptr;
@@ -107,6 +109,15 @@ int replay_nccl_init(ReplayState* r, const uint8_t idb[128], int world, int rank
   r->world = world;
   r->rank = rank;
   return 0;
+}
+
+// in-place sum over all ranks (data-parallel training: gradients, loss terms, running statistics)
+int replay_world(const ReplayState* r) { return (r && r->have_comm) ? r->world : 1; }
+
+int replay_allreduce_sum(ReplayState* r, float* buf, size_t n, cudaStream_t s) {
+  if (!r || !r->have_comm || r->world == 1) return 0;
+  ncclResult_t nr = nccl_api()->AllReduce(buf, buf, n, ncclFloat32, ncclSum, r->comm, s);
+  return nr == ncclSuccess ? 0 : 1;
 }
 
 // One warp per finished game: replay its moves from the empty board (replay_position, board.jl:557-578) and emit,

@@ -24,6 +24,10 @@ int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8
 int replay_sample(ReplayState* r, const Cfg& c, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices,
                   cudaStream_t s, char* err, size_t errlen, int8_t* boards_hist = nullptr);
 
+// data-parallel training: world size of the initialised communicator (1 without one) and an in-place float sum over the ranks
+int replay_world(const ReplayState* r);
+int replay_allreduce_sum(ReplayState* r, float* buf, size_t n, cudaStream_t s);
+
 // feature kernels over caller-supplied positions (agz_features / agz_net_forward), features.cu
 int engine_host_features(const Cfg& c, const int8_t* boards_hist, const int8_t* to_play, int B, float* out_host, float* out_dev, cudaStream_t s);
 }  // namespace agz

@@ -495,8 +495,12 @@ int train_store(TrainState* t, NNet* n, cudaStream_t s, char* err, size_t errlen
 
 bool train_dirty(const TrainState* t) { return t->dirty; }
 
+__global__ void k_scale(float* __restrict__ x, size_t n, float f) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= f;
+}
+
 int train_step(TrainState* t, const float* d_feats_in /* [B][17][N2] on the device */, const float* h_pi, const float* h_z, int B, float eta,
-               float rho, float* loss_out, cudaStream_t s, char* err, size_t errlen) {
+               float rho, float* loss_out, cudaStream_t s, char* err, size_t errlen, int world, train_allreduce_fn allreduce, void* ctx) {
   if (B < 1 || B > t->maxB) { snprintf(err, errlen, "batch %d outside [1, %d]", B, t->maxB); return 1; }
   const int C = t->C, N = t->N, N2 = t->N2, A = t->A, T = t->T;
   const int nl = 1 + 2 * T;
@@ -601,6 +605,22 @@ int train_step(TrainState* t, const float* d_feats_in /* [B][17][N2] on the devi
   }
   conv_bwd(0, t->dA, t->feats, nullptr, nullptr);
 
+  // ---- data parallel: average gradients, loss terms and running statistics over the ranks
+  if (world > 1 && allreduce) {
+    const float inv = 1.0f / (float)world;
+    const size_t nstat = (size_t)nl * C;
+    int arc = 0;
+    for (int k = 0; k < 3; ++k) arc |= allreduce(ctx, t->G[k], t->np[k], s);
+    arc |= allreduce(ctx, t->red, 8, s);
+    arc |= allreduce(ctx, t->mu_run, nstat, s) | allreduce(ctx, t->var_run, nstat, s) | allreduce(ctx, t->hmu_run, 3, s) | allreduce(ctx, t->hvar_run, 3, s);
+    if (arc) { snprintf(err, errlen, "gradient all-reduce failed"); return 1; }
+    for (int k = 0; k < 3; ++k) k_scale<<<grid_for(t->np[k]), 256, 0, s>>>(t->G[k], t->np[k], inv);
+    k_scale<<<1, 8, 0, s>>>(t->red, 8, inv);
+    k_scale<<<grid_for(nstat), 256, 0, s>>>(t->mu_run, nstat, inv);
+    k_scale<<<grid_for(nstat), 256, 0, s>>>(t->var_run, nstat, inv);
+    k_scale<<<1, 3, 0, s>>>(t->hmu_run, 3, inv);
+    k_scale<<<1, 3, 0, s>>>(t->hvar_run, 3, inv);
+  }
   // ---- loss value, then the Momentum update (train.jl:54)
   float red[8];
   cudaMemcpyAsync(red, t->red, sizeof(red), cudaMemcpyDeviceToHost, s);

@@ -157,7 +157,9 @@ int32_t agz_features(agz_engine* e, const int8_t* boards_hist, const int8_t* to_
  * train-mode forward (BatchNorm on batch statistics, running statistics moved with momentum 0.1), loss = 0.01 * crossentropy(p, pi)
  * + 0.01 * mse(z, v) + 1e-4 * sum(theta^2) (:75-83), back-propagation, Momentum(lr, momentum): v = momentum * v - lr * grad;
  * theta += v.  Inputs as agz_net_forward / agz_replay_sample: boards_hist B x 8 x N*N, to_play B, pis B x A, zs B.  The updated
- * parameters are what every later forward / self-play call of this engine uses; *loss_out = the loss before the update. */
+ * parameters are what every later forward / self-play call of this engine uses; *loss_out = the loss before the update.
+ * After agz_nccl_init (world_size > 1) the step is data parallel -- an extension, the reference trains in one process: every rank
+ * calls it with its own minibatch; gradients, loss and running statistics are averaged with ncclAllReduce before the update. */
 int32_t agz_train_step(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, const float* pis, const int8_t* zs, int32_t B,
                        float lr, float momentum, float* loss_out);
 /* gradients of the data loss of the last agz_train_step, chain's Flux params order (test hook) */

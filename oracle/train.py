@@ -44,7 +44,9 @@ class Trainer:
         lists = [nn.base_params(), nn.value_params(), nn.policy_params()]
         return [[torch.tensor(np.asarray(a, np.float32), requires_grad=True) for a in lst] for lst in lists]
 
-    def step(self, positions_or_feats, pis, zs, lr=0.02, rho=0.9):
+    def grads(self, positions_or_feats, pis, zs):
+        """Train-mode forward + back-propagation of the data loss.  Returns (loss incl. regulariser, leaves, gradients, BatchNorm
+        batch statistics); nothing is updated."""
         nn = self.nn
         x = positions_or_feats if isinstance(positions_or_feats, torch.Tensor) else onet.NeuralNet.feats_to_torch(positions_or_feats)
         pi = torch.from_numpy(np.asarray(pis, np.float32))          # (B, A)
@@ -73,24 +75,44 @@ class Trainer:
         leaves = base + value + policy
         data_grads = torch.autograd.grad(data_loss, leaves, retain_graph=False)
         reg = W_REG * sum((t.detach() ** 2).sum() for t in leaves)   # loss_reg (:80-83)
-        loss = float(data_loss.detach() + reg)
+        self._split = (len(base), len(value))
+        return float(data_loss.detach() + reg), leaves, list(data_grads), stats
+
+    def apply(self, leaves, data_grads, stats_list, lr=0.02, rho=0.9):
+        """Momentum (train.jl:54) with the regulariser's gradient, then the running statistics.  `stats_list` holds the batch
+        statistics of every contributing minibatch (one for the reference's single-process step; several = their mean)."""
+        nn = self.nn
         if self.vel is None:
             self.vel = [torch.zeros_like(t) for t in leaves]
         new = []
-        for t, g, vel in zip(leaves, data_grads, self.vel):          # Momentum (train.jl:54)
+        for t, g, vel in zip(leaves, data_grads, self.vel):
             g_total = g + 2.0 * W_REG * t.detach()
             vel.mul_(rho).sub_(lr * g_total)
             new.append((t.detach() + vel).numpy().astype(np.float32))
-        nb, nv = len(base), len(value)
+        nb, nv = self._split
         nn.load_flux_lists(new[:nb], new[nb:nb + nv], new[nb + nv:])
-        for bn, mu, var in stats:                                    # running statistics
+        k = len(stats_list)
+        for entries in zip(*stats_list):                             # the same BatchNorm layer in every minibatch
+            bn = entries[0][0]
             cur_var = bn.sigma ** 2 if bn.mode == onet.BN_STD else bn.sigma
-            bn.mu = ((1 - BN_MOMENTUM) * bn.mu + BN_MOMENTUM * mu).astype(np.float32)
-            bn.sigma = ((1 - BN_MOMENTUM) * cur_var + BN_MOMENTUM * var).astype(np.float32)
-            bn.mode = onet.BN_VAR_EPS
+            mu = sum(((1 - BN_MOMENTUM) * bn.mu + BN_MOMENTUM * e[1]) for e in entries) / k
+            var = sum(((1 - BN_MOMENTUM) * cur_var + BN_MOMENTUM * e[2]) for e in entries) / k
+            bn.mu, bn.sigma, bn.mode = mu.astype(np.float32), var.astype(np.float32), onet.BN_VAR_EPS
         lists = [data_grads[:nb], data_grads[nb:nb + nv], data_grads[nb + nv:]]
         self.last_grads = [np.concatenate([g.numpy().flatten(order="F") for g in lst]).astype(np.float32) for lst in lists]
+
+    def step(self, positions_or_feats, pis, zs, lr=0.02, rho=0.9):
+        loss, leaves, grads, stats = self.grads(positions_or_feats, pis, zs)
+        self.apply(leaves, grads, [stats], lr, rho)
         return loss
+
+    def step_data_parallel(self, batches, lr=0.02, rho=0.9):
+        """The engine's multi-GPU extension: one minibatch per rank, gradients / loss / moved running statistics averaged."""
+        outs = [self.grads(*b) for b in batches]
+        k = len(outs)
+        grads = [sum(o[2][i] for o in outs) / k for i in range(len(outs[0][2]))]
+        self.apply(outs[0][1], grads, [o[3] for o in outs], lr, rho)
+        return sum(o[0] for o in outs) / k
 
 
 def flat_params(nn):

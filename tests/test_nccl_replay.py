@@ -77,3 +77,73 @@ def test_nccl_replay_all_gather_two_gpus():
         assert m["total"] == n_all
         got = sorted((m["boards"][k].tobytes(), int(m["tp"][k]), m["pis"][k].tobytes(), int(m["zs"][k])) for k in range(n_all))
         assert got == want, "rank %d ring differs from the oracle's tuples" % r
+
+
+def _train_worker(rank, world, uid_q, out_q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import pkg
+    agz = pkg.load()
+    from oracle import net as onet, train as otrain
+    import test_abi_train as tt
+    N, T, B = 9, 1, 6
+    onn = onet.NeuralNet(N, T, seed=3)
+    onn.randomize_bn(seed=4)
+    eng = agz.Engine(N, n_games=8, readouts=8, tower_height=T, evaluator=agz.EVAL_NN_TC, device=rank, world_size=world, rank=rank)
+    flat = otrain.flat_params(onn)
+    bns = [onn.base_bns(), [onn.v_bn], [onn.p_bn]]
+    for k in range(3):
+        eng.net_set_params(k, flat[k])
+        eng.net_set_bn_stats(k, np.concatenate([b.mu for b in bns[k]]), np.concatenate([b.sigma for b in bns[k]]), agz.BN_VAR_EPS)
+    if rank == 0:
+        uid = eng.nccl_unique_id()
+        uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=120)
+    eng.nccl_init(uid)
+    losses = []
+    for step in range(2):
+        positions, pis, zs = tt._batch(N, B, 100 * step + rank)      # every rank trains on its own minibatch
+        bh, tp = tt._hist(positions, N)
+        losses.append(eng.train_step(bh, tp, pis, zs, lr=0.02, momentum=0.9))
+    out_q.put({"rank": rank, "losses": losses, "grads": [eng.train_read_grads(k) for k in range(3)], "params": [eng.net_get_params(k) for k in range(3)],
+               "bn": [eng.net_get_bn_stats(k)[:2] for k in range(3)]})
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_data_parallel_train_step_two_gpus():
+    """agz_train_step with an NCCL communicator: gradients, loss and moved running statistics are averaged over the ranks, both
+    ranks end with identical parameters, and they equal the oracle's step on the averaged gradients of the two minibatches."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import net as onet, train as otrain
+    import test_abi_train as tt
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, uid_q, out_q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    msgs = {m["rank"]: m for m in (out_q.get(timeout=600) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    N, T, B = 9, 1, 6
+    onn = onet.NeuralNet(N, T, seed=3)
+    onn.randomize_bn(seed=4)
+    tr = otrain.Trainer(onn)
+    want_losses = [tr.step_data_parallel([tt._batch(N, B, 100 * step + r) for r in range(2)]) for step in range(2)]
+    want = otrain.flat_params(onn)
+    bns = [onn.base_bns(), [onn.v_bn], [onn.p_bn]]
+    for r in (0, 1):
+        m = msgs[r]
+        assert np.allclose(m["losses"], want_losses, rtol=3e-4)
+        for k in range(3):
+            assert tt._rel(m["grads"][k], tr.last_grads[k]) < 2e-3
+            assert np.max(np.abs(m["params"][k] - want[k])) < 2e-5
+            assert np.allclose(m["bn"][k][0], np.concatenate([b.mu for b in bns[k]]), atol=2e-5, rtol=1e-4)
+            assert np.allclose(m["bn"][k][1], np.concatenate([b.sigma for b in bns[k]]), atol=2e-5, rtol=1e-4)
+    for k in range(3):
+        assert np.array_equal(msgs[0]["params"][k], msgs[1]["params"][k]), "ranks diverged"
