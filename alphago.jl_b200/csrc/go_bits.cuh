@@ -15,8 +15,7 @@
 //     groups that own a liberty which is not a candidate are found with one multi-source flood each; the rare groups whose
 //     liberties are all candidates are visited one by one;
 //   * score: empty points reached from black stones through empty points, same for white.
-// The shared-memory label/liberty-count code of go_rules.cuh is kept for the liberty-cache hook and the replay packer and
-// cross-checks this file in the tests (same reference test cases run through both).
+// (go_rules.cuh keeps a shared-memory label / liberty-count pass for the liberty-cache test hook only.)
 #pragma once
 #include "simt.h"
 

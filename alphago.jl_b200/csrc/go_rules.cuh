@@ -1,16 +1,12 @@
-// go_rules.cuh -- Go rules for one position, executed cooperatively by one warp.
+// go_rules.cuh -- connected-group labels and liberty counts for one position in per-warp shared memory.
 //
-// Replaces (reference paths): src/game/go/board.jl  play_move! :451-509, pass_move! :426-440,
-// add_stone!/captures :205-269, is_koish :47-56, all_legal_moves :393-424, is_move_suicidal :354-374,
-// score :511-533, LibertyTracker.liberty_cache :99-164.
+// Stands for LibertyTracker.liberty_cache (src/game/go/board.jl:99-164), which the reference's tests read
+// (test/test_go.jl:74-139) and which only the liberty-cache hook of the C ABI (agz_pos_liberties) needs.  The hot path does
+// not use this file: play / capture / ko / legality / score run on bitboard lines in registers (go_bits.cuh).
 //
-// Design: instead of the reference's incremental Dict{Int,Group}-of-Sets liberty tracker (deep-copied
-// for every new tree node), a position is two bitplanes in HBM.  When a child position is needed the
-// warp expands the planes into a per-warp shared-memory board (1 byte / point), labels connected
-// groups by min-label propagation with pointer jumping (lane l owns points l, l+32, ...), counts each
-// group's distinct liberties with shared-memory atomics, applies captures / ko / suicide rules and packs
-// the child's planes and legal-move mask back with warp ballots.  Results are identical to the
-// liberty tracker's (pinned by the reference's test_go.jl cases through the C ABI).
+// Design: 1 byte per point; groups are labelled by min-label propagation with pointer jumping in Jacobi sweeps (lane l owns
+// points l, l+32, ...; reads of a sweep are separated from its writes by a warp barrier), liberties are counted per label
+// with shared-memory atomics.
 #pragma once
 #include "simt.h"
 
@@ -76,15 +72,6 @@ AGZ_DEV RulesScratch rules_scratch_at(char* smem, int KB) {
     if (m__ & 8u) { q = (p) + (B).N; BODY }                   \
   }
 
-AGZ_DEV void rules_load(const Board& B, RulesScratch& s, const uint32_t* black, const uint32_t* white) {
-  const int lane = simt::lane();
-  for (int k = 0; k < B.KB; ++k) {
-    uint32_t b = black[k], w = white[k];  // warp-uniform addresses: one broadcast load each
-    s.bd[k * 32 + lane] = (int8_t)((int)((b >> lane) & 1u) - (int)((w >> lane) & 1u));
-  }
-  simt::sync();
-}
-
 AGZ_DEV void rules_load_bytes(const Board& B, RulesScratch& s, const int8_t* board) {
   const int lane = simt::lane();
   for (int k = 0; k < B.KB; ++k) {
@@ -92,22 +79,6 @@ AGZ_DEV void rules_load_bytes(const Board& B, RulesScratch& s, const int8_t* boa
     s.bd[p] = p < B.N2 ? board[p] : (int8_t)0;
   }
   simt::sync();
-}
-
-// pack the scratch board into bitplanes; every lane receives all words (KW >= B.KB keeps them in registers)
-template <int KW>
-AGZ_DEV void rules_pack(const Board& B, const RulesScratch& s, uint32_t (&black)[KW], uint32_t (&white)[KW]) {
-  const int lane = simt::lane();
-#pragma unroll
-  for (int k = 0; k < KW; ++k) {
-    black[k] = 0;
-    white[k] = 0;
-    if (k < B.KB) {
-      int v = s.bd[k * 32 + lane];
-      black[k] = simt::ballot(v == 1);
-      white[k] = simt::ballot(v == -1);
-    }
-  }
 }
 
 // mode 0: label stones (4-connected, same colour); mode 1: label empty regions
@@ -120,26 +91,35 @@ AGZ_DEV void rules_label(const Board& B, RulesScratch& s, int mode) {
     s.lab[p] = (int16_t)(in ? p : -1);
   }
   simt::sync();
-  for (;;) {
+  for (;;) {  // Jacobi sweeps: every lane reads the labels of the previous sweep, then all lanes write (no intra-warp races)
     bool changed = false;
-    for (int k = 0; k < B.KB; ++k) {
-      int p = k * 32 + lane;
-      int m0 = s.lab[p];
-      if (m0 >= 0) {
-        int v = s.bd[p];
-        int m = m0;
-        AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, {
-          int lq = s.lab[q];
-          if (lq >= 0 && s.bd[q] == v && lq < m) m = lq;
-        })
-        int mm = s.lab[m];  // pointer jumping
-        if (mm >= 0 && mm < m) m = mm;
-        if (m < m0) {
-          s.lab[p] = (int16_t)m;
-          changed = true;
+    int nl[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      nl[k] = -1;
+      if (k < B.KB) {
+        int p = k * 32 + lane;
+        int m0 = s.lab[p];
+        if (m0 >= 0) {
+          int v = s.bd[p];
+          int m = m0;
+          AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, {
+            int lq = s.lab[q];
+            if (lq >= 0 && s.bd[q] == v && lq < m) m = lq;
+          })
+          int mm = s.lab[m];  // pointer jumping
+          if (mm >= 0 && mm < m) m = mm;
+          if (m < m0) {
+            nl[k] = m;
+            changed = true;
+          }
         }
       }
     }
+    simt::sync();
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      if (k < B.KB && nl[k] >= 0) s.lab[k * 32 + lane] = (int16_t)nl[k];
     simt::sync();
     if (!simt::any(changed)) break;
   }
@@ -167,129 +147,6 @@ AGZ_DEV void rules_count_liberties(const Board& B, RulesScratch& s) {
     }
   }
   simt::sync();
-}
-
-// Play `color` at point c on the scratch board (labels + liberty counts are left valid for the result).
-// Returns 0, or 1 when check_legal is set and the move is on a stone or suicidal (scratch is then garbage).
-// ko_out = the point the opponent may not retake, or -1 (board.jl:473,487-491); ncap_out = stones captured.
-AGZ_DEV int rules_play(const Board& B, RulesScratch& s, int c, int color, bool check_legal, int& ko_out, int& ncap_out) {
-  const int lane = simt::lane();
-  ko_out = -1;
-  ncap_out = 0;
-  if (check_legal && s.bd[c] != 0) return 1;
-  // is_koish on the board before the move: every neighbour of c holds the opponent's colour
-  bool koish = true;
-  AGZ_FOR_NEIGHBORS(B, c, q, { koish = koish && (s.bd[q] == -color); })
-  simt::sync();
-  if (lane == 0) s.bd[c] = (int8_t)color;
-  simt::sync();
-  rules_label(B, s, 0);
-  rules_count_liberties(B, s);
-  // opponent groups next to c that are left without liberties are captured
-  int cr[4];
-  int ncr = 0;
-  AGZ_FOR_NEIGHBORS(B, c, q, {
-    if (s.bd[q] == -color) {
-      int l = s.lab[q];
-      if (s.cnt[l] == 0) {
-        bool dup = false;
-        for (int t = 0; t < ncr; ++t) dup = dup || (cr[t] == l);
-        if (!dup) cr[ncr++] = l;
-      }
-    }
-  })
-  int ncap = 0, cap_point = -1;
-  if (ncr > 0) {  // warp-uniform
-    simt::sync();
-    for (int k = 0; k < B.KB; ++k) {
-      int p = k * 32 + lane;
-      bool dead = false;
-      if (s.bd[p] == -color) {
-        int l = s.lab[p];
-        for (int t = 0; t < ncr; ++t) dead = dead || (l == cr[t]);
-      }
-      unsigned m = simt::ballot(dead);
-      if (dead) {
-        s.bd[p] = 0;
-        s.lab[p] = -1;
-      }
-      if (m) {
-        ncap += simt::popc(m);
-        cap_point = k * 32 + simt::ffs(m) - 1;
-      }
-    }
-    simt::sync();
-    rules_count_liberties(B, s);
-  }
-  if (check_legal && s.cnt[s.lab[c]] == 0) return 1;  // suicide (board.jl:264-266)
-  ncap_out = ncap;
-  if (ncap == 1 && koish) ko_out = cap_point;
-  return 0;
-}
-
-// all_legal_moves for the player `to_play` on the scratch board (labels + liberty counts valid).
-// legal[k] receives the bit mask of points k*32..k*32+31; pass is always legal and not part of the mask.
-template <int KW>
-AGZ_DEV void rules_legal_mask(const Board& B, const RulesScratch& s, int to_play, int ko, uint32_t (&legal)[KW]) {
-  const int lane = simt::lane();
-#pragma unroll
-  for (int k = 0; k < KW; ++k) {
-    legal[k] = 0;
-    if (k >= B.KB) continue;
-    int p = k * 32 + lane;
-    bool ok = false;
-    if (p < B.N2 && s.bd[p] == 0 && p != ko) {
-      AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, {
-        int v = s.bd[q];
-        if (v == 0) {
-          ok = true;
-        } else {
-          int libs = s.cnt[s.lab[q]];
-          if (v == to_play ? libs >= 2 : libs == 1) ok = true;
-        }
-      })
-    }
-    legal[k] = simt::ballot(ok);
-  }
-}
-
-// Tromp-Taylor area score from Black's view: Float32(#B - #W) - komi  (board.jl:511-533)
-AGZ_DEV float rules_score(const Board& B, RulesScratch& s, float komi) {
-  const int lane = simt::lane();
-  rules_label(B, s, 1);
-  for (int k = 0; k < B.KB; ++k) s.cnt[k * 32 + lane] = 0;
-  simt::sync();
-  for (int k = 0; k < B.KB; ++k) {
-    int p = k * 32 + lane;
-    if (p < B.N2 && s.bd[p] == 0) {
-      int f = 0;
-      AGZ_FOR_OWN_NEIGHBORS(B, k, p, q, {
-        int v = s.bd[q];
-        if (v == 1) f |= 1;
-        if (v == -1) f |= 2;
-      })
-      if (f) simt::atomic_or(&s.cnt[s.lab[p]], f);
-    }
-  }
-  simt::sync();
-  int nb = 0, nw = 0;
-  for (int k = 0; k < B.KB; ++k) {
-    int p = k * 32 + lane;
-    bool b = false, w = false;
-    if (p < B.N2) {
-      int v = s.bd[p];
-      if (v == 1) b = true;
-      else if (v == -1) w = true;
-      else {
-        int f = s.cnt[s.lab[p]];
-        b = (f == 1);
-        w = (f == 2);
-      }
-    }
-    nb += simt::popc(simt::ballot(b));
-    nw += simt::popc(simt::ballot(w));
-  }
-  return simt::fsub((float)(nb - nw), komi);
 }
 
 }  // namespace agz

@@ -130,16 +130,15 @@ struct PackOp {
   unsigned char* out;
   size_t stride;
   __device__ void operator()(int wi, char* smem) const {
+    (void)smem;
     const int lane = threadIdx.x & 31;
-    Board B;
-    B.N = c.N; B.N2 = c.N2; B.KB = c.KB;
-    board_init_masks(B);
-    RulesScratch rs = rules_scratch_at(smem, c.KB);
+    const BitsCtx B = bits_ctx(c.N, c.KB);   // Go rules on bitboard lines in registers (go_bits.cuh)
+    Lines pos;
+    pos.b = 0;
+    pos.w = 0;
     const int rslot = rec[2 * wi], first = rec[2 * wi + 1];
     const RingHeader hd = v.ring_hdr[rslot];
     const size_t L = c.max_game_length + 2;
-    for (int k = 0; k < c.KB; ++k) rs.bd[k * 32 + lane] = 0;
-    __syncwarp();
     int to_play = 1;
     for (int t = 0; t < hd.n_moves; ++t) {
       unsigned char* o = out + (size_t)(first + t) * stride;
@@ -147,7 +146,7 @@ struct PackOp {
       const float* pi = v.ring_pi + ((size_t)rslot * L + t) * c.A;
       for (int a = lane; a < c.A; a += 32) opi[a] = pi[a];
       int8_t* ob = reinterpret_cast<int8_t*>(o + (size_t)4 * c.A);
-      for (int p = lane; p < c.N2; p += 32) ob[p] = rs.bd[p];
+      bits_to_bytes(B, pos, ob);
       // boards 1..7 = the previous tuple's boards 0..6 (all empty before the first move)
       const int8_t* prev = t > 0 ? reinterpret_cast<const int8_t*>(o - stride + (size_t)4 * c.A) : nullptr;
       for (int p = lane; p < 7 * c.N2; p += 32) ob[c.N2 + p] = prev ? prev[p] : (int8_t)0;
@@ -159,7 +158,7 @@ struct PackOp {
       const int mv = v.ring_moves[(size_t)rslot * L + t];
       if (mv != c.N2) {
         int ko, ncap;
-        rules_play(B, rs, mv, to_play, false, ko, ncap);
+        bits_play(B, pos, mv, to_play, false, ko, ncap);
       }
       to_play = -to_play;
       __syncwarp();
