@@ -154,19 +154,19 @@ def test_features_hook(env):                             # test_features.jl:48-7
     assert (f[:, :, 10:16] == 0).all() and (f[:, :, 16] == -1).all()
 
 
-@pytest.mark.parametrize("N", [9, 19])
+@pytest.mark.parametrize("N", [5, 9, 13, 19])   # 5: one bit-plane word, 13: the 6-word kernel variant, 19: 12 words
 def test_random_playouts_match_oracle(request, N):
     """Random legal playouts: board, ko, captures, legal mask, liberties and score equal the oracle's at every ply."""
     backend = "emu"
     e = agz.GoEnv(N, lib_path=lib_for(backend))
-    _random_playouts(e, N, games=2 if N == 9 else 1, plies=120 if N == 9 else 150)
+    _random_playouts(e, N, games=2 if N <= 9 else 1, plies={5: 60, 9: 120, 13: 120, 19: 150}[N])
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N", [9, 19])
+@pytest.mark.parametrize("N", [5, 9, 13, 19])
 def test_random_playouts_match_oracle_cuda(N):
     e = agz.GoEnv(N, lib_path=lib_for("cuda"))
-    _random_playouts(e, N, games=3, plies=200 if N == 9 else 400)
+    _random_playouts(e, N, games=3, plies={5: 80, 9: 200, 13: 300, 19: 400}[N])
 
 
 def _random_playouts(env, N, games, plies):

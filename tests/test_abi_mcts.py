@@ -335,6 +335,14 @@ def test_selfplay_with_tiny_arena_compacts_every_move(env):
     check_selfplay_parity(env, 9, 16, seeds=[5], priors_seed=2, value=0.05, n_games=2, nodes_per_game=96)
 
 
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("N", [5, 13])
+def test_selfplay_matches_oracle_other_board_sizes(backend, N):
+    """5x5 (one bit-plane word, A = 26 < 32) and 13x13 (A = 170: the 6-word kernel variant) against the oracle."""
+    e = agz.GoEnv(N, lib_path=lib_for(backend))
+    check_selfplay_parity(e, N, 16, seeds=[8], priors_seed=3, value=0.05, n_games=2, **({"max_game_length": 40} if N == 13 else {}))
+
+
 @pytest.mark.gpu
 def test_selfplay_matches_oracle_bulk():
     """C2-like readouts on a handful of games, and many concurrent small games (slot refill, ring, compaction)."""

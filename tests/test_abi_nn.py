@@ -96,7 +96,7 @@ def test_shipped_agz_net_matches_golden(evaluator, tol):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("evaluator,tol", EVALS)
-@pytest.mark.parametrize("N,T,B", [(9, 1, 40), (9, 6, 70), (19, 2, 9)])
+@pytest.mark.parametrize("N,T,B", [(9, 1, 40), (9, 6, 70), (19, 2, 9), (13, 1, 5), (5, 2, 3)])
 def test_random_towers_match_oracle(evaluator, tol, N, T, B):
     nn = onet.NeuralNet(N, T, seed=10 + T)
     nn.randomize_bn(seed=T)
