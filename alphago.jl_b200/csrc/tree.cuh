@@ -30,7 +30,7 @@ enum { E_OK = 0, E_ILLEGAL = 1, E_ASSERT = 2, E_CAPACITY = 6 };
 enum { OP_VLOSS_ADD = 0, OP_VLOSS_REVERT = 1, OP_BACKUP = 2, OP_REVERT_VISITS = 3 };
 static const uint32_t SLOT_ROOT = 0xFFFFFFFFu;
 
-struct NodeMeta {  // 16 bytes
+struct alignas(16) NodeMeta {  // 16 bytes, moved as one 128-bit word
   int32_t parent;
   int16_t fmove;  // move that led here (-1 for an arena root)
   int16_t n;      // position.n
@@ -40,7 +40,7 @@ struct NodeMeta {  // 16 bytes
   int32_t pad;
 };
 
-struct PathEnt {  // 16 bytes; where this path node's own N / W live
+struct alignas(16) PathEnt {  // 16 bytes; where this path node's own N / W live
   uint32_t slot;  // index into N / W, or SLOT_ROOT
   int32_t node;
   int32_t to_play;
@@ -135,7 +135,15 @@ struct Warp {
   }
   AGZ_DEV size_t row(int node) const { return (nbase + node) * (size_t)c.AS; }
   AGZ_DEV uint32_t* bits_of(int node) const { return v.bits + (nbase + node) * (size_t)(3 * c.KB); }
-  AGZ_DEV NodeMeta load_meta(int node) const { return v.meta[nbase + node]; }
+  AGZ_DEV NodeMeta load_meta(int node) const {
+#if AGZ_CUDA
+    NodeMeta m;   // one 16-byte load instead of a load per field
+    *reinterpret_cast<uint4*>(&m) = *reinterpret_cast<const uint4*>(v.meta + nbase + node);
+    return m;
+#else
+    return v.meta[nbase + node];
+#endif
+  }
   AGZ_DEV bool terminal(const NodeMeta& m) const { return (m.flags & F_DONE) || m.n >= c.max_game_length; }
   AGZ_DEV PathEnt* path_of(int k) const { return v.path + ((size_t)g * c.pmax + k) * c.maxd; }
   AGZ_DEV void count(int which, unsigned long long n) {
@@ -392,14 +400,15 @@ struct Warp {
   AGZ_DEV void search_select(int parallel, bool seed_mode) {
     int nleaf = 0, attempts = 0;
     const int want = seed_mode ? 1 : parallel;
+    unsigned long long n_readouts = 0, n_pathnodes = 0;   // one atomic per counter per warp, not per readout
     while (nleaf < want && attempts < 2 * want) {
       ++attempts;
       PathEnt* path = path_of(nleaf);
       int plen = 0;
       int leaf = select_leaf(st.root, path, plen);
       if (st.err) break;
-      count(CTR_READOUTS, 1);
-      count(CTR_PATHNODES, (unsigned long long)plen);
+      n_readouts += 1;
+      n_pathnodes += (unsigned long long)plen;
       NodeMeta lm = load_meta(leaf);
       if (terminal(lm)) {  // game over: back up the true result, do not evaluate (mcts_play.jl:80-84)
         const uint32_t* lb = bits_of(leaf);
@@ -417,7 +426,11 @@ struct Warp {
     }
     st.nleaf = nleaf;
     st.seed_round = seed_mode ? 1 : 0;
-    count(CTR_POSITIONS, (unsigned long long)nleaf);
+    if (n_readouts) {
+      count(CTR_READOUTS, n_readouts);
+      count(CTR_PATHNODES, n_pathnodes);
+    }
+    if (nleaf) count(CTR_POSITIONS, (unsigned long long)nleaf);
   }
 
   // incorporate_results! for one node given its path (mcts.jl:188-213)
