@@ -399,6 +399,66 @@ def test_c2_full_size_properties():
         e.close()
 
 
+@pytest.mark.gpu
+def test_c5_full_size_matches_oracle():
+    """BASELINE config C5 at full size (9x9, 8192 trees x 1600 readouts, uniform prior, noise on): the first moves of sampled games
+    equal the oracle's bit for bit (visit counts, pi, q, chosen moves), whatever slot of the 8192 the game runs in."""
+    lib = lib_for("cuda")
+    G, R, moves = 8192, 1600, 2
+    eng = agz.Engine(9, lib_path=lib, n_games=G, readouts=R, seed=9, nodes_per_game=3600)
+    eng.set_dummy_evaluator(None, 0.0)
+    eng.selfplay_start(-1)
+    pr = eng.selfplay_step(moves * (R // 8) + 2)
+    assert pr.error == 0 and pr.moves_played >= moves * G
+    oenv = ogo.GoEnv(9)
+    net = DummyNet(82)
+
+    class Stop(Exception):
+        pass
+
+    for slot in (0, 4097, 8191):
+        n, mv, q, pi = eng.tree_read_record(slot)
+        assert n >= moves and eng.tree_pending_vlosses(slot) == 0
+        seen = []
+
+        def on_move(player, move):
+            seen.append(player)
+            if len(player.searches_pi) >= moves:
+                raise Stop()
+
+        try:
+            osp.selfplay(oenv, net, R, seed=9, game_id=slot, on_move=on_move)
+        except Stop:
+            pass
+        op = seen[-1]
+        assert [ogo.to_flat(m.move, oenv) for m in op.root.position.recent][:moves] == list(mv[:moves]), slot
+        assert np.array_equal(np.array(op.searches_pi[:moves], dtype=f32), pi[:moves]), slot
+        assert np.array_equal(np.array(op.qs[:moves], dtype=f32), q[:moves]), slot
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_c3_share_full_size_properties():
+    """One GPU's share of BASELINE config C3 (19x19, 512 games, 800 readouts, tower_height 19): one full move of every game on the
+    tensor-core network -- no device error, no pending virtual losses, pi sums to 1 with exactly the move's visits behind it, and
+    the recorded move is legal under the oracle's rules."""
+    lib = lib_for("cuda")
+    env = agz.GoEnv(19, lib_path=lib)
+    nn = agz.NeuralNet(env, tower_height=19, seed=0)
+    eng = agz.Engine(19, lib_path=lib, n_games=512, readouts=800, tower_height=19, seed=4, evaluator=agz.EVAL_NN_TC)
+    nn.push(eng)
+    eng.selfplay_start(-1)
+    pr = eng.selfplay_step(104)
+    assert pr.error == 0 and pr.moves_played >= 512
+    oenv = ogo.GoEnv(19)
+    for slot in range(0, 512, 73):
+        n, mv, q, pi = eng.tree_read_record(slot)
+        assert n >= 1 and eng.tree_pending_vlosses(slot) == 0
+        assert abs(float(pi[0].sum()) - 1.0) < 1e-5 and -1.0 <= q[0] <= 1.0
+        ogo.play_move(ogo.GoPosition(oenv), ogo.from_flat(int(mv[0]), oenv))
+    eng.close()
+
+
 # ------------------------------------------------------------ replay ring (extract_data / replay_position / get_replay_batch)
 @pytest.mark.gpu
 def test_replay_gather_read_sample():
