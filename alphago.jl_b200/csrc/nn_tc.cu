@@ -133,6 +133,13 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&v)[32]) {
                : "memory");
 }
 
+// 32-byte store (STG.256, sm_100): one full sector per thread instead of two half-sector 16-byte stores
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -1065,8 +1072,8 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int j = 0; j < 4; ++j) rv[cc & 1][j] = ld_nc_v4(rrow + (cc + 2) * 4 + j);
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+          st_global_256(orow + cc * 32, o[0], o[1]);
+          st_global_256(orow + cc * 32 + 16, o[2], o[3]);
         }
       }
       tc_fence_before();
@@ -1261,8 +1268,8 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
           }
           if (!heads) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
+            st_global_256(orow + cc * 32, o[0], o[1]);
+            st_global_256(orow + cc * 32 + 16, o[2], o[3]);
           }
         }
       }
