@@ -38,6 +38,7 @@ struct TCState {
   unsigned long long* trace;  // kernel timeline trace buffer or nullptr (nn_tc_set_trace)
   int fuse_heads;             // AGZ_FUSE_HEADS (default 1): head 1x1 convs in the last tower conv's epilogue, trunk not stored
   float4* head_pre;           // [rows_alloc] (value plane, policy plane 0, policy plane 1, 0) written by that epilogue
+  int l2pf;                   // AGZ_CONV_L2PF: L2 prefetch of the next tile in the conv producers
   int pdl;                    // AGZ_CONV_PDL (default 1): tower convolutions use programmatic dependent launch
   int max_pairs;              // AGZ_CONV_PAIRS
   int version;                // AGZ_CONV_KERNEL: 1 per-tap, 2 slab, 3 CTA pair, 4 CTA pair + slab (zero-bordered layout); 5 CTA pair + im2col (dense, default)
@@ -171,6 +172,7 @@ struct ConvArgs {
   int N, NP1, PP;
   int relu;
   unsigned long long* trace;   // kernel timeline trace (simt.h) or nullptr
+  int l2pf;                    // prefetch the next tile's activation (and shortcut) rows into L2 (AGZ_CONV_L2PF)
   // last convolution of the tower (conv3x3_tc6_kernel only): the 1x1 convolutions + BatchNorm + relu of the value and policy
   // heads (neural_net.jl:23-24,28-29) are evaluated in the epilogue from the fp32 trunk values and the trunk is not stored
   const float* head_vw;        // [256] value 1x1 conv weights, or nullptr
@@ -927,6 +929,15 @@ __device__ __forceinline__ void tma_load_im2col_2sm(void* dst, const CUtensorMap
                ::"r"(smem_u32(dst)), "l"(tm), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh) : "memory");
 }
 
+// L2 prefetch of a future tile's operands (no shared memory involved): the demand loads then hit L2 instead of HBM
+__device__ __forceinline__ void tma_prefetch_im2col(const CUtensorMap* tm, int c, int w, int h, int n, uint16_t ow, uint16_t oh) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.im2col [%0, {%1, %2, %3, %4}], {%5, %6};"
+               ::"l"(tm), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs a) {
   const unsigned long long trace_t0 = a.trace ? simt::gtimer() : 0ULL;
@@ -980,6 +991,11 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int t = pair; t < n_ptiles; t += n_pairs) {
         const int m0 = t * 256 + (int)rank * 128;
         const int b0 = m0 / N2, rem = m0 - b0 * N2, j0 = rem / a.N, i0 = rem - j0 * a.N;
+        if (a.l2pf && t + n_pairs < n_ptiles) {   // this pair's next tile: pull its rows (centre tap = the rows themselves) into L2 now
+          const int m1 = (t + n_pairs) * 256 + (int)rank * 128;
+          const int b1 = m1 / N2, rem1 = m1 - b1 * N2, j1 = rem1 / a.N, i1 = rem1 - j1 * a.N;
+          for (int kc = 0; kc < a.kchunks; ++kc) tma_prefetch_im2col(&tmA, kc * BK, i1 - 1, j1 - 1, b1, 1, 1);
+        }
         for (int tap = 0; tap < 9; ++tap) {
           const uint16_t oh = (uint16_t)(tap / 3), ow = (uint16_t)(tap % 3);
           for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -1168,6 +1184,12 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int t = pair; t < n_ptiles; t += n_pairs) {
         const int m0 = t * 256 + (int)rank * 128;
         const int b0 = m0 / N2, rem = m0 - b0 * N2, j0 = rem / a.N, i0 = rem - j0 * a.N;
+        if (a.l2pf && t + n_pairs < n_ptiles) {   // this pair's next tile: its rows and its shortcut rows into L2 now
+          const int m1 = (t + n_pairs) * 256 + (int)rank * 128;
+          const int b1 = m1 / N2, rem1 = m1 - b1 * N2, j1 = rem1 / a.N, i1 = rem1 - j1 * a.N;
+          for (int kc = 0; kc < a.kchunks; ++kc) tma_prefetch_im2col(&tmA, kc * BK, i1 - 1, j1 - 1, b1, 1, 1);
+          for (int bx = 0; bx < 4; ++bx) tma_prefetch_2d(&tmR, bx * BK, res_row0 + m1);
+        }
         int it = 0;
         for (int tap = 0; tap < 9; ++tap) {
           const uint16_t oh = (uint16_t)(tap / 3), ow = (uint16_t)(tap % 3);
@@ -1675,6 +1697,10 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
     t->fuse_heads = ef ? atoi(ef) : 1;
   }
   {
+    const char* el = getenv("AGZ_CONV_L2PF");
+    t->l2pf = el ? atoi(el) : 0;
+  }
+  {
     const char* ed = getenv("AGZ_CONV_PDL");
     t->pdl = ed ? atoi(ed) : 1;
   }
@@ -1783,6 +1809,7 @@ static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.relu = 1;
   a.trace = t->trace;
   a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
+  a.l2pf = t->l2pf;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
   conv3x3_tc3_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
@@ -1801,6 +1828,7 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.relu = 1;
   a.trace = t->trace;
   a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
+  a.l2pf = t->l2pf;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   // Same number of waves on as few CTA pairs as possible: 9x9 with 8192 (4096) positions is 2592 (1296) pair tiles =
   // 36 (18) waves on 72 pairs exactly, where 74 pairs would idle through a 37th (19th) wave's worth of tail.  The SMs
@@ -1846,6 +1874,7 @@ static int launch_conv4(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.relu = 1;
   a.trace = t->trace;
   a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
+  a.l2pf = t->l2pf;
   g.H8 = t->H8; g.slab_rows = 128 + 2 * t->H8; g.slab_bytes = g.slab_rows * 128;
   const int n_ptiles = (a.n_tiles + 1) / 2;
   int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
@@ -1864,6 +1893,7 @@ static int launch_conv(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tm
   a.relu = 1;
   a.trace = t->trace;
   a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
+  a.l2pf = t->l2pf;
   int grid = a.n_tiles < t->num_sms ? a.n_tiles : t->num_sms;
   conv3x3_tc_kernel<<<grid, 256, CONV_SMEM, s>>>(tmA, tmW, a);
   return (int)cudaGetLastError();
