@@ -5,7 +5,7 @@ from .binding import (Engine, Config, Position, NodeView, GameRecord, IllegalMov
                       SYMBOLS, EVAL_DUMMY, EVAL_NN_TC, EVAL_NN_F32, BN_VAR_EPS, BN_STD, CHAIN_BASE, CHAIN_VALUE,
                       CHAIN_POLICY)
 from . import api
-from .api import (GoEnv, GoPosition, NeuralNet, MCTSPlayer, MCTSNode, selfplay, evaluate, train, MatchGame, initialize_game, tree_search, pick_move,
+from .api import (GoEnv, GoPosition, NeuralNet, MCTSPlayer, MCTSNode, selfplay, evaluate, train, play, MatchGame, initialize_game, tree_search, pick_move,
                   play_move, should_resign, is_done, set_result, extract_data, select_leaf, incorporate_results,
                   maybe_add_child, add_virtual_loss, revert_virtual_loss, inject_noise, to_flat, from_flat, from_kgs,
                   to_kgs, all_legal_moves, score, result, get_feats, BLACK, WHITE, EMPTY)

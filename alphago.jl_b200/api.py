@@ -483,6 +483,48 @@ def evaluate(env, black_net, white_net, num_games=400, ro=800, verbose=False, se
     return games_won / G >= 0.55
 
 
+# ------------------------------------------------------------------ play (play.jl:25-77)
+def play(env, nn=None, tower_height=19, num_readouts=800, mode=0, input_fn=input, print_fn=print, seed=0):
+    """play(env, nn; tower_height, num_readouts, mode): a game against the engine on the terminal (mode 0: the human starts with
+    Black, otherwise with White).  Same loop as the reference: the human types KGS coordinates ("D4", "pass"), the engine searches
+    `num_readouts` more readouts from its current root and plays pick_move; both kinds of move go through play_move!(player, c),
+    which rejects illegal ones.  `input_fn` / `print_fn` make it scriptable.  Returns the MCTSPlayer (result set)."""
+    assert 0 <= tower_height <= 19
+    if nn is None:
+        nn = NeuralNet(env, tower_height=tower_height, seed=seed)
+    az = MCTSPlayer(env, nn, num_readouts=num_readouts, two_player_mode=True, seed=seed)
+    az.initialize_game()
+    num_moves = 0
+    mode = 0 if mode == 0 else 1
+    while not az.is_done():
+        print_fn(_board_string(az.position))
+        if num_moves % 2 == mode:
+            text = input_fn("Your turn: ")
+            try:
+                move = from_kgs(text.strip(), env)
+            except Exception:
+                print_fn("Try again.")
+                continue
+        else:
+            move = az.suggest_move()
+            print_fn("AlphaZero's turn: " + to_kgs(move, env))
+        if az.play_move(move):
+            num_moves += 1
+    print_fn(_board_string(az.position))
+    winner = result(az.position)
+    az.set_result(winner, False)
+    human = BLACK if mode == 0 else WHITE
+    print_fn(("You Win! " if winner == human else "AlphaZero wins! ") + az.result_string)
+    return az
+
+
+def _board_string(pos):
+    sym = {BLACK: "X", WHITE: "O", EMPTY: "."}
+    N = pos.env.N
+    rows = ["%2d %s" % (N - i, " ".join(sym[int(pos.board[i, j])] for j in range(N))) for i in range(N)]
+    return "\n".join(rows + ["   " + " ".join(_KGS_COLUMNS[:N])])
+
+
 # ------------------------------------------------------------------ train (train.jl:38-92)
 def train(env, num_games=25000, memory_size=500000, batch_size=32, epochs=1, ckp_freq=1000, readouts=800, tower_height=19,
           model=None, start_training_after=50000, concurrent=None, seed=0, model_dir=None, verbose=True, lr=0.02, momentum=0.9,

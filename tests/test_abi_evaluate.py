@@ -96,3 +96,19 @@ def test_evaluate_with_networks_on_gpu():
         for mv in x.moves:                                # every move is legal under the oracle's rules
             pos = ogo.play_move(pos, ogo.from_flat(mv, oenv))
         assert x.result != 0 or x.result_string == "DRAW"
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_play_scripted_game(backend):
+    """play(env, nn; ...) (src/play.jl:25-77) with a scripted human: illegal and unparsable inputs are asked again, the engine answers
+    with searched moves, two passes end the game and the result string is the area score."""
+    env = agz.GoEnv(5, lib_path=lib_for(backend))
+    net = DummyNet(26, fake_value=0.0)
+    script = iter(["C3", "zz", "C3", "pass", "pass", "pass", "pass", "pass", "pass", "pass", "pass", "pass", "pass", "pass", "pass"] + ["pass"] * 40)
+    said = []
+    az = agz.play(env, net, num_readouts=16, mode=0, input_fn=lambda prompt: next(script), print_fn=said.append)
+    assert az.is_done() and az.result_string
+    assert any(line == "Try again." for line in said)            # "zz" does not parse
+    assert said[-1].startswith(("You Win! ", "AlphaZero wins! "))
+    moves = [mv for _, mv in az.recent]
+    assert moves[0] == (2, 2) and len(moves) >= 3 and moves.count((2, 2)) == 1   # the second "C3" was rejected by play_move!
