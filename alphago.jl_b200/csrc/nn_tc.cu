@@ -38,6 +38,7 @@ struct TCState {
   unsigned long long* trace;  // kernel timeline trace buffer or nullptr (nn_tc_set_trace)
   int fuse_heads;             // AGZ_FUSE_HEADS (default 1): head 1x1 convs in the last tower conv's epilogue, trunk not stored
   float4* head_pre;           // [rows_alloc] (value plane, policy plane 0, policy plane 1, 0) written by that epilogue
+  int conv5_stages;           // AGZ_CONV5_STAGES: 6 (default) or 4 operand stages in conv3x3_tc5_kernel (experiment)
   int l2pf;                   // AGZ_CONV_L2PF: L2 prefetch of the next tile in the conv producers
   int pdl;                    // AGZ_CONV_PDL (default 1): tower convolutions use programmatic dependent launch
   int max_pairs;              // AGZ_CONV_PAIRS
@@ -938,6 +939,7 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, i
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
 
+template <int NSTAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs a) {
   const unsigned long long trace_t0 = a.trace ? simt::gtimer() : 0ULL;
@@ -945,14 +947,14 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;
-  float* s_scale = reinterpret_cast<float*>(smem + (size_t)V3_STAGES * V3_STAGE_BYTES);
+  float* s_scale = reinterpret_cast<float*>(smem + (size_t)NSTAGES * V3_STAGE_BYTES);
   float* s_shift = s_scale + 256;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
   uint64_t* full = bars;
-  uint64_t* empty = bars + V3_STAGES;
-  uint64_t* tfull = bars + 2 * V3_STAGES;
-  uint64_t* tempty = bars + 2 * V3_STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V3_STAGES + 4);
+  uint64_t* empty = bars + NSTAGES;
+  uint64_t* tfull = bars + 2 * NSTAGES;
+  uint64_t* tempty = bars + 2 * NSTAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -965,7 +967,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < V3_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1005,7 +1007,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             uint8_t* sa = tiles + (size_t)stage * V3_STAGE_BYTES;
             tma_load_im2col_2sm(sa, &tmA, lbar, kc * BK, i0 - 1, j0 - 1, b0, ow, oh);
             tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, kc * BK, tap * 256 + (int)rank * 128);
-            if (++stage == V3_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -1030,7 +1032,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int k = 0; k < BK / 16; ++k)
             tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M256_N256, (it > 0 || k > 0) ? 1u : 0u);
           tc_commit_2sm(&empty[stage]);
-          if (++stage == V3_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit_2sm(&tfull[as]);
       }
@@ -1697,6 +1699,10 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
     t->fuse_heads = ef ? atoi(ef) : 1;
   }
   {
+    const char* es = getenv("AGZ_CONV5_STAGES");
+    t->conv5_stages = (es && atoi(es) == 4) ? 4 : 6;
+  }
+  {
     const char* el = getenv("AGZ_CONV_L2PF");
     t->l2pf = el ? atoi(el) : 0;
   }
@@ -1857,7 +1863,9 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
     else rc = cudaLaunchKernelEx(&lc, conv3x3_tc6_kernel<false>, tmA, tmW, *res_map, a, res_row0);
   } else {
     lc.dynamicSmemBytes = CONV3_SMEM;
-    rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel, tmA, tmW, a);
+    // the stem (one K chunk per tap, bound by its epilogue) measures 9 % faster with 4 operand stages, the tower convs 1 % slower
+    if (t->conv5_stages == 4 || kchunks == 1) rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel<4>, tmA, tmW, a);
+    else rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel<6>, tmA, tmW, a);
   }
   return rc != cudaSuccess ? (int)rc : (int)cudaGetLastError();
 }
@@ -1911,7 +1919,8 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv4_smem(128 + 2 * t->H8));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem(n->N2, n->A));
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
