@@ -72,7 +72,7 @@ SYMBOLS = [
     "agz_tree_inject_noise", "agz_tree_pick_move", "agz_tree_play_move", "agz_tree_should_resign", "agz_tree_root",
     "agz_tree_read_node", "agz_tree_set_stats", "agz_tree_pending_vlosses", "agz_tree_read_record",
     "agz_tree_node_features", "agz_pos_play_move", "agz_pos_legal_moves", "agz_pos_score", "agz_pos_liberties",
-    "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read",
+    "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read", "agz_engine_info",
     "agz_match_start", "agz_match_search", "agz_match_play",
     "agz_replay_sample_hist", "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
 ]
@@ -409,6 +409,11 @@ class Engine:
         return out
 
     # ---- introspection
+    def info(self):
+        out = (C.c_int64 * 4)()
+        self._check(self.lib.agz_engine_info(self._h, out))
+        return {"nodes_per_game": out[0], "bytes_per_node": out[1], "n_games": out[2], "record_ring": out[3]}
+
     def kernel_launches(self):
         n = C.c_int64()
         self._check(self.lib.agz_kernel_launches(self._h, C.byref(n)))

@@ -54,6 +54,7 @@ struct agz_engine {
   uint8_t* d_match_active;
   long long* d_match_ids;
   bool train_loaded;
+  size_t bytes_per_node;
   unsigned long long* d_trace;   // AGZ_TRACE=<records>: kernel timeline trace (simt.h), read back with agz_trace_read
   int trace_cap;
   bool started;
@@ -256,8 +257,29 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   c.resign_disable_frac = cfg->resign_disable_frac;
   c.seed = cfg->seed;
   c.total_games = 0;
+  // Node arena per game.  The reference's tree is unbounded; a game can create at most (readouts + 2*parallel - 1) nodes per
+  // move, and with a sharp network nearly all of them stay alive in the re-used subtree, so only
+  // max_game_length * (readouts + 2*parallel) nodes are always enough.  Default: that worst case when it fits in 40 % of the free
+  // device memory, otherwise what fits, never less than 10 moves' worth (the emulation build keeps the small default).
   const int need = cfg->readouts + 2 * c.pmax + 4;
-  c.cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : std::max(256, 10 * need);
+  const long long base_cap = std::max(256, 10 * need);
+  long long cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : base_cap;
+  e->bytes_per_node = (size_t)c.AS * 16 + sizeof(NodeMeta) + (size_t)3 * c.KB * 4 + 8;
+#if AGZ_CUDA
+  if (cfg->nodes_per_game <= 0) {
+    if (const char* en = getenv("AGZ_NODES_PER_GAME")) cap = atoll(en) > 0 ? atoll(en) : base_cap;
+    else {
+      const long long worst = (long long)cfg->max_game_length * (need - 4) + need;
+      size_t free_b = 0, total_b = 0;
+      long long budget = base_cap;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        budget = (long long)(0.4 * (double)free_b / (double)cfg->n_games / (double)e->bytes_per_node);
+      cap = std::max(base_cap, std::min(worst, budget));
+    }
+  }
+#endif
+  if (cap > 0x7ffffff0LL) cap = 0x7ffffff0LL;   // node ids are 32-bit
+  c.cap = (int)cap;
   if (c.cap < need + 2) c.cap = need + 2;
   c.ring_cap = cfg->record_ring > 0 ? cfg->record_ring : 2 * cfg->n_games;
   e->smem_per_warp = (int)((c.KB * 32 * 7 + 15) / 16 * 16);
@@ -1129,6 +1151,15 @@ extern "C" int32_t agz_pos_liberties(agz_engine* e, const agz_position* in, uint
 }
 
 // ------------------------------------------------------------------------------------------- introspection
+extern "C" int32_t agz_engine_info(agz_engine* e, int64_t out[4]) {
+  if (!e || !out) return fail(e, AGZ_ERR_ARG, "null argument");
+  out[0] = e->c.cap;                 // node arena capacity per game
+  out[1] = (int64_t)e->bytes_per_node;
+  out[2] = e->c.n_games;
+  out[3] = e->c.ring_cap;
+  return AGZ_OK;
+}
+
 extern "C" int32_t agz_kernel_launches(agz_engine* e, int64_t* n) {
   if (!e || !n) return fail(e, AGZ_ERR_ARG, "null argument");
   *n = e->launches;

@@ -28,7 +28,7 @@ enum { PH_IDLE = 0, PH_SEED = 1, PH_SEARCH = 2, PH_WAIT_RING = 3, PH_MANUAL = 4,
 enum { F_EXPANDED = 1, F_DONE = 2, F_LASTPASS = 4 };
 enum { E_OK = 0, E_ILLEGAL = 1, E_ASSERT = 2, E_CAPACITY = 6 };
 enum { OP_VLOSS_ADD = 0, OP_VLOSS_REVERT = 1, OP_BACKUP = 2, OP_REVERT_VISITS = 3 };
-static const uint32_t SLOT_ROOT = 0xFFFFFFFFu;
+static const unsigned long long SLOT_ROOT = ~0ULL;
 
 struct alignas(16) NodeMeta {  // 16 bytes, moved as one 128-bit word
   int32_t parent;
@@ -41,10 +41,9 @@ struct alignas(16) NodeMeta {  // 16 bytes, moved as one 128-bit word
 };
 
 struct alignas(16) PathEnt {  // 16 bytes; where this path node's own N / W live
-  uint32_t slot;  // index into N / W, or SLOT_ROOT
+  unsigned long long slot;  // index into N / W (64-bit: arenas of all games can exceed 2^32 entries), or SLOT_ROOT
   int32_t node;
   int32_t to_play;
-  int32_t pad;
 };
 
 struct GameState {
@@ -256,8 +255,8 @@ struct Warp {
       NodeMeta m = load_meta(x);
       if (lane == 0) {
         PathEnt e;
-        e.slot = m.parent < 0 ? SLOT_ROOT : (uint32_t)(row(m.parent) + m.fmove);
-        e.node = x; e.to_play = m.to_play; e.pad = 0;
+        e.slot = m.parent < 0 ? SLOT_ROOT : (unsigned long long)(row(m.parent) + m.fmove);
+        e.node = x; e.to_play = m.to_play;
         path[d] = e;
       }
       --d;
@@ -273,7 +272,7 @@ struct Warp {
     uint32_t move_no = (uint32_t)load_meta(st.root).n;
     int cur = from;
     int depth = 0;
-    uint32_t slot;
+    unsigned long long slot;
     float cur_N;
     {
       NodeMeta fm = load_meta(cur);
@@ -282,7 +281,7 @@ struct Warp {
         st.root_N = simt::fadd(st.root_N, 1.0f);
         cur_N = st.root_N;
       } else {
-        slot = (uint32_t)(row(fm.parent) + fm.fmove);
+        slot = (unsigned long long)(row(fm.parent) + fm.fmove);
         cur_N = simt::fadd(v.N[slot], 1.0f);
         simt::sync();
         if (lane == 0) v.N[slot] = cur_N;
@@ -292,7 +291,7 @@ struct Warp {
       NodeMeta m = load_meta(cur);
       if (lane == 0) {
         PathEnt e;
-        e.slot = slot; e.node = cur; e.to_play = m.to_play; e.pad = 0;
+        e.slot = slot; e.node = cur; e.to_play = m.to_play;
         path[depth] = e;
       }
       if (!(m.flags & F_EXPANDED)) break;
@@ -386,7 +385,7 @@ struct Warp {
         if (lane == ol) v.child[r + best] = child;
       }
       if (lane == ol) v.N[r + best] = n_new;  // N(child) += 1 (mcts.jl:113-114)
-      slot = (uint32_t)(r + best);
+      slot = (unsigned long long)(r + best);
       cur_N = n_new;
       cur = child;
       ++depth;

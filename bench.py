@@ -238,6 +238,7 @@ def main():
         _, conv_flops_pos = eng.net_flops()
         flops_pos, _ = eng.net_flops()
         rows = args.games * 8
+        info = eng.info()
         conv_ms = kms[3] / max(1, kln[3])
         achieved = conv_flops_pos * rows / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         line = {
@@ -246,7 +247,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": "C2: 9x9 Go, %d concurrent self-play games per GPU, 400 readouts/move (50 rounds x 8 leaves per step), tower_height 6, 256 filters, random-init weights seed 0, empty-board starts, finished games refilled" % args.games,
                        "step": "50 tree_search rounds over all games (select -> leaf features -> stem + 12 tower convs -> heads -> incorporate/move logic, one stream) + replay all-gather of finished games",
-                       "l2": "inputs larger than L2: tree arenas %.1f GB and %.0f MB per activation buffer vs 126 MB L2" % (args.games * (eng.cfg.nodes_per_game or 10 * (READOUTS + 20)) * 1.5e-6, rows * 81 * 512 / 1e6)},
+                       "l2": "inputs larger than L2: tree arenas %.1f GB (%d nodes per game) and %.0f MB per activation buffer vs 126 MB L2" % (info["n_games"] * info["nodes_per_game"] * info["bytes_per_node"] / 1e9, info["nodes_per_game"], rows * 81 * 512 / 1e6)},
             "e2e": {"value": tot[1] / tmx[1], "unit": "moves/s", "h2d_bytes_per_step": param_bytes, "d2h_bytes_per_step": int(d2h / args.steps)},
             "gpu_launches": int(tot[2]),
             "clocks": sampler.summary(),

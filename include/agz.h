@@ -70,7 +70,7 @@ typedef struct agz_config {
   double resign_disable_frac; /* 0.05 */
   int32_t n_games;            /* concurrent games (slots) on this GPU */
   int32_t readouts;           /* num_readouts per move */
-  int32_t nodes_per_game;     /* node arena capacity per slot (0 = derive from readouts) */
+  int32_t nodes_per_game;     /* node arena capacity per slot (0 = default, see agz_engine_info) */
   uint64_t seed;              /* RNG spec: oracle/rng.py */
   int32_t device;             /* CUDA device ordinal */
   int32_t world_size;         /* game sharding: global slot s lives on rank s % world_size */
@@ -243,6 +243,10 @@ int32_t agz_pos_liberties(agz_engine* e, const agz_position* in, uint8_t* libert
 
 /* ---- introspection for bench/roofline ---------------------------------------------------------- */
 int32_t agz_kernel_launches(agz_engine* e, int64_t* n);  /* kernels of this library launched since create */
+/* out[0] = node arena capacity per game (nodes_per_game, or the default chosen at creation: the worst case max_game_length *
+ * (readouts + 2 * parallel) when it fits in 40 % of the free device memory), out[1] = bytes per node, out[2] = n_games,
+ * out[3] = finished-record ring capacity */
+int32_t agz_engine_info(agz_engine* e, int64_t out[4]);
 /* Per-kernel device time (ms, CUDA events on the engine's stream, accumulated while timing is enabled) and launch
  * counts since the last call with reset != 0: [0] select (tree descent + expansion), [1] leaf features,
  * [2] stem conv, [3] tower 3x3 conv (tcgen05), [4] heads, [5] incorporate + move logic. */

@@ -335,6 +335,29 @@ def test_selfplay_with_tiny_arena_compacts_every_move(env):
     check_selfplay_parity(env, 9, 16, seeds=[5], priors_seed=2, value=0.05, n_games=2, nodes_per_game=96)
 
 
+def test_sharp_network_keeps_the_whole_subtree(env):
+    """A one-hot-like prior sends every readout down one line, so the re-used subtree keeps almost every node the game ever
+    created (the reference's tree is unbounded).  With the worst-case arena (max_game_length * (readouts + 2 * parallel)) the games
+    equal the oracle's; an arena of a few moves' worth stops the game with AGZ_ERR_CAPACITY instead of corrupting anything."""
+    pri = np.full(A, 1e-4, f32)
+    pri[40] = 1.0
+    pri /= pri.sum()
+    oenv = ogo.GoEnv(9)
+    net = DummyNet(A, fake_priors=pri, fake_value=0.3)
+    OM.MAX_GAME_LENGTH_OVERRIDE = 30
+    try:
+        recs = agz.selfplay(env, net, 16, seed=6, n_games=2, max_game_length=30, nodes_per_game=30 * 36 + 40)
+        for gid, r in enumerate(recs):
+            op = osp.selfplay(oenv, net, 16, seed=6, game_id=gid)
+            assert list(r.record.moves) == [ogo.to_flat(m.move, oenv) for m in op.root.position.recent]
+            assert np.array_equal(np.array(op.searches_N), r.record.visits)
+        with pytest.raises(agz.AgzError) as ei:
+            agz.selfplay(env, net, 16, seed=6, n_games=2, max_game_length=30, nodes_per_game=40)
+        assert ei.value.code == 6
+    finally:
+        OM.MAX_GAME_LENGTH_OVERRIDE = None
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("N", [5, 13])
 def test_selfplay_matches_oracle_other_board_sizes(backend, N):
