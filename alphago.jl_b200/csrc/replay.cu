@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 #include <nccl.h>   // types only: libnccl is resolved at run time (see nccl_api) so that the library loads without it
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -70,6 +71,10 @@ ReplayState* replay_create(const Cfg& c, char* err, size_t errlen) {
   r->rank = c.rank;
   r->stride = ((size_t)4 * c.A + 8 * (size_t)c.N2 + 2 + 15) / 16 * 16;
   r->cap = kReplayCap;
+  if (const char* ec = getenv("AGZ_REPLAY_CAP")) {   // smaller rings for tests of the trim-oldest wrap-around
+    const long long v = atoll(ec);
+    if (v > 0) r->cap = v;
+  }
   if (cudaMalloc((void**)&r->ring, (size_t)r->cap * r->stride) != cudaSuccess || cudaMalloc((void**)&r->d_counts, sizeof(long long) * c.world) != cudaSuccess) {
     snprintf(err, errlen, "cudaMalloc of the replay ring failed");
     replay_destroy(r);

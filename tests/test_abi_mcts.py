@@ -541,3 +541,38 @@ def test_replay_gather_read_sample():
         assert any(np.array_equal(hb[j], want) for want in by_board.values()), j
     with pytest.raises(agz.AgzError):
         eng.replay_sample(total + 1)
+
+
+@pytest.mark.gpu
+def test_replay_ring_trims_oldest(monkeypatch):
+    """memory_size semantics (src/train.jl:52,63-65): once more tuples than the ring holds have been appended, the oldest are gone,
+    the newest `cap` are readable in order, and sampling draws only from them."""
+    monkeypatch.setenv("AGZ_REPLAY_CAP", "150")
+    eng = agz.Engine(9, lib_path=lib_for("cuda"), n_games=4, readouts=8, seed=31)
+    eng.set_dummy_evaluator(None, 0.0)
+    eng.selfplay_start(8)
+    seen, total = [], 0
+    for _ in range(2000):
+        pr = eng.selfplay_step(16)
+        before = total
+        total = eng.replay_gather()
+        recs = sorted(eng.selfplay_harvest(16), key=lambda r: r.game_id)
+        if total > before:
+            seen.append((before, total))
+        if pr.games_finished == 8:
+            break
+    assert total > 300                                     # the ring (150) has wrapped at least once
+    with pytest.raises(agz.AgzError):
+        eng.replay_read(0, 1)                              # trimmed
+    with pytest.raises(agz.AgzError):
+        eng.replay_read(total - 150 - 1, 1)
+    boards, tp, pis, zs = eng.replay_read(total - 150, 150)
+    assert np.allclose(pis.sum(axis=1), 1.0, atol=1e-5) and set(np.unique(zs)) <= {-1, 0, 1} and set(np.unique(tp)) <= {-1, 1}
+    sb, stp, spi, sz, idx = eng.replay_sample(100, seed=1)
+    assert idx.min() >= total - 150 and idx.max() < total and len(set(idx.tolist())) == 100
+    for j in range(0, 100, 9):
+        k = int(idx[j] - (total - 150))
+        assert np.array_equal(sb[j], boards[k]) and np.array_equal(spi[j], pis[k])
+    with pytest.raises(agz.AgzError):
+        eng.replay_sample(151)
+    eng.close()
