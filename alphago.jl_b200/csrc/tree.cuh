@@ -458,14 +458,59 @@ struct Warp {
     const bool seed_mode = st.seed_round != 0;
     for (int k = 0; k < st.nleaf; ++k) {
       const PathEnt* path = path_of(k);
-      int leaf = v.leaf_node[(size_t)g * c.pmax + k];
-      int plen = v.leaf_plen[(size_t)g * c.pmax + k];
-      if (!seed_mode) apply_path(path, plen, OP_VLOSS_REVERT, 0.f);
-      size_t b = (size_t)g * c.pmax + k;
-      incorporate(leaf, path, plen, v.eval_pi + b * v.pi_stride, v.eval_v[b * v.v_stride]);
-      if (st.err) break;
+      const int leaf = v.leaf_node[(size_t)g * c.pmax + k];
+      const int plen = v.leaf_plen[(size_t)g * c.pmax + k];
+      const size_t b = (size_t)g * c.pmax + k;
+      // revert_virtual_loss!, then incorporate_results! (mcts_play.jl:92-95, mcts.jl:188-213)
+      const NodeMeta lm = load_meta(leaf);
+      simt::sync();  // every lane has read the flags before lane 0 rewrites them below
+      if (lm.flags & F_DONE) { st.err = E_ASSERT; break; }  // @assert !position.done (mcts.jl:196)
+      const bool dup = (lm.flags & F_EXPANDED) != 0;        // expanded by an earlier leaf of this batch: revert_visits! (:197-200)
+      const float value = v.eval_v[b * v.v_stride];
+      if (!dup) {
+        if (lane == 0) v.meta[nbase + leaf].flags = (uint8_t)(lm.flags | F_EXPANDED);
+        const float* probs = v.eval_pi + b * v.pi_stride;
+        const size_t r = row(leaf);
+#pragma unroll
+        for (int q = 0; q < KA; ++q) {
+          int a = q * 32 + lane;
+          bool in = a < c.A;
+          v.P[r + a] = in ? probs[a] : 0.f;
+          v.W[r + a] = in ? value : 0.f;  // children start from the parent's value (mcts.jl:211)
+        }
+      }
+      finish_path(path, plen, !seed_mode, dup, value);
     }
     st.nleaf = 0;
+  }
+
+  // revert_virtual_loss! followed by backup_value!(value) (fresh leaf) or by revert_visits! (duplicate): one read-modify-write per
+  // path entry instead of two; every W slot sees the same two fp32 additions in the same order as the two separate passes.
+  AGZ_DEV void finish_path(const PathEnt* path, int plen, bool had_vloss, bool dup, float value) {
+    simt::sync();
+    for (int d0 = 0; d0 < plen; d0 += 32) {
+      int d = d0 + lane;
+      if (d < plen) {
+        PathEnt e = path[d];
+        if (e.slot != SLOT_ROOT) {
+          if (had_vloss || !dup) {
+            float w = v.W[e.slot];
+            if (had_vloss) w = simt::fadd(w, (float)(-e.to_play));
+            if (!dup) w = simt::fadd(w, value);
+            v.W[e.slot] = w;
+          }
+          if (dup) v.N[e.slot] = simt::fsub(v.N[e.slot], 1.0f);
+        }
+      }
+    }
+    PathEnt e0 = path[0];
+    if (e0.slot == SLOT_ROOT) {
+      if (had_vloss) st.root_W = simt::fadd(st.root_W, (float)(-e0.to_play));
+      if (!dup) st.root_W = simt::fadd(st.root_W, value);
+      if (dup) st.root_N = simt::fsub(st.root_N, 1.0f);
+    }
+    if (had_vloss) st.vloss_balance -= plen;
+    simt::sync();
   }
 
   // ---- inject_noise! (mcts.jl:233-239) -------------------------------------------------------------
