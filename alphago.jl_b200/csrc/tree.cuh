@@ -288,17 +288,15 @@ struct Warp {
       }
     }
     for (;;) {
-      NodeMeta m = load_meta(cur);
-      if (lane == 0) {
-        PathEnt e;
-        e.slot = slot; e.node = cur; e.to_play = m.to_play;
-        path[depth] = e;
-      }
-      if (!(m.flags & F_EXPANDED)) break;
-      if (depth + 1 >= c.maxd) { st.err = E_ASSERT; break; }
+      // Everything this level needs depends only on `cur`: the node's meta word, its four statistic rows and its legal-move
+      // words are requested together, before the expanded flag is known (an unexpanded leaf's rows exist and are zero), so a
+      // level costs one dependent memory round trip instead of two -- the descent is a latency chain, one warp per tree.
       const size_t r = row(cur);
+      NodeMeta m = load_meta(cur);
       float n[KA], w[KA], p[KA];
       int ch[KA];
+      uint32_t lwv[KA];
+      const uint32_t* lw = bits_of(cur) + 2 * c.KB;
 #pragma unroll
       for (int k = 0; k < KA; ++k) {
         int a = k * 32 + lane;
@@ -306,7 +304,15 @@ struct Warp {
         w[k] = v.W[r + a];
         p[k] = v.P[r + a];
         ch[k] = v.child[r + a];
+        lwv[k] = k < c.KB ? lw[k] : 0u;  // word k is a warp-uniform address
       }
+      if (lane == 0) {
+        PathEnt e;
+        e.slot = slot; e.node = cur; e.to_play = m.to_play;
+        path[depth] = e;
+      }
+      if (!(m.flags & F_EXPANDED)) break;
+      if (depth + 1 >= c.maxd) { st.err = E_ASSERT; break; }
       const int pass = c.N2;
       int best;
       // HACK of the reference: after a pass, look at the double pass first (mcts.jl:119-126)
@@ -319,7 +325,6 @@ struct Warp {
         best = pass;
       } else {
         // score = Float64(Float32(W/(1+N)) * to_play) + ((c_puct * Float64(sqrt_f32(1+N_parent))) * Float64(P)) / Float64(1+N)
-        const uint32_t* lw = bits_of(cur) + 2 * c.KB;
         const double cu = simt::dmul(c.c_puct, (double)simt::fsqrt(simt::fadd(1.0f, cur_N)));
         const float tp = (float)m.to_play;
         double s[KA];
@@ -328,7 +333,7 @@ struct Warp {
         for (int k = 0; k < KA; ++k) {
           int a = k * 32 + lane;
           bool legal = false;
-          if (a < c.N2) legal = (lw[k] >> lane) & 1u;  // word k is a warp-uniform address
+          if (a < c.N2) legal = (lwv[k] >> lane) & 1u;
           else if (a == pass) legal = true;
           float den = simt::fadd(1.0f, n[k]);
           float q = simt::fmul(simt::fdiv(w[k], den), tp);
