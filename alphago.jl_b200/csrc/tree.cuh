@@ -461,30 +461,47 @@ struct Warp {
   // ---- tree_search! second half (mcts_play.jl:88-96) ---------------------------------------------
   AGZ_DEV void search_incorporate() {
     const bool seed_mode = st.seed_round != 0;
-    for (int k = 0; k < st.nleaf; ++k) {
-      const PathEnt* path = path_of(k);
-      const int leaf = v.leaf_node[(size_t)g * c.pmax + k];
-      const int plen = v.leaf_plen[(size_t)g * c.pmax + k];
-      const size_t b = (size_t)g * c.pmax + k;
-      // revert_virtual_loss!, then incorporate_results! (mcts_play.jl:92-95, mcts.jl:188-213)
-      const NodeMeta lm = load_meta(leaf);
-      simt::sync();  // every lane has read the flags before lane 0 rewrites them below
-      if (lm.flags & F_DONE) { st.err = E_ASSERT; break; }  // @assert !position.done (mcts.jl:196)
-      const bool dup = (lm.flags & F_EXPANDED) != 0;        // expanded by an earlier leaf of this batch: revert_visits! (:197-200)
-      const float value = v.eval_v[b * v.v_stride];
-      if (!dup) {
-        if (lane == 0) v.meta[nbase + leaf].flags = (uint8_t)(lm.flags | F_EXPANDED);
-        const float* probs = v.eval_pi + b * v.pi_stride;
-        const size_t r = row(leaf);
-#pragma unroll
-        for (int q = 0; q < KA; ++q) {
-          int a = q * 32 + lane;
-          bool in = a < c.A;
-          v.P[r + a] = in ? probs[a] : 0.f;
-          v.W[r + a] = in ? value : 0.f;  // children start from the parent's value (mcts.jl:211)
-        }
+    const int nleaf = st.nleaf;
+    // Lane k fetches everything leaf k needs up front (node id, path length, value, meta word): the leaves are processed in
+    // order, but their inputs do not depend on each other except for "expanded by an earlier leaf of this batch", which is the
+    // same node id appearing earlier in the batch.
+    for (int k0 = 0; k0 < nleaf && !st.err; k0 += 32) {   // 32 leaves per pass (parallel_readouts can exceed the warp width)
+      int my_leaf = -1, my_plen = 0, my_flags = 0;
+      float my_value = 0.f;
+      if (k0 + lane < nleaf) {
+        const size_t b = (size_t)g * c.pmax + k0 + lane;
+        my_leaf = v.leaf_node[b];
+        my_plen = v.leaf_plen[b];
+        my_value = v.eval_v[b * v.v_stride];
+        my_flags = load_meta(my_leaf).flags;
       }
-      finish_path(path, plen, !seed_mode, dup, value);
+      simt::sync();  // every lane has read its flags before any lane rewrites them below
+      const int kn = nleaf - k0 < 32 ? nleaf - k0 : 32;
+      for (int kk = 0; kk < kn; ++kk) {
+        const int k = k0 + kk;
+        const PathEnt* path = path_of(k);
+        const int leaf = simt::shfl(my_leaf, kk), plen = simt::shfl(my_plen, kk), flags = simt::shfl(my_flags, kk);
+        const float value = simt::shfl(my_value, kk);
+        const size_t b = (size_t)g * c.pmax + k;
+        // revert_virtual_loss!, then incorporate_results! (mcts_play.jl:92-95, mcts.jl:188-213)
+        if (flags & F_DONE) { st.err = E_ASSERT; break; }  // @assert !position.done (mcts.jl:196)
+        const unsigned same = simt::ballot(lane < kk && my_leaf == leaf);
+        const bool dup = (flags & F_EXPANDED) != 0 || same != 0u;   // already expanded (:197-200): revert_visits!
+        if (!dup) {
+          if (lane == 0) v.meta[nbase + leaf].flags = (uint8_t)(flags | F_EXPANDED);
+          const float* probs = v.eval_pi + b * v.pi_stride;
+          const size_t r = row(leaf);
+#pragma unroll
+          for (int q = 0; q < KA; ++q) {
+            int a = q * 32 + lane;
+            bool in = a < c.A;
+            v.P[r + a] = in ? probs[a] : 0.f;
+            v.W[r + a] = in ? value : 0.f;  // children start from the parent's value (mcts.jl:211)
+          }
+        }
+        finish_path(path, plen, !seed_mode, dup, value);
+      }
+      simt::sync();  // the flag writes of this pass are visible to the next pass's loads
     }
     st.nleaf = 0;
   }
