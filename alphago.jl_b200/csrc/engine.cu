@@ -614,6 +614,23 @@ extern "C" int32_t agz_selfplay_step(agz_engine* e, int32_t rounds, agz_progress
     rounds = 0;
   }
 #endif
+  // DummyNet evaluator: all rounds of the call in one launch per game (ops.cuh DummyRoundsOp); per-kernel timing keeps the split
+  static const int fuse_dummy = getenv("AGZ_FUSE_DUMMY") ? atoi(getenv("AGZ_FUSE_DUMMY")) : 1;
+  if (rounds > 0 && fuse_dummy && e->evaluator == AGZ_EVAL_DUMMY && !e->timing) {
+    if (e->c.n_games >= 2048) {
+      DISPATCH_KA(e, {
+        DummyRoundsOp<KA, 1> op{e->c, e->v, rounds};
+        DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+      });
+    } else {
+      DISPATCH_KA(e, {
+        DummyRoundsOp<KA> op{e->c, e->v, rounds};
+        DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+      });
+    }
+    e->launches += 1;
+    rounds = 0;
+  }
   for (int r = 0; r < rounds; ++r) {
     int rc = one_round(e);
     if (rc) return rc;

@@ -149,6 +149,30 @@ struct MatchOp {
   }
 };
 
+// With the DummyNet evaluator (fixed priors and value: test/test_mcts_player.jl:10-32, BASELINE config C5) nothing runs between
+// the two halves of tree_search!, and games never interact: one warp plays `rounds` whole rounds of its game in one launch
+// (select -> incorporate -> move logic), so there is no per-round launch, no per-round tail and no state round trip.
+template <int KA, int OCC = 0>
+struct DummyRoundsOp {
+  Cfg c;
+  View v;
+  int rounds;
+  AGZ_DEV void operator()(int g, char* smem) const {
+    Warp<KA> w(c, v, g, smem);
+    for (int r = 0; r < rounds; ++r) {
+      if (w.st.phase == PH_SEED) w.search_select(1, true);
+      else if (w.st.phase == PH_SEARCH || w.st.phase == PH_MATCH_SEARCH) w.search_select(c.parallel, false);
+      else { w.st.nleaf = 0; w.st.seed_round = 0; }
+      simt::sync();  // the leaf records written by lane 0 are read by every lane below
+      w.search_incorporate();
+      w.after_round();
+      w.st.seed_round = 0;
+      if (w.st.phase == PH_IDLE) break;
+    }
+    w.store_state();
+  }
+};
+
 // get_feats for every leaf collected this round, reference layout: out[b][17][N2] float (N x N x 17 x B)
 template <int KA>
 struct LeafFeaturesF32Op {
@@ -186,6 +210,8 @@ template <> struct MinBlocks<agz::IncorporateOp<3>> { static const int v = 7; };
 template <class Op> struct TraceTag;
 template <int KA, int OCC> struct TraceTag<agz::SelectOp<KA, OCC>> { static const int v = 1; };
 template <int KA> struct TraceTag<agz::IncorporateOp<KA>> { static const int v = 2; };
+template <> struct MinBlocks<agz::DummyRoundsOp<3, 1>> { static const int v = 7; };
+template <> struct MinBlocks<agz::DummyRoundsOp<6, 1>> { static const int v = 6; };
 }  // namespace devrt
 #endif
 namespace agz {

@@ -22,6 +22,12 @@ def run(name, N, games, readouts, tower, evaluator, warm_rounds, rounds, nodes_p
         agz.NeuralNet(env, tower_height=tower, seed=0).push(eng)
     eng.selfplay_start(-1)
     pr0 = eng.selfplay_step(warm_rounds)
+    # plain run first (no per-kernel events): with the DummyNet evaluator all rounds of a call are one launch per game
+    t0 = time.perf_counter()
+    prp = eng.selfplay_step(rounds)
+    plain_wall = time.perf_counter() - t0
+    plain = {"ms_per_round_plain": 1e3 * plain_wall / rounds, "moves_per_s_plain": (prp.moves_played - pr0.moves_played) / plain_wall,
+             "readouts_per_s_plain": (prp.readouts - pr0.readouts) / plain_wall}
     eng.set_timing(True)
     eng.phase_times(reset=True)
     pr1 = eng.selfplay_step(1)
@@ -41,6 +47,8 @@ def run(name, N, games, readouts, tower, evaluator, warm_rounds, rounds, nodes_p
            "kernel_ms_per_round": {n: kms[i] / max(1, kln[0]) for i, n in enumerate(agz.binding.KERNEL_NAMES)},
            "tree_GBps_algorithmic": tree_bytes / (tree_ms * 1e-3) / 1e9 if tree_ms > 0 else None,
            "tree_frac_of_hbm": tree_bytes / (tree_ms * 1e-3) / 1e9 / PEAKS["hbm_gbs"] if tree_ms > 0 else None, "error": pr.error}
+    out.update(plain)
+    out["tree_frac_of_hbm_plain"] = (tree_bytes / readouts_done) * plain["readouts_per_s_plain"] / 1e9 / PEAKS["hbm_gbs"] if readouts_done else None
     if evaluator != agz.EVAL_DUMMY:
         fpos, fconv = eng.net_flops()
         rows = games * 8
