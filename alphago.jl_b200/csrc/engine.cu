@@ -615,7 +615,8 @@ extern "C" int32_t agz_selfplay_step(agz_engine* e, int32_t rounds, agz_progress
   }
 #endif
   // DummyNet evaluator: all rounds of the call in one launch per game (ops.cuh DummyRoundsOp); per-kernel timing keeps the split
-  static const int fuse_dummy = getenv("AGZ_FUSE_DUMMY") ? atoi(getenv("AGZ_FUSE_DUMMY")) : 1;
+  const char* fd_env = getenv("AGZ_FUSE_DUMMY");
+  const int fuse_dummy = fd_env ? atoi(fd_env) : 1;
   if (rounds > 0 && fuse_dummy && e->evaluator == AGZ_EVAL_DUMMY && !e->timing) {
     if (e->c.n_games >= 2048) {
       DISPATCH_KA(e, {

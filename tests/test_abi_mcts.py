@@ -326,6 +326,14 @@ def test_selfplay_matches_oracle(env):
     check_selfplay_parity(env, 9, 16, seeds=[2], priors_seed=7, value=-0.2)
 
 
+def test_selfplay_matches_oracle_with_separate_kernels(env, monkeypatch):
+    """With the DummyNet evaluator agz_selfplay_step plays all rounds of a call in one launch per game; AGZ_FUSE_DUMMY=0 runs the
+    select / incorporate kernels of the network path instead.  Both must reproduce the oracle."""
+    monkeypatch.setenv("AGZ_FUSE_DUMMY", "0")
+    check_selfplay_parity(env, 9, 24, seeds=[0])
+    check_selfplay_parity(env, 9, 16, seeds=[3], priors_seed=4, value=0.1, n_games=3)
+
+
 def test_selfplay_concurrent_games_match_oracle(env):
     check_selfplay_parity(env, 9, 16, seeds=[3], n_games=3)
 
