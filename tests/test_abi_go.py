@@ -194,3 +194,31 @@ def _random_playouts(env, N, games, plies):
             if op.done:
                 assert gp.done
                 break
+
+
+@pytest.mark.parametrize("N,games,plies", [(5, 12, 250), (7, 6, 250)])
+def test_small_board_capture_stress(N, games, plies):
+    """Long random games on small boards: thousands of captured stones, ko positions and enclosed (suicide-candidate) points, the
+    regime where the legal-mask code visits groups one by one.  Legal mask, board, ko, captures at every ply; score every 7."""
+    e = agz.GoEnv(N, lib_path=lib_for("emu"))
+    oenv = ogo.GoEnv(N)
+    rs = np.random.RandomState(100 + N)
+    captured = kos = enclosed = 0
+    for g in range(games):
+        op, gp = ogo.GoPosition(oenv), agz.GoPosition(e)
+        for t in range(plies):
+            ol, gl = ogo.all_legal_moves(op), agz.all_legal_moves(gp)
+            assert (ol == gl).all(), (g, t)
+            enclosed += int(((op.board.flatten(order="F") == 0) & (ol[:-1] == 0)).sum())
+            cand = np.flatnonzero(ol[:-1])
+            mv = None if (len(cand) == 0 or rs.rand() < 0.02) else ogo.from_flat(int(rs.choice(cand)), oenv)
+            c0 = sum(op.caps)
+            op, gp = ogo.play_move(op, mv), agz.play_move(gp, mv)
+            captured += sum(op.caps) - c0
+            kos += int(op.ko is not None)
+            assert (op.board == gp.board).all() and op.ko == gp.ko and op.caps == gp.caps, (g, t)
+            if t % 7 == 0:
+                assert float(ogo.score(op)) == agz.score(gp)
+            if op.done:
+                break
+    assert captured > 300 and enclosed > 300 and (N != 5 or kos > 0)
