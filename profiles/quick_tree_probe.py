@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe used during development: timing of the tree kernels with the dummy evaluator."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import pkg
 agz = pkg.load()
