@@ -28,6 +28,13 @@ class GoEnv:
         self.lib_path = lib_path
         self.device = device
         self._util = None
+        self._fwd = {}
+
+    def forward_engine(self, tower_height):
+        """A small engine whose network has `tower_height` blocks, for NeuralNet.__call__ (one per tower height)."""
+        if tower_height not in self._fwd:
+            self._fwd[tower_height] = B.Engine(self.N, lib_path=self.lib_path, n_games=8, readouts=8, device=self.device, tower_height=tower_height)
+        return self._fwd[tower_height]
 
     def util_engine(self):
         """A one-slot engine used for position-level calls (rules run on the device)."""
@@ -217,7 +224,7 @@ class NeuralNet:
         """(nn::NeuralNet)(positions) -> (pi: A x B, v: B) (neural_net.jl:57-68); a single Position gives (pi, v)."""
         single = isinstance(positions, GoPosition)
         plist = [positions] if single else list(positions)
-        eng = self.env.util_engine()
+        eng = self.env.forward_engine(self.tower_height)   # the engine's network shape is fixed at creation (tower_height)
         self.push(eng)
         bh = np.stack([_hist_stack(p) for p in plist])
         tp = np.array([p.to_play for p in plist], np.int8)
@@ -535,11 +542,10 @@ def train(env, num_games=25000, memory_size=500000, batch_size=32, epochs=1, ckp
     run at once on the GPU with the current network; every harvested game triggers the same per-game step, so the ratio of
     optimisation steps to games is the reference's.  The replay ring is the engine's (500 000 deep, trim-oldest)."""
     from . import weights_io
-    assert memory_size == 500000, "the device replay ring is fixed at the reference's default memory_size"
     cur_nn = model if model is not None else NeuralNet(env, tower_height=tower_height, seed=seed)
     conc = concurrent or min(num_games, 1024)
     eng = B.Engine(env.N, lib_path=env.lib_path, n_games=conc, readouts=readouts, seed=seed, device=env.device,
-                   tower_height=cur_nn.tower_height, evaluator=cur_nn.evaluator, **engine_overrides)
+                   tower_height=cur_nn.tower_height, evaluator=cur_nn.evaluator, options={"replay.capacity": memory_size}, **engine_overrides)
     losses = []
     try:
         cur_nn.push(eng)
@@ -613,12 +619,12 @@ class SelfPlayResult:
         return positions, self.searches_pi, results
 
 
-def selfplay(env, nn, num_ro=800, seed=0, n_games=1, concurrent=None, **engine_overrides):
+def selfplay(env, nn, num_ro=800, seed=0, n_games=1, concurrent=None, options=None, **engine_overrides):
     """selfplay(env, nn, num_ro) -> player; with n_games > 1 plays that many games concurrently on the GPU and
-    returns a list (game ids 0..n_games-1).  `nn` is a NeuralNet or a DummyNet-like object."""
+    returns a list (game ids 0..n_games-1).  `nn` is a NeuralNet or a DummyNet-like object.  `options`: agz_set_option keys."""
     conc = concurrent or n_games
     eng = B.Engine(env.N, lib_path=env.lib_path, n_games=conc, readouts=num_ro, seed=seed, device=env.device,
-                   tower_height=getattr(nn, "tower_height", 1), **engine_overrides)
+                   tower_height=getattr(nn, "tower_height", 1), options=options, **engine_overrides)
     try:
         if isinstance(nn, NeuralNet):
             nn.push(eng)

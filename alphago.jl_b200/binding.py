@@ -75,6 +75,7 @@ SYMBOLS = [
     "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read", "agz_engine_info",
     "agz_match_start", "agz_match_search", "agz_match_play",
     "agz_replay_sample_hist", "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
+    "agz_set_option", "agz_get_option", "agz_replay_info",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -113,7 +114,8 @@ def _ptr(a, t):
 class Engine:
     """One agz_engine handle (one GPU)."""
 
-    def __init__(self, board_n=9, lib_path=None, **overrides):
+    def __init__(self, board_n=9, lib_path=None, options=None, **overrides):
+        """`overrides` are agz_config fields; `options` is a dict of named integer options (agz_set_option)."""
         self.lib = load_library(lib_path)
         self.cfg = Config()
         self._h = C.c_void_p()
@@ -131,6 +133,8 @@ class Engine:
         self.N2 = self.N * self.N
         self.A = self.N2 + 1
         self.L = self.cfg.max_game_length + 2
+        for k, v in (options or {}).items():
+            self.set_option(k, v)
 
     def close(self):
         if self._h:
@@ -153,6 +157,15 @@ class Engine:
         if rc == ERR_ASSERT:
             raise AssertionError(msg)
         raise AgzError(rc, msg)
+
+    # ---- options (include/agz.h: agz_set_option)
+    def set_option(self, key, value):
+        self._check(self.lib.agz_set_option(self._h, key.encode(), C.c_int64(int(value))))
+
+    def get_option(self, key):
+        v = C.c_int64()
+        self._check(self.lib.agz_get_option(self._h, key.encode(), C.byref(v)))
+        return v.value
 
     # ---- network
     def net_param_count(self, chain):
@@ -262,6 +275,11 @@ class Engine:
         n = C.c_int64()
         self._check(self.lib.agz_replay_gather(self._h, C.byref(n)))
         return n.value
+
+    def replay_info(self):
+        out = (C.c_int64 * 5)()
+        self._check(self.lib.agz_replay_info(self._h, out))
+        return {"tuple_bytes": out[0], "capacity": out[1], "total": out[2], "last_gather_bytes": out[3], "gathered_bytes": out[4]}
 
     def replay_read(self, first, count):
         boards = np.zeros((count, self.N2), np.int8)
@@ -451,7 +469,7 @@ class Engine:
         return done.astype(bool), sc
 
     def trace_read(self, max_records=1 << 16, reset=True):
-        """Kernel timeline trace (AGZ_TRACE=<records> at engine creation): array of (tag, block, grid, start_ns, end_ns, sm)."""
+        """Kernel timeline trace (set_option("trace.records", n)): array of (tag, block, grid, start_ns, end_ns, sm)."""
         buf = np.zeros((max_records, 4), np.uint64)
         n = C.c_int32()
         self._check(self.lib.agz_trace_read(self._h, _ptr(buf, C.c_uint64), C.c_int32(max_records), C.byref(n), C.c_int32(1 if reset else 0)))

@@ -75,6 +75,8 @@ struct agz_engine {
   int pipeline;              // 1: two half batches on two streams (tree work of one hides under the network of the other)
   ReplayState* replay;
 #endif
+  int fuse_dummy;            // option dummy.fused_rounds
+  long long replay_cap;      // option replay.capacity (0 = memory_size default of src/train.jl:38)
 };
 
 static int fail(agz_engine* e, int code, const char* fmt, ...) {
@@ -221,13 +223,11 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithPriority(&e->gstream[i], cudaStreamNonBlocking, least);
     cudaStreamCreateWithPriority(&e->cstream, cudaStreamNonBlocking, greatest);
   }
-  {
-    // 0 (default): one batch per round on one stream.  1: two half batches, convolutions on a high-priority stream and the
-    // tree / heads kernels of the other half underneath (pipelined_rounds).  On a power-capped B200 the overlap does not pay:
-    // measured back to back on one box, 2551 / 2545 moves/s sequential vs 2522 / 2516 pipelined (profiles/r01_schedule_ab.md).
-    const char* pe = getenv("AGZ_PIPELINE");
-    e->pipeline = pe ? atoi(pe) : 0;
-  }
+  // option schedule.pipeline -- 0 (default): one batch per round on one stream.  1: two half batches, convolutions on a
+  // high-priority stream and the tree / heads kernels of the other half underneath (pipelined_rounds).  On a power-capped B200 the
+  // overlap does not pay: measured back to back on one box, 2551 / 2545 moves/s sequential vs 2522 / 2516 pipelined
+  // (profiles/r01_schedule_ab.md).
+  e->pipeline = 0;
 #else
   e->stream = 0;
 #endif
@@ -257,6 +257,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   c.resign_disable_frac = cfg->resign_disable_frac;
   c.seed = cfg->seed;
   c.total_games = 0;
+  c.stagger_rounds = 0;
   // Node arena per game.  The reference's tree is unbounded; a game can create at most (readouts + 2*parallel - 1) nodes per
   // move, and with a sharp network nearly all of them stay alive in the re-used subtree, so only
   // max_game_length * (readouts + 2*parallel) nodes are always enough.  Default: that worst case when it fits in 40 % of the free
@@ -267,15 +268,12 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   e->bytes_per_node = (size_t)c.AS * 16 + sizeof(NodeMeta) + (size_t)3 * c.KB * 4 + 8;
 #if AGZ_CUDA
   if (cfg->nodes_per_game <= 0) {
-    if (const char* en = getenv("AGZ_NODES_PER_GAME")) cap = atoll(en) > 0 ? atoll(en) : base_cap;
-    else {
-      const long long worst = (long long)cfg->max_game_length * (need - 4) + need;
-      size_t free_b = 0, total_b = 0;
-      long long budget = base_cap;
-      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
-        budget = (long long)(0.4 * (double)free_b / (double)cfg->n_games / (double)e->bytes_per_node);
-      cap = std::max(base_cap, std::min(worst, budget));
-    }
+    const long long worst = (long long)cfg->max_game_length * (need - 4) + need;
+    size_t free_b = 0, total_b = 0;
+    long long budget = base_cap;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+      budget = (long long)(0.4 * (double)free_b / (double)cfg->n_games / (double)e->bytes_per_node);
+    cap = std::max(base_cap, std::min(worst, budget));
   }
 #endif
   if (cap > 0x7ffffff0LL) cap = 0x7ffffff0LL;   // node ids are 32-bit
@@ -330,19 +328,8 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   e->d_match_f = nullptr;
   e->d_match_active = nullptr;
   e->d_match_ids = nullptr;
-#if AGZ_CUDA
-  if (const char* et = getenv("AGZ_TRACE")) {
-    e->trace_cap = atoi(et) > 0 ? atoi(et) : 0;
-    if (e->trace_cap) {
-      rc |= dalloc(e, &e->d_trace, (size_t)2 + 4 * (size_t)e->trace_cap);
-      if (!rc) {
-        unsigned long long cap = (unsigned long long)e->trace_cap;
-        rc |= devrt::h2d(e->d_trace + 1, &cap, sizeof(cap), e->stream);
-        v.trace = e->d_trace;
-      }
-    }
-  }
-#endif
+  e->fuse_dummy = 1;
+  e->replay_cap = 0;
   if (rc) {
     int code = fail(nullptr, AGZ_ERR_CUDA, "device allocation failed (n_games=%d, nodes_per_game=%d)", c.n_games, c.cap);
     agz_engine_destroy(e);
@@ -365,7 +352,6 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
       agz_engine_destroy(e);
       return code;
     }
-    nn_tc_set_trace(e->nn, e->d_trace);
     int r2 = dalloc(e, &e->d_feats_f32, rows * 17 * c.N2);
     if (r2) {
       agz_engine_destroy(e);
@@ -380,6 +366,65 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   }
   *out = e;
   return AGZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------- options
+// Everything round 1 read from environment variables is a named integer option of the engine (include/agz.h).
+extern "C" int32_t agz_set_option(agz_engine* e, const char* key, int64_t value) {
+  if (!e || !key) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (!strcmp(key, "dummy.fused_rounds")) { e->fuse_dummy = value != 0; return AGZ_OK; }
+  if (!strcmp(key, "selfplay.stagger_rounds")) {
+    if (value < 0) return fail(e, AGZ_ERR_ARG, "selfplay.stagger_rounds must be >= 0");
+    e->c.stagger_rounds = value;   // read by the next agz_selfplay_start
+    return AGZ_OK;
+  }
+#if AGZ_CUDA
+  if (!strcmp(key, "schedule.pipeline")) { e->pipeline = value != 0; return AGZ_OK; }
+  if (!strcmp(key, "replay.capacity")) {
+    if (value < 1) return fail(e, AGZ_ERR_ARG, "replay.capacity must be >= 1");
+    if (e->replay) return fail(e, AGZ_ERR_ARG, "replay.capacity must be set before the replay ring exists (first agz_replay_gather / agz_nccl_init)");
+    e->replay_cap = value;
+    return AGZ_OK;
+  }
+  if (!strcmp(key, "trace.records")) {   // kernel timeline trace (agz_trace_read); the buffer is allocated once
+    if (value < 0 || value > (1 << 24)) return fail(e, AGZ_ERR_ARG, "trace.records out of range");
+    if (e->d_trace) return fail(e, AGZ_ERR_ARG, "trace.records is already set");
+    if (value == 0) return AGZ_OK;
+    cudaSetDevice(e->cfg.device);
+    e->trace_cap = (int)value;
+    if (dalloc(e, &e->d_trace, (size_t)2 + 4 * (size_t)e->trace_cap)) return fail(e, AGZ_ERR_CUDA, "trace buffer allocation failed");
+    unsigned long long cap = (unsigned long long)e->trace_cap;
+    DCHECK(e, devrt::h2d(e->d_trace + 1, &cap, sizeof(cap), e->stream));
+    e->v.trace = e->d_trace;
+    nn_tc_set_trace(e->nn, e->d_trace);
+    return AGZ_OK;
+  }
+  if (!strncmp(key, "conv.", 5)) {
+    const int rc = nn_tc_set_option(e->nn, key, value);
+    if (rc == 1) return fail(e, AGZ_ERR_ARG, "unknown option %s", key);
+    if (rc) return fail(e, AGZ_ERR_ARG, "bad value %lld for option %s", (long long)value, key);
+    return AGZ_OK;
+  }
+#endif
+  return fail(e, AGZ_ERR_ARG, "unknown option %s", key);
+}
+
+extern "C" int32_t agz_get_option(agz_engine* e, const char* key, int64_t* value) {
+  if (!e || !key || !value) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (!strcmp(key, "dummy.fused_rounds")) { *value = e->fuse_dummy; return AGZ_OK; }
+  if (!strcmp(key, "selfplay.stagger_rounds")) { *value = e->c.stagger_rounds; return AGZ_OK; }
+#if AGZ_CUDA
+  if (!strcmp(key, "schedule.pipeline")) { *value = e->pipeline; return AGZ_OK; }
+  if (!strcmp(key, "replay.capacity")) { *value = e->replay ? replay_capacity(e->replay) : (e->replay_cap > 0 ? e->replay_cap : replay_default_capacity()); return AGZ_OK; }
+  if (!strcmp(key, "trace.records")) { *value = e->trace_cap; return AGZ_OK; }
+  if (!strncmp(key, "conv.", 5)) {
+    long long v = 0;
+    if (nn_tc_get_option(e->nn, key, &v)) return fail(e, AGZ_ERR_ARG, "unknown option %s", key);
+    *value = v;
+    return AGZ_OK;
+  }
+#endif
+  return fail(e, AGZ_ERR_ARG, "unknown option %s", key);
 }
 
 // ------------------------------------------------------------------------------------------- evaluator
@@ -464,7 +509,7 @@ static int read_progress(agz_engine* e, agz_progress* p) {
   p->games_live = 0;
   p->error = 0;
   for (auto& g : gs) {
-    if (g.phase == PH_SEED || g.phase == PH_SEARCH || g.phase == PH_WAIT_RING) p->games_live++;
+    if (g.phase == PH_SEED || g.phase == PH_SEARCH || g.phase == PH_WAIT_RING) p->games_live++;   // PH_DELAY (staggered start) is not live yet
     if (g.err && !p->error) p->error = g.err;
   }
   return AGZ_OK;
@@ -614,10 +659,9 @@ extern "C" int32_t agz_selfplay_step(agz_engine* e, int32_t rounds, agz_progress
     rounds = 0;
   }
 #endif
-  // DummyNet evaluator: all rounds of the call in one launch per game (ops.cuh DummyRoundsOp); per-kernel timing keeps the split
-  const char* fd_env = getenv("AGZ_FUSE_DUMMY");
-  const int fuse_dummy = fd_env ? atoi(fd_env) : 1;
-  if (rounds > 0 && fuse_dummy && e->evaluator == AGZ_EVAL_DUMMY && !e->timing) {
+  // DummyNet evaluator: all rounds of the call in one launch per game (ops.cuh DummyRoundsOp); per-kernel timing and the option
+  // dummy.fused_rounds = 0 keep the split
+  if (rounds > 0 && e->fuse_dummy && e->evaluator == AGZ_EVAL_DUMMY && !e->timing) {
     if (e->c.n_games >= 2048) {
       DISPATCH_KA(e, {
         DummyRoundsOp<KA, 1> op{e->c, e->v, rounds};
@@ -1293,6 +1337,7 @@ extern "C" int32_t agz_net_set_bn_stats(agz_engine* e, int32_t chain, const floa
   if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
   if (n_each != nn_bn_count(e->nn, chain)) return fail(e, AGZ_ERR_ARG, "chain %d has %zu BatchNorm channels, got %zu", chain, nn_bn_count(e->nn, chain), n_each);
   if (bn_mode != AGZ_BN_VAR_EPS && bn_mode != AGZ_BN_STD) return fail(e, AGZ_ERR_ARG, "bad bn_mode");
+  e->train_loaded = false;   // the device copy of the running statistics kept by the training path is stale now
   return nn_set_bn(e->nn, chain, mu, sigma, n_each, bn_mode) ? fail(e, AGZ_ERR_ARG, "nn_set_bn failed") : AGZ_OK;
 }
 
@@ -1357,7 +1402,7 @@ extern "C" int32_t agz_nccl_init(agz_engine* e, const uint8_t id[128]) {
   if (!e || !id) return fail(e, AGZ_ERR_ARG, "null argument");
   cudaSetDevice(e->cfg.device);
   char rerr[256] = "";
-  if (!e->replay) e->replay = replay_create(e->c, rerr, sizeof(rerr));
+  if (!e->replay) e->replay = replay_create(e->c, e->replay_cap, rerr, sizeof(rerr));
   if (!e->replay) return fail(e, AGZ_ERR_CUDA, "replay_create: %s", rerr);
   if (replay_nccl_init(e->replay, id, e->c.world, e->c.rank, rerr, sizeof(rerr))) return fail(e, AGZ_ERR_NCCL, "%s", rerr);
   return AGZ_OK;
@@ -1367,12 +1412,19 @@ extern "C" int32_t agz_replay_gather(agz_engine* e, int64_t* n_tuples_total) {
   if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
   cudaSetDevice(e->cfg.device);
   char rerr[256] = "";
-  if (!e->replay) e->replay = replay_create(e->c, rerr, sizeof(rerr));
+  if (!e->replay) e->replay = replay_create(e->c, e->replay_cap, rerr, sizeof(rerr));
   if (!e->replay) return fail(e, AGZ_ERR_CUDA, "replay_create: %s", rerr);
   long long nl = 0;
   int rc = replay_gather(e->replay, e->c, e->v, e->smem_per_warp, e->stream, n_tuples_total, &nl, rerr, sizeof(rerr));
   e->launches += nl;
   if (rc) return fail(e, rc, "%s", rerr);
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_replay_info(agz_engine* e, int64_t out[5]) {
+  if (!e || !out) return fail(e, AGZ_ERR_ARG, "null argument");
+  if (!e->replay) return fail(e, AGZ_ERR_ARG, "no replay ring (call agz_replay_gather first)");
+  replay_info(e->replay, out);
   return AGZ_OK;
 }
 
@@ -1404,6 +1456,7 @@ extern "C" int32_t agz_replay_sample_hist(agz_engine* e, int32_t batch, uint64_t
 }
 #else
 extern "C" int32_t agz_replay_sample_hist(agz_engine* e, int32_t, uint64_t, int8_t*, int8_t*, float*, int8_t*, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
+extern "C" int32_t agz_replay_info(agz_engine* e, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
 extern "C" size_t agz_net_param_count(agz_engine*, int32_t) { return 0; }
 extern "C" size_t agz_net_bn_count(agz_engine*, int32_t) { return 0; }
 extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t, const float*, size_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }

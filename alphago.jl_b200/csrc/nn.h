@@ -29,21 +29,12 @@ bool nn_ready(const NNet* n);
 
 // Input of both paths: packed history planes written by the feature kernels.
 //   feats_f32 : [B][17][N2] float, reference (W x H x C x B) order               (NN_F32)
-//   feats_tc  : see nn_tc_input_layout()                                          (NN_TC)
+//   feats_tc  : dense fp16 rows [B*N^2][64], written by engine_tc_features / engine_host_features_tc (NN_TC)
 // Output: pi [B][A] float (softmax over all A actions, no legality masking), v [B] float (Black's view).
 int nn_forward_f32(NNet* n, const float* feats_f32, int B, float* pi, float* v, cudaStream_t s, cudaEvent_t* ev = nullptr);
 
-// The tensor-core path consumes activations as fp16 rows of `cin_pad` channels in a zero-bordered board
-// layout: every board is (N+1) rows of (N+1) points plus one leading pad row, so a 3x3 tap is a constant
-// row offset.  The feature kernel writes straight into this buffer.
-struct TCInput {
-  void* act;          // __half [rows_total][cin_pad]
-  int rows_per_board; // (N+1)*(N+1)
-  int row_stride_pts; // N+1
-  int cin_pad;        // 32
-  long long rows_total;
-};
-TCInput nn_tc_input(NNet* n);
+// The tensor-core path (nn_tc.cu) consumes activations as dense fp16 NHWC rows (row = b*N^2 + N*j + i); the feature kernels
+// below write the stem input (64 channels per row, 17 used) directly.
 // ev (optional): 4 events recorded before the stem, after the stem, after the tower, after the heads
 // group >= 0: evaluate only half batch `group` (rows [group*max_batch/2, ...)); pi / v point at that half's first row
 int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev = nullptr, int group = -1,
@@ -51,6 +42,9 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
                   cudaStream_t heads_stream = nullptr /* with convs_done: launch the heads there instead of on s */);
 int nn_tc_groups(const NNet* n);
 void nn_tc_set_trace(NNet* n, unsigned long long* trace);   // kernel timeline trace buffer (simt.h), nullptr = off
+// agz_set_option / agz_get_option keys "conv.*": 0 ok, 1 unknown key, 2 bad value
+int nn_tc_set_option(NNet* n, const char* key, long long value);
+int nn_tc_get_option(const NNet* n, const char* key, long long* value);
 // feature kernels that write the tensor-core input directly (nn_tc.cu): from the leaves of the current round
 // (batch rows [0, row0+nrows)), and from caller-supplied positions.
 struct Cfg;

@@ -2,19 +2,20 @@
 // src/neural_net.jl:16-21 and src/resnet.jl:26-32, which the reference sends to NNlib / cuDNN).
 //
 // A 3x3 convolution is an implicit GEMM  D[M, 256] = sum over 9 taps of A_tap[M, Cin] * W_tap[Cin, 256].
-// Activations live in HBM as fp16 rows of C channels (NHWC) in a zero-bordered board layout: every board is one
-// pad row of N+1 zero points followed by N rows of N points + 1 zero point.  With that layout the input of tap
-// (dj, di) for output row m is simply row m + dj*(N+1) + di, so each tap's A tile is ONE plain 2-D TMA box at a
-// shifted row coordinate (negative / past-the-end rows are zero-filled by TMA) -- no im2col buffer, no halo logic.
+// Activations live in HBM as dense fp16 NHWC rows (row = b*N^2 + N*j + i, 256 channels; the stem input has 64).
+// The A tile of a tap is ONE TMA im2col load (the TMA unit walks 128 consecutive output pixels across board rows
+// and boards and zero-fills the halo), so M = B*N^2 exactly and no border rows exist.
 //
-// Kernel conv3x3_tc_kernel (persistent, 1 CTA per SM, 256 threads, warp-specialised):
-//   warp 0   : TMA producer -- per (tap, 64-channel chunk): A box 128 rows x 64 ch, W box 256 cout x 64 ch, both
-//              SWIZZLE_128B, 4-stage mbarrier ring (48 KB / stage)
-//   warp 1   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16  M=128, N=256, K=16 (4 per stage),
-//              fp32 accumulators in TMEM; tcgen05.commit releases the smem stage / publishes the accumulator
+// Kernels conv3x3_tc5_kernel / conv3x3_tc6_kernel (persistent, clusters of 2 CTAs = one TPC, 256 threads, warp-specialised):
+//   warp 0   : TMA producer -- per (tap, 64-channel chunk): A im2col box 128 pixels x 64 ch, W box 128 cout x 64 ch (this
+//              CTA's half of the weight tile), both SWIZZLE_128B, mbarrier ring of 6 (tc5) / 4 (tc6) stages of 32 KB
+//   warp 1   : one elected lane of the leader CTA issues tcgen05.mma.cta_group::2.kind::f16  M=256, N=256, K=16 (4 per stage),
+//              fp32 accumulators in the TMEM of both CTAs; tcgen05.commit (multicast) releases the stage / publishes the tile
 //   warp 2   : allocates / frees the 512 TMEM columns (2 accumulator stages of 256 columns)
-//   warps 4-7: epilogue -- tcgen05.ld 32 lanes x 32 columns, fused (conv bias + BatchNorm) scale/shift,
-//              residual add, ReLU, fp16 pack, 16-byte global stores; overlaps the next tile's MMAs
+//   warps 4-7: epilogue -- software-pipelined tcgen05.ld 32 lanes x 32 columns, fused (conv bias + BatchNorm) scale/shift,
+//              residual add, ReLU, fp16 pack, 32-byte global stores; overlaps the next tile's MMAs
+// (Earlier variants -- per-tap 2-D boxes on zero-bordered boards, a shared-memory slab with row-shifted descriptor views, the
+// first CTA-pair kernel -- are in the git history of round 1 and in profiles/r01_conv3x3_tc_ncu_full.md; they were removed.)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
@@ -29,39 +30,31 @@
 
 namespace agz {
 
-static const int BM = 128, BN = 256, BK = 64, STAGES = 4;
-static const int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+static const int BM = 128, BK = 64;
+static const int A_BYTES = BM * BK * 2;
 static const int CIN0 = 64;  // stem input channels: 17 planes zero-padded to one 64-channel K chunk
-static const size_t CONV_SMEM = (size_t)STAGES * STAGE_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 
 struct TCState {
   unsigned long long* trace;  // kernel timeline trace buffer or nullptr (nn_tc_set_trace)
-  int fuse_heads;             // AGZ_FUSE_HEADS (default 1): head 1x1 convs in the last tower conv's epilogue, trunk not stored
-  float4* head_pre;           // [rows_alloc] (value plane, policy plane 0, policy plane 1, 0) written by that epilogue
-  int conv5_stages;           // AGZ_CONV5_STAGES: 6 (default) or 4 operand stages in conv3x3_tc5_kernel (experiment)
-  int l2pf;                   // AGZ_CONV_L2PF: L2 prefetch of the next tile in the conv producers
-  int pdl;                    // AGZ_CONV_PDL (default 1): tower convolutions use programmatic dependent launch
-  int max_pairs;              // AGZ_CONV_PAIRS
-  int version;                // AGZ_CONV_KERNEL: 1 per-tap, 2 slab, 3 CTA pair, 4 CTA pair + slab (zero-bordered layout); 5 CTA pair + im2col (dense, default)
-  int base_offset_mode;       // debug knob (AGZ_CONV_BASEOFF): measured on B200 -- the swizzle is a function of the absolute smem address, so 0 is correct
-  int H8, arows;              // v2: halo rows rounded up to 8, slab rows = 256 + 2*H8
-  CUtensorMap tm2_in64, tm2_act[3];
-  CUtensorMap tm4_in64, tm4_act[3];   // v4: box = one CTA's slab (128 + 2*H8 rows)
-  std::vector<CUtensorMap> tm2_w;
-  int N, NP1, PP, C, T, max_batch;
-  int res_tma;                // AGZ_CONV_RES_TMA (default 1): residual convs use conv3x3_tc6_kernel (shortcut tile by TMA)
-  int dense;                  // 1: dense NHWC rows (b*N^2 + p), im2col TMA (v5); 0: zero-bordered boards (v1-v4)
-  int rowbase, pitch;         // row of point (j, i) of board b = b*PP + rowbase + j*pitch + i
-  CUtensorMap tm5_in64, tm5_act[3];
-  int groups;                 // 2 when the batch can be split into two half batches (dense layout, even max_batch)
+  // options (agz_set_option "conv.*"; all read at launch time)
+  int fuse_heads;             // conv.fuse_heads (default 1): head 1x1 convs in the last tower conv's epilogue, trunk not stored
+  int conv5_stages;           // conv.stages: 6 (default) or 4 operand stages in conv3x3_tc5_kernel (experiment)
+  int l2pf;                   // conv.l2_prefetch: L2 prefetch of the next tile in the conv producers (default 0)
+  int pdl;                    // conv.pdl (default 1): tower convolutions use programmatic dependent launch
+  int max_pairs;              // conv.max_pairs: cap on the CTA pairs of the persistent conv kernels (0 = all SMs)
+  int res_tma;                // conv.res_tma (default 1): residual convs use conv3x3_tc6_kernel (shortcut tile by TMA)
+  float4* head_pre;           // [rows_alloc] (value plane, policy plane 0, policy plane 1, 0) written by the fused-heads epilogue
+  int N, PP, C, T, max_batch; // PP = N*N rows per board
+  CUtensorMap tm5_in64, tm5_act[3];   // im2col maps over the stem input / the three rotating activation buffers
+  int groups;                 // 2 when the batch can be split into two half batches (even max_batch)
   long long grp_rows;         // rows per group
   CUtensorMap tm5g_in64[2], tm5g_act[2][3];
-  long long rows_alloc;       // rows allocated per activation buffer (multiple of 128, >= max_batch*PP + N+2)
+  long long rows_alloc;       // rows allocated per activation buffer (whole boards + spare boards for the last 256-row tile)
   __half* in64;               // [rows_alloc][64]
   __half* act[3];             // [rows_alloc][256]
   std::vector<__half*> w;     // per conv layer: [9*256][cin] fp16, tap-major, K (cin) contiguous
-  CUtensorMap tm_in64, tm_act[3];
-  std::vector<CUtensorMap> tm_w;
+  CUtensorMap tm_act[3];      // plain 2-D maps (128 rows x 64 channel boxes): the shortcut tile of conv3x3_tc6_kernel
+  std::vector<CUtensorMap> tm_w;   // per conv layer: boxes of 128 output channels x 64 input channels
   int num_sms;
   bool attr_set;
   float* stage;               // device staging copy of the raw Flux parameter list (base chain)
@@ -79,27 +72,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  const uint32_t a = smem_u32(bar);
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
-  } while (!done);
-}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
@@ -159,9 +137,6 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return d;
 }
 
-// instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = 256
-static const uint32_t IDESC_F16_M128_N256 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
 struct ConvArgs {
   const float* scale;   // [256] folded BatchNorm scale
   const float* shift;   // [256] folded BatchNorm shift (+ scale * conv bias)
@@ -170,7 +145,7 @@ struct ConvArgs {
   int n_tiles;          // ceil(rows_valid / 128)
   long long rows_valid; // rows of real boards (B * PP)
   int kchunks;          // Cin / 64
-  int N, NP1, PP;
+  int N, PP;
   int relu;
   unsigned long long* trace;   // kernel timeline trace (simt.h) or nullptr
   int l2pf;                    // prefetch the next tile's activation (and shortcut) rows into L2 (AGZ_CONV_L2PF)
@@ -182,368 +157,13 @@ struct ConvArgs {
   float4* head_out;            // [rows] (value plane, policy plane 0, policy plane 1, 0)
 };
 
-__global__ void __launch_bounds__(256, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                                                            const ConvArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* tiles = smem;
-  float* s_scale = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
-  float* s_shift = s_scale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
-  uint64_t* full = bars;             // [STAGES]
-  uint64_t* empty = bars + STAGES;   // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;      // [2]
-  uint64_t* tempty = bars + 2 * STAGES + 2; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 256; i += 256) {
-    s_scale[i] = a.scale[i];
-    s_shift[i] = a.shift[i];
-  }
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int iters = 9 * a.kchunks;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int m0 = tile * BM;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int off = (tap / 3 - 1) * a.NP1 + (tap % 3 - 1);
-          for (int kc = 0; kc < a.kchunks; ++kc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], STAGE_BYTES);
-            uint8_t* sa = tiles + (size_t)stage * STAGE_BYTES;
-            tma_load_2d(sa, &tmA, &full[stage], kc * BK, m0 + off);
-            tma_load_2d(sa + A_BYTES, &tmW, &full[stage], kc * BK, tap * BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int titer = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++titer) {
-        const int as = titer & 1;
-        const uint32_t aphase = (titer >> 1) & 1;
-        mbar_wait(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * BN;
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
-          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)  // advancing 16 fp16 = 32 B inside the 128 B swizzle row: +2 in 16 B units
-            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M128_N256, (it > 0 || k > 0) ? 1u : 0u);
-          tc_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        tc_commit(&tfull[as]);
-      }
-    }
-  } else if (warp >= 4) {
-    const int q = warp - 4;  // TMEM lane quarter of this warp (warp id % 4)
-    int titer = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++titer) {
-      const int as = titer & 1;
-      const uint32_t aphase = (titer >> 1) & 1;
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      const long long row = (long long)tile * BM + q * 32 + lane;
-      const bool valid = row < a.rows_valid;
-      bool pad = true;
-      if (valid) {
-        const int r = (int)(row % a.PP);
-        pad = r < a.NP1 || ((r - a.NP1) % a.NP1) == a.N;
-      }
-      __half* orow = a.out + row * 256;
-      const __half* rrow = a.res ? a.res + row * 256 : nullptr;
-#pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + (uint32_t)as * BN + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
-        if (valid) {
-          uint4 o[4];
-          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-          uint4 rv[4];
-          if (rrow && !pad) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rv[j] = *reinterpret_cast<const uint4*>(rrow + cc * 32 + j * 8);
-          }
-          const __half2* rh = reinterpret_cast<const __half2*>(rv);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c0 = cc * 32 + 2 * j;
-            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
-            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
-            if (rrow && !pad) {
-              float2 rr = __half22float2(rh[j]);
-              y0 += rr.x;
-              y1 += rr.y;
-            }
-            if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-            if (pad) { y0 = 0.f; y1 = 0.f; }
-            __half2 h = __floats2half2_rn(y0, y1);
-            ow[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------- v2: slab kernel
-// Work item = 256 output rows x 128 output channels.  Per 64-channel chunk the producer loads ONE activation slab of
-// (256 + 2*H8) rows (H8 = halo N+2 rounded up to 8) and the 9 taps are taken as row-shifted views of it by moving the
-// start address of the A descriptor by whole 128-byte rows (measured on B200: the SWIZZLE_128B XOR is a function of the
-// absolute shared-memory address, exactly like the TMA write side, so any 128-byte-aligned start is valid and the
-// descriptor's base-offset field stays 0).  Each 16 KB weight stage (128 cout x 64 ch) feeds two M = 128 MMAs.
-// L2 -> SM operand traffic per (128 rows x 256 cout): 737 KB instead of 1770 KB for the per-tap kernel above.
-static const int V2_BM = 256, V2_BN = 128, V2_SA = 2, V2_SB = 6;
-static const int V2_B_BYTES = V2_BN * BK * 2;
-static const uint32_t IDESC_F16_M128_N128 = (1u << 4) | ((uint32_t)(V2_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-struct Conv2Args {
-  const float* scale;
-  const float* shift;
-  const __half* res;
-  __half* out;
-  int n_work;           // 2 * ceil(rows_valid / 256): (m tile, cout half)
-  long long rows_valid;
-  int kchunks;
-  int N, NP1, PP;
-  int H8, arows;        // slab geometry
-  int slab_bytes;       // arows * 128
-  int base_offset_mode;
-  int relu;
-};
-
-__device__ __forceinline__ uint64_t make_sw128_desc_shifted(uint32_t saddr, int mode) {
-  uint64_t d = make_sw128_desc(saddr);
-  if (mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;   // debug only: setting the base-offset field gives WRONG results on B200
-  return d;
-}
-
-__global__ void __launch_bounds__(256, 1) conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                                                             const Conv2Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* slabs = smem;                                        // [V2_SA][slab_bytes]
-  uint8_t* wst = smem + (size_t)V2_SA * a.slab_bytes;           // [V2_SB][16 KB]
-  float* s_scale = reinterpret_cast<float*>(wst + (size_t)V2_SB * V2_B_BYTES);
-  float* s_shift = s_scale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + V2_SA;
-  uint64_t* b_full = a_empty + V2_SA;
-  uint64_t* b_empty = b_full + V2_SB;
-  uint64_t* tfull = b_empty + V2_SB;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  s_scale[threadIdx.x] = a.scale[threadIdx.x];
-  s_shift[threadIdx.x] = a.shift[threadIdx.x];
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < V2_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < V2_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int half_rows = a.arows / 2;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
-        const int m0 = (w >> 1) * V2_BM, nh = w & 1;
-        for (int kc = 0; kc < a.kchunks; ++kc) {
-          mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_expect_tx(&a_full[sa], (uint32_t)a.slab_bytes);
-          uint8_t* sl = slabs + (size_t)sa * a.slab_bytes;
-          tma_load_2d(sl, &tmA, &a_full[sa], kc * BK, m0 - a.H8);
-          tma_load_2d(sl + (size_t)half_rows * 128, &tmA, &a_full[sa], kc * BK, m0 - a.H8 + half_rows);
-          if (++sa == V2_SA) { sa = 0; pa ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&b_empty[sb], pb ^ 1);
-            mbar_expect_tx(&b_full[sb], V2_B_BYTES);
-            tma_load_2d(wst + (size_t)sb * V2_B_BYTES, &tmW, &b_full[sb], kc * BK, tap * 256 + nh * V2_BN);
-            if (++sb == V2_SB) { sb = 0; pb ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int titer = 0;
-      for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++titer) {
-        const int as = titer & 1;
-        const uint32_t aphase = (titer >> 1) & 1;
-        mbar_wait(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
-        for (int kc = 0; kc < a.kchunks; ++kc) {
-          mbar_wait(&a_full[sa], pa);
-          tc_fence_after();
-          const uint32_t slab = smem_u32(slabs + (size_t)sa * a.slab_bytes);
-          for (int tap = 0; tap < 9; ++tap) {
-            const int off = (tap / 3 - 1) * a.NP1 + (tap % 3 - 1);
-            mbar_wait(&b_full[sb], pb);
-            tc_fence_after();
-            const uint64_t bdesc = make_sw128_desc(smem_u32(wst + (size_t)sb * V2_B_BYTES));
-#pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              const uint64_t adesc = make_sw128_desc_shifted(slab + (uint32_t)(a.H8 + sub * 128 + off) * 128u, a.base_offset_mode);
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k)
-                tc_mma_f16(d_tmem + (uint32_t)sub * V2_BN, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M128_N128,
-                           (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            }
-            tc_commit(&b_empty[sb]);
-            if (++sb == V2_SB) { sb = 0; pb ^= 1; }
-          }
-          tc_commit(&a_empty[sa]);
-          if (++sa == V2_SA) { sa = 0; pa ^= 1; }
-        }
-        tc_commit(&tfull[as]);
-      }
-    }
-  } else if (warp >= 4) {
-    const int q = warp - 4;
-    int titer = 0;
-    for (int w = blockIdx.x; w < a.n_work; w += gridDim.x, ++titer) {
-      const int as = titer & 1;
-      const uint32_t aphase = (titer >> 1) & 1;
-      const int m0 = (w >> 1) * V2_BM, nh = w & 1;
-      // the residual rows do not depend on the MMAs: fetch them while the accumulator is still being produced
-      uint4 rbuf[2][16];
-      bool valid[2], pad[2];
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const long long row = (long long)m0 + sub * 128 + q * 32 + lane;
-        valid[sub] = row < a.rows_valid;
-        pad[sub] = true;
-        if (valid[sub]) {
-          const int r = (int)(row % a.PP);
-          pad[sub] = r < a.NP1 || ((r - a.NP1) % a.NP1) == a.N;
-        }
-        if (a.res && !pad[sub]) {
-          const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256 + nh * V2_BN);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) rbuf[sub][j] = ld_nc_v4(rrow + j);
-        }
-      }
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-#pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
-        const long long row = (long long)m0 + sub * 128 + q * 32 + lane;
-        __half* orow = a.out + row * 256 + nh * V2_BN;
-        const bool addres = a.res && !pad[sub];
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint32_t v[32];
-          tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)sub * V2_BN + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
-          if (valid[sub]) {
-            uint4 o[4];
-            uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c0 = nh * V2_BN + cc * 32 + 2 * j;
-              float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
-              float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
-              if (addres) {
-                const uint4& rq = rbuf[sub][cc * 4 + (j >> 2)];
-                const uint32_t rw = (j & 3) == 0 ? rq.x : ((j & 3) == 1 ? rq.y : ((j & 3) == 2 ? rq.z : rq.w));
-                float2 rr = __half22float2(*reinterpret_cast<const __half2*>(&rw));
-                y0 += rr.x;
-                y1 += rr.y;
-              }
-              if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-              if (pad[sub]) { y0 = 0.f; y1 = 0.f; }
-              __half2 h = __floats2half2_rn(y0, y1);
-              ow[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
-static size_t conv2_smem(int arows) {
-  return (size_t)V2_SA * arows * 128 + (size_t)V2_SB * V2_B_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
-}
-
-
-// ------------------------------------------------------------------------------------------- v3: CTA-pair kernel
+// ------------------------------------------------------------------------------------------- CTA pair
 // cta_group::2: two CTAs of a cluster (one TPC) work on one 256-row x 256-channel tile.  Each CTA stages only ITS
 // 128 activation rows and HALF of the weight tile (128 of the 256 output channels); one tcgen05.mma issued by the
 // leader CTA consumes both halves, so per-SM shared-memory operand traffic per FLOP drops by a third versus
 // cta_group::1 (A 4 KB + B 4 KB per 128-cycle MMA instead of 4 + 8).  TMA completions of both CTAs land on the
 // leader's mbarrier; tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs.
-static const int V3_STAGES = 6;
+static const int V3_STAGES = 6;   // operand stages of conv3x3_tc5_kernel<6>
 static const int V3_STAGE_BYTES = A_BYTES + A_BYTES;   // A 128x64 + B-half 128x64
 static const size_t CONV3_SMEM = (size_t)V3_STAGES * V3_STAGE_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
 static const uint32_t IDESC_F16_M256_N256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -585,339 +205,6 @@ __device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, 
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
-conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* tiles = smem;
-  float* s_scale = reinterpret_cast<float*>(smem + (size_t)V3_STAGES * V3_STAGE_BYTES);
-  float* s_shift = s_scale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
-  uint64_t* full = bars;                       // [V3_STAGES]  (the leader's copy is the one in use)
-  uint64_t* empty = bars + V3_STAGES;          // [V3_STAGES]  local, fed by the multicast commit
-  uint64_t* tfull = bars + 2 * V3_STAGES;      // [2] local, fed by the multicast commit
-  uint64_t* tempty = bars + 2 * V3_STAGES + 2; // [2] the leader's copy collects 8 arrivals (4 epilogue warps x 2 CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * V3_STAGES + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int n_ptiles = (a.n_tiles + 1) >> 1;   // 256-row tiles
-  s_scale[threadIdx.x] = a.scale[threadIdx.x];
-  s_shift[threadIdx.x] = a.shift[threadIdx.x];
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < V3_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int iters = 9 * a.kchunks;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = pair; t < n_ptiles; t += n_pairs) {
-        const int m0 = t * 256 + (int)rank * 128;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int off = (tap / 3 - 1) * a.NP1 + (tap % 3 - 1);
-          for (int kc = 0; kc < a.kchunks; ++kc) {
-            mbar_wait_guard(&empty[stage], phase ^ 1);
-            if (rank == 0) mbar_expect_tx(&full[stage], 2 * V3_STAGE_BYTES);
-            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
-            uint8_t* sa = tiles + (size_t)stage * V3_STAGE_BYTES;
-            tma_load_2d_2sm(sa, &tmA, lbar, kc * BK, m0 + off);
-            tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, kc * BK, tap * 256 + (int)rank * 128);
-            if (++stage == V3_STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int titer = 0;
-      for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
-        const int as = titer & 1;
-        const uint32_t aphase = (titer >> 1) & 1;
-        mbar_wait_guard(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait_guard(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(tiles + (size_t)stage * V3_STAGE_BYTES);
-          const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M256_N256, (it > 0 || k > 0) ? 1u : 0u);
-          tc_commit_2sm(&empty[stage]);
-          if (++stage == V3_STAGES) { stage = 0; phase ^= 1; }
-        }
-        tc_commit_2sm(&tfull[as]);
-      }
-    }
-  } else if (warp >= 4) {
-    const int q = warp - 4;
-    int titer = 0;
-    for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
-      const int as = titer & 1;
-      const uint32_t aphase = (titer >> 1) & 1;
-      const long long row = (long long)t * 256 + rank * 128 + q * 32 + lane;
-      const bool valid = row < a.rows_valid;
-      bool pad = true;
-      if (valid) {
-        const int r = (int)(row % a.PP);
-        pad = r < a.NP1 || ((r - a.NP1) % a.NP1) == a.N;
-      }
-      __half* orow = a.out + row * 256;
-      const bool addres = a.res != nullptr && !pad;
-      mbar_wait_guard(&tfull[as], aphase);
-      tc_fence_after();
-#pragma unroll 2
-      for (int cc = 0; cc < 8; ++cc) {
-        uint4 rv[4];
-        if (addres) {
-          const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256 + cc * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = ld_nc_v4(rrow + j);
-        }
-        uint32_t v[32];
-        tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
-        if (valid) {
-          uint4 o[4];
-          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-          const __half2* rh = reinterpret_cast<const __half2*>(rv);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c0 = cc * 32 + 2 * j;
-            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
-            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
-            if (addres) {
-              float2 rr = __half22float2(rh[j]);
-              y0 += rr.x;
-              y1 += rr.y;
-            }
-            if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-            if (pad) { y0 = 0.f; y1 = 0.f; }
-            __half2 h = __floats2half2_rn(y0, y1);
-            ow[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t lb = mapa_u32(smem_u32(&tempty[as]), 0);
-        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lb) : "memory");
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
-
-// ------------------------------------------------------------------------------------------- v4: CTA pair + slab
-// v3's operand sharing across the CTA pair combined with v2's resident activation slab: per 64-channel chunk each CTA
-// loads ONE slab of 128 + 2*H8 rows and takes the 9 taps as row-shifted descriptor views; only the 16 KB half weight
-// tile is streamed per (tap, chunk).  L2 -> SM traffic per 256x256 tile: 2*(4*slab) + 1.18 MB instead of 2*1.77 MB.
-static const int V4_SA = 3, V4_SB = 7;
-
-struct Conv4Args {
-  ConvArgs c;
-  int H8, slab_rows, slab_bytes;
-};
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
-conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Conv4Args g) {
-  const ConvArgs& a = g.c;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* slabs = smem;                                          // [V4_SA][slab_bytes]
-  uint8_t* wst = smem + (size_t)V4_SA * g.slab_bytes;             // [V4_SB][16 KB]
-  float* s_scale = reinterpret_cast<float*>(wst + (size_t)V4_SB * A_BYTES);
-  float* s_shift = s_scale + 256;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + 256);
-  uint64_t* a_full = bars;               // leader's copy in use
-  uint64_t* a_empty = a_full + V4_SA;    // local
-  uint64_t* b_full = a_empty + V4_SA;    // leader's copy in use
-  uint64_t* b_empty = b_full + V4_SB;    // local
-  uint64_t* tfull = b_empty + V4_SB;     // local
-  uint64_t* tempty = tfull + 2;          // leader's copy: 8 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int n_ptiles = (a.n_tiles + 1) >> 1;
-  s_scale[threadIdx.x] = a.scale[threadIdx.x];
-  s_shift[threadIdx.x] = a.shift[threadIdx.x];
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < V4_SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < V4_SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      for (int t = pair; t < n_ptiles; t += n_pairs) {
-        const int m0 = t * 256 + (int)rank * 128;
-        for (int kc = 0; kc < a.kchunks; ++kc) {
-          mbar_wait_guard(&a_empty[sa], pa ^ 1);
-          if (rank == 0) mbar_expect_tx(&a_full[sa], 2u * (uint32_t)g.slab_bytes);
-          tma_load_2d_2sm(slabs + (size_t)sa * g.slab_bytes, &tmA, mapa_u32(smem_u32(&a_full[sa]), 0), kc * BK, m0 - g.H8);
-          if (++sa == V4_SA) { sa = 0; pa ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait_guard(&b_empty[sb], pb ^ 1);
-            if (rank == 0) mbar_expect_tx(&b_full[sb], 2u * A_BYTES);
-            tma_load_2d_2sm(wst + (size_t)sb * A_BYTES, &tmW, mapa_u32(smem_u32(&b_full[sb]), 0), kc * BK, tap * 256 + (int)rank * 128);
-            if (++sb == V4_SB) { sb = 0; pb ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int titer = 0;
-      for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
-        const int as = titer & 1;
-        const uint32_t aphase = (titer >> 1) & 1;
-        mbar_wait_guard(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256;
-        for (int kc = 0; kc < a.kchunks; ++kc) {
-          mbar_wait_guard(&a_full[sa], pa);
-          tc_fence_after();
-          const uint32_t slab = smem_u32(slabs + (size_t)sa * g.slab_bytes);
-          for (int tap = 0; tap < 9; ++tap) {
-            const int off = (tap / 3 - 1) * a.NP1 + (tap % 3 - 1);
-            mbar_wait_guard(&b_full[sb], pb);
-            tc_fence_after();
-            const uint64_t adesc = make_sw128_desc(slab + (uint32_t)(g.H8 + off) * 128u);
-            const uint64_t bdesc = make_sw128_desc(smem_u32(wst + (size_t)sb * A_BYTES));
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC_F16_M256_N256, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            tc_commit_2sm(&b_empty[sb]);
-            if (++sb == V4_SB) { sb = 0; pb ^= 1; }
-          }
-          tc_commit_2sm(&a_empty[sa]);
-          if (++sa == V4_SA) { sa = 0; pa ^= 1; }
-        }
-        tc_commit_2sm(&tfull[as]);
-      }
-    }
-  } else if (warp >= 4) {
-    const int q = warp - 4;
-    int titer = 0;
-    for (int t = pair; t < n_ptiles; t += n_pairs, ++titer) {
-      const int as = titer & 1;
-      const uint32_t aphase = (titer >> 1) & 1;
-      const long long row = (long long)t * 256 + rank * 128 + q * 32 + lane;
-      const bool valid = row < a.rows_valid;
-      bool pad = true;
-      if (valid) {
-        const int r = (int)(row % a.PP);
-        pad = r < a.NP1 || ((r - a.NP1) % a.NP1) == a.N;
-      }
-      __half* orow = a.out + row * 256;
-      const bool addres = a.res != nullptr && !pad;
-      mbar_wait_guard(&tfull[as], aphase);
-      tc_fence_after();
-#pragma unroll 2
-      for (int cc = 0; cc < 8; ++cc) {
-        uint4 rv[4];
-        if (addres) {
-          const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256 + cc * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = ld_nc_v4(rrow + j);
-        }
-        uint32_t v[32];
-        tc_ld32(tmem_base + (uint32_t)as * 256 + (uint32_t)cc * 32 + ((uint32_t)(q * 32) << 16), v);
-        if (valid) {
-          uint4 o[4];
-          uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-          const __half2* rh = reinterpret_cast<const __half2*>(rv);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c0 = cc * 32 + 2 * j;
-            float y0 = fmaf(__uint_as_float(v[2 * j]), s_scale[c0], s_shift[c0]);
-            float y1 = fmaf(__uint_as_float(v[2 * j + 1]), s_scale[c0 + 1], s_shift[c0 + 1]);
-            if (addres) {
-              float2 rr = __half22float2(rh[j]);
-              y0 += rr.x;
-              y1 += rr.y;
-            }
-            if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-            if (pad) { y0 = 0.f; y1 = 0.f; }
-            __half2 h = __floats2half2_rn(y0, y1);
-            ow[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + cc * 32 + j * 8) = o[j];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        const uint32_t lb = mapa_u32(smem_u32(&tempty[as]), 0);
-        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(lb) : "memory");
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 2) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
-  }
-}
-
-static size_t conv4_smem(int slab_rows) {
-  return (size_t)V4_SA * slab_rows * 128 + (size_t)V4_SB * A_BYTES + 2 * 256 * sizeof(float) + 256 + 1024;
-}
-
 
 // ------------------------------------------------------------------------------------------- v5: CTA pair + TMA im2col
 // Dense NHWC activations (row = b*N^2 + N*j + i, no border rows): the A tile of tap (kj, ki) is ONE TMA im2col load --
@@ -1331,7 +618,7 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
                                                        const float* __restrict__ D1W, const float* __restrict__ D1b,
                                                        const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                        const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
-                                                       float* __restrict__ v, int B, int N, int PP, int rowbase, int pitch,
+                                                       float* __restrict__ v, int B, int N,
                                                        unsigned long long* trace, const float4* __restrict__ pre) {
   const unsigned long long trace_t0 = trace ? simt::gtimer() : 0ULL;
   extern __shared__ float sm[];
@@ -1362,8 +649,7 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
   }
   for (int it = warp; it < nb * N2; it += 8) {
     const int pb = it / N2, p = it - pb * N2;
-    const int jj = p / N, ii = p - jj * N;
-    const uint4 raw = *reinterpret_cast<const uint4*>(trunk + ((size_t)(b0 + pb) * PP + rowbase + (size_t)jj * pitch + ii) * 256 + lane * 8);
+    const uint4 raw = *reinterpret_cast<const uint4*>(trunk + ((size_t)(b0 + pb) * N2 + p) * 256 + lane * 8);
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
@@ -1480,7 +766,6 @@ struct LeafFeaturesTCOp {
   Cfg c;
   View v;
   __half* in64;
-  int PP, rowbase, pitch;
   int row0;  // first batch row handled by this launch
   __device__ void operator()(int wi, char* smem) const {
     const int b = row0 + wi;
@@ -1501,8 +786,7 @@ struct LeafFeaturesTCOp {
     for (int q = 0; q < KA; ++q) {
       const int p = q * 32 + lane;
       if (p < c.N2) {
-        const int jj = p / c.N, ii = p % c.N;
-        __half* row = in64 + ((size_t)b * PP + rowbase + (size_t)jj * pitch + ii) * CIN0;
+        __half* row = in64 + ((size_t)b * c.N2 + p) * CIN0;
         __align__(16) __half h[24];
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) h[ch] = ((planes[q] >> ch) & 1u) ? one : zero;
@@ -1522,15 +806,13 @@ template <int KA> struct TraceTag<agz::LeafFeaturesTCOp<KA>> { static const int 
 }
 namespace agz {
 
-__global__ void host_features_tc_kernel(const int8_t* __restrict__ bh, const int8_t* __restrict__ tp, __half* __restrict__ in64, int B, int N,
-                                        int PP, int rowbase, int pitch) {
+__global__ void host_features_tc_kernel(const int8_t* __restrict__ bh, const int8_t* __restrict__ tp, __half* __restrict__ in64, int B, int N) {
   const int N2 = N * N;
   const size_t total = (size_t)B * N2;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int p = (int)(idx % N2), b = (int)(idx / N2);
     const int t = tp[b];
-    const int jj = p / N, ii = p % N;
-    __half* row = in64 + ((size_t)b * PP + rowbase + (size_t)jj * pitch + ii) * CIN0;
+    __half* row = in64 + ((size_t)b * N2 + p) * CIN0;
     __align__(16) __half h[24];
 #pragma unroll
     for (int kq = 0; kq < 8; ++kq) {
@@ -1612,20 +894,7 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   TCState* t = new TCState();
   n->tc = t;
   t->N = n->s.N;
-  t->NP1 = t->N + 1;
-  {
-    const char* ev0 = getenv("AGZ_CONV_KERNEL");
-    t->version = ev0 ? atoi(ev0) : 5;
-    if (t->version < 1 || t->version > 5) t->version = 5;
-  }
-  t->dense = t->version == 5;
-  {
-    const char* er = getenv("AGZ_CONV_RES_TMA");
-    t->res_tma = er ? atoi(er) : 1;
-  }
-  t->PP = t->dense ? t->N * t->N : t->NP1 * t->NP1;
-  t->rowbase = t->dense ? 0 : t->NP1;
-  t->pitch = t->dense ? t->N : t->NP1;
+  t->PP = t->N * t->N;
   t->C = n->C;
   t->T = n->s.tower;
   t->max_batch = n->max_batch;
@@ -1635,17 +904,20 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   t->stage = nullptr;
   t->stage_cap = 0;
   t->in64 = nullptr;
+  t->fuse_heads = 1;
+  t->conv5_stages = 6;
+  t->l2pf = 0;
+  t->pdl = 1;
+  t->max_pairs = 0;
+  t->res_tma = 1;
   for (int i = 0; i < 3; ++i) t->act[i] = nullptr;
   if (n->C != 256) {
     snprintf(err, errlen, "the tensor-core path is built for 256 filters");
     return 1;
   }
-  long long rows = (long long)t->max_batch * t->PP + t->N + 2;
-  t->rows_alloc = (rows + 255) / 256 * 256 + 256;
-  if (t->dense) {  // whole boards, with enough spare boards for the last 256-row tile
-    const long long n2 = (long long)t->N * t->N;
-    t->rows_alloc = ((long long)t->max_batch + (256 + n2 - 1) / n2 + 1) * n2;
-  }
+  // whole boards, with enough spare boards for the last 256-row tile
+  const long long n2 = t->PP;
+  t->rows_alloc = ((long long)t->max_batch + (256 + n2 - 1) / n2 + 1) * n2;
   cudaDeviceProp prop;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1664,62 +936,51 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   }
   cudaMemset(t->in64, 0, (size_t)t->rows_alloc * CIN0 * 2);
   for (int i = 0; i < 3; ++i) cudaMemset(t->act[i], 0, (size_t)t->rows_alloc * 256 * 2);
-  int rc = make_map(&t->tm_in64, t->in64, t->rows_alloc, CIN0, BM);
+  int rc = 0;
   for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm_act[i], t->act[i], t->rows_alloc, 256, BM);
-  for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm_w[l], t->w[l], 9 * 256, l == 0 ? CIN0 : 256, BN);
-  // v2 maps: activation boxes of half a slab, weight boxes of 128 output channels
-  t->H8 = (t->N + 2 + 7) / 8 * 8;
-  t->arows = V2_BM + 2 * t->H8;
-  t->tm2_w.resize(nconv);
-  if (!rc) rc = make_map(&t->tm2_in64, t->in64, t->rows_alloc, CIN0, t->arows / 2);
-  for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm2_act[i], t->act[i], t->rows_alloc, 256, t->arows / 2);
-  for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm2_w[l], t->w[l], 9 * 256, l == 0 ? CIN0 : 256, V2_BN);
-  if (!rc) rc = make_map(&t->tm4_in64, t->in64, t->rows_alloc, CIN0, 128 + 2 * t->H8);
-  for (int i = 0; i < 3 && !rc; ++i) rc = make_map(&t->tm4_act[i], t->act[i], t->rows_alloc, 256, 128 + 2 * t->H8);
-  if (t->dense) {
-    // boards dimension covers the whole allocation so that tiles running past the batch read zero-initialised rows
-    const long long boards = t->rows_alloc / (t->N * t->N);
-    if (!rc) rc = make_map_im2col(&t->tm5_in64, t->in64, t->N, boards, CIN0);
-    for (int i = 0; i < 3 && !rc; ++i) rc = make_map_im2col(&t->tm5_act[i], t->act[i], t->N, boards, 256);
-    t->groups = (t->max_batch % 2 == 0 && t->max_batch >= 2) ? 2 : 1;
-    t->grp_rows = (long long)(t->max_batch / 2) * t->PP;
-    if (t->groups == 2) {
-      for (int g = 0; g < 2 && !rc; ++g) {  // same buffers, base shifted by one group; the boards dimension ends where the allocation ends
-        const long long gb = boards - (long long)g * (t->max_batch / 2);
-        rc = make_map_im2col(&t->tm5g_in64[g], t->in64 + (size_t)g * t->grp_rows * CIN0, t->N, gb, CIN0);
-        for (int i = 0; i < 3 && !rc; ++i) rc = make_map_im2col(&t->tm5g_act[g][i], t->act[i] + (size_t)g * t->grp_rows * 256, t->N, gb, 256);
-      }
+  for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm_w[l], t->w[l], 9 * 256, l == 0 ? CIN0 : 256, 128);
+  // the boards dimension covers the whole allocation so that tiles running past the batch read zero-initialised rows
+  const long long boards = t->rows_alloc / n2;
+  if (!rc) rc = make_map_im2col(&t->tm5_in64, t->in64, t->N, boards, CIN0);
+  for (int i = 0; i < 3 && !rc; ++i) rc = make_map_im2col(&t->tm5_act[i], t->act[i], t->N, boards, 256);
+  t->groups = (t->max_batch % 2 == 0 && t->max_batch >= 2) ? 2 : 1;
+  t->grp_rows = (long long)(t->max_batch / 2) * t->PP;
+  if (t->groups == 2) {
+    for (int g = 0; g < 2 && !rc; ++g) {  // same buffers, base shifted by one group; the boards dimension ends where the allocation ends
+      const long long gb = boards - (long long)g * (t->max_batch / 2);
+      rc = make_map_im2col(&t->tm5g_in64[g], t->in64 + (size_t)g * t->grp_rows * CIN0, t->N, gb, CIN0);
+      for (int i = 0; i < 3 && !rc; ++i) rc = make_map_im2col(&t->tm5g_act[g][i], t->act[i] + (size_t)g * t->grp_rows * 256, t->N, gb, 256);
     }
-  } else {
-    t->groups = 1;
-    t->grp_rows = 0;
   }
-  {
-    const char* ef = getenv("AGZ_FUSE_HEADS");
-    t->fuse_heads = ef ? atoi(ef) : 1;
-  }
-  {
-    const char* es = getenv("AGZ_CONV5_STAGES");
-    t->conv5_stages = (es && atoi(es) == 4) ? 4 : 6;
-  }
-  {
-    const char* el = getenv("AGZ_CONV_L2PF");
-    t->l2pf = el ? atoi(el) : 0;
-  }
-  {
-    const char* ed = getenv("AGZ_CONV_PDL");
-    t->pdl = ed ? atoi(ed) : 1;
-  }
-  {
-    const char* ep = getenv("AGZ_CONV_PAIRS");   // cap on the CTA pairs of the persistent conv kernels (0 = all SMs)
-    t->max_pairs = ep ? atoi(ep) : 0;
-  }
-  const char* eb = getenv("AGZ_CONV_BASEOFF");
-  t->base_offset_mode = eb ? atoi(eb) : 0;
   if (rc) {
-    snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d)", rc);
+    snprintf(err, errlen, "cuTensorMapEncode failed (%d)", rc);
     return 1;
   }
+  return 0;
+}
+
+// agz_set_option "conv.*" (include/agz.h): experiment knobs of the tensor-core path, all read at launch time
+int nn_tc_set_option(NNet* n, const char* key, long long value) {
+  TCState* t = (TCState*)n->tc;
+  if (!strcmp(key, "conv.fuse_heads")) t->fuse_heads = value != 0;
+  else if (!strcmp(key, "conv.stages")) { if (value != 4 && value != 6) return 2; t->conv5_stages = (int)value; }
+  else if (!strcmp(key, "conv.l2_prefetch")) t->l2pf = value != 0;
+  else if (!strcmp(key, "conv.pdl")) t->pdl = value != 0;
+  else if (!strcmp(key, "conv.max_pairs")) { if (value < 0) return 2; t->max_pairs = (int)value; }
+  else if (!strcmp(key, "conv.res_tma")) t->res_tma = value != 0;
+  else return 1;
+  return 0;
+}
+
+int nn_tc_get_option(const NNet* n, const char* key, long long* value) {
+  const TCState* t = (const TCState*)n->tc;
+  if (!strcmp(key, "conv.fuse_heads")) *value = t->fuse_heads;
+  else if (!strcmp(key, "conv.stages")) *value = t->conv5_stages;
+  else if (!strcmp(key, "conv.l2_prefetch")) *value = t->l2pf;
+  else if (!strcmp(key, "conv.pdl")) *value = t->pdl;
+  else if (!strcmp(key, "conv.max_pairs")) *value = t->max_pairs;
+  else if (!strcmp(key, "conv.res_tma")) *value = t->res_tma;
+  else return 1;
   return 0;
 }
 
@@ -1779,48 +1040,7 @@ int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t 
   return 0;
 }
 
-TCInput nn_tc_input(NNet* n) {
-  TCState* t = (TCState*)n->tc;
-  TCInput r;
-  r.act = t->in64; r.rows_per_board = t->PP; r.row_stride_pts = t->NP1; r.cin_pad = CIN0; r.rows_total = t->rows_alloc;
-  return r;
-}
-
 long long nn_tc_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower + 1; }
-
-static int launch_conv2(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
-                        __half* out, int B, int kchunks, cudaStream_t s) {
-  Conv2Args a;
-  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
-  a.rows_valid = (long long)B * t->PP;
-  a.n_work = 2 * (int)((a.rows_valid + V2_BM - 1) / V2_BM);
-  a.kchunks = kchunks;
-  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
-  a.H8 = t->H8; a.arows = t->arows; a.slab_bytes = t->arows * 128;
-  a.base_offset_mode = t->base_offset_mode;
-  a.relu = 1;
-  int grid = a.n_work < t->num_sms ? a.n_work : t->num_sms;
-  conv3x3_tc2_kernel<<<grid, 256, conv2_smem(t->arows), s>>>(tmA, tmW, a);
-  return (int)cudaGetLastError();
-}
-
-static int launch_conv3(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
-                        __half* out, int B, int kchunks, cudaStream_t s) {
-  ConvArgs a;
-  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
-  a.rows_valid = (long long)B * t->PP;
-  a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
-  a.kchunks = kchunks;
-  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
-  a.relu = 1;
-  a.trace = t->trace;
-  a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
-  a.l2pf = t->l2pf;
-  const int n_ptiles = (a.n_tiles + 1) / 2;
-  int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
-  conv3x3_tc3_kernel<<<2 * pairs, 256, CONV3_SMEM, s>>>(tmA, tmW, a);
-  return (int)cudaGetLastError();
-}
 
 static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
                         __half* out, int B, int kchunks, cudaStream_t s, const CUtensorMap* res_map = nullptr, int res_row0 = 0, bool pdl = false,
@@ -1830,7 +1050,7 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   a.rows_valid = (long long)B * t->PP;
   a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
   a.kchunks = kchunks;
-  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
+  a.N = t->N; a.PP = t->PP;
   a.relu = 1;
   a.trace = t->trace;
   a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
@@ -1870,43 +1090,6 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   return rc != cudaSuccess ? (int)rc : (int)cudaGetLastError();
 }
 
-static int launch_conv4(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
-                        __half* out, int B, int kchunks, cudaStream_t s) {
-  Conv4Args g;
-  ConvArgs& a = g.c;
-  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
-  a.rows_valid = (long long)B * t->PP;
-  a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
-  a.kchunks = kchunks;
-  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
-  a.relu = 1;
-  a.trace = t->trace;
-  a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
-  a.l2pf = t->l2pf;
-  g.H8 = t->H8; g.slab_rows = 128 + 2 * t->H8; g.slab_bytes = g.slab_rows * 128;
-  const int n_ptiles = (a.n_tiles + 1) / 2;
-  int pairs = n_ptiles < t->num_sms / 2 ? n_ptiles : t->num_sms / 2;
-  conv3x3_tc4_kernel<<<2 * pairs, 256, conv4_smem(g.slab_rows), s>>>(tmA, tmW, g);
-  return (int)cudaGetLastError();
-}
-
-static int launch_conv(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
-                       __half* out, int B, int kchunks, cudaStream_t s) {
-  ConvArgs a;
-  a.scale = scale; a.shift = shift; a.res = res; a.out = out;
-  a.rows_valid = (long long)B * t->PP;
-  a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
-  a.kchunks = kchunks;
-  a.N = t->N; a.NP1 = t->NP1; a.PP = t->PP;
-  a.relu = 1;
-  a.trace = t->trace;
-  a.head_vw = nullptr; a.head_pw = nullptr; a.head_aff = nullptr; a.head_out = nullptr;
-  a.l2pf = t->l2pf;
-  int grid = a.n_tiles < t->num_sms ? a.n_tiles : t->num_sms;
-  conv3x3_tc_kernel<<<grid, 256, CONV_SMEM, s>>>(tmA, tmW, a);
-  return (int)cudaGetLastError();
-}
-
 int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev, int group, cudaEvent_t convs_done,
                   cudaStream_t heads_stream) {
   TCState* t = (TCState*)n->tc;
@@ -1914,38 +1097,28 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   const size_t roff = group > 0 ? (size_t)t->grp_rows : 0;   // row offset of this group inside the shared buffers
   if (B > t->max_batch) { snprintf(err, errlen, "batch %d exceeds max_batch %d", B, t->max_batch); return 1; }
   if (!t->attr_set) {
-    cudaError_t rc = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv2_smem(t->arows));
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv4_smem(128 + 2 * t->H8));
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem(n->N2, n->A));
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
     t->attr_set = true;
   }
   if (ev) cudaEventRecord(ev[0], s);
-  const bool v2 = t->version == 2;
-  const bool fuse = t->fuse_heads && t->version == 5 && t->res_tma && t->T >= 1;
+  const bool fuse = t->fuse_heads && t->res_tma && t->T >= 1;
   auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
     const bool pdl = in_buf >= 0;   // tower convolutions directly follow another convolution on the same stream
     const NNet* hf = (fuse && layer == 2 * t->T) ? n : nullptr;   // the last convolution feeds the heads directly
     const int kch = in_buf < 0 ? CIN0 / BK : 4;
     const __half* res = res_buf >= 0 ? t->act[res_buf] + roff * 256 : nullptr;
     const CUtensorMap* rmap = res_buf >= 0 ? &t->tm_act[res_buf] : nullptr;   // plain 2-D map (128 rows x 64 ch boxes) over the shortcut buffer
-    if (t->version == 5 && group >= 0)
-      return launch_conv5(t, in_buf < 0 ? t->tm5g_in64[group] : t->tm5g_act[group][in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res,
+    if (group >= 0)
+      return launch_conv5(t, in_buf < 0 ? t->tm5g_in64[group] : t->tm5g_act[group][in_buf], t->tm_w[layer], n->f_scale[layer], n->f_shift[layer], res,
                           t->act[out_buf] + roff * 256, B, kch, s, rmap, (int)roff, pdl, hf);
-    if (t->version == 5)
-      return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s,
-                          rmap, 0, pdl, hf);
-    if (t->version == 4) return launch_conv4(t, in_buf < 0 ? t->tm4_in64 : t->tm4_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
-    if (t->version == 3) return launch_conv3(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
-    if (v2) return launch_conv2(t, in_buf < 0 ? t->tm2_in64 : t->tm2_act[in_buf], t->tm2_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
-    return launch_conv(t, in_buf < 0 ? t->tm_in64 : t->tm_act[in_buf], t->tm_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s);
+    return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_act[in_buf], t->tm_w[layer], n->f_scale[layer], n->f_shift[layer], res, t->act[out_buf], B, kch, s,
+                        rmap, 0, pdl, hf);
   };
   int rc = conv(-1, 0, -1, 0);
   if (ev) cudaEventRecord(ev[1], s);
@@ -1964,7 +1137,7 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   }
   const size_t hsm = heads_smem(n->N2, n->A);
   heads_tc_kernel<<<(B + HPB - 1) / HPB, 256, hsm, s>>>(t->act[h] + roff * 256, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW,
-                                                        n->f_Pb, pi, v, B, t->N, t->PP, t->rowbase, t->pitch, t->trace, fuse ? t->head_pre + roff : nullptr);
+                                                        n->f_Pb, pi, v, B, t->N, t->trace, fuse ? t->head_pre + roff : nullptr);
   if (ev) cudaEventRecord(ev[3], s);
   cudaError_t e2 = cudaGetLastError();
   if (e2 != cudaSuccess) { snprintf(err, errlen, "heads launch: %s", cudaGetErrorString(e2)); return 1; }
@@ -1975,9 +1148,9 @@ int engine_tc_features(const Cfg& c, const View& v, NNet* n, int row0, int nrows
   TCState* t = (TCState*)n->tc;
   int rc = 0;
   switch (c.KA) {
-    case 3: { LeafFeaturesTCOp<3> op{c, v, t->in64, t->PP, t->rowbase, t->pitch, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
-    case 6: { LeafFeaturesTCOp<6> op{c, v, t->in64, t->PP, t->rowbase, t->pitch, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
-    default: { LeafFeaturesTCOp<12> op{c, v, t->in64, t->PP, t->rowbase, t->pitch, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
+    case 3: { LeafFeaturesTCOp<3> op{c, v, t->in64, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
+    case 6: { LeafFeaturesTCOp<6> op{c, v, t->in64, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
+    default: { LeafFeaturesTCOp<12> op{c, v, t->in64, row0}; rc = devrt::launch_warps(op, nrows, smem_per_warp, s); } break;
   }
   return rc;
 }
@@ -1995,7 +1168,7 @@ int engine_host_features_tc(const Cfg& c, NNet* n, const int8_t* boards_hist, co
   if (rc == cudaSuccess) rc = cudaMemcpyAsync(dtp, to_play, (size_t)B, cudaMemcpyHostToDevice, s);
   if (rc == cudaSuccess) {
     int blocks = (int)(((size_t)B * c.N2 + 255) / 256);
-    host_features_tc_kernel<<<blocks, 256, 0, s>>>(dbh, dtp, t->in64, B, c.N, t->PP, t->rowbase, t->pitch);
+    host_features_tc_kernel<<<blocks, 256, 0, s>>>(dbh, dtp, t->in64, B, c.N);
     rc = cudaGetLastError();
   }
   cudaError_t rs = cudaStreamSynchronize(s);

@@ -15,8 +15,15 @@ struct StartOp {
   AGZ_DEV void operator()(int g, char* smem) const {
     Warp<KA> w(c, v, g, smem);
     long long id = (long long)c.rank + (long long)c.world * g;
-    if (c.total_games < 0 || id < c.total_games) w.start_game(id);
-    else w.st.phase = PH_IDLE;
+    const long long delay = c.stagger_rounds > 0 ? (long long)g * c.stagger_rounds / c.n_games : 0;
+    if (!(c.total_games < 0 || id < c.total_games)) w.st.phase = PH_IDLE;
+    else if (delay > 0) {
+      w.st.game_id = id;
+      w.st.delay = (int32_t)delay;
+      w.st.err = 0;
+      w.st.nleaf = 0;
+      w.st.phase = PH_DELAY;
+    } else w.start_game(id);
     w.store_state();
   }
 };

@@ -5,10 +5,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "devrt.h"
 #include "replay.h"
+
+#define AGZ_HD __host__ __device__
 
 namespace agz {
 
@@ -62,19 +65,19 @@ struct ReplayState {
   long long* d_counts;      // [world]
   int* d_rec_idx;           // per packed record: ring slot, tuple offset
   size_t rec_cap;
+  unsigned char* stage;     // sampled tuples [batch][stride] (replay_sample_device)
+  long long* d_idx;         // their ring indices
+  size_t stage_cap, idx_cap;
+  long long last_payload_bytes, gathered_bytes;   // tuple bytes appended by the last gather (all ranks) / since creation
 };
 
-ReplayState* replay_create(const Cfg& c, char* err, size_t errlen) {
+ReplayState* replay_create(const Cfg& c, long long capacity, char* err, size_t errlen) {
   ReplayState* r = new ReplayState();
   memset(r, 0, sizeof(*r));
   r->world = c.world;
   r->rank = c.rank;
   r->stride = ((size_t)4 * c.A + 8 * (size_t)c.N2 + 2 + 15) / 16 * 16;
-  r->cap = kReplayCap;
-  if (const char* ec = getenv("AGZ_REPLAY_CAP")) {   // smaller rings for tests of the trim-oldest wrap-around
-    const long long v = atoll(ec);
-    if (v > 0) r->cap = v;
-  }
+  r->cap = capacity > 0 ? capacity : kReplayCap;   // option replay.capacity (smaller rings: tests of the trim-oldest wrap-around)
   if (cudaMalloc((void**)&r->ring, (size_t)r->cap * r->stride) != cudaSuccess || cudaMalloc((void**)&r->d_counts, sizeof(long long) * c.world) != cudaSuccess) {
     snprintf(err, errlen, "cudaMalloc of the replay ring failed");
     replay_destroy(r);
@@ -86,7 +89,7 @@ ReplayState* replay_create(const Cfg& c, char* err, size_t errlen) {
 void replay_destroy(ReplayState* r) {
   if (!r) return;
   if (r->have_comm && nccl_api()) nccl_api()->CommDestroy(r->comm);
-  cudaFree(r->ring); cudaFree(r->send); cudaFree(r->recv); cudaFree(r->d_counts); cudaFree(r->d_rec_idx);
+  cudaFree(r->ring); cudaFree(r->send); cudaFree(r->recv); cudaFree(r->d_counts); cudaFree(r->d_rec_idx); cudaFree(r->stage); cudaFree(r->d_idx);
   delete r;
 }
 
@@ -175,6 +178,7 @@ static int grow(unsigned char** p, size_t* cap, size_t need) {
   if (need <= *cap) return 0;
   cudaFree(*p);
   *p = nullptr;
+  *cap = 0;   // a failed allocation must not leave a stale capacity behind a null pointer
   size_t n = need + need / 2 + 4096;
   if (cudaMalloc((void**)p, n) != cudaSuccess) return 1;
   *cap = n;
@@ -195,29 +199,52 @@ static void ring_append(ReplayState* r, const unsigned char* src, long long n, c
 int replay_gather(ReplayState* r, const Cfg& c, const View& v, int smem_per_warp, cudaStream_t s, int64_t* n_total, long long* launches,
                   char* err, size_t errlen) {
   *launches = 0;
+  r->last_payload_bytes = 0;
   cudaStreamSynchronize(s);
   unsigned long long ctr[CTR_COUNT];
   cudaMemcpy(ctr, v.ctr, sizeof(ctr), cudaMemcpyDeviceToHost);
   unsigned long long head = ctr[CTR_RING_HEAD], tail = ctr[CTR_RING_TAIL];
   if (r->gather_pos < head) r->gather_pos = head;  // records released before being gathered are gone
+  // headers of all finished records not gathered yet: the ring is fixed-stride, so they are at most two contiguous ranges
+  const unsigned long long npend = tail - r->gather_pos;
+  std::vector<RingHeader> hd((size_t)npend);
+  for (unsigned long long done = 0; done < npend;) {
+    const size_t rs = (size_t)((r->gather_pos + done) % (unsigned long long)c.ring_cap);
+    const size_t run = (size_t)std::min<unsigned long long>(npend - done, (unsigned long long)c.ring_cap - rs);
+    cudaMemcpy(hd.data() + done, v.ring_hdr + rs, run * sizeof(RingHeader), cudaMemcpyDeviceToHost);
+    done += run;
+  }
   std::vector<int> rec;
+  rec.reserve(2 * (size_t)npend);
   long long n_local = 0;
-  for (unsigned long long q = r->gather_pos; q < tail; ++q) {
-    int rslot = (int)(q % (unsigned long long)c.ring_cap);
-    RingHeader hd;
-    cudaMemcpy(&hd, v.ring_hdr + rslot, sizeof(hd), cudaMemcpyDeviceToHost);
-    rec.push_back(rslot);
+  for (unsigned long long q = 0; q < npend; ++q) {
+    rec.push_back((int)((r->gather_pos + q) % (unsigned long long)c.ring_cap));
     rec.push_back((int)n_local);
-    n_local += hd.n_moves;
+    n_local += hd[(size_t)q].n_moves;
   }
   r->gather_pos = tail;
-  const int nrec = (int)rec.size() / 2;
-  if (grow(&r->send, &r->send_cap, (size_t)(n_local ? n_local : 1) * r->stride)) { snprintf(err, errlen, "replay send buffer allocation failed"); return 3; }
+  const int nrec = (int)npend;
+  const bool multi = r->have_comm && r->world > 1;
+  // Ragged all-gather, step 1: the counts.  They go round BEFORE anything is packed, so the send buffer can be sized once for
+  // max(own, largest) tuples -- growing it after the pack kernel would discard this rank's tuples.
+  std::vector<long long> counts((size_t)(multi ? r->world : 1), n_local);
+  long long mx = n_local;
+  if (multi) {
+    cudaMemcpyAsync(r->d_counts + r->rank, &n_local, sizeof(long long), cudaMemcpyHostToDevice, s);
+    ncclResult_t nr = nccl_api()->AllGather(r->d_counts + r->rank, r->d_counts, 1, ncclInt64, r->comm, s);
+    if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(counts): %s", nccl_api()->GetErrorString(nr)); return 4; }
+    cudaMemcpyAsync(counts.data(), r->d_counts, sizeof(long long) * r->world, cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) { snprintf(err, errlen, "replay gather (counts): %s", cudaGetErrorString(cudaGetLastError())); return 3; }
+    for (long long x : counts) mx = x > mx ? x : mx;
+  }
+  if (grow(&r->send, &r->send_cap, (size_t)(mx ? mx : 1) * r->stride)) { snprintf(err, errlen, "replay send buffer allocation failed"); return 3; }
   if (nrec) {
     if (rec.size() * sizeof(int) > r->rec_cap) {
       cudaFree(r->d_rec_idx);
+      r->d_rec_idx = nullptr;
+      r->rec_cap = 0;
+      if (cudaMalloc((void**)&r->d_rec_idx, rec.size() * sizeof(int) * 2) != cudaSuccess) { snprintf(err, errlen, "replay index allocation failed"); return 3; }
       r->rec_cap = rec.size() * sizeof(int) * 2;
-      if (cudaMalloc((void**)&r->d_rec_idx, r->rec_cap) != cudaSuccess) { snprintf(err, errlen, "replay index allocation failed"); return 3; }
     }
     cudaMemcpyAsync(r->d_rec_idx, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice, s);
     PackOp op{c, v, r->d_rec_idx, r->send, r->stride};
@@ -225,30 +252,37 @@ int replay_gather(ReplayState* r, const Cfg& c, const View& v, int smem_per_warp
     if (rc) { snprintf(err, errlen, "pack kernel: %s", cudaGetErrorString((cudaError_t)rc)); return 3; }
     *launches += 1;
   }
-  if (!r->have_comm || r->world == 1) {
+  if (!multi) {
     ring_append(r, r->send, n_local, s);
-  } else {
-    // ragged all-gather: counts first, then fixed-stride padded blocks
-    cudaMemcpyAsync(r->d_counts + r->rank, &n_local, sizeof(long long), cudaMemcpyHostToDevice, s);
-    ncclResult_t nr = nccl_api()->AllGather(r->d_counts + r->rank, r->d_counts, 1, ncclInt64, r->comm, s);
-    if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(counts): %s", nccl_api()->GetErrorString(nr)); return 4; }
-    std::vector<long long> counts((size_t)r->world);
-    cudaMemcpyAsync(counts.data(), r->d_counts, sizeof(long long) * r->world, cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
-    long long mx = 0;
-    for (long long x : counts) mx = x > mx ? x : mx;
-    if (mx > 0) {
-      if (grow(&r->send, &r->send_cap, (size_t)mx * r->stride) && n_local == 0) { snprintf(err, errlen, "replay send buffer allocation failed"); return 3; }
-      if ((size_t)mx * r->stride > r->send_cap) { snprintf(err, errlen, "replay send buffer too small"); return 3; }
-      if (grow(&r->recv, &r->recv_cap, (size_t)mx * r->stride * r->world)) { snprintf(err, errlen, "replay recv buffer allocation failed"); return 3; }
-      nr = nccl_api()->AllGather(r->send, r->recv, (size_t)mx * r->stride, ncclUint8, r->comm, s);
-      if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(tuples): %s", nccl_api()->GetErrorString(nr)); return 4; }
-      for (int k = 0; k < r->world; ++k) ring_append(r, r->recv + (size_t)k * mx * r->stride, counts[(size_t)k], s);
+    r->last_payload_bytes = (long long)n_local * (long long)r->stride;
+  } else if (mx > 0) {
+    // step 2: fixed-stride padded blocks (every rank sends mx tuples' worth; only counts[k] of block k are appended)
+    if (grow(&r->recv, &r->recv_cap, (size_t)mx * r->stride * r->world)) { snprintf(err, errlen, "replay recv buffer allocation failed"); return 3; }
+    ncclResult_t nr = nccl_api()->AllGather(r->send, r->recv, (size_t)mx * r->stride, ncclUint8, r->comm, s);
+    if (nr != ncclSuccess) { snprintf(err, errlen, "ncclAllGather(tuples): %s", nccl_api()->GetErrorString(nr)); return 4; }
+    for (int k = 0; k < r->world; ++k) {
+      ring_append(r, r->recv + (size_t)k * mx * r->stride, counts[(size_t)k], s);
+      r->last_payload_bytes += counts[(size_t)k] * (long long)r->stride;
     }
   }
   if (cudaStreamSynchronize(s) != cudaSuccess) { snprintf(err, errlen, "replay gather: %s", cudaGetErrorString(cudaGetLastError())); return 3; }
+  r->gathered_bytes += r->last_payload_bytes;
   if (n_total) *n_total = r->total;
   return 0;
+}
+
+// copy tuples out of a host image of `count` packed tuples
+static void unpack(const ReplayState* r, const Cfg& c, const unsigned char* img, int count, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs,
+                   int8_t* boards_hist) {
+  for (int i = 0; i < count; ++i) {
+    const unsigned char* t = img + (size_t)i * r->stride;
+    if (pis) memcpy(pis + (size_t)i * c.A, t, (size_t)4 * c.A);
+    const int8_t* b = reinterpret_cast<const int8_t*>(t + (size_t)4 * c.A);
+    if (boards) memcpy(boards + (size_t)i * c.N2, b, (size_t)c.N2);
+    if (boards_hist) memcpy(boards_hist + (size_t)i * 8 * c.N2, b, (size_t)8 * c.N2);
+    if (to_play) to_play[i] = b[8 * c.N2];
+    if (zs) zs[i] = b[8 * c.N2 + 1];
+  }
 }
 
 int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs,
@@ -258,48 +292,110 @@ int replay_read(ReplayState* r, const Cfg& c, int64_t first, int32_t count, int8
     snprintf(err, errlen, "replay tuples [%lld, %lld) not in the ring [%lld, %lld)", (long long)first, (long long)(first + count), oldest, r->total);
     return 5;
   }
-  std::vector<unsigned char> buf(r->stride);
-  for (int i = 0; i < count; ++i) {
-    long long pos = (first + i) % r->cap;
-    cudaMemcpyAsync(buf.data(), r->ring + (size_t)pos * r->stride, r->stride, cudaMemcpyDeviceToHost, s);
-    cudaStreamSynchronize(s);
-    if (pis) memcpy(pis + (size_t)i * c.A, buf.data(), (size_t)4 * c.A);
-    const int8_t* b = reinterpret_cast<const int8_t*>(buf.data() + (size_t)4 * c.A);
-    if (boards) memcpy(boards + (size_t)i * c.N2, b, (size_t)c.N2);
-    if (boards_hist) memcpy(boards_hist + (size_t)i * 8 * c.N2, b, (size_t)8 * c.N2);
-    if (to_play) to_play[i] = b[8 * c.N2];
-    if (zs) zs[i] = b[8 * c.N2 + 1];
+  if (count == 0) return 0;
+  std::vector<unsigned char> img((size_t)count * r->stride);
+  for (long long done = 0; done < count;) {   // at most two contiguous ranges of the ring
+    const long long pos = (first + done) % r->cap;
+    const long long run = std::min<long long>(count - done, r->cap - pos);
+    cudaMemcpyAsync(img.data() + (size_t)done * r->stride, r->ring + (size_t)pos * r->stride, (size_t)run * r->stride, cudaMemcpyDeviceToHost, s);
+    done += run;
   }
+  if (cudaStreamSynchronize(s) != cudaSuccess) { snprintf(err, errlen, "replay read: %s", cudaGetErrorString(cudaGetLastError())); return 3; }
+  unpack(r, c, img.data(), count, boards, to_play, pis, zs, boards_hist);
   return 0;
 }
 
-// uniform sample without replacement (src/train.jl:5): partial Fisher-Yates over the ring's index range, splitmix64 stream
-int replay_sample(ReplayState* r, const Cfg& c, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices,
-                  cudaStream_t s, char* err, size_t errlen, int8_t* boards_hist) {
-  const long long oldest = r->total > r->cap ? r->total - r->cap : 0, n = r->total - oldest;
-  if (batch < 0 || batch > n) {
-    snprintf(err, errlen, "cannot sample %d tuples without replacement from %lld", batch, n);
-    return 5;
-  }
-  std::vector<long long> pool((size_t)n);
-  for (long long i = 0; i < n; ++i) pool[(size_t)i] = oldest + i;
+// ---- get_replay_batch (src/train.jl:4-12): uniform sample without replacement, drawn ON THE DEVICE.
+// Draw k of a batch is tuple oldest + perm(k), where perm is a keyed pseudo-random permutation of [0, n): a 6-round Feistel
+// network over 2w >= log2(n) bits with cycle walking (values >= n are fed back until they land inside).  A permutation gives
+// distinct indices by construction, every draw is independent of the others (one CTA per draw: compute the index, copy the
+// tuple), and nothing O(ring) is ever built.  Restated in oracle/replay.py (sample_indices); the reference's own draw comes
+// from StatsBase.sample on Julia's global RNG and is unpinned.
+AGZ_HD inline uint32_t mix32(uint32_t h) {   // murmur3 finaliser
+  h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+  return h;
+}
+struct FeistelKeys { uint32_t k[6]; int w; };
+static FeistelKeys feistel_keys(uint64_t seed, long long n) {
+  FeistelKeys f;
+  int bits = 2;
+  while ((1LL << bits) < n) ++bits;
+  if (bits & 1) ++bits;
+  f.w = bits / 2;
   uint64_t x = seed;
-  auto next = [&x]() {
+  for (int i = 0; i < 6; ++i) {   // splitmix64 stream
     uint64_t z = (x += 0x9E3779B97F4A7C15ull);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-  };
-  for (int k = 0; k < batch; ++k) {
-    const size_t j = (size_t)k + (size_t)(next() % (uint64_t)(n - k));
-    std::swap(pool[(size_t)k], pool[j]);
-    if (indices) indices[k] = pool[(size_t)k];
-    int rc = replay_read(r, c, pool[(size_t)k], 1, boards ? boards + (size_t)k * c.N2 : nullptr, to_play ? to_play + k : nullptr,
-                         pis ? pis + (size_t)k * c.A : nullptr, zs ? zs + k : nullptr, s, err, errlen,
-                         boards_hist ? boards_hist + (size_t)k * 8 * c.N2 : nullptr);
-    if (rc) return rc;
+    f.k[i] = (uint32_t)((z ^ (z >> 31)) >> 32);
   }
+  return f;
+}
+AGZ_HD inline long long feistel_perm(const FeistelKeys& f, long long k, long long n) {
+  const uint32_t mask = (1u << f.w) - 1u;
+  long long y = k;
+  do {
+    uint32_t L = (uint32_t)(y >> f.w), R = (uint32_t)y & mask;
+    for (int i = 0; i < 6; ++i) {
+      const uint32_t F = mix32(R ^ f.k[i]) & mask;
+      const uint32_t t = L ^ F;
+      L = R;
+      R = t;
+    }
+    y = ((long long)L << f.w) | R;
+  } while (y >= n);
+  return y;
+}
+
+__global__ void __launch_bounds__(128) replay_sample_kernel(const unsigned char* __restrict__ ring, long long cap, long long oldest, long long n,
+                                                            FeistelKeys f, size_t stride, unsigned char* __restrict__ out, long long* __restrict__ idx_out) {
+  const int k = blockIdx.x;
+  const long long idx = oldest + feistel_perm(f, k, n);
+  if (threadIdx.x == 0) idx_out[k] = idx;
+  const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)(idx % cap) * stride);
+  uint4* dst = reinterpret_cast<uint4*>(out + (size_t)k * stride);
+  for (size_t i = threadIdx.x; i < stride / 16; i += blockDim.x) dst[i] = src[i];
+}
+
+// draws `batch` tuples into the device staging buffer (r->stage: [batch][stride], r->d_idx: [batch]); no host synchronisation
+int replay_sample_device(ReplayState* r, int32_t batch, uint64_t seed, cudaStream_t s, const unsigned char** stage_out, const long long** idx_out,
+                         char* err, size_t errlen) {
+  const long long oldest = r->total > r->cap ? r->total - r->cap : 0, n = r->total - oldest;
+  if (batch < 1 || batch > n) {
+    snprintf(err, errlen, "cannot sample %d tuples without replacement from %lld", batch, n);
+    return 5;
+  }
+  if (grow(&r->stage, &r->stage_cap, (size_t)batch * r->stride) || grow((unsigned char**)&r->d_idx, &r->idx_cap, (size_t)batch * sizeof(long long))) {
+    snprintf(err, errlen, "replay sample staging allocation failed");
+    return 3;
+  }
+  replay_sample_kernel<<<batch, 128, 0, s>>>(r->ring, r->cap, oldest, n, feistel_keys(seed, n), r->stride, r->stage, r->d_idx);
+  if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "replay sample kernel launch failed"); return 3; }
+  if (stage_out) *stage_out = r->stage;
+  if (idx_out) *idx_out = r->d_idx;
   return 0;
 }
+
+int replay_sample(ReplayState* r, const Cfg& c, int32_t batch, uint64_t seed, int8_t* boards, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices,
+                  cudaStream_t s, char* err, size_t errlen, int8_t* boards_hist) {
+  if (batch == 0) return 0;
+  int rc = replay_sample_device(r, batch, seed, s, nullptr, nullptr, err, errlen);
+  if (rc) return rc;
+  std::vector<unsigned char> img((size_t)batch * r->stride);   // one transfer for the tuples, one for the indices
+  std::vector<long long> idx((size_t)batch);
+  cudaMemcpyAsync(img.data(), r->stage, img.size(), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(idx.data(), r->d_idx, idx.size() * sizeof(long long), cudaMemcpyDeviceToHost, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) { snprintf(err, errlen, "replay sample: %s", cudaGetErrorString(cudaGetLastError())); return 3; }
+  unpack(r, c, img.data(), batch, boards, to_play, pis, zs, boards_hist);
+  if (indices) for (int k = 0; k < batch; ++k) indices[k] = idx[(size_t)k];
+  return 0;
+}
+
+void replay_info(const ReplayState* r, int64_t out[5]) {
+  out[0] = (int64_t)r->stride; out[1] = r->cap; out[2] = r->total; out[3] = r->last_payload_bytes; out[4] = r->gathered_bytes;
+}
+long long replay_capacity(const ReplayState* r) { return r->cap; }
+long long replay_default_capacity() { return kReplayCap; }
+size_t replay_stride(const ReplayState* r) { return r->stride; }
 
 }  // namespace agz

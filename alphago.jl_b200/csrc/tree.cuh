@@ -24,7 +24,8 @@ namespace agz {
 
 enum { PH_IDLE = 0, PH_SEED = 1, PH_SEARCH = 2, PH_WAIT_RING = 3, PH_MANUAL = 4,
        PH_MATCH_WAIT = 5,      // two-player match slot (evaluate / play): waiting for the host to arm a search or play a move
-       PH_MATCH_SEARCH = 6 };  // ... searching until N(root) >= target_N
+       PH_MATCH_SEARCH = 6,    // ... searching until N(root) >= target_N
+       PH_DELAY = 7 };         // staggered start (option selfplay.stagger_rounds): the slot's first game begins after `delay` rounds
 enum { F_EXPANDED = 1, F_DONE = 2, F_LASTPASS = 4 };
 enum { E_OK = 0, E_ILLEGAL = 1, E_ASSERT = 2, E_CAPACITY = 6 };
 enum { OP_VLOSS_ADD = 0, OP_VLOSS_REVERT = 1, OP_BACKUP = 2, OP_REVERT_VISITS = 3 };
@@ -59,7 +60,8 @@ struct GameState {
   int32_t vloss_balance;  // path entries with a virtual loss outstanding
   int32_t result, resigned;
   float final_score;
-  int32_t pad[2];
+  int32_t delay;          // PH_DELAY: rounds left before the first game of this slot starts
+  int32_t pad;
 };
 
 struct Cfg {
@@ -72,6 +74,7 @@ struct Cfg {
   double c_puct, noise_weight, noise_alpha, resign_threshold, resign_disable_frac;
   uint64_t seed;
   long long total_games;
+  long long stagger_rounds;  // 0 = every slot starts at once; R = slot g starts after g*R/n_games rounds (throughput runs: slots spread over all plies)
 };
 
 enum { CTR_MOVES = 0, CTR_FINISHED, CTR_STARTED, CTR_POSITIONS, CTR_READOUTS, CTR_PATHNODES, CTR_RING_TAIL, CTR_RING_HEAD,
@@ -961,6 +964,10 @@ struct Warp {
       return;
     }
     if (st.phase == PH_WAIT_RING) { finish_or_wait(); return; }
+    if (st.phase == PH_DELAY) {
+      if (--st.delay <= 0) start_game(st.game_id);
+      return;
+    }
     if (st.phase == PH_SEED) {
       if (st.seed_round) {
         st.phase = PH_SEARCH;

@@ -4,10 +4,20 @@
   python bench.py --gpus N --steps K --warmup W            our arm (under torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K ...   the reference's CPU path (oracle port), rank 0 only
 
-Workload (config C2 of BASELINE.json): 9x9 Go, 1024 concurrent self-play games per GPU, 400 readouts per move,
-tower_height 6, random-init weights (Flux default init restated, seed 0), all games from empty boards.
-One "step" = 50 batched tree_search! rounds = 400 readouts for every live game = one move-step of the whole
-job; moves are counted from the device counter, so `value` = moves actually played / device time.
+Headline workload (config C2 of BASELINE.json): 9x9 Go, 1024 concurrent self-play games per GPU, 400 readouts per move,
+tower_height 6, random-init weights (Flux default init restated, seed 0), all games from empty boards, finished games
+refilled.  One "step" = 50 batched tree_search! rounds = 400 readouts for every live game = one move-step of the whole job;
+moves are counted from the device counter, so `value` = moves actually played / device time.
+
+Steady state (src/train.jl:56-61): the slots are started staggered (option selfplay.stagger_rounds: slot g begins
+g*R/n_games rounds late, R = --burnin move-steps) and --burnin untimed move-steps are played first, so that inside the timed
+region the games sit at every ply, some finish and are refilled in every step, the harvest / replay-pack / NCCL all-gather
+carry real payloads, and arena compaction runs under load.
+
+Extra legs (same engine and kernels, each a few seconds, reported as extra keys of the one JSON line):
+  roofline_tree  C5: MCTS-only 9x9, uniform prior (DummyNet), 8192 trees x 1600 readouts -> tree-kernel HBM roofline
+  c4             C4: network only, 19x19, batch 8192, tower_height 19 -> conv tensor roofline at the north-star shape
+  c3             C3 per-GPU share: 19x19, 512 games per GPU, 800 readouts, tower_height 19 (+ NCCL replay gather when N > 1)
 """
 import argparse
 import json
@@ -65,12 +75,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
 
 
-def oracle_moves_per_sec(max_moves, budget_s, torch_threads=None):
-    """The reference's CPU path (oracle port): one game at a time, <= 8 leaves per network call, fp32 torch-CPU net."""
+def oracle_moves_per_sec(max_moves, budget_s):
+    """The reference's CPU path (oracle port): one game at a time, <= 8 leaves per network call, fp32 torch-CPU net on ALL host
+    cores (torchrun exports OMP_NUM_THREADS=1, so the thread count is set explicitly: the arm is the same at every N)."""
     import torch
     from oracle import go as ogo, net as onet, selfplay as osp
-    if torch_threads:
-        torch.set_num_threads(torch_threads)
+    torch.set_num_threads(os.cpu_count() or 1)
     env = ogo.GoEnv(BOARD)
     nn = onet.NeuralNet(BOARD, TOWER, seed=0)
     state = {"moves": 0, "t0": time.perf_counter(), "elapsed": 0.0}
@@ -102,7 +112,7 @@ def run_reference(args):
     t0 = time.perf_counter()
     for _ in range(max(0, min(args.warmup, 1))):
         oracle_moves_per_sec(1, 30)
-    vals = []
+    vals, cores = [], os.cpu_count() or 1
     for _ in range(args.steps):
         v, m, el, cores = oracle_moves_per_sec(per_step_moves, 60)
         vals.append((m, el))
@@ -124,14 +134,89 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ extra legs
+def tree_bytes_per_readout(N, d):
+    """(d-1)*(3*4*A + A) select reads + 4*4*A expand writes + 8*N^2 child boards + 16*d path read-modify-writes."""
+    A = N * N + 1
+    return (d - 1) * 13 * A + 16 * A + 8 * N * N + 16 * d
+
+
+def leg_c5(agz, device, hbm):
+    """BASELINE config C5: MCTS-only, 9x9, uniform prior / value 0 (DummyNet), 8192 trees x 1600 readouts per move."""
+    trees, readouts, rounds = 8192, 1600, 200
+    eng = agz.Engine(9, n_games=trees, readouts=readouts, tower_height=1, seed=0, evaluator=agz.EVAL_DUMMY, nodes_per_game=3600, device=device)
+    try:
+        eng.selfplay_start(-1)
+        pr0 = eng.selfplay_step(rounds + 10)              # warm-up: past the first move of every tree
+        ms, pr1 = 0.0, pr0
+        reps = 3
+        for _ in range(reps):                             # timed: device time (CUDA events on the engine's stream)
+            pr1 = eng.selfplay_step(rounds)
+            ms += pr1.step_ms
+        ro, pn, mv = pr1.readouts - pr0.readouts, pr1.path_nodes - pr0.path_nodes, pr1.moves_played - pr0.moves_played
+        d = pn / max(1, ro)
+        bpr = tree_bytes_per_readout(9, d)
+        achieved = ro * bpr / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "k_warps<DummyRoundsOp<3,1>> (select_leaf + expand + virtual loss + incorporate + backup + move logic, one warp per tree, %d rounds per launch)" % rounds,
+                "workload": "C5: MCTS-only 9x9, uniform prior (DummyNet), %d trees x %d readouts/move; %d x %d rounds timed after %d warm-up rounds" % (trees, readouts, reps, rounds, rounds + 10),
+                "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                "bytes_per_readout": bpr, "mean_path_nodes": d, "readouts_per_launch": ro / reps, "ms_per_launch": ms / reps, "ms_per_round": ms / (reps * rounds),
+                "moves_per_s": mv / (ms * 1e-3), "readouts_per_s": ro / (ms * 1e-3), "error": int(pr1.error)}
+    finally:
+        eng.close()
+
+
+def leg_19(agz, device, tf_sus, games, rounds, world, rank, dist, name):
+    """19x19, tower_height 19, 800 readouts: `games` concurrent games on this GPU (8 leaves each per round).  C4 = the network on a
+    batch of 8192 positions harvested from this self-play; C3 = one GPU's share of the 4096-game config."""
+    env = agz.GoEnv(19, device=device)
+    nn = agz.NeuralNet(env, tower_height=19, seed=0)
+    eng = agz.Engine(19, n_games=games, readouts=800, tower_height=19, seed=0, device=device, world_size=world, rank=rank, evaluator=agz.EVAL_NN_TC,
+                     nodes_per_game=4000)
+    try:
+        nn.push(eng)
+        if dist is not None and name == "c3":
+            ids = [eng.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            eng.nccl_init(ids[0])
+        eng.selfplay_start(-1)
+        eng.selfplay_step(3)
+        pr = eng.selfplay_step(rounds)                   # plain rounds: device time of the whole round
+        ms_round = pr.step_ms / rounds
+        if name == "c3":
+            eng.replay_gather()
+        eng.set_timing(True)
+        eng.phase_times(reset=True)
+        eng.selfplay_step(2)
+        kms, kln = eng.phase_times(reset=True)
+        eng.set_timing(False)
+        fpos, fconv = eng.net_flops()
+        rows = games * 8
+        conv_ms = kms[3] / max(1, kln[3])
+        net_ms = (kms[2] + kms[3] + kms[4]) / max(1, kln[0])
+        out = {"workload": "19x19, %d games x 8 leaves = %d positions per batch, tower_height 19, 256 filters, positions from live self-play" % (games, rows),
+               "ms_per_round": ms_round, "network_ms_per_batch": net_ms, "positions_per_s": rows / (net_ms * 1e-3),
+               "network_tflops": fpos * rows / (net_ms * 1e-3) / 1e12,
+               "roofline": {"bound": "tensor", "kernel": "conv3x3_tc5_kernel / conv3x3_tc6_kernel", "achieved": fconv * rows / (conv_ms * 1e-3) / 1e12, "peak": tf_sus,
+                            "unit": "TFLOP/s", "frac": fconv * rows / (conv_ms * 1e-3) / 1e12 / tf_sus, "flops_per_launch": fconv * rows, "ms_per_launch": conv_ms, "traffic": None},
+               "kernel_ms_per_round": {n: kms[i] / max(1, kln[0]) for i, n in enumerate(agz.binding.KERNEL_NAMES)}, "error": int(pr.error)}
+        if name == "c3":
+            out["moves_per_s_per_gpu_at_100_rounds_per_move"] = games / (ms_round * 100 / 1e3)
+        return out
+    finally:
+        eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="agz")
     ap.add_argument("--games", type=int, default=GAMES)
+    ap.add_argument("--burnin", type=int, default=112, help="untimed move-steps before the warm-up (staggered start; ~ one mean game length)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the C5 / C4 / C3 legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -152,7 +237,7 @@ def main():
     env = agz.GoEnv(BOARD, device=local)
     nn = agz.NeuralNet(env, tower_height=TOWER, seed=0)
     eng = agz.Engine(BOARD, n_games=args.games, readouts=READOUTS, tower_height=TOWER, seed=0, device=local, world_size=world, rank=rank,
-                     evaluator=agz.EVAL_NN_TC)
+                     evaluator=agz.EVAL_NN_TC, options={"selfplay.stagger_rounds": args.burnin * ROUNDS_PER_STEP})
     nn.push(eng)
     if world > 1:  # NCCL communicator of the replay all-gather: rank 0's unique id goes round through torch.distributed
         ids = [eng.nccl_unique_id() if rank == 0 else None]
@@ -175,10 +260,16 @@ def main():
         return pr
 
     eng.selfplay_start(-1)
+    t_burn = time.perf_counter()
+    for _ in range(args.burnin):          # untimed: reach the steady state (every slot live, games spread over all plies)
+        pr = device_step()
+    t_burn = time.perf_counter() - t_burn
     for _ in range(warmup):
         pr = device_step()
+    slots_live = pr.games_live
     # ---- timed region 1: device-resident throughput (`value`) ---------------------------------------------------
     l0 = eng.kernel_launches()
+    g0 = eng.replay_info()["gathered_bytes"]
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -192,13 +283,13 @@ def main():
     wall = time.perf_counter() - t0
     sampler.stop_flag = True
     launches = eng.kernel_launches() - l0
+    gathered = eng.replay_info()["gathered_bytes"] - g0
     moves = pr.moves_played - m0
     fill = (pr.positions_evaluated - p0) / float(args.steps * ROUNDS_PER_STEP * args.games * 8)
     readouts_done, finished = pr.readouts - r0, pr.games_finished - f0
     # device time of the steps (CUDA events on the engine stream) plus the gather/harvest tail measured by wall clock
     t_rank = max(wall, dev_ms / 1e3)
-    # ---- per-kernel CUDA-event timing on the same workload, sequential schedule (with the two half batches
-    #      overlapped, a kernel's event interval would include the other group's kernels) -----------------------------
+    # ---- per-kernel CUDA-event timing on the same workload, sequential schedule ---------------------------------
     eng.set_timing(True)
     eng.phase_times(reset=True)
     for _ in range(min(2, args.steps)):
@@ -211,34 +302,42 @@ def main():
     m1 = pr.moves_played
     d2h = 0
     glen = []
+    L, A = eng.L, eng.A
     t1 = time.perf_counter()
     for _ in range(args.steps):
         for k in range(3):                      # H2D: the caller's current network parameters (train.jl hands selfplay cur_nn)
             eng.net_set_params(k, flat_params[k])
         pr = eng.selfplay_step(ROUNDS_PER_STEP)
         eng.replay_gather()
-        recs = eng.selfplay_harvest(4 * args.games)   # D2H: finished games (moves, pi, q, result)
+        recs = eng.selfplay_harvest(4 * args.games)   # D2H: finished games (headers, moves, q, pi, visits)
         glen += [r.n_moves for r in recs]
-        d2h += sum(r.searches_pi.nbytes + r.visits.nbytes + r.moves.nbytes + r.qs.nbytes + 40 for r in recs) + 80
+        d2h += len(recs) * (40 + L * (2 + 4 + 8 * A)) + 80   # what agz_selfplay_harvest transfers: fixed-stride records + counters
     barrier()
     t_e2e = time.perf_counter() - t1
     moves_e2e = pr.moves_played - m1
+    info = eng.info()
+    _, conv_flops_pos = eng.net_flops()
+    flops_pos, _ = eng.net_flops()
+    err = pr.error
+    eng.close()
 
-    if pr.error:
-        print(json.dumps({"metric": METRIC, "error": "a game stopped on the device with status %d (6 = node arena full)" % pr.error}), flush=True)
+    if err:
+        print(json.dumps({"metric": METRIC, "error": "a game stopped on the device with status %d (6 = node arena full)" % err}), flush=True)
         sys.exit(2)
-    tot = torch.tensor([float(moves), float(moves_e2e), float(launches)], device="cuda", dtype=torch.float64)
-    tmx = torch.tensor([t_rank, t_e2e], device="cuda", dtype=torch.float64)
+    hbm, tf_sus, tf_burst, src = peaks()
+    legs = {}
+    if not args.no_legs:
+        legs["roofline_tree"] = leg_c5(agz, local, hbm)
+        legs["c4"] = leg_19(agz, local, tf_sus, 1024, 5, 1, 0, None, "c4")
+        legs["c3"] = leg_19(agz, local, tf_sus, 512, 8, world, rank, dist, "c3")
+    tot = torch.tensor([float(moves), float(moves_e2e), float(launches), float(gathered), float(finished), float(len(glen)), float(d2h)], device="cuda", dtype=torch.float64)
+    tmx = torch.tensor([t_rank, t_e2e, legs["c3"]["ms_per_round"] if legs else 0.0], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
     tot, tmx = tot.cpu().numpy(), tmx.cpu().numpy()
     if rank == 0:
-        hbm, tf_sus, tf_burst, src = peaks()
-        _, conv_flops_pos = eng.net_flops()
-        flops_pos, _ = eng.net_flops()
         rows = args.games * 8
-        info = eng.info()
         conv_ms = kms[3] / max(1, kln[3])
         achieved = conv_flops_pos * rows / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         line = {
@@ -246,9 +345,10 @@ def main():
             "ms_per_step": 1e3 * tmx[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
             "config": {"workload": "C2: 9x9 Go, %d concurrent self-play games per GPU, 400 readouts/move (50 rounds x 8 leaves per step), tower_height 6, 256 filters, random-init weights seed 0, empty-board starts, finished games refilled" % args.games,
-                       "step": "50 tree_search rounds over all games (select -> leaf features -> stem + 12 tower convs -> heads -> incorporate/move logic, one stream) + replay all-gather of finished games",
+                       "step": "50 tree_search rounds over all games (select -> leaf features -> stem + 12 tower convs -> heads -> incorporate/move logic, one stream) + replay pack / all-gather of the games that finished",
+                       "steady_state": "staggered start + %d untimed burn-in move-steps (%.0f s) before the %d warm-up steps: %d of %d slots live, games at every ply" % (args.burnin, t_burn, warmup, slots_live, args.games),
                        "l2": "inputs larger than L2: tree arenas %.1f GB (%d nodes per game) and %.0f MB per activation buffer vs 126 MB L2" % (info["n_games"] * info["nodes_per_game"] * info["bytes_per_node"] / 1e9, info["nodes_per_game"], rows * 81 * 512 / 1e6)},
-            "e2e": {"value": tot[1] / tmx[1], "unit": "moves/s", "h2d_bytes_per_step": param_bytes, "d2h_bytes_per_step": int(d2h / args.steps)},
+            "e2e": {"value": tot[1] / tmx[1], "unit": "moves/s", "h2d_bytes_per_step": param_bytes, "d2h_bytes_per_step": int(tot[6] / world / args.steps)},
             "gpu_launches": int(tot[2]),
             "clocks": sampler.summary(),
             "roofline": {"bound": "tensor", "kernel": "conv3x3_tc5_kernel / conv3x3_tc6_kernel (tower 3x3 conv 256->256, fp16 tcgen05 cta_group::2 + TMA im2col; tc6 = second conv of a block, shortcut tile by TMA)",
@@ -258,16 +358,22 @@ def main():
                          "peak_source": src + " bf16 sustained",
                          "flops_per_launch": conv_flops_pos * rows, "ms_per_launch": conv_ms},
             "kernel_ms_per_round": {n: kms[i] / max(1, kln[0]) for i, n in enumerate(agz.binding.KERNEL_NAMES)},
-            "harvested_games_e2e": len(glen), "mean_game_length_e2e": (sum(glen) / len(glen)) if glen else None,
-            "leaf_fill": fill, "readouts_per_s": readouts_done / tmx[0], "games_finished_rank0": int(finished),
+            "games_finished_timed": int(tot[4]), "harvested_games_e2e": int(tot[5]), "mean_game_length_e2e": (sum(glen) / len(glen)) if glen else None,
+            "replay_gathered_bytes_per_step": tot[3] / world / args.steps,   # tuple bytes every rank appended to its ring per step (all ranks' payload)
+            "leaf_fill": fill, "readouts_per_s": readouts_done / tmx[0],
             "network_tflops": flops_pos * rows / ((kms[2] + kms[3] + kms[4]) / max(1, kln[0]) * 1e-3) / 1e12 if kln[0] else None,
         }
+        if legs:
+            c3 = legs["c3"]
+            c3["n_gpus"] = world
+            c3["ms_per_round_max_over_ranks"] = tmx[2]
+            c3["moves_per_s_all_gpus_at_100_rounds_per_move"] = 512 * world / (tmx[2] * 100 / 1e3)
+            line.update(legs)
         if world == 1 and not args.no_cpu_baseline:
             v, m, el, cores = oracle_moves_per_sec(8, 25)
             line["cpu_baseline"] = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
                                     "sample": "first %d moves of one 9x9 game, 400 readouts, tower_height 6 (oracle port of src/selfplay.jl, %.1f s)" % (m, el)}
         print(json.dumps(line), flush=True)
-    eng.close()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -138,6 +138,21 @@ void agz_engine_destroy(agz_engine* e);
 const char* agz_last_error(agz_engine* e);                      /* valid until the next call on e (e may be NULL) */
 int32_t agz_version(void);
 
+/* Named integer options: every knob that is not part of the reference's own configuration surface (agz_config).  Nothing in the
+ * library reads environment variables.  Keys (default):
+ *   selfplay.stagger_rounds (0)  read by the next agz_selfplay_start: slot g starts its first game after g*R/n_games rounds, so a
+ *                                throughput run reaches the steady state of src/train.jl:56-61 (games at every ply, some finishing
+ *                                in every step) after one game length instead of moving through the plies in lock step
+ *   dummy.fused_rounds (1)       DummyNet evaluator: all rounds of an agz_selfplay_step call in one launch per game
+ *   schedule.pipeline (0)        two half batches on separate streams (tree kernels of one under the network of the other)
+ *   replay.capacity (500000)     memory_size of src/train.jl:38; must be set before the replay ring exists
+ *   trace.records (0)            kernel timeline trace capacity (agz_trace_read); can be set once
+ *   conv.fuse_heads (1), conv.stages (6), conv.l2_prefetch (0), conv.pdl (1), conv.max_pairs (0 = all), conv.res_tma (1)
+ *                                experiment knobs of the tensor-core convolution (alphago.jl_b200/csrc/nn_tc.cu)
+ * Unknown keys and bad values return AGZ_ERR_ARG. */
+int32_t agz_set_option(agz_engine* e, const char* key, int64_t value);
+int32_t agz_get_option(agz_engine* e, const char* key, int64_t* value);
+
 /* ---- network: NeuralNet (src/neural_net.jl:13-33) -------------------------------------------- */
 /* `flat` = the chain's Flux `params` list concatenated, each tensor column-major, in the order
  * save_model writes them (src/train.jl:27-33): Conv(W,b), BatchNorm(beta,gamma), per ResidualBlock
@@ -198,6 +213,9 @@ int32_t agz_replay_sample(agz_engine* e, int32_t batch, uint64_t seed, int8_t* b
 /* Same draw as agz_replay_sample, returning what the network trains on: boards_hist batch x 8 x N*N = the position before the
  * move and the 7 positions before it (oldest repeated), i.e. what get_feats rebuilds from board_deltas (features.jl:7-14). */
 int32_t agz_replay_sample_hist(agz_engine* e, int32_t batch, uint64_t seed, int8_t* boards_hist, int8_t* to_play, float* pis, int8_t* zs, int64_t* indices);
+/* Replay ring bookkeeping: out[0] = bytes per packed tuple, out[1] = capacity in tuples, out[2] = tuples ever appended,
+ * out[3] = tuple bytes appended by the last agz_replay_gather (the payload of all ranks), out[4] = bytes appended since creation. */
+int32_t agz_replay_info(agz_engine* e, int64_t out[5]);
 /* NCCL bootstrap for world_size > 1: rank 0 fills a 128-byte id, every rank passes the same bytes. */
 int32_t agz_nccl_unique_id(uint8_t id_out[128]);
 int32_t agz_nccl_init(agz_engine* e, const uint8_t id[128]);
@@ -253,7 +271,7 @@ int32_t agz_engine_info(agz_engine* e, int64_t out[4]);
 #define AGZ_NKERNELS 6
 int32_t agz_phase_times(agz_engine* e, float ms[AGZ_NKERNELS], int64_t launches[AGZ_NKERNELS], int32_t reset);
 int32_t agz_set_timing(agz_engine* e, int32_t enabled);
-/* Kernel timeline trace (debug aid; enabled by the environment variable AGZ_TRACE=<records> at engine creation): every
+/* Kernel timeline trace (debug aid; enabled by agz_set_option(e, "trace.records", n)): every
  * kernel's first and last CTA append {tag | block << 8 | grid << 32, start ns, end ns, SM id} (%globaltimer).  Tags:
  * 1 select, 2 incorporate, 3 leaf features, 4 stem conv, 5 tower conv, 6 tower conv with shortcut, 7 heads, 9 other. */
 int32_t agz_trace_read(agz_engine* e, uint64_t* out, int32_t max_records, int32_t* n_out, int32_t reset);

@@ -18,6 +18,13 @@ Pinning status
   reproduced here (no Julia).  The oracle and the engine share ONE explicit
   counter-based spec instead (`oracle/rng.py`); draws happen at exactly the
   reference's five call sites.  "parity unpinned" for the random stream itself.
+* pi = children_as_pi (src/mcts.jl:241-252): the reference computes child_N .^ 0.98 with libm `pow` and sums with Julia's
+  pairwise `sum`; neither is bit-reproducible across platforms, so the oracle restates them in the engine's deterministic form
+  (`rng.det_pow`: exp/log built from +,-,*,/ only; `rng.butterfly_sum32`: the 32-lane xor-butterfly order).  pi "bit-exact" is
+  therefore engine-vs-this-spec at the last ulp; against libm it agrees to ~1e-15 relative (tests/test_oracle_mcts.py checks
+  det_pow against math.pow).  The same holds for the Dirichlet sampler's log/exp.
+* Replay sampling (src/train.jl:4-12, StatsBase.sample on the global RNG): unpinned by the reference; shared explicit spec in
+  `oracle/replay.py` (keyed Feistel permutation of the ring's index range).
 * Network arithmetic: lives in Flux 0.10.4 / NNlib 0.6.6 (not vendored in the
   reference, Manifest.toml:193-197,298-302) and no reference test constructs a
   NeuralNet => "parity unpinned" for NN outputs; anchored on the layer

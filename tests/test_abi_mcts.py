@@ -8,6 +8,7 @@ from oracle import go as ogo
 from oracle import mcts as OM
 from oracle import mcts_play as OP
 from oracle import selfplay as osp
+from oracle import replay as orp
 from refboards import load_board, ALMOST_DONE_BOARD, TT_FTW_BOARD
 
 BLACK, WHITE = 1, -1
@@ -328,12 +329,30 @@ def test_selfplay_matches_oracle(env):
     check_selfplay_parity(env, 9, 16, seeds=[2], priors_seed=7, value=-0.2)
 
 
-def test_selfplay_matches_oracle_with_separate_kernels(env, monkeypatch):
-    """With the DummyNet evaluator agz_selfplay_step plays all rounds of a call in one launch per game; AGZ_FUSE_DUMMY=0 runs the
-    select / incorporate kernels of the network path instead.  Both must reproduce the oracle."""
-    monkeypatch.setenv("AGZ_FUSE_DUMMY", "0")
-    check_selfplay_parity(env, 9, 24, seeds=[0])
-    check_selfplay_parity(env, 9, 16, seeds=[3], priors_seed=4, value=0.1, n_games=3)
+def test_selfplay_matches_oracle_with_separate_kernels(env):
+    """With the DummyNet evaluator agz_selfplay_step plays all rounds of a call in one launch per game; the option
+    dummy.fused_rounds = 0 runs the select / incorporate kernels of the network path instead.  Both must reproduce the oracle."""
+    check_selfplay_parity(env, 9, 24, seeds=[0], options={"dummy.fused_rounds": 0})
+    check_selfplay_parity(env, 9, 16, seeds=[3], priors_seed=4, value=0.1, n_games=3, options={"dummy.fused_rounds": 0})
+
+
+def test_staggered_start_changes_timing_not_games(env):
+    """Option selfplay.stagger_rounds delays the first game of slot g by g*R/n_games rounds (steady-state throughput runs); the
+    games themselves are keyed by game id and stay bit-exact."""
+    check_selfplay_parity(env, 9, 16, seeds=[5], n_games=6, concurrent=3, options={"selfplay.stagger_rounds": 40})
+    check_selfplay_parity(env, 9, 16, seeds=[5], n_games=4, options={"selfplay.stagger_rounds": 7, "dummy.fused_rounds": 0})
+
+
+def test_options_surface(env):
+    eng = env.util_engine()
+    assert eng.get_option("dummy.fused_rounds") == 1 and eng.get_option("selfplay.stagger_rounds") == 0
+    eng.set_option("selfplay.stagger_rounds", 12)
+    assert eng.get_option("selfplay.stagger_rounds") == 12
+    eng.set_option("selfplay.stagger_rounds", 0)
+    with pytest.raises(agz.AgzError):
+        eng.set_option("no.such.option", 1)
+    with pytest.raises(agz.AgzError):
+        eng.set_option("selfplay.stagger_rounds", -1)
 
 
 def test_selfplay_parity_sweep():
@@ -541,6 +560,11 @@ def test_replay_gather_read_sample():
     assert len(used) == total
     sb, stp, spi, sz, idx = eng.replay_sample(8, seed=3)
     assert len(set(idx.tolist())) == 8 and idx.min() >= 0 and idx.max() < total
+    info = eng.replay_info()
+    assert info["total"] == total and info["capacity"] == 500000 and info["last_gather_bytes"] == total * info["tuple_bytes"]
+    assert idx.tolist() == orp.sample_indices(total, info["capacity"], 8, seed=3)       # the device draw = the oracle's spec
+    full = eng.replay_sample(total, seed=9)[4]
+    assert sorted(full.tolist()) == list(range(total)) and full.tolist() == orp.sample_indices(total, 500000, total, seed=9)
     for j, i in enumerate(idx):
         assert np.array_equal(sb[j], boards[i]) and np.array_equal(spi[j], pis[i]) and sz[j] == zs[i] and stp[j] == tp[i]
     # the history variant returns the same draw with the 8 boards get_feats needs: board k = the position k plies earlier in the
@@ -565,11 +589,11 @@ def test_replay_gather_read_sample():
 
 
 @pytest.mark.gpu
-def test_replay_ring_trims_oldest(monkeypatch):
+def test_replay_ring_trims_oldest():
     """memory_size semantics (src/train.jl:52,63-65): once more tuples than the ring holds have been appended, the oldest are gone,
     the newest `cap` are readable in order, and sampling draws only from them."""
-    monkeypatch.setenv("AGZ_REPLAY_CAP", "150")
-    eng = agz.Engine(9, lib_path=lib_for("cuda"), n_games=4, readouts=8, seed=31)
+    eng = agz.Engine(9, lib_path=lib_for("cuda"), n_games=4, readouts=8, seed=31, options={"replay.capacity": 150})
+    assert eng.get_option("replay.capacity") == 150
     eng.set_dummy_evaluator(None, 0.0)
     eng.selfplay_start(8)
     seen, total = [], 0
@@ -590,6 +614,7 @@ def test_replay_ring_trims_oldest(monkeypatch):
     boards, tp, pis, zs = eng.replay_read(total - 150, 150)
     assert np.allclose(pis.sum(axis=1), 1.0, atol=1e-5) and set(np.unique(zs)) <= {-1, 0, 1} and set(np.unique(tp)) <= {-1, 1}
     sb, stp, spi, sz, idx = eng.replay_sample(100, seed=1)
+    assert idx.tolist() == orp.sample_indices(total, 150, 100, seed=1)
     assert idx.min() >= total - 150 and idx.max() < total and len(set(idx.tolist())) == 100
     for j in range(0, 100, 9):
         k = int(idx[j] - (total - 150))

@@ -79,6 +79,71 @@ def test_nccl_replay_all_gather_two_gpus():
         assert got == want, "rank %d ring differs from the oracle's tuples" % r
 
 
+def _worker_ragged(rank, world, uid_q, out_q):
+    """ONE gather after all games are over: rank 0 holds two finished games, rank 1 one -- the largest block is then bigger than
+    the smaller rank's own payload (round 1 re-allocated the send buffer after packing in that case and sent garbage)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import pkg
+    agz = pkg.load()
+    eng = agz.Engine(9, n_games=4, readouts=16, seed=9, device=rank, world_size=world, rank=rank)
+    eng.set_dummy_evaluator(None, 0.0)
+    if rank == 0:
+        uid = eng.nccl_unique_id()
+        uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=120)
+    eng.nccl_init(uid)
+    eng.selfplay_start(3)                     # game ids 0, 2 on rank 0; 1 on rank 1
+    mine = 2 if rank == 0 else 1
+    for _ in range(400):
+        pr = eng.selfplay_step(64)
+        assert pr.error == 0
+        if pr.games_finished == mine:
+            break
+    assert pr.games_finished == mine
+    total = eng.replay_gather()               # the only collective call: both ranks make exactly one
+    recs = eng.selfplay_harvest(16)
+    boards, tp, pis, zs = eng.replay_read(0, total)
+    info = eng.replay_info()
+    out_q.put({"rank": rank, "total": int(total), "boards": boards, "tp": tp, "pis": pis, "zs": zs, "last_gather_bytes": info["last_gather_bytes"],
+               "tuple_bytes": info["tuple_bytes"], "recs": [(int(r.game_id), r.moves.tolist(), r.searches_pi.copy(), int(r.result)) for r in recs]})
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_nccl_replay_ragged_single_gather_two_gpus():
+    import torch
+    import torch.multiprocessing as mp
+    from oracle import go as ogo
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker_ragged, args=(r, 2, uid_q, out_q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    msgs = {m["rank"]: m for m in (out_q.get(timeout=600) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    games = sorted(msgs[0]["recs"] + msgs[1]["recs"])
+    assert [g[0] for g in games] == [0, 1, 2] and len(msgs[0]["recs"]) == 2 and len(msgs[1]["recs"]) == 1
+    oenv = ogo.GoEnv(9)
+    expected = []
+    for gid, moves, pis, result in games:
+        pos = ogo.GoPosition(oenv)
+        for t, m in enumerate(moves):
+            expected.append((pos.board.flatten(order="F").tobytes(), int(pos.to_play), pis[t].tobytes(), result))
+            pos = ogo.play_move(pos, ogo.from_flat(int(m), oenv))
+    want = sorted(expected)
+    for r in (0, 1):
+        m = msgs[r]
+        assert m["total"] == len(want) and m["last_gather_bytes"] == len(want) * m["tuple_bytes"]
+        got = sorted((m["boards"][k].tobytes(), int(m["tp"][k]), m["pis"][k].tobytes(), int(m["zs"][k])) for k in range(m["total"]))
+        assert got == want, "rank %d ring differs from the oracle's tuples" % r
+
+
 def _train_worker(rank, world, uid_q, out_q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)

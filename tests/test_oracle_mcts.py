@@ -145,3 +145,30 @@ def test_stone_features():                               # test_features.jl:39-7
         assert (f[:, :, i] == 0).all()
     full = features.get_feats(pos)
     assert full.shape == (9, 9, 17) and (full[:, :, 16] == -1).all()
+
+
+def test_replay_sample_spec_is_a_permutation():
+    """oracle/replay.py: the keyed Feistel permutation behind agz_replay_sample visits every index exactly once, for ring sizes
+    around powers of two and for the reference's memory_size, and different seeds give different draws."""
+    from oracle import replay as orp
+    for n in (1, 2, 3, 4, 5, 16, 17, 255, 256, 257, 1000):
+        idx = orp.sample_indices(n, 10 ** 9, n, seed=n)
+        assert sorted(idx) == list(range(n)), n
+    a = orp.sample_indices(700000, 500000, 4096, seed=1)
+    b = orp.sample_indices(700000, 500000, 4096, seed=2)
+    assert len(set(a)) == 4096 and min(a) >= 200000 and max(a) < 700000 and a != b
+    # roughly uniform: mean of 4096 draws from [200000, 700000) within 3 sigma of the centre
+    mean = sum(a) / len(a)
+    assert abs(mean - 450000) < 3 * (500000 / 12 ** 0.5) / 64
+
+
+def test_det_pow_agrees_with_libm():
+    """children_as_pi uses the deterministic pow of oracle/rng.py (shared with the engine) instead of libm's: it must agree with
+    math.pow to a few ulp over the range of visit counts (oracle/__init__.py, pinning status)."""
+    import math
+    from oracle import rng
+    worst = 0.0
+    for n in list(range(1, 2000)) + [5000, 12345, 65536, 10 ** 6]:
+        a, b = rng.det_pow(float(n), 0.98), math.pow(float(n), 0.98)
+        worst = max(worst, abs(a - b) / b)
+    assert worst < 1e-14, worst
