@@ -75,7 +75,7 @@ SYMBOLS = [
     "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read", "agz_engine_info",
     "agz_match_start", "agz_match_search", "agz_match_play",
     "agz_replay_sample_hist", "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
-    "agz_set_option", "agz_get_option", "agz_replay_info",
+    "agz_set_option", "agz_get_option", "agz_replay_info", "agz_selftest_division",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -476,6 +476,11 @@ class Engine:
         b = buf[:n.value]
         w0 = b[:, 0]
         return np.stack([w0 & np.uint64(0xFF), (w0 >> np.uint64(8)) & np.uint64(0xFFFFFF), w0 >> np.uint64(32), b[:, 1], b[:, 2], b[:, 3]], axis=1).astype(np.int64)
+
+    def selftest_division(self, n_samples, seed=0):
+        out = (C.c_uint64 * 2)()
+        self._check(self.lib.agz_selftest_division(self._h, C.c_uint64(n_samples), C.c_uint64(seed), out))
+        return int(out[0]), int(out[1])
 
     def net_flops(self):
         a, b = C.c_double(), C.c_double()

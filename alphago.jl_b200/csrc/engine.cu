@@ -265,7 +265,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   const int need = cfg->readouts + 2 * c.pmax + 4;
   const long long base_cap = std::max(256, 10 * need);
   long long cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : base_cap;
-  e->bytes_per_node = (size_t)c.AS * 16 + sizeof(NodeMeta) + (size_t)3 * c.KB * 4 + 8;
+  e->bytes_per_node = (size_t)c.AS * 16 + sizeof(NodeMeta) + (size_t)3 * c.KA * 4 + 8;
 #if AGZ_CUDA
   if (cfg->nodes_per_game <= 0) {
     const long long worst = (long long)cfg->max_game_length * (need - 4) + need;
@@ -291,7 +291,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   rc |= dalloc(e, &v.P, nodes * c.AS);
   rc |= dalloc(e, &v.child, nodes * c.AS);
   rc |= dalloc(e, &v.meta, nodes);
-  rc |= dalloc(e, &v.bits, nodes * 3 * c.KB);
+  rc |= dalloc(e, &v.bits, nodes * 3 * c.KA);   // node stride 3*KA words, planes KB words apart (tree.cuh bits_of)
   rc |= dalloc(e, &v.gs, G);
   rc |= dalloc(e, &v.hist, G * 7 * 2 * c.KB);
   rc |= dalloc(e, &v.path, rows * c.maxd);
@@ -309,6 +309,21 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   rc |= dalloc(e, &v.ring_pi, (size_t)c.ring_cap * L * c.A);
   rc |= dalloc(e, &v.ring_vis, (size_t)c.ring_cap * L * c.A);
   rc |= dalloc(e, &v.ctr, (size_t)CTR_COUNT);
+  // rcp[k] = RN(1/k): the PUCT score divides by 1 + N(child), and N(child) never exceeds the visits a game can accumulate on one
+  // line (max_game_length searches of readouts + 2*parallel visits); larger divisors (test hooks) take the IEEE-division path
+  {
+    const long long worst = (long long)cfg->max_game_length * (cfg->readouts + 2 * c.pmax) + 64;
+    const int rn = (int)std::min<long long>(std::max<long long>(worst, 4096), 1 << 20);
+    double* d_rcp = nullptr;
+    rc |= dalloc(e, &d_rcp, (size_t)rn);
+    if (!rc) {
+      std::vector<double> h((size_t)rn, 0.0);
+      for (int k = 1; k < rn; ++k) { volatile double q = 1.0 / (double)k; h[(size_t)k] = q; }
+      rc |= devrt::h2d(d_rcp, h.data(), h.size() * sizeof(double), e->stream);
+      v.rcp = d_rcp;
+      v.rcp_n = rn;
+    }
+  }
   rc |= dalloc(e, &e->d_dummy_pi, (size_t)c.A);
   rc |= dalloc(e, &e->d_dummy_v, (size_t)1);
   rc |= dalloc(e, &e->d_eval_pi, rows * c.A);
@@ -1083,9 +1098,13 @@ extern "C" int32_t agz_tree_read_node(agz_engine* e, int32_t slot, int32_t node,
   DCHECK(e, devrt::d2h(out->child_prior, e->v.P + r, sizeof(float) * c.A, e->stream));
   DCHECK(e, devrt::d2h(out->children, e->v.child + r, sizeof(int32_t) * c.A, e->stream));
   std::vector<uint32_t> bits((size_t)3 * c.KB);
-  DCHECK(e, devrt::d2h(bits.data(), e->v.bits + gi * 3 * c.KB, bits.size() * sizeof(uint32_t), e->stream));
+  DCHECK(e, devrt::d2h(bits.data(), e->v.bits + gi * 3 * c.KA, bits.size() * sizeof(uint32_t), e->stream));
   out->parent = m.parent; out->fmove = m.fmove; out->to_play = m.to_play; out->n = m.n; out->ko = m.ko;
   out->is_expanded = (m.flags & F_EXPANDED) ? 1 : 0;
+  if (!out->is_expanded) {   // child_W / child_prior of a node are first written by incorporate_results! (tree.cuh init_rows)
+    memset(out->child_W, 0, sizeof(out->child_W));
+    memset(out->child_prior, 0, sizeof(out->child_prior));
+  }
   out->done = (m.flags & F_DONE) ? 1 : 0;
   out->last_move_pass = (m.flags & F_LASTPASS) ? 1 : 0;
   for (int p = 0; p < c.N2; ++p) {
@@ -1380,6 +1399,55 @@ extern "C" int32_t agz_net_forward(agz_engine* e, int32_t evaluator, const int8_
   return AGZ_OK;
 }
 
+// Self-test of the reciprocal-table quotients of select_leaf (tree.cuh) against the IEEE divisions they replace: every thread draws
+// divisors d in [1, rcp_n) (half of them below 2048) and numerators (fp32 w of every magnitude, fp64 x = cu * p as the score builds
+// them, and fp64 x with random exponents) from a counter-based stream and counts disagreements.
+__global__ void division_selftest_kernel(const double* __restrict__ rcp, int rcp_n, unsigned long long n, uint64_t seed, unsigned long long* bad) {
+  unsigned long long bad32 = 0, bad64 = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const U4 a = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x51u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const U4 b = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x52u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+    int d = (a.x & 1u) ? 1 + (int)((a.x >> 1) % 2047u) : 1 + (int)((a.x >> 1) % (uint32_t)(rcp_n - 1));
+    const float den = (float)d;
+    const double dd = (double)den, r = rcp[d];
+    // fp32 numerator: random sign / mantissa, exponent in [-100, 20]
+    const float w = __uint_as_float((a.y & 0x807fffffu) | ((27u + a.z % 121u) << 23));
+    const float q_fast = (float)__dmul_rn((double)w, r), q_ref = __fdiv_rn(w, den);
+    if (__float_as_uint(q_fast) != __float_as_uint(q_ref)) ++bad32;
+    // fp64 numerators: c_puct * sqrt(1 + N) * p, and a raw random double
+    const float pr = __uint_as_float((b.x & 0x007fffffu) | ((90u + b.y % 38u) << 23));   // p in [2^-37, 2)
+    const double cu = __dmul_rn(0.96, (double)__fsqrt_rn(1.0f + (float)(b.z % 100000u)));
+    double xs[2];
+    xs[0] = __dmul_rn(cu, (double)pr);
+    xs[1] = __longlong_as_double((long long)((((unsigned long long)(a.w & 0xfffffu)) << 32 | b.w) | ((unsigned long long)(900u + b.z % 200u) << 52)));
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const double x = xs[t], q0 = __dmul_rn(x, r);
+      const double u_fast = __fma_rn(__fma_rn(-q0, dd, x), r, q0), u_ref = __ddiv_rn(x, dd);
+      if (__double_as_longlong(u_fast) != __double_as_longlong(u_ref)) ++bad64;
+    }
+  }
+  if (bad32) atomicAdd(bad, bad32);
+  if (bad64) atomicAdd(bad + 1, bad64);
+}
+
+extern "C" int32_t agz_selftest_division(agz_engine* e, uint64_t n_samples, uint64_t seed, uint64_t mismatches[2]) {
+  if (!e || !mismatches) return fail(e, AGZ_ERR_ARG, "null argument");
+  cudaSetDevice(e->cfg.device);
+  unsigned long long* d_bad = nullptr;
+  if (cudaMalloc((void**)&d_bad, 2 * sizeof(unsigned long long)) != cudaSuccess) return fail(e, AGZ_ERR_CUDA, "allocation failed");
+  cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), e->stream);
+  division_selftest_kernel<<<148 * 8, 256, 0, e->stream>>>(e->v.rcp, e->v.rcp_n, n_samples, seed, d_bad);
+  e->launches += 1;
+  unsigned long long h[2] = {0, 0};
+  int rc = devrt::d2h(h, d_bad, sizeof(h), e->stream);
+  cudaFree(d_bad);
+  if (rc) return fail(e, AGZ_ERR_CUDA, "division self-test: %s", devrt::last_error_string(rc));
+  mismatches[0] = h[0];
+  mismatches[1] = h[1];
+  return AGZ_OK;
+}
+
 extern "C" int32_t agz_trace_read(agz_engine* e, uint64_t* out, int32_t max_records, int32_t* n_out, int32_t reset) {
   if (!e || !n_out) return fail(e, AGZ_ERR_ARG, "null argument");
   *n_out = 0;
@@ -1468,6 +1536,7 @@ extern "C" int32_t agz_net_get_params(agz_engine* e, int32_t, float*, size_t) { 
 extern "C" int32_t agz_net_get_bn_stats(agz_engine* e, int32_t, float*, float*, size_t, int32_t*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_net_forward(agz_engine* e, int32_t, const int8_t*, const int8_t*, int32_t, float*, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_trace_read(agz_engine*, uint64_t*, int32_t, int32_t* n_out, int32_t) { if (n_out) *n_out = 0; return AGZ_OK; }
+extern "C" int32_t agz_selftest_division(agz_engine* e, uint64_t, uint64_t, uint64_t*) { return fail(e, AGZ_ERR_CUDA, "not in the emulation build"); }
 extern "C" int32_t agz_nccl_unique_id(uint8_t*) { return AGZ_ERR_NCCL; }
 extern "C" int32_t agz_nccl_init(agz_engine* e, const uint8_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
 extern "C" int32_t agz_replay_gather(agz_engine* e, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }

@@ -41,6 +41,7 @@ struct SelectOp {
   AGZ_DEV void operator()(int wi, char* smem) const {
     const int g = only_slot >= 0 ? only_slot : slot0 + wi;
     Warp<KA> w(c, v, g, smem);
+    w.prefetch = OCC == 0;   // few trees per SM: the descent is a latency chain
     if (only_slot >= 0) {
       w.search_select(parallel, false);
     } else if (w.st.phase == PH_SEED) {

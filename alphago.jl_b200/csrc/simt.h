@@ -36,6 +36,9 @@ AGZ_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
 AGZ_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
 AGZ_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
 AGZ_DEV double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+AGZ_DEV double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }   // ONE rounding: only where the algorithm asks for a fused operation
+AGZ_DEV unsigned reduce_max(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
+AGZ_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 AGZ_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 AGZ_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
 AGZ_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
@@ -43,6 +46,7 @@ AGZ_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
 AGZ_DEV float fsqrt(float a) { return __fsqrt_rn(a); }
 AGZ_DEV double dfloor(double a) { return floor(a); }
 AGZ_DEV long long dbits(double a) { return __double_as_longlong(a); }
+AGZ_DEV unsigned fbits(float a) { return __float_as_uint(a); }
 AGZ_DEV double bitsd(long long a) { return __longlong_as_double(a); }
 AGZ_DEV uint32_t mulhi(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 // ---- kernel timeline trace (debug aid, AGZ_TRACE=<records>): tr[0] = records written, tr[1] = capacity, then 4 words per
@@ -157,6 +161,18 @@ inline double dmul(double a, double b) { volatile double r = a * b; return r; }
 inline double dadd(double a, double b) { volatile double r = a + b; return r; }
 inline double dsub(double a, double b) { volatile double r = a - b; return r; }
 inline double ddiv(double a, double b) { volatile double r = a / b; return r; }
+inline double dfma(double a, double b, double c) { return fma(a, b, c); }
+inline unsigned reduce_max(unsigned v) {
+  EmuWarp* w = g_warp;
+  int me = w->cur;
+  int par = w->ncoll[me]++ & 1;
+  w->slot[par][me] = v;
+  barrier();
+  unsigned m = 0;
+  for (int i = 0; i < 32; ++i) m = (unsigned)w->slot[par][i] > m ? (unsigned)w->slot[par][i] : m;
+  return m;
+}
+inline void prefetch_l2(const void*) {}
 inline float fdiv(float a, float b) { volatile float r = a / b; return r; }
 inline float fadd(float a, float b) { volatile float r = a + b; return r; }
 inline float fsub(float a, float b) { volatile float r = a - b; return r; }
@@ -164,6 +180,7 @@ inline float fmul(float a, float b) { volatile float r = a * b; return r; }
 inline float fsqrt(float a) { return sqrtf(a); }
 inline double dfloor(double a) { return floor(a); }
 inline long long dbits(double a) { long long r; memcpy(&r, &a, 8); return r; }
+inline unsigned fbits(float a) { unsigned r; memcpy(&r, &a, 4); return r; }
 inline double bitsd(long long a) { double r; memcpy(&r, &a, 8); return r; }
 inline uint32_t mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 }  // namespace simt

@@ -110,6 +110,8 @@ struct View {
   float *ring_q, *ring_pi, *ring_vis;
   unsigned long long* ctr;
   unsigned long long* trace;  // kernel timeline trace buffer (simt.h) or nullptr
+  const double* rcp;          // rcp[k] = RN(1/k), k in [1, rcp_n): the divisor 1 + N(child) of the PUCT score is a small integer
+  int rcp_n;
 };
 
 template <int KA>
@@ -123,6 +125,7 @@ struct Warp {
   char* smem;    // per-warp scratch of the shared-memory rules code (go_rules.cuh; liberty-cache hook only)
   GameState st;  // register copy (warp-uniform); written back by store_state()
   size_t nbase;
+  bool prefetch;  // latency mode (few trees per SM): pull the most-visited child's rows into L2 while this level is scored
 
   AGZ_DEV Warp(const Cfg& c_, const View& v_, int g_, char* smem_) : c(c_), v(v_), g(g_), lane(simt::lane()), smem(smem_) {
     B = bits_ctx(c.N, c.KB);
@@ -130,13 +133,23 @@ struct Warp {
     pos.w = 0;
     st = v.gs[g];
     nbase = (size_t)g * c.cap;
+    prefetch = false;
   }
   AGZ_DEV void store_state() {
     simt::sync();
     if (lane == 0) v.gs[g] = st;
   }
-  AGZ_DEV size_t row(int node) const { return (nbase + node) * (size_t)c.AS; }
-  AGZ_DEV uint32_t* bits_of(int node) const { return v.bits + (nbase + node) * (size_t)(3 * c.KB); }
+  // AS = 32*KA and the bit planes' node stride 3*KA are compile-time constants here (the planes themselves sit KB words apart)
+  AGZ_DEV size_t row(int node) const { return (nbase + node) * (size_t)(KA * 32); }
+  AGZ_DEV uint32_t* bits_of(int node) const { return v.bits + (nbase + node) * (size_t)(3 * KA); }
+  // element `idx` of a per-lane register array, as a select chain (a dynamically indexed array would be spilled to local memory)
+  template <class T>
+  AGZ_DEV static T pick(const T (&a)[KA], int idx) {
+    T x = a[0];
+#pragma unroll
+    for (int k = 1; k < KA; ++k) x = idx == k ? a[k] : x;
+    return x;
+  }
   AGZ_DEV NodeMeta load_meta(int node) const {
 #if AGZ_CUDA
     NodeMeta m;   // one 16-byte load instead of a load per field
@@ -153,20 +166,21 @@ struct Warp {
   }
 
   // ---- node creation -----------------------------------------------------------------------
+  // A new node starts with child_N = 0 and no children.  Its child_W / child_prior rows are NOT written here: nothing reads them
+  // before incorporate_results! fills them (only expanded nodes are scored, mcts.jl:116-118), which saves two of the six row
+  // writes of an expansion; agz_tree_read_node reports them as zeros for an unexpanded node, like the reference's fresh arrays.
   AGZ_DEV void init_rows(int node) {
     size_t r = row(node);
 #pragma unroll
     for (int k = 0; k < KA; ++k) {
       int a = k * 32 + lane;
       v.N[r + a] = 0.f;
-      v.W[r + a] = 0.f;
-      v.P[r + a] = 0.f;
       v.child[r + a] = -1;
     }
   }
 
   // Write a node whose position is `pos` (terminal nodes carry no legal-move mask: `skip_legal`).
-  AGZ_DEV void write_node(int node, int parent, int fmove, int n, int ko, int to_play, int flags, bool skip_legal) {
+  AGZ_DEV NodeMeta write_node(int node, int parent, int fmove, int n, int ko, int to_play, int flags, bool skip_legal) {
     uint32_t bw[KA], ww[KA], lw[KA];
     bits_pack<KA>(B, pos.b, bw);
     bits_pack<KA>(B, pos.w, ww);
@@ -182,18 +196,17 @@ struct Warp {
         bp[2 * c.KB + k] = lw[k];
       }
     }
-    if (lane == 0) {
-      NodeMeta m;
-      m.parent = parent; m.fmove = (int16_t)fmove; m.n = (int16_t)n; m.ko = (int16_t)ko;
-      m.to_play = (int8_t)to_play; m.flags = (uint8_t)flags; m.pad = 0;
-      v.meta[nbase + node] = m;
-    }
+    NodeMeta m;
+    m.parent = parent; m.fmove = (int16_t)fmove; m.n = (int16_t)n; m.ko = (int16_t)ko;
+    m.to_play = (int8_t)to_play; m.flags = (uint8_t)flags; m.pad = 0;
+    if (lane == 0) v.meta[nbase + node] = m;
     init_rows(node);
+    return m;
   }
 
   // maybe_add_child! when the child is missing: play `move` from `parent` (mcts.jl:140-147 -> board.jl:451-509).
   // Returns the new node id, or -1 with st.err set (E_CAPACITY, or E_ILLEGAL when check_legal).
-  AGZ_DEV int create_child(int parent, const NodeMeta& pm, int move, bool check_legal) {
+  AGZ_DEV int create_child(int parent, const NodeMeta& pm, int move, bool check_legal, NodeMeta* child_meta = nullptr) {
     if (st.count >= c.cap) { st.err = E_CAPACITY; return -1; }
     const uint32_t* pb = bits_of(parent);
     if (check_legal && move != c.N2) {
@@ -213,7 +226,8 @@ struct Warp {
       bits_play(B, pos, move, color, false, ko, ncap);
       term = n >= c.max_game_length;
     }
-    write_node(idx, parent, move, n, ko, -color, flags, term);
+    const NodeMeta cm = write_node(idx, parent, move, n, ko, -color, flags, term);
+    if (child_meta) *child_meta = cm;
     simt::sync();
     return idx;
   }
@@ -270,9 +284,9 @@ struct Warp {
   }
 
   // ---- select_leaf (mcts.jl:108-138) ------------------------------------------------------------
-  AGZ_DEV int select_leaf(int from, PathEnt* path, int& plen) {
+  AGZ_DEV int select_leaf(int from, PathEnt* path, int& plen, NodeMeta* leaf_meta = nullptr) {
     uint32_t sel_idx = st.sel_ctr++;
-    uint32_t move_no = (uint32_t)load_meta(st.root).n;
+    int move_no = -1;   // position.n of the root (RNG key of the tie-break draw): known for free when the descent starts at the root
     int cur = from;
     int depth = 0;
     unsigned long long slot;
@@ -296,6 +310,8 @@ struct Warp {
       // level costs one dependent memory round trip instead of two -- the descent is a latency chain, one warp per tree.
       const size_t r = row(cur);
       NodeMeta m = load_meta(cur);
+      if (depth == 0 && cur == st.root) move_no = m.n;
+      if (leaf_meta) *leaf_meta = m;
       float n[KA], w[KA], p[KA];
       int ch[KA];
       uint32_t lwv[KA];
@@ -316,38 +332,94 @@ struct Warp {
       }
       if (!(m.flags & F_EXPANDED)) break;
       if (depth + 1 >= c.maxd) { st.err = E_ASSERT; break; }
+      if (prefetch) {   // the most-visited child is where a sharp policy goes next: its rows travel while this level is scored
+        float nm = -1.f;
+        int cm = -1;
+#pragma unroll
+        for (int k = 0; k < KA; ++k)
+          if (ch[k] >= 0 && n[k] > nm) { nm = n[k]; cm = ch[k]; }
+        const unsigned key = cm >= 0 ? simt::fbits(nm) + 1u : 0u;
+        const unsigned best_key = simt::reduce_max(key);
+        if (best_key) {
+          const unsigned who = simt::ballot(key == best_key);
+          const int pc = simt::shfl(cm, simt::ffs(who) - 1);
+          const size_t pr = row(pc);
+          const int rl = (KA * 32 * 4 + 127) / 128;   // 128-byte lines per statistics row
+          const char* q = nullptr;
+          if (lane < rl) q = (const char*)(v.N + pr) + 128 * lane;
+          else if (lane < 2 * rl) q = (const char*)(v.W + pr) + 128 * (lane - rl);
+          else if (lane < 3 * rl) q = (const char*)(v.P + pr) + 128 * (lane - 2 * rl);
+          else if (lane < 4 * rl) q = (const char*)(v.child + pr) + 128 * (lane - 3 * rl);
+          else if (lane == 4 * rl) q = (const char*)(v.meta + nbase + pc);
+          else if (lane == 4 * rl + 1) q = (const char*)bits_of(pc);
+          if (q) simt::prefetch_l2(q);
+        }
+      }
       const int pass = c.N2;
       int best;
       // HACK of the reference: after a pass, look at the double pass first (mcts.jl:119-126)
-      float n_pass = 0.f;
-#pragma unroll
-      for (int k = 0; k < KA; ++k)
-        if (k == (pass >> 5)) n_pass = n[k];
-      n_pass = simt::shfl(n_pass, pass & 31);
-      if ((m.flags & F_LASTPASS) && n_pass == 0.f) {
+      bool pass_first = false;
+      if (m.flags & F_LASTPASS) pass_first = simt::shfl(pick(n, pass >> 5), pass & 31) == 0.f;
+      if (pass_first) {
         best = pass;
       } else {
         // score = Float64(Float32(W/(1+N)) * to_play) + ((c_puct * Float64(sqrt_f32(1+N_parent))) * Float64(P)) / Float64(1+N)
+        // The divisor d = 1 + N(child) is a small integer, so both correctly-rounded quotients are computed from r = RN(1/d)
+        // (table, or one exact division when d is past the table) instead of two IEEE divisions per child:
+        //   Float32 w/d = RN32(Float64(w) * r)             -- |w*r - w/d| <= 2^-52 relative, a quotient by d < 2^24 is >= 2^-49
+        //                                                      relative away from every fp32 rounding boundary (never on one);
+        //   Float64 x/d = fma(fma(-q0, d, x), r, q0), q0 = RN(x*r)   -- Markstein's correction; the remainder is exact (d small) and
+        //                                                      a quotient by d < 2^24 is >= 2^-78 relative away from a midpoint.
         const double cu = simt::dmul(c.c_puct, (double)simt::fsqrt(simt::fadd(1.0f, cur_N)));
         const float tp = (float)m.to_play;
-        double s[KA];
-        double mx = -1.0e300;
+        float den[KA];
+        double rc[KA];
+        // Take the IEEE divisions when a divisor could lie past the table -- N(child) <= N(node) in a search, only the test hooks
+        // (PH_MANUAL trees, agz_tree_set_stats) can break that -- or when a Float32 quotient could be subnormal (0 < |w| < 2^-100).
+        bool odd = st.phase == PH_MANUAL || !(simt::fadd(cur_N, 2.0f) < (float)v.rcp_n);
+        unsigned tiny = 0u;
 #pragma unroll
         for (int k = 0; k < KA; ++k) {
-          int a = k * 32 + lane;
-          bool legal = false;
-          if (a < c.N2) legal = (lwv[k] >> lane) & 1u;
-          else if (a == pass) legal = true;
-          float den = simt::fadd(1.0f, n[k]);
-          float q = simt::fmul(simt::fdiv(w[k], den), tp);
-          double u = simt::ddiv(simt::dmul(cu, (double)p[k]), (double)den);
-          s[k] = legal ? simt::dadd((double)q, u) : -1.0e300;
-          mx = s[k] > mx ? s[k] : mx;
+          den[k] = simt::fadd(1.0f, n[k]);
+          tiny |= ((simt::fbits(w[k]) << 1) - 1u) < ((27u << 24) - 1u) ? 1u : 0u;   // exponent field below 27 and not +-0
         }
+        odd = odd || simt::any(tiny != 0u);
+        double s[KA];
+        double mx = -1.0e300;
+        if (!odd) {
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          double o = simt::shfl_xor(mx, off);
-          mx = o > mx ? o : mx;
+          for (int k = 0; k < KA; ++k) rc[k] = v.rcp[(int)den[k]];
+#pragma unroll
+          for (int k = 0; k < KA; ++k) {
+            const bool legal = (((lwv[k] >> lane) & 1u) | (unsigned)(k * 32 + lane == pass)) != 0u;   // mask bits past N^2 are 0
+            const double dd = (double)den[k];
+            const float q = simt::fmul((float)simt::dmul((double)w[k], rc[k]), tp);
+            const double x = simt::dmul(cu, (double)p[k]);
+            const double q0 = simt::dmul(x, rc[k]);
+            const double u = simt::dfma(simt::dfma(-q0, dd, x), rc[k], q0);
+            s[k] = legal ? simt::dadd((double)q, u) : -1.0e300;
+            mx = s[k] > mx ? s[k] : mx;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KA; ++k) {
+            const bool legal = (((lwv[k] >> lane) & 1u) | (unsigned)(k * 32 + lane == pass)) != 0u;
+            float q = simt::fmul(simt::fdiv(w[k], den[k]), tp);
+            double u = simt::ddiv(simt::dmul(cu, (double)p[k]), (double)den[k]);
+            s[k] = legal ? simt::dadd((double)q, u) : -1.0e300;
+            mx = s[k] > mx ? s[k] : mx;
+          }
+        }
+        // warp maximum of the doubles through two 32-bit REDUX.MAX on an order-preserving integer key (scores are never -0.0:
+        // u >= +0 and (-0) + (+0) = +0) instead of five shuffle rounds
+        {
+          const long long b = simt::dbits(mx);
+          const unsigned long long key = (unsigned long long)b ^ (b < 0 ? ~0ULL : 0x8000000000000000ULL);
+          const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+          const unsigned mhi = simt::reduce_max(hi);
+          const unsigned mlo = simt::reduce_max(hi == mhi ? lo : 0u);
+          const unsigned long long mkey = ((unsigned long long)mhi << 32) | mlo;
+          mx = simt::bitsd((long long)(mkey ^ ((mkey >> 63) ? 0x8000000000000000ULL : ~0ULL)));
         }
         unsigned tm[KA];
         int total = 0;
@@ -358,7 +430,8 @@ struct Warp {
         }
         int pick = 0;   // mulhi(r, 1) = 0: the draw only matters when several children tie (warp-uniform branch)
         if (total > 1) {
-          U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_SELECT, move_no, sel_idx, (uint32_t)depth);
+          if (move_no < 0) move_no = load_meta(st.root).n;
+          U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_SELECT, (uint32_t)move_no, sel_idx, (uint32_t)depth);
           pick = (int)simt::mulhi(rr.x, (uint32_t)total);
         }
         best = pass;
@@ -379,18 +452,28 @@ struct Warp {
         }
       }
       const int ok = best >> 5, ol = best & 31;
-      float n_old = 0.f;
-      int child = -1;
-#pragma unroll
-      for (int k = 0; k < KA; ++k)
-        if (k == ok) { n_old = n[k]; child = ch[k]; }
-      n_old = simt::shfl(n_old, ol);
-      child = simt::shfl(child, ol);
+      const float n_old = simt::shfl(pick(n, ok), ol);
+      int child = simt::shfl(pick(ch, ok), ol);
       const float n_new = simt::fadd(n_old, 1.0f);
       if (child < 0) {
-        child = create_child(cur, m, best, false);
+        // A child created here is the leaf of this readout (not expanded, mcts.jl:116-118): everything the next level would load
+        // back from memory is known, so the descent ends without that round trip.
+        NodeMeta cm;
+        child = create_child(cur, m, best, false, &cm);
         if (child < 0) break;
-        if (lane == ol) v.child[r + best] = child;
+        if (lane == ol) {
+          v.child[r + best] = child;
+          v.N[r + best] = n_new;  // N(child) += 1 (mcts.jl:113-114)
+        }
+        ++depth;
+        if (lane == 0) {
+          PathEnt e;
+          e.slot = (unsigned long long)(r + best); e.node = child; e.to_play = cm.to_play;
+          path[depth] = e;
+        }
+        if (leaf_meta) *leaf_meta = cm;
+        cur = child;
+        break;
       }
       if (lane == ol) v.N[r + best] = n_new;  // N(child) += 1 (mcts.jl:113-114)
       slot = (unsigned long long)(r + best);
@@ -412,11 +495,11 @@ struct Warp {
       ++attempts;
       PathEnt* path = path_of(nleaf);
       int plen = 0;
-      int leaf = select_leaf(st.root, path, plen);
+      NodeMeta lm;
+      int leaf = select_leaf(st.root, path, plen, &lm);   // lm = the leaf's meta word as the last level of the descent loaded it
       if (st.err) break;
       n_readouts += 1;
       n_pathnodes += (unsigned long long)plen;
-      NodeMeta lm = load_meta(leaf);
       if (terminal(lm)) {  // game over: back up the true result, do not evaluate (mcts_play.jl:80-84)
         const uint32_t* lb = bits_of(leaf);
         float sc = bits_score(B, bits_load(B, lb, lb + c.KB), c.komi);

@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--burnin", type=int, default=112, help="untimed move-steps before the warm-up (staggered start; ~ one mean game length)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the C5 / C4 / C3 legs")
+    ap.add_argument("--pipeline", type=int, default=0, help="option schedule.pipeline (two half batches on separate streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -237,7 +238,7 @@ def main():
     env = agz.GoEnv(BOARD, device=local)
     nn = agz.NeuralNet(env, tower_height=TOWER, seed=0)
     eng = agz.Engine(BOARD, n_games=args.games, readouts=READOUTS, tower_height=TOWER, seed=0, device=local, world_size=world, rank=rank,
-                     evaluator=agz.EVAL_NN_TC, options={"selfplay.stagger_rounds": args.burnin * ROUNDS_PER_STEP})
+                     evaluator=agz.EVAL_NN_TC, options={"selfplay.stagger_rounds": args.burnin * ROUNDS_PER_STEP, "schedule.pipeline": args.pipeline})
     nn.push(eng)
     if world > 1:  # NCCL communicator of the replay all-gather: rank 0's unique id goes round through torch.distributed
         ids = [eng.nccl_unique_id() if rank == 0 else None]

@@ -275,6 +275,11 @@ int32_t agz_set_timing(agz_engine* e, int32_t enabled);
  * kernel's first and last CTA append {tag | block << 8 | grid << 32, start ns, end ns, SM id} (%globaltimer).  Tags:
  * 1 select, 2 incorporate, 3 leaf features, 4 stem conv, 5 tower conv, 6 tower conv with shortcut, 7 heads, 9 other. */
 int32_t agz_trace_read(agz_engine* e, uint64_t* out, int32_t max_records, int32_t* n_out, int32_t reset);
+/* Self-test of the arithmetic shortcut in select_leaf's PUCT score (the reference divides by 1 + N(child), mcts.jl:89-92; the
+ * kernel multiplies by a table of correctly rounded reciprocals and corrects, alphago.jl_b200/csrc/tree.cuh): n_samples random
+ * (numerator, divisor) pairs on the device, mismatches[0] = fp32 quotients, mismatches[1] = fp64 quotients that differ from the
+ * IEEE divisions in any bit.  Both must be 0. */
+int32_t agz_selftest_division(agz_engine* e, uint64_t n_samples, uint64_t seed, uint64_t mismatches[2]);
 /* FLOPs (2*MAC) of one position through the whole network / through one tower 3x3 convolution. */
 int32_t agz_net_flops(agz_engine* e, double* per_position, double* per_tower_conv_position);
 

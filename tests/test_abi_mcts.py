@@ -622,3 +622,16 @@ def test_replay_ring_trims_oldest():
     with pytest.raises(agz.AgzError):
         eng.replay_sample(151)
     eng.close()
+
+
+@pytest.mark.gpu
+def test_reciprocal_quotients_equal_ieee_divisions_on_device():
+    """select_leaf's score divides by 1 + N(child) through a table of correctly rounded reciprocals (fp32: one fp64 product; fp64:
+    Markstein's fused correction).  3 x 10^8 random (numerator, divisor) pairs against __fdiv_rn / __ddiv_rn: no bit may differ."""
+    eng = agz.Engine(9, lib_path=lib_for("cuda"), n_games=1, readouts=1600)
+    bad32, bad64 = eng.selftest_division(100_000_000, seed=1)
+    assert (bad32, bad64) == (0, 0)
+    eng.close()
+    eng = agz.Engine(19, lib_path=lib_for("cuda"), n_games=1, readouts=800)   # 412 000-entry table
+    assert eng.selftest_division(50_000_000, seed=2) == (0, 0)
+    eng.close()

@@ -172,3 +172,35 @@ def test_det_pow_agrees_with_libm():
         a, b = rng.det_pow(float(n), 0.98), math.pow(float(n), 0.98)
         worst = max(worst, abs(a - b) / b)
     assert worst < 1e-14, worst
+
+
+def test_reciprocal_quotients_equal_true_division():
+    """The engine's PUCT score (tree.cuh select_leaf) replaces w / d (Float32) and x / d (Float64), d = 1 + N(child) a small
+    integer, by products with r = RN(1/d): RN32(w * r) and Markstein's fma(fma(-q0, d, x), r, q0) with q0 = RN(x * r).  Exact
+    rational arithmetic check of both against correctly rounded division (the device twin, 10^8 samples, is a gpu test)."""
+    from fractions import Fraction as F
+    import struct
+    rs = np.random.RandomState(3)
+
+    def rn64(fr):
+        return fr.numerator / fr.denominator            # int / int true division is correctly rounded in CPython
+
+    def rn32(fr):
+        # round an exact rational to fp32: via fp64 is NOT allowed here (double rounding), so search the two neighbours
+        x = np.float32(fr.numerator / fr.denominator)
+        cands = [x, np.nextafter(x, np.float32(np.inf)), np.nextafter(x, np.float32(-np.inf))]
+        best = min(cands, key=lambda c: (abs(F(float(c)) - fr), int(struct.unpack("<I", struct.pack("<f", c))[0]) & 1))
+        return best
+
+    divisors = list(range(1, 600)) + [int(d) for d in rs.randint(600, 1 << 20, 400)]
+    for d in divisors:
+        r = rn64(F(1, d))
+        for _ in range(6):
+            w = np.float32(rs.standard_normal() * 10.0 ** rs.randint(-6, 3))
+            q_fast = np.float32(float(w) * r)           # fp64 product, then one rounding to fp32
+            assert q_fast == rn32(F(float(w)) / d), (d, w)
+            x = float(np.float64(0.96) * np.float64(np.sqrt(np.float32(1 + rs.randint(0, 5000)))) * np.float64(np.float32(rs.rand() ** 4)))
+            q0 = x * r
+            rem = rn64(F(x) - F(q0) * d)                # fma: exact product and sum, one rounding
+            u = rn64(F(q0) + F(rem) * F(r))
+            assert u == rn64(F(x) / d), (d, x)
