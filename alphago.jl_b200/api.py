@@ -563,10 +563,9 @@ def train(env, num_games=25000, memory_size=500000, batch_size=32, epochs=1, ckp
             for r in recs:
                 done += 1
                 if n_tuples >= start_training_after and n_tuples >= batch_size:
-                    bh, tp, pis, zs, _ = eng.replay_sample_hist(batch_size, seed=seed * 1000003 + done)
                     loss = 0.0
-                    for _ in range(epochs):
-                        loss += eng.train_step(bh, tp, pis, zs, lr=lr, momentum=momentum)
+                    for ep in range(epochs):     # get_replay_batch + _train (train.jl:66-70), all on the device
+                        loss += eng.train_step_from_replay(batch_size, seed=seed * 1000003 + done * 131 + ep, lr=lr, momentum=momentum)
                     losses.append(loss / epochs)
                     if verbose:
                         print("Episode %d over. Loss: %s. Winner: %s. Moves: %d." % (done, losses[-1], r.result_string, r.n_moves))

@@ -75,7 +75,7 @@ SYMBOLS = [
     "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read", "agz_engine_info",
     "agz_match_start", "agz_match_search", "agz_match_play",
     "agz_replay_sample_hist", "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
-    "agz_set_option", "agz_get_option", "agz_replay_info", "agz_selftest_division",
+    "agz_set_option", "agz_get_option", "agz_replay_info", "agz_selftest_division", "agz_train_step_from_replay",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -193,6 +193,11 @@ class Engine:
         loss = C.c_float()
         self._check(self.lib.agz_train_step(self._h, _ptr(bh, C.c_int8), _ptr(tp, C.c_int8), _ptr(pi, C.c_float), _ptr(z, C.c_int8),
                                             C.c_int32(B), C.c_float(lr), C.c_float(momentum), C.byref(loss)))
+        return loss.value
+
+    def train_step_from_replay(self, batch, seed=0, lr=0.02, momentum=0.9):
+        loss = C.c_float()
+        self._check(self.lib.agz_train_step_from_replay(self._h, C.c_int32(batch), C.c_uint64(seed), C.c_float(lr), C.c_float(momentum), C.byref(loss)))
         return loss.value
 
     def train_read_grads(self, chain):

@@ -54,6 +54,7 @@ struct agz_engine {
   uint8_t* d_match_active;
   long long* d_match_ids;
   bool train_loaded;
+  bool host_stale;           // the device master copy (training) is newer than the host copy of the parameters kept in NNet
   size_t bytes_per_node;
   unsigned long long* d_trace;   // AGZ_TRACE=<records>: kernel timeline trace (simt.h), read back with agz_trace_read
   int trace_cap;
@@ -339,6 +340,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   e->d_trace = nullptr;
   e->trace_cap = 0;
   e->train_loaded = false;
+  e->host_stale = false;
   e->d_match_i = e->d_match_j = e->d_match_in = nullptr;
   e->d_match_f = nullptr;
   e->d_match_active = nullptr;
@@ -477,6 +479,7 @@ extern "C" int32_t agz_set_evaluator(agz_engine* e, int32_t evaluator) {
 }
 
 #if AGZ_CUDA
+static int sync_host(agz_engine* e);
 // features + network for batch rows [row0, row0 + nrows): writes d_eval_pi / d_eval_v
 static int run_network(agz_engine* e, int row0, int nrows) {
   char nerr[256] = "";
@@ -486,6 +489,7 @@ static int run_network(agz_engine* e, int row0, int nrows) {
   if (e->timing) cudaEventRecord(e->ev[1], e->stream);
   cudaEvent_t* nev = e->timing ? &e->ev[2] : nullptr;   // ev[2..5]: before stem, after stem, after tower, after heads
   if (e->evaluator == AGZ_EVAL_NN_F32) {
+    { int rc = sync_host(e); if (rc) return rc; }   // the fp32 cross-check path builds its weights from the host copy
     float* feats = e->d_feats_f32 + (size_t)row0 * 17 * e->c.N2;
     DISPATCH_KA(e, {
       LeafFeaturesF32Op<KA> op{e->c, e->v, e->d_feats_f32};
@@ -1276,6 +1280,16 @@ extern "C" int32_t agz_net_flops(agz_engine* e, double* per_position, double* pe
   return AGZ_OK;
 }
 #if AGZ_CUDA
+// After a training step the fp32 master parameters live on the device and the inference paths were refreshed there (train_publish);
+// the host copy is brought up to date only when somebody reads or partially overwrites it.
+static int sync_host(agz_engine* e) {
+  if (!e->host_stale || !e->train) return AGZ_OK;
+  char terr[256] = "";
+  if (train_store(e->train, e->nn, e->stream, terr, sizeof(terr))) return fail(e, AGZ_ERR_CUDA, "%s", terr);
+  e->host_stale = false;
+  return AGZ_OK;
+}
+
 extern "C" size_t agz_net_param_count(agz_engine* e, int32_t chain) { return e ? nn_param_count(e->nn, chain) : 0; }
 extern "C" size_t agz_net_bn_count(agz_engine* e, int32_t chain) { return e ? nn_bn_count(e->nn, chain) : 0; }
 
@@ -1284,20 +1298,18 @@ extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t chain, const float*
   if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
   if (n != nn_param_count(e->nn, chain)) return fail(e, AGZ_ERR_ARG, "chain %d expects %zu parameters, got %zu", chain, nn_param_count(e->nn, chain), n);
   cudaSetDevice(e->cfg.device);
+  { int rc = sync_host(e); if (rc) return rc; }   // the other chains' host copies must be current before the network is re-committed
   e->train_loaded = false;   // the device master copy of the training path is stale now
   return nn_set_params(e->nn, chain, flat, n) ? fail(e, AGZ_ERR_ARG, "nn_set_params failed") : AGZ_OK;
 }
 
 // ---- training step: _train / losses (neural_net.jl:75-101), Momentum (train.jl:54)
-extern "C" int32_t agz_train_step(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, const float* pis, const int8_t* zs, int32_t B,
-                                  float lr, float momentum, float* loss_out) {
-  if (!e || !boards_hist || !to_play || !pis || !zs) return fail(e, AGZ_ERR_ARG, "null argument");
+static int train_prepare(agz_engine* e, int32_t B) {
   if (B < 1 || B > 4096) return fail(e, AGZ_ERR_ARG, "batch must be in [1, 4096]");
   cudaSetDevice(e->cfg.device);
   char terr[256] = "";
-  if (e->train && train_max_batch(e->train) < B) {   // grow: keep the momentum by going through the host copy is not possible; refuse instead
-    return fail(e, AGZ_ERR_ARG, "batch %d exceeds the training state's batch %d (the first agz_train_step fixes it)", B, train_max_batch(e->train));
-  }
+  if (e->train && train_max_batch(e->train) < B)   // the momentum lives in the training state: it is not re-created for a larger batch
+    return fail(e, AGZ_ERR_ARG, "batch %d exceeds the training state's batch %d (the first training step fixes it)", B, train_max_batch(e->train));
   if (!e->train) {
     e->train = train_create(e->nn, B < 32 ? 32 : B, terr, sizeof(terr));
     if (!e->train) return fail(e, AGZ_ERR_CUDA, "%s", terr);
@@ -1307,23 +1319,61 @@ extern "C" int32_t agz_train_step(agz_engine* e, const int8_t* boards_hist, cons
     if (train_load(e->train, e->nn, e->stream, terr, sizeof(terr))) return fail(e, AGZ_ERR_ARG, "%s", terr);
     e->train_loaded = true;
   }
+  return AGZ_OK;
+}
+
+// hand the updated parameters to the inference paths on the device (fold + fp16 reorder); the host copy is synchronised lazily
+static int train_finish(agz_engine* e) {
+  char terr[256] = "";
+  e->launches += 60 + 40 * (long long)e->cfg.tower_height;
+  if (train_publish(e->train, e->nn, e->stream, terr, sizeof(terr))) return fail(e, AGZ_ERR_CUDA, "%s", terr);
+  e->launches += 3 + 2 * (1 + 2 * (long long)e->cfg.tower_height);
+  e->host_stale = true;
+  return AGZ_OK;
+}
+
+static int train_allreduce_cb(void* ctx, float* buf, size_t n, cudaStream_t st) { return replay_allreduce_sum((ReplayState*)ctx, buf, n, st); }
+
+extern "C" int32_t agz_train_step(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, const float* pis, const int8_t* zs, int32_t B,
+                                  float lr, float momentum, float* loss_out) {
+  if (!e || !boards_hist || !to_play || !pis || !zs) return fail(e, AGZ_ERR_ARG, "null argument");
+  int rc = train_prepare(e, B);
+  if (rc) return rc;
+  char terr[256] = "";
   float* d_feats = nullptr;
   if (cudaMalloc((void**)&d_feats, (size_t)B * 17 * e->c.N2 * sizeof(float)) != cudaSuccess) return fail(e, AGZ_ERR_CUDA, "feature buffer allocation failed");
-  int rc = engine_host_features(e->c, boards_hist, to_play, B, nullptr, d_feats, e->stream);
+  rc = engine_host_features(e->c, boards_hist, to_play, B, nullptr, d_feats, e->stream);
   if (rc) { cudaFree(d_feats); return fail(e, AGZ_ERR_CUDA, "feature kernel: %s", cudaGetErrorString((cudaError_t)rc)); }
   std::vector<float> z((size_t)B);
   for (int b = 0; b < B; ++b) z[b] = (float)zs[b];
   // with an initialised NCCL communicator (agz_nccl_init) the step is data parallel: every rank calls it with its own minibatch
   const int world = replay_world(e->replay);
   rc = train_step(e->train, d_feats, pis, z.data(), B, lr, momentum, loss_out, e->stream, terr, sizeof(terr), world,
-                  world > 1 ? [](void* ctx, float* buf, size_t n, cudaStream_t st) { return replay_allreduce_sum((ReplayState*)ctx, buf, n, st); } : (train_allreduce_fn) nullptr,
-                  e->replay);
+                  world > 1 ? train_allreduce_cb : (train_allreduce_fn) nullptr, e->replay);
   cudaFree(d_feats);
-  e->launches += 60 + 40 * (long long)e->cfg.tower_height;
   if (rc) return fail(e, AGZ_ERR_CUDA, "%s", terr);
-  // the inference paths read the host copy: hand the new parameters and running statistics over (re-committed lazily)
-  if (train_store(e->train, e->nn, e->stream, terr, sizeof(terr))) return fail(e, AGZ_ERR_CUDA, "%s", terr);
-  return AGZ_OK;
+  return train_finish(e);
+}
+
+// get_replay_batch + _train (src/train.jl:66-70) without leaving the device: the draw (replay.cu: keyed permutation + gather kernel),
+// the feature planes, the step and the hand-over of the new parameters to the self-play path; only the loss travels to the host
+extern "C" int32_t agz_train_step_from_replay(agz_engine* e, int32_t batch, uint64_t seed, float lr, float momentum, float* loss_out) {
+  if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
+  if (!e->replay) return fail(e, AGZ_ERR_ARG, "no replay ring (call agz_replay_gather first)");
+  int rc = train_prepare(e, batch);
+  if (rc) return rc;
+  char terr[256] = "";
+  const int world = replay_world(e->replay);
+  // data parallel: the rings of all ranks hold the same tuples, so every rank draws with its own key
+  const uint64_t rseed = seed ^ ((uint64_t)e->c.rank * 0x9E3779B97F4A7C15ull);
+  const unsigned char* stage = nullptr;
+  rc = replay_sample_device(e->replay, batch, world > 1 ? rseed : seed, e->stream, &stage, nullptr, terr, sizeof(terr));
+  if (rc) return fail(e, rc, "%s", terr);
+  e->launches += 2;
+  rc = train_step_from_tuples(e->train, stage, replay_stride(e->replay), batch, lr, momentum, loss_out, e->stream, terr, sizeof(terr), world,
+                              world > 1 ? train_allreduce_cb : (train_allreduce_fn) nullptr, e->replay);
+  if (rc) return fail(e, AGZ_ERR_CUDA, "%s", terr);
+  return train_finish(e);
 }
 
 extern "C" int32_t agz_train_read_grads(agz_engine* e, int32_t chain, float* grads, size_t n) {
@@ -1336,6 +1386,8 @@ extern "C" int32_t agz_train_read_grads(agz_engine* e, int32_t chain, float* gra
 extern "C" int32_t agz_net_get_params(agz_engine* e, int32_t chain, float* flat, size_t n) {
   if (!e || !flat) return fail(e, AGZ_ERR_ARG, "null argument");
   if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
+  cudaSetDevice(e->cfg.device);
+  { int rc = sync_host(e); if (rc) return rc; }
   if (n != nn_param_count(e->nn, chain) || e->nn->hparams[chain].size() != n) return fail(e, AGZ_ERR_ARG, "chain %d has %zu parameters set, asked for %zu", chain, e->nn->hparams[chain].size(), n);
   memcpy(flat, e->nn->hparams[chain].data(), n * sizeof(float));
   return AGZ_OK;
@@ -1345,6 +1397,8 @@ extern "C" int32_t agz_net_get_bn_stats(agz_engine* e, int32_t chain, float* mu,
   if (!e || !mu || !sigma) return fail(e, AGZ_ERR_ARG, "null argument");
   if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
   if (n_each != nn_bn_count(e->nn, chain)) return fail(e, AGZ_ERR_ARG, "chain %d has %zu BatchNorm channels, got %zu", chain, nn_bn_count(e->nn, chain), n_each);
+  cudaSetDevice(e->cfg.device);
+  { int rc = sync_host(e); if (rc) return rc; }
   memcpy(mu, e->nn->hmu[chain].data(), n_each * sizeof(float));
   memcpy(sigma, e->nn->hsigma[chain].data(), n_each * sizeof(float));
   if (bn_mode) *bn_mode = e->nn->bn_mode[chain];
@@ -1356,6 +1410,8 @@ extern "C" int32_t agz_net_set_bn_stats(agz_engine* e, int32_t chain, const floa
   if (chain < 0 || chain > 2) return fail(e, AGZ_ERR_ARG, "chain must be 0..2");
   if (n_each != nn_bn_count(e->nn, chain)) return fail(e, AGZ_ERR_ARG, "chain %d has %zu BatchNorm channels, got %zu", chain, nn_bn_count(e->nn, chain), n_each);
   if (bn_mode != AGZ_BN_VAR_EPS && bn_mode != AGZ_BN_STD) return fail(e, AGZ_ERR_ARG, "bad bn_mode");
+  cudaSetDevice(e->cfg.device);
+  { int rc = sync_host(e); if (rc) return rc; }
   e->train_loaded = false;   // the device copy of the running statistics kept by the training path is stale now
   return nn_set_bn(e->nn, chain, mu, sigma, n_each, bn_mode) ? fail(e, AGZ_ERR_ARG, "nn_set_bn failed") : AGZ_OK;
 }
@@ -1381,6 +1437,8 @@ extern "C" int32_t agz_net_forward(agz_engine* e, int32_t evaluator, const int8_
     const int nb = std::min(maxb, B - b0);
     int rc;
     if (evaluator == AGZ_EVAL_NN_F32) {
+      rc = sync_host(e);
+      if (rc) return rc;
       rc = engine_host_features(e->c, boards_hist + (size_t)b0 * 8 * N2, to_play + b0, nb, nullptr, e->d_feats_f32, e->stream);
       if (rc) return fail(e, AGZ_ERR_CUDA, "feature kernel: %s", cudaGetErrorString((cudaError_t)rc));
       rc = nn_forward_f32(e->nn, e->d_feats_f32, nb, e->d_eval_pi, e->d_eval_v, e->stream);
@@ -1531,6 +1589,7 @@ extern "C" int32_t agz_net_set_params(agz_engine* e, int32_t, const float*, size
 extern "C" int32_t agz_net_set_bn_stats(agz_engine* e, int32_t, const float*, const float*, size_t, int32_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_features(agz_engine* e, const int8_t*, const int8_t*, int32_t, float*) { return fail(e, AGZ_ERR_CUDA, "not in the emulation build"); }
 extern "C" int32_t agz_train_step(agz_engine* e, const int8_t*, const int8_t*, const float*, const int8_t*, int32_t, float, float, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
+extern "C" int32_t agz_train_step_from_replay(agz_engine* e, int32_t, uint64_t, float, float, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_train_read_grads(agz_engine* e, int32_t, float*, size_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_net_get_params(agz_engine* e, int32_t, float*, size_t) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_net_get_bn_stats(agz_engine* e, int32_t, float*, float*, size_t, int32_t*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }

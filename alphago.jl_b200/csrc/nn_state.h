@@ -45,5 +45,6 @@ int nn_fold_layers(const NNet* n, std::vector<ConvLayerHost>& convs, char* err, 
 int nn_tc_create(NNet* n, char* err, size_t errlen);
 void nn_tc_destroy(NNet* n);
 int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t s, char* err, size_t errlen);
+int nn_tc_commit_device(NNet* n, const float* d_base, cudaStream_t s, char* err, size_t errlen);   // base-chain parameters already on the device
 
 }  // namespace agz

@@ -1040,6 +1040,23 @@ int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t 
   return 0;
 }
 
+// the same reorder with the fp32 base-chain parameters already on the device (training master copy, train.cu train_publish)
+int nn_tc_commit_device(NNet* n, const float* d_base, cudaStream_t s, char* err, size_t errlen) {
+  TCState* t = (TCState*)n->tc;
+  const size_t C = 256, P = (size_t)n->s.planes;
+  const int nconv = 1 + 2 * n->s.tower;
+  size_t off = 0;
+  for (int l = 0; l < nconv; ++l) {
+    const int cin = l == 0 ? (int)P : 256, cin_pad = l == 0 ? CIN0 : 256;
+    reorder_weights_kernel<<<296, 256, 0, s>>>(d_base + off, t->w[l], cin, cin_pad);
+    if (l == 0) off += 9 * P * C + 3 * C;
+    else if (l % 2 == 1) off += 9 * C * C + C;
+    else off += 9 * C * C + C + 4 * C;
+  }
+  if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "reordering the conv weights failed"); return 1; }
+  return 0;
+}
+
 long long nn_tc_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower + 1; }
 
 static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,

@@ -469,7 +469,50 @@ int train_load(TrainState* t, const NNet* n, cudaStream_t s, char* err, size_t e
   return 0;
 }
 
-// device training buffers -> host copy in the NNet (parameters in Flux order, running statistics as mean / variance)
+// ---- hand-over of the updated parameters to the inference paths WITHOUT a host round trip: fold conv bias + BatchNorm (running
+// statistics, variance + eps convention) into the per-channel scale / shift of every convolution, refresh the head parameters, and
+// let the tensor-core path re-read its fp16 tap-major weights straight from the fp32 master copy (nn_tc_commit_device).
+__global__ void k_fold_bn(const float* __restrict__ beta, const float* __restrict__ gamma, const float* __restrict__ mu, const float* __restrict__ var,
+                          const float* __restrict__ bias, int C, float* __restrict__ scale, float* __restrict__ shift, int stride_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  // same expression, operation order and roundings as the host fold_bn (nn_f32.cu, mode AGZ_BN_VAR_EPS): no FMA contraction
+  const float sc = __fdiv_rn(gamma[c], __fsqrt_rn(__fadd_rn(var[c], BN_EPS)));
+  scale[(size_t)c * stride_out] = sc;
+  shift[(size_t)c * stride_out] = __fadd_rn(__fsub_rn(beta[c], __fmul_rn(mu[c], sc)), __fmul_rn(sc, bias[c]));
+}
+
+int train_publish(TrainState* t, NNet* n, cudaStream_t s, char* err, size_t errlen) {
+  const int C = t->C, N2 = t->N2, A = t->A, nl = 1 + 2 * t->T;
+  const float* Pb = t->P[0];
+  for (int l = 0; l < nl; ++l) {
+    const ConvOff& o = t->conv[l];
+    k_fold_bn<<<(C + 127) / 128, 128, 0, s>>>(Pb + o.beta, Pb + o.gamma, t->mu_run + (size_t)l * C, t->var_run + (size_t)l * C, Pb + o.b, C,
+                                               n->f_scale[l], n->f_shift[l], 1);
+  }
+  const float *Pv = t->P[1], *Pp = t->P[2];
+  const size_t vD1W = (size_t)C + 3, vD1b = vD1W + (size_t)256 * N2, vD2W = vD1b + 256, vD2b = vD2W + 256;
+  const size_t pb = 2 * (size_t)C, pDW = pb + 6, pDb = pDW + (size_t)A * 2 * N2;
+  // f_head_aff_d = (v scale, v shift, p0 scale, p0 shift, p1 scale, p1 shift): stride 2 interleaves scale / shift
+  k_fold_bn<<<1, 32, 0, s>>>(Pv + C + 1, Pv + C + 2, t->hmu_run, t->hvar_run, Pv + C, 1, n->f_head_aff_d, n->f_head_aff_d + 1, 2);
+  k_fold_bn<<<1, 32, 0, s>>>(Pp + pb + 2, Pp + pb + 4, t->hmu_run + 1, t->hvar_run + 1, Pp + pb, 2, n->f_head_aff_d + 2, n->f_head_aff_d + 3, 2);
+  const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+  cudaMemcpyAsync(n->f_vw, Pv, (size_t)C * 4, dd, s);
+  cudaMemcpyAsync(n->f_D1W, Pv + vD1W, (size_t)256 * N2 * 4, dd, s);
+  cudaMemcpyAsync(n->f_D1b, Pv + vD1b, 256 * 4, dd, s);
+  cudaMemcpyAsync(n->f_D2W, Pv + vD2W, 256 * 4, dd, s);
+  cudaMemcpyAsync(n->f_D2b, Pv + vD2b, 4, dd, s);
+  cudaMemcpyAsync(n->f_pw, Pp, (size_t)2 * C * 4, dd, s);
+  cudaMemcpyAsync(n->f_PW, Pp + pDW, (size_t)A * 2 * N2 * 4, dd, s);
+  cudaMemcpyAsync(n->f_Pb, Pp + pDb, (size_t)A * 4, dd, s);
+  if (nn_tc_commit_device(n, Pb, s, err, errlen)) return 1;
+  n->f32_weights_ready = false;   // the fp32 cross-check path rebuilds its weights from the host copy (synchronised lazily)
+  n->ready = true;
+  return 0;
+}
+
+// device training buffers -> host copy in the NNet (parameters in Flux order, running statistics as mean / variance); the
+// inference paths are NOT invalidated (train_publish has already handed them the same values)
 int train_store(TrainState* t, NNet* n, cudaStream_t s, char* err, size_t errlen) {
   for (int k = 0; k < 3; ++k) {
     n->hparams[k].resize(t->np[k]);
@@ -487,7 +530,6 @@ int train_store(TrainState* t, NNet* n, cudaStream_t s, char* err, size_t errlen
   n->hmu[1][0] = hm[0]; n->hmu[2][0] = hm[1]; n->hmu[2][1] = hm[2];
   n->hsigma[1][0] = hv[0]; n->hsigma[2][0] = hv[1]; n->hsigma[2][1] = hv[2];
   for (int k = 0; k < 3; ++k) n->bn_mode[k] = 0;   // variance + eps convention from here on
-  n->ready = false;                                  // the inference paths fold and upload again before their next forward
   n->f32_weights_ready = false;
   t->dirty = false;
   return 0;
@@ -499,17 +541,52 @@ __global__ void k_scale(float* __restrict__ x, size_t n, float f) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= f;
 }
 
+static int train_step_core(TrainState* t, int B, float eta, float rho, float* loss_out, cudaStream_t s, char* err, size_t errlen, int world,
+                           train_allreduce_fn allreduce, void* ctx);
+
 int train_step(TrainState* t, const float* d_feats_in /* [B][17][N2] on the device */, const float* h_pi, const float* h_z, int B, float eta,
                float rho, float* loss_out, cudaStream_t s, char* err, size_t errlen, int world, train_allreduce_fn allreduce, void* ctx) {
   if (B < 1 || B > t->maxB) { snprintf(err, errlen, "batch %d outside [1, %d]", B, t->maxB); return 1; }
+  cudaMemcpyAsync(t->feats, d_feats_in, (size_t)B * 17 * t->N2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  cudaMemcpyAsync(t->d_pi, h_pi, (size_t)B * t->A * sizeof(float), cudaMemcpyHostToDevice, s);
+  cudaMemcpyAsync(t->d_z, h_z, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, s);
+  return train_step_core(t, B, eta, rho, loss_out, s, err, errlen, world, allreduce, ctx);
+}
+
+// packed replay tuples (replay.cu: pi[A] f32 | 8 boards N2 int8 each, current first | to_play | z | pad) -> the step's inputs:
+// get_feats planes (features.jl:3-26) [B][17][N2], pi [B][A], z [B]
+__global__ void k_unpack_tuples(const unsigned char* __restrict__ stage, size_t stride, int B, int N2, int A, float* __restrict__ feats,
+                                float* __restrict__ pi, float* __restrict__ z) {
+  const int b = blockIdx.x;
+  const unsigned char* t = stage + (size_t)b * stride;
+  const float* tpi = reinterpret_cast<const float*>(t);
+  const signed char* boards = reinterpret_cast<const signed char*>(t + (size_t)4 * A);
+  const int tp = boards[8 * N2];
+  for (int a = threadIdx.x; a < A; a += blockDim.x) pi[(size_t)b * A + a] = tpi[a];
+  float* f = feats + (size_t)b * 17 * N2;
+  for (int i = threadIdx.x; i < 8 * N2; i += blockDim.x) {
+    const int k = i / N2, p = i - k * N2, sv = boards[i];
+    f[(2 * k) * N2 + p] = sv == tp ? 1.f : 0.f;
+    f[(2 * k + 1) * N2 + p] = sv == -tp ? 1.f : 0.f;
+  }
+  for (int p = threadIdx.x; p < N2; p += blockDim.x) f[16 * N2 + p] = (float)tp;
+  if (threadIdx.x == 0) z[b] = (float)boards[8 * N2 + 1];
+}
+
+int train_step_from_tuples(TrainState* t, const unsigned char* d_stage, size_t stride, int B, float eta, float rho, float* loss_out, cudaStream_t s,
+                           char* err, size_t errlen, int world, train_allreduce_fn allreduce, void* ctx) {
+  if (B < 1 || B > t->maxB) { snprintf(err, errlen, "batch %d outside [1, %d]", B, t->maxB); return 1; }
+  k_unpack_tuples<<<B, 128, 0, s>>>(d_stage, stride, B, t->N2, t->A, t->feats, t->d_pi, t->d_z);
+  return train_step_core(t, B, eta, rho, loss_out, s, err, errlen, world, allreduce, ctx);
+}
+
+static int train_step_core(TrainState* t, int B, float eta, float rho, float* loss_out, cudaStream_t s, char* err, size_t errlen, int world,
+                           train_allreduce_fn allreduce, void* ctx) {
   const int C = t->C, N = t->N, N2 = t->N2, A = t->A, T = t->T;
   const int nl = 1 + 2 * T;
   const size_t act = (size_t)B * C * N2;
   float* Pb = t->P[0];
   float* Gb = t->G[0];
-  cudaMemcpyAsync(t->feats, d_feats_in, (size_t)B * 17 * N2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-  cudaMemcpyAsync(t->d_pi, h_pi, (size_t)B * A * sizeof(float), cudaMemcpyHostToDevice, s);
-  cudaMemcpyAsync(t->d_z, h_z, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, s);
   cudaMemsetAsync(t->red, 0, 8 * sizeof(float), s);
   const size_t wsm = (size_t)(WG_CI * (N + 2) * (N + 2) + WG_CO * N2) * sizeof(float);
   cudaFuncSetAttribute(k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);

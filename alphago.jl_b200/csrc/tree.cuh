@@ -323,7 +323,7 @@ struct Warp {
         w[k] = v.W[r + a];
         p[k] = v.P[r + a];
         ch[k] = v.child[r + a];
-        lwv[k] = k < c.KB ? lw[k] : 0u;  // word k is a warp-uniform address
+        lwv[k] = lw[k];  // warp-uniform address; words past KB lie in the node's never-written (zero) tail: the stride is 3*KA words
       }
       if (lane == 0) {
         PathEnt e;

@@ -172,11 +172,17 @@ int32_t agz_features(agz_engine* e, const int8_t* boards_hist, const int8_t* to_
  * train-mode forward (BatchNorm on batch statistics, running statistics moved with momentum 0.1), loss = 0.01 * crossentropy(p, pi)
  * + 0.01 * mse(z, v) + 1e-4 * sum(theta^2) (:75-83), back-propagation, Momentum(lr, momentum): v = momentum * v - lr * grad;
  * theta += v.  Inputs as agz_net_forward / agz_replay_sample: boards_hist B x 8 x N*N, to_play B, pis B x A, zs B.  The updated
- * parameters are what every later forward / self-play call of this engine uses; *loss_out = the loss before the update.
+ * parameters are what every later forward / self-play call of this engine uses (handed over on the device: BatchNorm fold and fp16
+ * weight conversion run there; agz_net_get_params synchronises the host copy on demand); *loss_out = the loss before the update.
  * After agz_nccl_init (world_size > 1) the step is data parallel -- an extension, the reference trains in one process: every rank
  * calls it with its own minibatch; gradients, loss and running statistics are averaged with ncclAllReduce before the update. */
 int32_t agz_train_step(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, const float* pis, const int8_t* zs, int32_t B,
                        float lr, float momentum, float* loss_out);
+/* The same step with get_replay_batch (src/train.jl:4-12) in front of it, entirely on the device: `batch` distinct tuples are drawn
+ * from the replay ring (the draw of agz_replay_sample for this seed; with world_size > 1 every rank's draw is keyed by its rank),
+ * the feature planes are built there and the updated parameters are folded / converted for the self-play path there as well --
+ * nothing but the loss crosses the bus.  The first training step of an engine fixes the largest batch (>= 32). */
+int32_t agz_train_step_from_replay(agz_engine* e, int32_t batch, uint64_t seed, float lr, float momentum, float* loss_out);
 /* gradients of the data loss of the last agz_train_step, chain's Flux params order (test hook) */
 int32_t agz_train_read_grads(agz_engine* e, int32_t chain, float* grads, size_t n);
 /* current parameters / BatchNorm running statistics of a chain (what save_model writes, src/train.jl:14-35) */

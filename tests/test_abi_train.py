@@ -123,3 +123,70 @@ def test_train_loop_selfplay_replay_train(tmp_path):
     games = []
     agz.evaluate(env, nn, agz.NeuralNet(env, tower_height=1, seed=2), num_games=4, ro=16, details=games)
     assert len(games) == 4 and all(g.result_string for g in games)
+
+
+def _ring_engine(seed_net):
+    """A small engine whose replay ring holds a few finished 5x5 games (identical for identical arguments: games are deterministic)."""
+    env = agz.GoEnv(5)
+    nn = agz.NeuralNet(env, tower_height=1, seed=seed_net)
+    eng = agz.Engine(5, n_games=8, readouts=16, tower_height=1, evaluator=agz.EVAL_NN_TC, seed=4)
+    nn.push(eng)
+    eng.selfplay_start(8)
+    for _ in range(400):
+        pr = eng.selfplay_step(8)
+        if pr.games_finished == 8:
+            break
+    assert pr.games_finished == 8 and pr.error == 0
+    total = eng.replay_gather()
+    assert total >= 32
+    return env, nn, eng, total
+
+
+def test_train_step_from_replay_equals_sample_then_step():
+    """agz_train_step_from_replay (draw, feature planes, step and hand-over on the device) = agz_replay_sample_hist +
+    agz_train_step through host buffers: same loss, bit-identical parameters and running statistics after two steps."""
+    lib_for("cuda")
+    _, _, dev, total = _ring_engine(7)
+    _, _, host, total_h = _ring_engine(7)
+    assert total == total_h
+    for step in range(2):
+        loss_d = dev.train_step_from_replay(16, seed=100 + step)
+        bh, tp, pis, zs, idx = host.replay_sample_hist(16, seed=100 + step)
+        loss_h = host.train_step(bh, tp, pis, zs)
+        assert loss_d == loss_h, (step, loss_d, loss_h)
+    for k in range(3):
+        assert np.array_equal(dev.net_get_params(k), host.net_get_params(k)), k
+        assert all(np.array_equal(a, b) for a, b in zip(dev.net_get_bn_stats(k)[:2], host.net_get_bn_stats(k)[:2])), k
+    dev.close()
+    host.close()
+
+
+def test_parameters_published_on_device_equal_a_host_reload():
+    """After a training step the self-play / forward path uses parameters folded and converted ON THE DEVICE (train_publish); a fresh
+    engine loaded with the same parameters through the host (agz_net_set_params: host fold + upload) must give the same outputs."""
+    lib_for("cuda")
+    env, nn, eng, _ = _ring_engine(3)
+    for step in range(3):
+        eng.train_step_from_replay(32, seed=step)
+    positions, _, _ = _batch(5, 16, 1)
+    bh, tp = _hist(positions, 5)
+    pi_a, v_a = eng.net_forward(agz.EVAL_NN_TC, bh, tp)           # published weights
+    fresh = agz.Engine(5, n_games=8, readouts=16, tower_height=1, evaluator=agz.EVAL_NN_TC)
+    for k in range(3):
+        fresh.net_set_params(k, eng.net_get_params(k))
+        mu, var, mode = eng.net_get_bn_stats(k)
+        fresh.net_set_bn_stats(k, mu, var, mode)
+    pi_b, v_b = fresh.net_forward(agz.EVAL_NN_TC, bh, tp)
+    assert np.array_equal(pi_a, pi_b) and np.array_equal(v_a, v_b)
+    # ... and the fp32 cross-check path (built from the lazily synchronised host copy) agrees within the usual tolerance
+    pi_f, v_f = eng.net_forward(agz.EVAL_NN_F32, bh, tp)
+    assert np.max(np.abs(pi_f - pi_a)) < 1e-3 and np.max(np.abs(v_f - v_a)) < 1e-3
+    # self-play continues on the updated network without a reload
+    eng.selfplay_start(4)
+    for _ in range(300):
+        pr = eng.selfplay_step(8)
+        if pr.games_finished == 4:
+            break
+    assert pr.games_finished == 4 and pr.error == 0
+    eng.close()
+    fresh.close()
