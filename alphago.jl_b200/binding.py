@@ -75,7 +75,7 @@ SYMBOLS = [
     "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read", "agz_engine_info",
     "agz_match_start", "agz_match_search", "agz_match_play",
     "agz_replay_sample_hist", "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
-    "agz_set_option", "agz_get_option", "agz_replay_info", "agz_selftest_division", "agz_train_step_from_replay",
+    "agz_set_option", "agz_get_option", "agz_replay_info", "agz_selftest_division", "agz_train_step_from_replay", "agz_net_forward_debug",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -227,6 +227,23 @@ class Engine:
         self._check(self.lib.agz_net_forward(self._h, C.c_int32(evaluator), _ptr(bh, C.c_int8), _ptr(tp, C.c_int8),
                                              C.c_int32(B), _ptr(pi, C.c_float), _ptr(v, C.c_float)))
         return pi, v
+
+    def net_forward_debug(self, evaluator, boards_hist, to_play, n_blocks=-1, want_trunk=False):
+        """Test hook: dict with pi, v, logits, v_pre (whole network only) and, if asked, the trunk [B][256][N2] after n_blocks blocks."""
+        bh = np.ascontiguousarray(boards_hist, dtype=np.int8)
+        tp = np.ascontiguousarray(to_play, dtype=np.int8)
+        B = tp.shape[0]
+        full = n_blocks < 0 or n_blocks >= self.cfg.tower_height
+        out = {}
+        if full:
+            out = {"pi": np.empty((B, self.A), np.float32), "v": np.empty(B, np.float32), "logits": np.empty((B, self.A), np.float32),
+                   "v_pre": np.empty(B, np.float32)}
+        if want_trunk or not full:
+            out["trunk"] = np.empty((B, 256, self.N2), np.float32)
+        g = lambda k: _ptr(out.get(k), C.c_float)
+        self._check(self.lib.agz_net_forward_debug(self._h, C.c_int32(evaluator), _ptr(bh, C.c_int8), _ptr(tp, C.c_int8), C.c_int32(B), C.c_int32(n_blocks),
+                                                   g("pi"), g("v"), g("logits"), g("v_pre"), g("trunk")))
+        return out
 
     def features(self, boards_hist, to_play):
         bh = np.ascontiguousarray(boards_hist, dtype=np.int8)

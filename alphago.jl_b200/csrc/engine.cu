@@ -609,7 +609,9 @@ static int one_round(agz_engine* e) {
 // hold the next stem back for its whole duration (measured with the AGZ_TRACE timeline: a 135 us bubble per half round).
 // Results are identical to the sequential schedule: games never interact.
 static bool can_pipeline(agz_engine* e) {
-  return e->pipeline && !e->timing && e->evaluator == AGZ_EVAL_NN_TC && e->c.n_games >= 2 && e->c.n_games % 2 == 0 && nn_tc_groups(e->nn) == 2;
+  long long prec = 1;
+  nn_tc_get_option(e->nn, "conv.precision", &prec);
+  return prec == 1 && e->pipeline && !e->timing && e->evaluator == AGZ_EVAL_NN_TC && e->c.n_games >= 2 && e->c.n_games % 2 == 0 && nn_tc_groups(e->nn) == 2;
 }
 
 static int pipelined_rounds(agz_engine* e, int rounds) {
@@ -1506,6 +1508,48 @@ extern "C" int32_t agz_selftest_division(agz_engine* e, uint64_t n_samples, uint
   return AGZ_OK;
 }
 
+// Test hook behind the network parity tests: one forward of at most one internal batch with the intermediate values exposed.
+extern "C" int32_t agz_net_forward_debug(agz_engine* e, int32_t evaluator, const int8_t* boards_hist, const int8_t* to_play, int32_t B, int32_t n_blocks,
+                                         float* pi, float* v, float* logits, float* v_pre, float* trunk) {
+  if (!e || !boards_hist || !to_play || B < 1) return fail(e, AGZ_ERR_ARG, "bad argument");
+  if (evaluator != AGZ_EVAL_NN_TC && evaluator != AGZ_EVAL_NN_F32) return fail(e, AGZ_ERR_ARG, "evaluator must be a network");
+  if (B > e->c.n_games * e->c.pmax) return fail(e, AGZ_ERR_ARG, "the debug forward takes at most n_games * max_parallel = %d positions", e->c.n_games * e->c.pmax);
+  cudaSetDevice(e->cfg.device);
+  char nerr[256] = "";
+  int rc = sync_host(e);
+  if (rc) return rc;
+  if (!nn_ready(e->nn) && nn_commit(e->nn, e->stream, nerr, sizeof(nerr))) return fail(e, AGZ_ERR_ARG, "network not ready: %s", nerr);
+  const size_t A = e->c.A, N2 = e->c.N2, C = e->cfg.filters;
+  const bool full = n_blocks < 0 || n_blocks >= e->cfg.tower_height;
+  NNDebug dbg{n_blocks, nullptr, nullptr};
+  if (trunk && cudaMalloc((void**)&dbg.trunk, (size_t)B * C * N2 * sizeof(float)) != cudaSuccess) return fail(e, AGZ_ERR_CUDA, "debug buffer allocation failed");
+  if ((logits || v_pre) && cudaMalloc((void**)&dbg.raw, (size_t)B * (A + 1) * sizeof(float)) != cudaSuccess) { cudaFree(dbg.trunk); return fail(e, AGZ_ERR_CUDA, "debug buffer allocation failed"); }
+  if (evaluator == AGZ_EVAL_NN_F32) {
+    rc = engine_host_features(e->c, boards_hist, to_play, B, nullptr, e->d_feats_f32, e->stream);
+    if (!rc) rc = nn_forward_f32(e->nn, e->d_feats_f32, B, e->d_eval_pi, e->d_eval_v, e->stream, nullptr, &dbg);
+  } else {
+    rc = engine_host_features_tc(e->c, e->nn, boards_hist, to_play, B, e->stream);
+    if (!rc) rc = nn_forward_tc(e->nn, B, e->d_eval_pi, e->d_eval_v, e->stream, nerr, sizeof(nerr), nullptr, -1, nullptr, nullptr, &dbg);
+  }
+  e->launches += 3 + 2 * (long long)e->cfg.tower_height;
+  if (!rc) rc = devrt::sync(e->stream);
+  if (!rc && full && pi) rc = devrt::d2h(pi, e->d_eval_pi, sizeof(float) * A * B, e->stream);
+  if (!rc && full && v) rc = devrt::d2h(v, e->d_eval_v, sizeof(float) * B, e->stream);
+  if (!rc && trunk) rc = devrt::d2h(trunk, dbg.trunk, sizeof(float) * B * C * N2, e->stream);
+  if (!rc && full && dbg.raw) {
+    std::vector<float> raw((size_t)B * (A + 1));
+    rc = devrt::d2h(raw.data(), dbg.raw, raw.size() * sizeof(float), e->stream);
+    for (int b = 0; b < B && !rc; ++b) {
+      if (logits) memcpy(logits + (size_t)b * A, raw.data() + (size_t)b * (A + 1), A * sizeof(float));
+      if (v_pre) v_pre[b] = raw[(size_t)b * (A + 1) + A];
+    }
+  }
+  cudaFree(dbg.trunk);
+  cudaFree(dbg.raw);
+  if (rc) return fail(e, AGZ_ERR_CUDA, "debug forward failed: %s", nerr[0] ? nerr : devrt::last_error_string(rc));
+  return AGZ_OK;
+}
+
 extern "C" int32_t agz_trace_read(agz_engine* e, uint64_t* out, int32_t max_records, int32_t* n_out, int32_t reset) {
   if (!e || !n_out) return fail(e, AGZ_ERR_ARG, "null argument");
   *n_out = 0;
@@ -1596,6 +1640,7 @@ extern "C" int32_t agz_net_get_bn_stats(agz_engine* e, int32_t, float*, float*, 
 extern "C" int32_t agz_net_forward(agz_engine* e, int32_t, const int8_t*, const int8_t*, int32_t, float*, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_trace_read(agz_engine*, uint64_t*, int32_t, int32_t* n_out, int32_t) { if (n_out) *n_out = 0; return AGZ_OK; }
 extern "C" int32_t agz_selftest_division(agz_engine* e, uint64_t, uint64_t, uint64_t*) { return fail(e, AGZ_ERR_CUDA, "not in the emulation build"); }
+extern "C" int32_t agz_net_forward_debug(agz_engine* e, int32_t, const int8_t*, const int8_t*, int32_t, int32_t, float*, float*, float*, float*, float*) { return fail(e, AGZ_ERR_CUDA, "no network in the emulation build"); }
 extern "C" int32_t agz_nccl_unique_id(uint8_t*) { return AGZ_ERR_NCCL; }
 extern "C" int32_t agz_nccl_init(agz_engine* e, const uint8_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }
 extern "C" int32_t agz_replay_gather(agz_engine* e, int64_t*) { return fail(e, AGZ_ERR_NCCL, "not in the emulation build"); }

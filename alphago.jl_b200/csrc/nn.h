@@ -31,7 +31,14 @@ bool nn_ready(const NNet* n);
 //   feats_f32 : [B][17][N2] float, reference (W x H x C x B) order               (NN_F32)
 //   feats_tc  : dense fp16 rows [B*N^2][64], written by engine_tc_features / engine_host_features_tc (NN_TC)
 // Output: pi [B][A] float (softmax over all A actions, no legality masking), v [B] float (Black's view).
-int nn_forward_f32(NNet* n, const float* feats_f32, int B, float* pi, float* v, cudaStream_t s, cudaEvent_t* ev = nullptr);
+// Debug outputs of a forward pass (agz_net_forward_debug, test hook): stop after `n_blocks` residual blocks (< 0 or >= tower: the
+// whole network), the trunk at that point as fp32 [B][C][N2] (reference layout), and the heads' values before softmax / tanh.
+struct NNDebug {
+  int n_blocks;
+  float* trunk;   // device [B][C][N2] or nullptr
+  float* raw;     // device [B][A + 1]: A logits then the value before tanh, or nullptr
+};
+int nn_forward_f32(NNet* n, const float* feats_f32, int B, float* pi, float* v, cudaStream_t s, cudaEvent_t* ev = nullptr, const NNDebug* dbg = nullptr);
 
 // The tensor-core path (nn_tc.cu) consumes activations as dense fp16 NHWC rows (row = b*N^2 + N*j + i); the feature kernels
 // below write the stem input (64 channels per row, 17 used) directly.
@@ -39,7 +46,7 @@ int nn_forward_f32(NNet* n, const float* feats_f32, int B, float* pi, float* v, 
 // group >= 0: evaluate only half batch `group` (rows [group*max_batch/2, ...)); pi / v point at that half's first row
 int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev = nullptr, int group = -1,
                   cudaEvent_t convs_done = nullptr /* recorded after the last convolution, before the heads */,
-                  cudaStream_t heads_stream = nullptr /* with convs_done: launch the heads there instead of on s */);
+                  cudaStream_t heads_stream = nullptr /* with convs_done: launch the heads there instead of on s */, const NNDebug* dbg = nullptr);
 int nn_tc_groups(const NNet* n);
 void nn_tc_set_trace(NNet* n, unsigned long long* trace);   // kernel timeline trace buffer (simt.h), nullptr = off
 // agz_set_option / agz_get_option keys "conv.*": 0 ok, 1 unknown key, 2 bad value

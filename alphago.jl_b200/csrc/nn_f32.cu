@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) heads_f32_kernel(const float* __restrict_
                                                         const float* __restrict__ D1W, const float* __restrict__ D1b,
                                                         const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                         const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
-                                                        float* __restrict__ v, int C, int N2) {
+                                                        float* __restrict__ v, int C, int N2, float* __restrict__ raw) {
   extern __shared__ float sm[];
   float* vf = sm;             // [N2]
   float* pf = sm + N2;        // [2*N2], index p + N2*c
@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(256) heads_f32_kernel(const float* __restrict_
     if (tid < s) red[tid] += red[tid + s];
     __syncthreads();
   }
-  if (tid == 0) v[b] = tanhf(red[0] + D2b[0]);
+  if (tid == 0) {
+    v[b] = tanhf(red[0] + D2b[0]);
+    if (raw) raw[(size_t)b * (A + 1) + A] = red[0] + D2b[0];
+  }
   __syncthreads();
   // Dense(2*N2 -> A) + softmax
   float lg[2];
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(256) heads_f32_kernel(const float* __restrict_
       for (int i = 0; i < 2 * N2; ++i) acc = fmaf(PW[a + (size_t)A * i], pf[i], acc);
       lg[q] = acc;
       mx = fmaxf(mx, acc);
+      if (raw) raw[(size_t)b * (A + 1) + a] = acc;
     }
   }
   red[tid] = mx;
@@ -397,7 +401,8 @@ static int upload_f32_weights(NNet* n, cudaStream_t s) {
   return (int)cudaGetLastError();
 }
 
-int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cudaStream_t s, cudaEvent_t* ev) {
+// debug: trunk [B][C][N2] is already the reference layout in the fp32 path
+int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cudaStream_t s, cudaEvent_t* ev, const NNDebug* dbg) {
   const int C = n->C, N = n->s.N, N2 = n->N2;
   if (B > n->max_batch) return (int)cudaErrorInvalidValue;
   if (!n->f32_weights_ready) {
@@ -413,14 +418,18 @@ int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cuda
   conv3x3_f32_kernel<<<grid, 128, smem, s>>>(feats, n->f_w[0], n->f_scale[0], n->f_shift[0], nullptr, n->f_act[0], n->s.planes, C, N, 1);
   if (ev) cudaEventRecord(ev[1], s);
   float *h = n->f_act[0], *t1 = n->f_act[1], *t2 = n->f_act[2];
-  for (int t = 0; t < n->s.tower; ++t) {
+  const int n_blocks = (dbg && dbg->n_blocks >= 0 && dbg->n_blocks < n->s.tower) ? dbg->n_blocks : n->s.tower;
+  for (int t = 0; t < n_blocks; ++t) {
     conv3x3_f32_kernel<<<grid, 128, smem, s>>>(h, n->f_w[1 + 2 * t], n->f_scale[1 + 2 * t], n->f_shift[1 + 2 * t], nullptr, t1, C, C, N, 1);
     conv3x3_f32_kernel<<<grid, 128, smem, s>>>(t1, n->f_w[2 + 2 * t], n->f_scale[2 + 2 * t], n->f_shift[2 + 2 * t], h, t2, C, C, N, 1);
     float* tmp = h; h = t2; t2 = tmp;
   }
   if (ev) cudaEventRecord(ev[2], s);
+  if (dbg && dbg->trunk) cudaMemcpyAsync(dbg->trunk, h, (size_t)B * C * N2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (n_blocks < n->s.tower) return (int)cudaGetLastError();
   const size_t hsm = (size_t)(3 * N2 + 512) * sizeof(float);
-  heads_f32_kernel<<<B, 256, hsm, s>>>(h, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb, pi, v, C, N2);
+  heads_f32_kernel<<<B, 256, hsm, s>>>(h, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb, pi, v, C, N2,
+                                       dbg ? dbg->raw : nullptr);
   if (ev) cudaEventRecord(ev[3], s);
   return (int)cudaGetLastError();
 }

@@ -43,6 +43,12 @@ struct TCState {
   int pdl;                    // conv.pdl (default 1): tower convolutions use programmatic dependent launch
   int max_pairs;              // conv.max_pairs: cap on the CTA pairs of the persistent conv kernels (0 = all SMs)
   int res_tma;                // conv.res_tma (default 1): residual convs use conv3x3_tc6_kernel (shortcut tile by TMA)
+  int split;                  // conv.precision = 2: split-precision activations / weights (hi + lo fp16 pairs), see conv3x3_tc5_kernel
+  __half* sact[3];            // split precision: [rows_alloc][512] (hi | lo)
+  std::vector<__half*> sw;    // split precision: per conv layer [9*256][2*cin_pad] (hi | lo)
+  CUtensorMap tm5_sact[3];
+  std::vector<CUtensorMap> tm_sw;
+  bool split_weights_ready;
   float4* head_pre;           // [rows_alloc] (value plane, policy plane 0, policy plane 1, 0) written by the fused-heads epilogue
   int N, PP, C, T, max_batch; // PP = N*N rows per board
   CUtensorMap tm5_in64, tm5_act[3];   // im2col maps over the stem input / the three rotating activation buffers
@@ -144,7 +150,10 @@ struct ConvArgs {
   __half* out;          // [rows][256]
   int n_tiles;          // ceil(rows_valid / 128)
   long long rows_valid; // rows of real boards (B * PP)
-  int kchunks;          // Cin / 64
+  int kchunks;          // K chunks of 64 channels per tap (Cin / 64; three times that in split precision)
+  int16_t a_off[12];    // activation / weight channel offset of K chunk kc: identity (64*kc) in fp16 mode; in split precision the
+  int16_t w_off[12];    // three products a_hi*w_hi, a_lo*w_hi, a_hi*w_lo are laid out as 3*Cin/64 chunks
+  int stem;             // first convolution (trace tag only)
   int N, PP;
   int relu;
   unsigned long long* trace;   // kernel timeline trace (simt.h) or nullptr
@@ -226,7 +235,10 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, i
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int NSTAGES>
+// SPLIT = split precision (option conv.precision = 2): activations and weights are pairs of fp16 numbers x = hi + lo (rows of 512
+// channels: hi | lo), the three significant products are three times the K chunks of the same MMA loop (the producer's chunk
+// tables), and the epilogue writes hi = fp16(y), lo = fp16(y - hi): ~21 significant bits instead of 11 at a third of the speed.
+template <int NSTAGES, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const ConvArgs a) {
   const unsigned long long trace_t0 = a.trace ? simt::gtimer() : 0ULL;
@@ -283,7 +295,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (a.l2pf && t + n_pairs < n_ptiles) {   // this pair's next tile: pull its rows (centre tap = the rows themselves) into L2 now
           const int m1 = (t + n_pairs) * 256 + (int)rank * 128;
           const int b1 = m1 / N2, rem1 = m1 - b1 * N2, j1 = rem1 / a.N, i1 = rem1 - j1 * a.N;
-          for (int kc = 0; kc < a.kchunks; ++kc) tma_prefetch_im2col(&tmA, kc * BK, i1 - 1, j1 - 1, b1, 1, 1);
+          for (int kc = 0; kc < a.kchunks; ++kc) tma_prefetch_im2col(&tmA, a.a_off[kc], i1 - 1, j1 - 1, b1, 1, 1);
         }
         for (int tap = 0; tap < 9; ++tap) {
           const uint16_t oh = (uint16_t)(tap / 3), ow = (uint16_t)(tap % 3);
@@ -292,8 +304,8 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * V3_STAGE_BYTES);
             const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
             uint8_t* sa = tiles + (size_t)stage * V3_STAGE_BYTES;
-            tma_load_im2col_2sm(sa, &tmA, lbar, kc * BK, i0 - 1, j0 - 1, b0, ow, oh);
-            tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, kc * BK, tap * 256 + (int)rank * 128);
+            tma_load_im2col_2sm(sa, &tmA, lbar, a.a_off[kc], i0 - 1, j0 - 1, b0, ow, oh);
+            tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, a.w_off[kc], tap * 256 + (int)rank * 128);
             if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -332,13 +344,14 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t aphase = (titer >> 1) & 1;
       const long long row = (long long)t * 256 + rank * 128 + q * 32 + lane;
       const bool valid = row < a.rows_valid;
-      __half* orow = a.out + row * 256;
+      constexpr int ROWC = SPLIT ? 512 : 256;   // channels per stored row
+      __half* orow = a.out + row * ROWC;
       const bool addres = a.res != nullptr && valid;
       // residual rows do not depend on the MMAs: chunks 0-1 are fetched before waiting for the accumulator and chunk
       // cc+2 while chunk cc is processed (2 register buffers; keeps the CTA small enough for tree CTAs to co-reside)
       uint4 rv[2][4];
-      const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * 256);
-      if (addres) {
+      const uint4* rrow = reinterpret_cast<const uint4*>(a.res + row * ROWC);
+      if (addres && !SPLIT) {
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2)
 #pragma unroll
@@ -357,6 +370,38 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (valid) {
           uint4 o[4];
           uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+          if (SPLIT) {
+            uint4 ol[4], rh4[4], rl4[4];
+            uint32_t* owl = reinterpret_cast<uint32_t*>(ol);
+            if (addres) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { rh4[j] = ld_nc_v4(rrow + cc * 4 + j); rl4[j] = ld_nc_v4(rrow + 32 + cc * 4 + j); }
+            }
+            const __half2* rhh = reinterpret_cast<const __half2*>(rh4);
+            const __half2* rll = reinterpret_cast<const __half2*>(rl4);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c0 = cc * 32 + 2 * j;
+              const float4 ss = *reinterpret_cast<const float4*>(s_scale + 2 * c0);
+              float y0 = fmaf(__uint_as_float(v[2 * j]), ss.x, ss.y);
+              float y1 = fmaf(__uint_as_float(v[2 * j + 1]), ss.z, ss.w);
+              if (addres) {
+                const float2 a2 = __half22float2(rhh[j]), b2 = __half22float2(rll[j]);
+                y0 += a2.x + b2.x;
+                y1 += a2.y + b2.y;
+              }
+              if (a.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+              const __half2 h = __floats2half2_rn(y0, y1);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(y0 - hf.x, y1 - hf.y);
+              ow[j] = *reinterpret_cast<const uint32_t*>(&h);
+              owl[j] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            st_global_256(orow + cc * 32, o[0], o[1]);
+            st_global_256(orow + cc * 32 + 16, o[2], o[3]);
+            st_global_256(orow + 256 + cc * 32, ol[0], ol[1]);
+            st_global_256(orow + 256 + cc * 32 + 16, ol[2], ol[3]);
+          } else {
           const __half2* rh = reinterpret_cast<const __half2*>(rv[cc & 1]);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -379,6 +424,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
           st_global_256(orow + cc * 32, o[0], o[1]);
           st_global_256(orow + cc * 32 + 16, o[2], o[3]);
+          }
         }
       }
       tc_fence_before();
@@ -396,7 +442,7 @@ conv3x3_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
-  if (a.trace && simt::trace_cta()) simt::trace_rec(a.trace, a.kchunks == 1 ? 4 : 5, trace_t0);
+  if (a.trace && simt::trace_cta()) simt::trace_rec(a.trace, a.stem ? 4 : 5, trace_t0);
 }
 
 
@@ -476,7 +522,7 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (a.l2pf && t + n_pairs < n_ptiles) {   // this pair's next tile: its rows and its shortcut rows into L2 now
           const int m1 = (t + n_pairs) * 256 + (int)rank * 128;
           const int b1 = m1 / N2, rem1 = m1 - b1 * N2, j1 = rem1 / a.N, i1 = rem1 - j1 * a.N;
-          for (int kc = 0; kc < a.kchunks; ++kc) tma_prefetch_im2col(&tmA, kc * BK, i1 - 1, j1 - 1, b1, 1, 1);
+          for (int kc = 0; kc < a.kchunks; ++kc) tma_prefetch_im2col(&tmA, a.a_off[kc], i1 - 1, j1 - 1, b1, 1, 1);
           for (int bx = 0; bx < 4; ++bx) tma_prefetch_2d(&tmR, bx * BK, res_row0 + m1);
         }
         int it = 0;
@@ -487,8 +533,8 @@ conv3x3_tc6_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * V3_STAGE_BYTES);
             const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
             uint8_t* sa = tiles + (size_t)stage * V3_STAGE_BYTES;
-            tma_load_im2col_2sm(sa, &tmA, lbar, kc * BK, i0 - 1, j0 - 1, b0, ow, oh);
-            tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, kc * BK, tap * 256 + (int)rank * 128);
+            tma_load_im2col_2sm(sa, &tmA, lbar, a.a_off[kc], i0 - 1, j0 - 1, b0, ow, oh);
+            tma_load_2d_2sm(sa + A_BYTES, &tmW, lbar, a.w_off[kc], tap * 256 + (int)rank * 128);
             if (++stage == V6_STAGES) { stage = 0; phase ^= 1; }
             if (it == iters / 2) {  // the previous tile's epilogue is long done by now: fetch this tile's shortcut rows
               mbar_wait_guard(rempty, rphase ^ 1);
@@ -619,7 +665,7 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
                                                        const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                        const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
                                                        float* __restrict__ v, int B, int N,
-                                                       unsigned long long* trace, const float4* __restrict__ pre) {
+                                                       unsigned long long* trace, const float4* __restrict__ pre, float* __restrict__ raw, int split) {
   const unsigned long long trace_t0 = trace ? simt::gtimer() : 0ULL;
   extern __shared__ float sm[];
   const int N2 = N * N, A = N2 + 1;
@@ -649,12 +695,19 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
   }
   for (int it = warp; it < nb * N2; it += 8) {
     const int pb = it / N2, p = it - pb * N2;
-    const uint4 raw = *reinterpret_cast<const uint4*>(trunk + ((size_t)(b0 + pb) * N2 + p) * 256 + lane * 8);
-    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+    const __half* trow = trunk + ((size_t)(b0 + pb) * N2 + p) * (split ? 512 : 256) + lane * 8;
+    const uint4 rawh = *reinterpret_cast<const uint4*>(trow);
+    const __half2* h = reinterpret_cast<const __half2*>(&rawh);
+    uint4 rawl = make_uint4(0u, 0u, 0u, 0u);
+    if (split) rawl = *reinterpret_cast<const uint4*>(trow + 256);   // split precision: trunk value = hi + lo
+    const __half2* hl = reinterpret_cast<const __half2*>(&rawl);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float2 x = __half22float2(h[j]);
+      const float2 xl = __half22float2(hl[j]);
+      x.x += xl.x;
+      x.y += xl.y;
       a0 = fmaf(wv[2 * j], x.x, a0); a0 = fmaf(wv[2 * j + 1], x.y, a0);
       a1 = fmaf(wp0[2 * j], x.x, a1); a1 = fmaf(wp0[2 * j + 1], x.y, a1);
       a2 = fmaf(wp1[2 * j], x.x, a2); a2 = fmaf(wp1[2 * j + 1], x.y, a2);
@@ -693,7 +746,10 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
     for (int o = lane; o < 256; o += 32) acc = fmaf(D2W[o], hid[warp * 256 + o], acc);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) v[b0 + warp] = tanhf(acc + D2b[0]);
+    if (lane == 0) {
+      v[b0 + warp] = tanhf(acc + D2b[0]);
+      if (raw) raw[(size_t)(b0 + warp) * (A + 1) + A] = acc + D2b[0];   // debug: the value before tanh
+    }
   }
   // Dense(2*N2 -> A).  Small boards (A <= 128): the K range is split over S = 256 / A thread groups so that all 256
   // threads stream weights (partials are summed through shared memory in a fixed order); otherwise thread a, a + 256.
@@ -751,6 +807,8 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
     for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     float* out = pi + (size_t)(b0 + warp) * A;
     for (int a0i = lane; a0i < A; a0i += 32) out[a0i] = expf(l[a0i] - mx) / sum;
+    if (raw)   // debug: the logits before softmax
+      for (int a0i = lane; a0i < A; a0i += 32) raw[(size_t)(b0 + warp) * (A + 1) + a0i] = l[a0i];
   }
   if (trace) {
     __syncthreads();
@@ -910,7 +968,10 @@ int nn_tc_create(NNet* n, char* err, size_t errlen) {
   t->pdl = 1;
   t->max_pairs = 0;
   t->res_tma = 1;
+  t->split = 0;
+  t->split_weights_ready = false;
   for (int i = 0; i < 3; ++i) t->act[i] = nullptr;
+  for (int i = 0; i < 3; ++i) t->sact[i] = nullptr;
   if (n->C != 256) {
     snprintf(err, errlen, "the tensor-core path is built for 256 filters");
     return 1;
@@ -968,6 +1029,26 @@ int nn_tc_set_option(NNet* n, const char* key, long long value) {
   else if (!strcmp(key, "conv.pdl")) t->pdl = value != 0;
   else if (!strcmp(key, "conv.max_pairs")) { if (value < 0) return 2; t->max_pairs = (int)value; }
   else if (!strcmp(key, "conv.res_tma")) t->res_tma = value != 0;
+  else if (!strcmp(key, "conv.precision")) {
+    if (value != 1 && value != 2) return 2;
+    if (value == 2 && !t->sact[0]) {   // split precision: its own activation buffers and weight arrays, allocated on first use
+      const int nconv = 1 + 2 * t->T;
+      bool ok = true;
+      for (int i = 0; i < 3 && ok; ++i) ok = cudaMalloc((void**)&t->sact[i], (size_t)t->rows_alloc * 512 * 2) == cudaSuccess;
+      t->sw.assign(nconv, nullptr);
+      t->tm_sw.resize(nconv);
+      for (int l = 0; l < nconv && ok; ++l) ok = cudaMalloc((void**)&t->sw[l], (size_t)9 * 256 * 2 * (l == 0 ? CIN0 : 256) * 2) == cudaSuccess;
+      if (!ok) return 2;
+      for (int i = 0; i < 3; ++i) cudaMemset(t->sact[i], 0, (size_t)t->rows_alloc * 512 * 2);
+      int rc = 0;
+      const long long boards = t->rows_alloc / t->PP;
+      for (int i = 0; i < 3 && !rc; ++i) rc = make_map_im2col(&t->tm5_sact[i], t->sact[i], t->N, boards, 512);
+      for (int l = 0; l < nconv && !rc; ++l) rc = make_map(&t->tm_sw[l], t->sw[l], 9 * 256, 2 * (l == 0 ? CIN0 : 256), 128);
+      if (rc) return 2;
+      t->split_weights_ready = false;
+    }
+    t->split = value == 2;
+  }
   else return 1;
   return 0;
 }
@@ -980,6 +1061,7 @@ int nn_tc_get_option(const NNet* n, const char* key, long long* value) {
   else if (!strcmp(key, "conv.pdl")) *value = t->pdl;
   else if (!strcmp(key, "conv.max_pairs")) *value = t->max_pairs;
   else if (!strcmp(key, "conv.res_tma")) *value = t->res_tma;
+  else if (!strcmp(key, "conv.precision")) *value = t->split ? 2 : 1;
   else return 1;
   return 0;
 }
@@ -991,7 +1073,9 @@ void nn_tc_destroy(NNet* n) {
   cudaFree(t->head_pre);
   cudaFree(t->stage);
   for (int i = 0; i < 3; ++i) cudaFree(t->act[i]);
+  for (int i = 0; i < 3; ++i) cudaFree(t->sact[i]);
   for (auto p : t->w) cudaFree(p);
+  for (auto p : t->sw) cudaFree(p);
   delete t;
   n->tc = nullptr;
 }
@@ -1012,6 +1096,41 @@ __global__ void reorder_weights_kernel(const float* __restrict__ flux, __half* _
   }
 }
 
+// split precision: Wt[tap][co][0..cin_pad) = fp16(w), Wt[tap][co][cin_pad..2*cin_pad) = fp16(w - hi)
+__global__ void reorder_weights_split_kernel(const float* __restrict__ flux, __half* __restrict__ out, int cin, int cin_pad) {
+  const size_t total = (size_t)9 * 256 * cin_pad;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(idx % cin_pad);
+    const int co = (int)((idx / cin_pad) % 256);
+    const int tap = (int)(idx / ((size_t)cin_pad * 256));
+    const int kj = tap / 3, ki = tap % 3;
+    float w = 0.f;
+    if (ci < cin) w = flux[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)cin * co];
+    const __half hi = __float2half(w);
+    const size_t o = ((size_t)tap * 256 + co) * (2 * (size_t)cin_pad);
+    out[o + ci] = hi;
+    out[o + cin_pad + ci] = __float2half(w - __half2float(hi));
+  }
+}
+
+// conv weights of both precisions from the fp32 base-chain parameter list on the device
+static void reorder_all(NNet* n, const float* d_base, cudaStream_t s) {
+  TCState* t = (TCState*)n->tc;
+  const size_t C = 256, P = (size_t)n->s.planes;
+  const int nconv = 1 + 2 * n->s.tower;
+  size_t off = 0;
+  for (int l = 0; l < nconv; ++l) {
+    const int cin = l == 0 ? (int)P : 256, cin_pad = l == 0 ? CIN0 : 256;
+    reorder_weights_kernel<<<296, 256, 0, s>>>(d_base + off, t->w[l], cin, cin_pad);
+    if (t->sact[0]) reorder_weights_split_kernel<<<296, 256, 0, s>>>(d_base + off, t->sw[l], cin, cin_pad);
+    // next conv weight inside the Flux list: stem = W,b,beta,gamma; block = W1,b1,W2,b2,beta1,gamma1,beta2,gamma2
+    if (l == 0) off += 9 * P * C + 3 * C;
+    else if (l % 2 == 1) off += 9 * C * C + C;          // W1, b1 -> W2
+    else off += 9 * C * C + C + 4 * C;                   // W2, b2, beta1, gamma1, beta2, gamma2 -> next block
+  }
+  t->split_weights_ready = t->sact[0] != nullptr;
+}
+
 int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t s, char* err, size_t errlen) {
   TCState* t = (TCState*)n->tc;
   // raw base-chain parameters (Flux order) go up in one transfer; conv weights are located inside it
@@ -1023,16 +1142,8 @@ int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t 
     t->stage_cap = nbase;
   }
   cudaMemcpyAsync(t->stage, n->hparams[0].data(), nbase * sizeof(float), cudaMemcpyHostToDevice, s);
-  const size_t C = 256, P = (size_t)n->s.planes;
-  size_t off = 0;
-  for (size_t l = 0; l < convs.size(); ++l) {
-    const int cin = l == 0 ? (int)P : 256, cin_pad = l == 0 ? CIN0 : 256;
-    reorder_weights_kernel<<<296, 256, 0, s>>>(t->stage + off, t->w[l], cin, cin_pad);
-    // next conv weight inside the Flux list: stem = W,b,beta,gamma; block = W1,b1,W2,b2,beta1,gamma1,beta2,gamma2
-    if (l == 0) off += 9 * P * C + 3 * C;
-    else if (l % 2 == 1) off += 9 * C * C + C;          // W1, b1 -> W2
-    else off += 9 * C * C + C + 4 * C;                   // W2, b2, beta1, gamma1, beta2, gamma2 -> next block
-  }
+  (void)convs;
+  reorder_all(n, t->stage, s);
   if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
     snprintf(err, errlen, "uploading / reordering the conv weights failed");
     return 1;
@@ -1043,16 +1154,17 @@ int nn_tc_commit(NNet* n, const std::vector<ConvLayerHost>& convs, cudaStream_t 
 // the same reorder with the fp32 base-chain parameters already on the device (training master copy, train.cu train_publish)
 int nn_tc_commit_device(NNet* n, const float* d_base, cudaStream_t s, char* err, size_t errlen) {
   TCState* t = (TCState*)n->tc;
-  const size_t C = 256, P = (size_t)n->s.planes;
-  const int nconv = 1 + 2 * n->s.tower;
-  size_t off = 0;
-  for (int l = 0; l < nconv; ++l) {
-    const int cin = l == 0 ? (int)P : 256, cin_pad = l == 0 ? CIN0 : 256;
-    reorder_weights_kernel<<<296, 256, 0, s>>>(d_base + off, t->w[l], cin, cin_pad);
-    if (l == 0) off += 9 * P * C + 3 * C;
-    else if (l % 2 == 1) off += 9 * C * C + C;
-    else off += 9 * C * C + C + 4 * C;
+  // keep the staging copy current too: a later switch to split precision re-reads the weights from it
+  const size_t nbase = nn_param_count(n, 0);
+  if (t->stage_cap < nbase) {
+    cudaFree(t->stage);
+    t->stage = nullptr;
+    t->stage_cap = 0;
+    if (cudaMalloc((void**)&t->stage, nbase * sizeof(float)) != cudaSuccess) { snprintf(err, errlen, "staging buffer allocation failed"); return 1; }
+    t->stage_cap = nbase;
   }
+  cudaMemcpyAsync(t->stage, d_base, nbase * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  reorder_all(n, t->stage, s);
   if (cudaGetLastError() != cudaSuccess) { snprintf(err, errlen, "reordering the conv weights failed"); return 1; }
   return 0;
 }
@@ -1061,12 +1173,28 @@ long long nn_tc_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower 
 
 static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& tmW, const float* scale, const float* shift, const __half* res,
                         __half* out, int B, int kchunks, cudaStream_t s, const CUtensorMap* res_map = nullptr, int res_row0 = 0, bool pdl = false,
-                        const NNet* heads_of = nullptr /* fuse this network's head 1x1 convs into the epilogue */) {
+                        const NNet* heads_of = nullptr /* fuse this network's head 1x1 convs into the epilogue */, bool split = false) {
   ConvArgs a;
   a.scale = scale; a.shift = shift; a.res = res; a.out = out;
   a.rows_valid = (long long)B * t->PP;
   a.n_tiles = (int)((a.rows_valid + BM - 1) / BM);
-  a.kchunks = kchunks;
+  a.stem = kchunks == 1;
+  const int cin = kchunks * BK;   // channels per precision half
+  if (!split) {
+    a.kchunks = kchunks;
+    for (int k = 0; k < kchunks; ++k) { a.a_off[k] = (int16_t)(k * BK); a.w_off[k] = (int16_t)(k * BK); }
+  } else if (a.stem) {            // the stem's input planes are exact in fp16: x * w_hi + x * w_lo
+    a.kchunks = 2;
+    a.a_off[0] = 0; a.w_off[0] = 0;
+    a.a_off[1] = 0; a.w_off[1] = (int16_t)cin;
+  } else {                        // x_hi * w_hi + x_lo * w_hi + x_hi * w_lo (the lo * lo term is below fp32 resolution)
+    a.kchunks = 3 * kchunks;
+    for (int k = 0; k < kchunks; ++k) {
+      a.a_off[k] = (int16_t)(k * BK);                      a.w_off[k] = (int16_t)(k * BK);
+      a.a_off[kchunks + k] = (int16_t)(cin + k * BK);      a.w_off[kchunks + k] = (int16_t)(k * BK);
+      a.a_off[2 * kchunks + k] = (int16_t)(k * BK);        a.w_off[2 * kchunks + k] = (int16_t)(cin + k * BK);
+    }
+  }
   a.N = t->N; a.PP = t->PP;
   a.relu = 1;
   a.trace = t->trace;
@@ -1094,21 +1222,37 @@ static int launch_conv5(TCState* t, const CUtensorMap& tmA, const CUtensorMap& t
   lc.attrs = at;
   lc.numAttrs = (pdl && t->pdl) ? 1 : 0;
   cudaError_t rc;
-  if (res_map && t->res_tma) {
+  if (split) {
+    lc.dynamicSmemBytes = CONV3_SMEM;
+    if (a.stem) rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel<4, true>, tmA, tmW, a);
+    else rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel<6, true>, tmA, tmW, a);
+  } else if (res_map && t->res_tma) {
     lc.dynamicSmemBytes = CONV6_SMEM;
     if (a.head_vw) rc = cudaLaunchKernelEx(&lc, conv3x3_tc6_kernel<true>, tmA, tmW, *res_map, a, res_row0);
     else rc = cudaLaunchKernelEx(&lc, conv3x3_tc6_kernel<false>, tmA, tmW, *res_map, a, res_row0);
   } else {
     lc.dynamicSmemBytes = CONV3_SMEM;
     // the stem (one K chunk per tap, bound by its epilogue) measures 9 % faster with 4 operand stages, the tower convs 1 % slower
-    if (t->conv5_stages == 4 || kchunks == 1) rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel<4>, tmA, tmW, a);
-    else rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel<6>, tmA, tmW, a);
+    if (t->conv5_stages == 4 || kchunks == 1) rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel<4, false>, tmA, tmW, a);
+    else rc = cudaLaunchKernelEx(&lc, conv3x3_tc5_kernel<6, false>, tmA, tmW, a);
   }
   return rc != cudaSuccess ? (int)rc : (int)cudaGetLastError();
 }
 
+// debug: trunk rows fp16 [b*N2 + p][256] -> reference layout fp32 [b][c][p]
+__global__ void trunk_to_f32_kernel(const __half* __restrict__ act, float* __restrict__ out, int B, int N2, int split) {
+  const size_t total = (size_t)B * N2 * 256;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % 256);
+    const size_t row = idx / 256;
+    const int p = (int)(row % N2), b = (int)(row / N2);
+    const float x = split ? __half2float(act[row * 512 + c]) + __half2float(act[row * 512 + 256 + c]) : __half2float(act[idx]);
+    out[((size_t)b * 256 + c) * N2 + p] = x;
+  }
+}
+
 int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err, size_t errlen, cudaEvent_t* ev, int group, cudaEvent_t convs_done,
-                  cudaStream_t heads_stream) {
+                  cudaStream_t heads_stream, const NNDebug* dbg) {
   TCState* t = (TCState*)n->tc;
   if (group >= 0 && (t->groups != 2 || group > 1 || B > t->max_batch / 2)) { snprintf(err, errlen, "bad group"); return 1; }
   const size_t roff = group > 0 ? (size_t)t->grp_rows : 0;   // row offset of this group inside the shared buffers
@@ -1116,21 +1260,33 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   if (!t->attr_set) {
     cudaError_t rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(heads_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heads_smem(n->N2, n->A));
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
-    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
+    if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc5_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV3_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
     if (rc == cudaSuccess) rc = cudaFuncSetAttribute(conv3x3_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV6_SMEM);
     if (rc != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute: %s", cudaGetErrorString(rc)); return 1; }
     t->attr_set = true;
   }
   if (ev) cudaEventRecord(ev[0], s);
-  const bool fuse = t->fuse_heads && t->res_tma && t->T >= 1;
+  const int n_blocks = (dbg && dbg->n_blocks >= 0 && dbg->n_blocks < t->T) ? dbg->n_blocks : t->T;   // debug: stop after n_blocks blocks
+  const bool split = t->split != 0;
+  if (split && group >= 0) { snprintf(err, errlen, "split precision does not run half batches"); return 1; }
+  if (split && !t->split_weights_ready) {   // the option was switched on after the last commit: build the hi / lo weights now
+    if (!t->stage || t->stage_cap < nn_param_count(n, 0)) { snprintf(err, errlen, "split precision: no parameters committed yet"); return 1; }
+    reorder_all(n, t->stage, s);
+  }
+  const bool fuse = !split && t->fuse_heads && t->res_tma && t->T >= 1 && !(dbg && dbg->trunk) && n_blocks == t->T;
   auto conv = [&](int in_buf /* -1 = stem input */, int layer, int res_buf, int out_buf) {
     const bool pdl = in_buf >= 0;   // tower convolutions directly follow another convolution on the same stream
     const NNet* hf = (fuse && layer == 2 * t->T) ? n : nullptr;   // the last convolution feeds the heads directly
     const int kch = in_buf < 0 ? CIN0 / BK : 4;
     const __half* res = res_buf >= 0 ? t->act[res_buf] + roff * 256 : nullptr;
     const CUtensorMap* rmap = res_buf >= 0 ? &t->tm_act[res_buf] : nullptr;   // plain 2-D map (128 rows x 64 ch boxes) over the shortcut buffer
+    if (split)
+      return launch_conv5(t, in_buf < 0 ? t->tm5_in64 : t->tm5_sact[in_buf], t->tm_sw[layer], n->f_scale[layer], n->f_shift[layer],
+                          res_buf >= 0 ? t->sact[res_buf] : nullptr, t->sact[out_buf], B, kch, s, nullptr, 0, pdl, nullptr, true);
     if (group >= 0)
       return launch_conv5(t, in_buf < 0 ? t->tm5g_in64[group] : t->tm5g_act[group][in_buf], t->tm_w[layer], n->f_scale[layer], n->f_shift[layer], res,
                           t->act[out_buf] + roff * 256, B, kch, s, rmap, (int)roff, pdl, hf);
@@ -1140,7 +1296,7 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   int rc = conv(-1, 0, -1, 0);
   if (ev) cudaEventRecord(ev[1], s);
   int h = 0, t1 = 1, t2 = 2;
-  for (int blk = 0; blk < t->T && !rc; ++blk) {
+  for (int blk = 0; blk < n_blocks && !rc; ++blk) {
     rc = conv(h, 1 + 2 * blk, -1, t1);
     if (!rc) rc = conv(t1, 2 + 2 * blk, h, t2);
     int tmp = h; h = t2; t2 = tmp;
@@ -1152,9 +1308,11 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
     cudaStreamWaitEvent(heads_stream, convs_done, 0);
     s = heads_stream;
   }
+  if (dbg && dbg->trunk) trunk_to_f32_kernel<<<592, 256, 0, s>>>(split ? t->sact[h] : t->act[h] + roff * 256, dbg->trunk, B, n->N2, split ? 1 : 0);
+  if (n_blocks < t->T) return cudaGetLastError() == cudaSuccess ? 0 : 1;   // debug: a truncated tower has no heads
   const size_t hsm = heads_smem(n->N2, n->A);
-  heads_tc_kernel<<<(B + HPB - 1) / HPB, 256, hsm, s>>>(t->act[h] + roff * 256, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW,
-                                                        n->f_Pb, pi, v, B, t->N, t->trace, fuse ? t->head_pre + roff : nullptr);
+  heads_tc_kernel<<<(B + HPB - 1) / HPB, 256, hsm, s>>>(split ? t->sact[h] : t->act[h] + roff * 256, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW,
+                                                        n->f_Pb, pi, v, B, t->N, t->trace, fuse ? t->head_pre + roff : nullptr, dbg ? dbg->raw : nullptr, split ? 1 : 0);
   if (ev) cudaEventRecord(ev[3], s);
   cudaError_t e2 = cudaGetLastError();
   if (e2 != cudaSuccess) { snprintf(err, errlen, "heads launch: %s", cudaGetErrorString(e2)); return 1; }

@@ -147,6 +147,10 @@ int32_t agz_version(void);
  *   schedule.pipeline (0)        two half batches on separate streams (tree kernels of one under the network of the other)
  *   replay.capacity (500000)     memory_size of src/train.jl:38; must be set before the replay ring exists
  *   trace.records (0)            kernel timeline trace capacity (agz_trace_read); can be set once
+ *   conv.precision (1)           arithmetic of the tensor-core network: 1 = fp16 operands, fp32 accumulation (11 significant bits per
+ *                                operand; within 1e-3 of fp32 on the shipped / random-init networks, ~5e-3 on sharp trained-like ones at
+ *                                tower_height 19, profiles/r02_nn_error_vs_depth.jsonl); 2 = split precision, every activation and weight
+ *                                a pair of fp16 numbers (hi + lo, three MMA passes): fp32-like accuracy at a third of the throughput
  *   conv.fuse_heads (1), conv.stages (6), conv.l2_prefetch (0), conv.pdl (1), conv.max_pairs (0 = all), conv.res_tma (1)
  *                                experiment knobs of the tensor-core convolution (alphago.jl_b200/csrc/nn_tc.cu)
  * Unknown keys and bad values return AGZ_ERR_ARG. */
@@ -165,6 +169,12 @@ size_t agz_net_bn_count(agz_engine* e, int32_t chain);
 /* (nn::NeuralNet)(positions) (src/neural_net.jl:57-68): boards_hist is B x 8 x N*N int8 (board k moves ago,
  * flat order), to_play is B int8.  pi is A x B column-major (pi[a + A*b]), v is B.  `evaluator` picks the path. */
 int32_t agz_net_forward(agz_engine* e, int32_t evaluator, const int8_t* boards_hist, const int8_t* to_play, int32_t B, float* pi, float* v);
+/* Test hook of the network parity tests: the same forward for at most n_games * max_parallel positions with its intermediate values.
+ * n_blocks < 0 or >= tower_height: the whole network -- pi (A x B), v (B), logits (A x B, before softmax), v_pre (B, before tanh) and
+ * trunk (the tower output, 256 x N*N per position in the reference's W x H x C x B order).  0 <= n_blocks < tower_height: only `trunk`
+ * after the stem and n_blocks residual blocks is produced (bisecting a deviation to a block).  Any output pointer may be NULL. */
+int32_t agz_net_forward_debug(agz_engine* e, int32_t evaluator, const int8_t* boards_hist, const int8_t* to_play, int32_t B, int32_t n_blocks,
+                              float* pi, float* v, float* logits, float* v_pre, float* trunk);
 /* get_feats (src/features.jl:24-26): out is N x N x 17 x B column-major (row fastest), values in {-1,0,1}. */
 int32_t agz_features(agz_engine* e, const int8_t* boards_hist, const int8_t* to_play, int32_t B, float* out);
 

@@ -90,6 +90,49 @@ class NeuralNet:
             bn.mu = (0.1 * rs.randn(C)).astype(np.float32)
             bn.sigma = (0.5 + rs.random_sample(C)).astype(np.float32)
 
+    def sharpen(self, seed=1, policy_gain=6.0, bias_scale=0.05):
+        """Trained-like statistics for parity tests: non-zero conv / dense biases and a policy head whose logits spread over tens of
+        units (a Glorot-init net gives a near-uniform policy, under which wrong arithmetic can hide)."""
+        rs = np.random.RandomState(seed)
+        self.stem_b = (bias_scale * rs.randn(self.C)).astype(np.float32)
+        for b in self.blocks:
+            b["b1"] = (bias_scale * rs.randn(self.C)).astype(np.float32)
+            b["b2"] = (bias_scale * rs.randn(self.C)).astype(np.float32)
+        self.v_b = (bias_scale * rs.randn(1)).astype(np.float32)
+        self.p_b = (bias_scale * rs.randn(2)).astype(np.float32)
+        self.v_D1b = (bias_scale * rs.randn(256)).astype(np.float32)
+        self.v_D2b = (bias_scale * rs.randn(1)).astype(np.float32)
+        self.p_Db = (bias_scale * rs.randn(self.p_Db.shape[0])).astype(np.float32)
+        self.p_DW = (self.p_DW * np.float32(policy_gain)).astype(np.float32)
+        self.v_D2W = (self.v_D2W * np.float32(2.0)).astype(np.float32)
+
+    def calibrate_bn(self, x, seed=1, jitter=0.1):
+        """Set every BatchNorm's running statistics to the statistics of its own input over the batch x (what training's moving
+        averages converge to), times a (1 +- jitter) perturbation, with random gamma / beta: activations stay O(1) at every depth, as
+        in a trained network, instead of growing block by block."""
+        rs = np.random.RandomState(seed)
+        t = torch.from_numpy
+
+        def fit(bn, z):
+            C = z.shape[1]
+            mu = z.mean(dim=(0, 2, 3)).numpy()
+            var = z.var(dim=(0, 2, 3), unbiased=False).numpy()
+            bn.mode = BN_VAR_EPS
+            bn.mu = (mu * (1 + jitter * rs.randn(C))).astype(np.float32)
+            bn.sigma = (np.maximum(var, 1e-4) * (1 + jitter * rs.rand(C))).astype(np.float32)
+            bn.gamma = (1 + 0.2 * rs.randn(C)).astype(np.float32)
+            bn.beta = (0.2 * rs.randn(C)).astype(np.float32)
+            return bn(z)
+
+        with torch.no_grad():
+            h = F.relu(fit(self.stem_bn, F.conv2d(x, flux_conv_to_torch(self.stem_W), t(self.stem_b), padding=1)))
+            for b in self.blocks:
+                y = F.relu(fit(b["bn1"], F.conv2d(h, flux_conv_to_torch(b["W1"]), t(b["b1"]), padding=1)))
+                y = fit(b["bn2"], F.conv2d(y, flux_conv_to_torch(b["W2"]), t(b["b2"]), padding=1))
+                h = F.relu(y + h)
+            fit(self.v_bn, F.conv2d(h, flux_conv_to_torch(self.v_W), t(self.v_b)))
+            fit(self.p_bn, F.conv2d(h, flux_conv_to_torch(self.p_W), t(self.p_b)))
+
     def all_bns(self):
         out = [self.stem_bn]
         for b in self.blocks:
@@ -144,6 +187,29 @@ class NeuralNet:
             p = p.reshape(B, -1)
             p = torch.softmax(p @ t(self.p_DW).T + t(self.p_Db), dim=1)   # :30
             return p.numpy().T.copy(), v.numpy()[:, 0].copy()
+
+    def forward_debug(self, x):
+        """forward_feats with the intermediate values: trunk after the stem and after every block (list of (B, C, N*N) arrays in
+        the reference's W x H x C order, p = N*j + i), logits (B, A) before softmax, v_pre (B,) before tanh, pi (B, A), v (B,)."""
+        with torch.no_grad():
+            t = torch.from_numpy
+            B = x.shape[0]
+            flat = lambda h: h.reshape(B, self.C, -1).numpy().copy()     # [b, c, j, i] row-major = p = N*j + i
+            h = F.conv2d(x, flux_conv_to_torch(self.stem_W), t(self.stem_b), padding=1)
+            h = F.relu(self.stem_bn(h))
+            trunks = [flat(h)]
+            for b in self.blocks:
+                y = F.relu(b["bn1"](F.conv2d(h, flux_conv_to_torch(b["W1"]), t(b["b1"]), padding=1)))
+                y = b["bn2"](F.conv2d(y, flux_conv_to_torch(b["W2"]), t(b["b2"]), padding=1))
+                h = F.relu(y + h)
+                trunks.append(flat(h))
+            v = F.relu(self.v_bn(F.conv2d(h, flux_conv_to_torch(self.v_W), t(self.v_b)))).reshape(B, -1)
+            v = F.relu(v @ t(self.v_D1W).T + t(self.v_D1b))
+            v_pre = (v @ t(self.v_D2W).T + t(self.v_D2b))[:, 0]
+            p = F.relu(self.p_bn(F.conv2d(h, flux_conv_to_torch(self.p_W), t(self.p_b)))).reshape(B, -1)
+            logits = p @ t(self.p_DW).T + t(self.p_Db)
+            return {"trunks": trunks, "logits": logits.numpy().copy(), "v_pre": v_pre.numpy().copy(),
+                    "pi": torch.softmax(logits, dim=1).numpy().copy(), "v": torch.tanh(v_pre).numpy().copy()}
 
     @staticmethod
     def feats_to_torch(positions):

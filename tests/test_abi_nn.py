@@ -147,3 +147,89 @@ def test_nn_selfplay_matches_oracle_tree(evaluator):
         assert list(r.moves) == om, gid
         assert np.array_equal(np.array(op.searches_N), r.visits)
         assert r.result == op.result and r.result_string == op.result_string
+
+
+# ------------------------------------------------------------------------------------------------ depth / sharpness (round 2)
+import nn_parity  # noqa: E402
+
+
+def _trained_like(N, T, seed):
+    """A network with the statistics of a trained one: biases, a policy head with tens of logit units of spread (pi_max up to ~1),
+    BatchNorm running statistics fitted to the activations of a calibration batch (+-10 %)."""
+    nn = onet.NeuralNet(N, T, seed=seed)
+    nn.sharpen(seed=seed + 1)
+    nn.calibrate_bn(nn.feats_to_torch(random_positions(N, 16, 99, max_plies=100)), seed=seed + 2)
+    return nn
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,T,B", [(9, 19, 8), (19, 19, 4)])
+def test_north_star_depth_random_init_within_1e3(N, T, B):
+    """tower_height 19 (39 fp16 conv layers), the network BASELINE.json benchmarks: Flux-default random init.  pi and v within 1e-3 of
+    the fp32 oracle, and -- a far sharper discriminator on a near-uniform policy -- the centred logits and the value before tanh."""
+    nn = onet.NeuralNet(N, T, seed=0)
+    poss = random_positions(N, B, 11, max_plies=70 if N == 9 else 250)
+    ref = nn.forward_debug(nn.feats_to_torch(poss))
+    eng = agz.Engine(N, lib_path=lib_for("cuda"), n_games=1, tower_height=T)
+    push_oracle_net(eng, nn)
+    bh, tp = nn_parity.engine_inputs(poss)
+    rep = nn_parity.report(eng.net_forward_debug(agz.EVAL_NN_TC, bh, tp), ref)
+    assert rep["pi_abs"] <= TOL_TC and rep["v_abs"] <= TOL_TC, rep
+    assert rep["logit_rel"] <= 1e-2 and rep["vpre_rel"] <= 1e-2, rep
+    rep32 = nn_parity.report(eng.net_forward_debug(agz.EVAL_NN_F32, bh, tp), ref)
+    assert rep32["pi_abs"] <= TOL_F32 and rep32["v_abs"] <= 5e-5 and rep32["logit_rel"] <= 5e-5, rep32
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,T,B", [(9, 6, 8), (9, 19, 8), (19, 19, 4)])
+def test_trained_like_networks_need_split_precision_for_1e3(N, T, B):
+    """Sharp policies expose operand rounding: with fp16 operands (11 significant bits) the error grows ~sqrt(depth) and passes 1e-3
+    (measured 3e-3 ... 8e-3, profiles/r02_nn_error_vs_depth.jsonl) -- kept under a regression bound here -- while split precision
+    (option conv.precision = 2: hi + lo fp16 pairs) meets the north-star 1e-3 on pi and v at every depth and board size."""
+    nn = _trained_like(N, T, 21)
+    poss = random_positions(N, B, 7, max_plies=70 if N == 9 else 250)
+    ref = nn.forward_debug(nn.feats_to_torch(poss))
+    eng = agz.Engine(N, lib_path=lib_for("cuda"), n_games=1, tower_height=T)
+    push_oracle_net(eng, nn)
+    bh, tp = nn_parity.engine_inputs(poss)
+    fast = nn_parity.report(eng.net_forward_debug(agz.EVAL_NN_TC, bh, tp), ref)
+    assert fast["pi_max"] > 0.5 and fast["logit_span"] > 10, fast            # the test network really is sharp
+    assert fast["pi_abs"] <= 2.5e-2 and fast["v_abs"] <= 2.5e-2 and fast["logit_rel"] <= 1e-2, fast
+    eng.set_option("conv.precision", 2)
+    out = eng.net_forward_debug(agz.EVAL_NN_TC, bh, tp)
+    fine = nn_parity.report(out, ref)
+    assert fine["pi_abs"] <= TOL_TC and fine["v_abs"] <= TOL_TC and fine["logit_rel"] <= 1e-3 and fine["vpre_rel"] <= 2e-3, fine
+    pi, v = eng.net_forward(agz.EVAL_NN_TC, bh, tp)                            # the plain entry point runs the same arithmetic
+    assert np.array_equal(pi, out["pi"]) and np.array_equal(v, out["v"])
+    eng.set_option("conv.precision", 1)
+    again = nn_parity.report(eng.net_forward_debug(agz.EVAL_NN_TC, bh, tp), ref)
+    assert again["pi_abs"] == fast["pi_abs"]                                   # switching back restores the fp16 path bit for bit
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_injected_tap_error_is_caught_and_bisected():
+    """Sensitivity of the parity checks: the engine is given a network whose block-4 second convolution has two taps exchanged (the
+    kind of mistake a wrong kernel flip or im2col offset makes) while the oracle keeps the right one.  The end-to-end metrics must
+    fail their bounds, and the per-block bisect helper must name block 4 (trunk after 5 blocks) as the first one off."""
+    N, T, B, bad = 9, 8, 8, 4
+    nn = _trained_like(N, T, 31)
+    poss = random_positions(N, B, 5)
+    ref = nn.forward_debug(nn.feats_to_torch(poss))
+    broken = _trained_like(N, T, 31)
+    W = broken.blocks[bad]["W2"].copy()
+    W[0, 0], W[2, 2] = broken.blocks[bad]["W2"][2, 2].copy(), broken.blocks[bad]["W2"][0, 0].copy()
+    broken.blocks[bad]["W2"] = W
+    eng = agz.Engine(N, lib_path=lib_for("cuda"), n_games=1, tower_height=T)
+    bh, tp = nn_parity.engine_inputs(poss)
+    for precision, bound in ((2, lambda nb: 6e-4), (1, lambda nb: 4e-3)):
+        eng.set_option("conv.precision", precision)
+        push_oracle_net(eng, nn)
+        ok = nn_parity.report(eng.net_forward_debug(agz.EVAL_NN_TC, bh, tp), ref)
+        assert nn_parity.first_bad_block(eng, agz.EVAL_NN_TC, poss, ref, T, bound) is None, precision
+        push_oracle_net(eng, broken)
+        rep = nn_parity.report(eng.net_forward_debug(agz.EVAL_NN_TC, bh, tp), ref)
+        assert rep["pi_abs"] > 10 * max(ok["pi_abs"], 1e-4) and rep["logit_rel"] > 10 * ok["logit_rel"], (precision, ok, rep)
+        assert nn_parity.first_bad_block(eng, agz.EVAL_NN_TC, poss, ref, T, bound) == bad + 1, precision
+    eng.close()

@@ -144,16 +144,18 @@ def _ring_engine(seed_net):
 
 def test_train_step_from_replay_equals_sample_then_step():
     """agz_train_step_from_replay (draw, feature planes, step and hand-over on the device) = agz_replay_sample_hist +
-    agz_train_step through host buffers: same loss, bit-identical parameters and running statistics after two steps."""
+    agz_train_step through host buffers: same loss, bit-identical parameters and running statistics after two steps.  (The host-path
+    engine has no ring of its own: the order in which concurrently finishing games enter a ring is not deterministic, so it trains
+    on the batches read back from the device-path engine's ring.)"""
     lib_for("cuda")
-    _, _, dev, total = _ring_engine(7)
-    _, _, host, total_h = _ring_engine(7)
-    assert total == total_h
+    env, nn, dev, total = _ring_engine(7)
+    host = agz.Engine(5, n_games=8, readouts=16, tower_height=1, evaluator=agz.EVAL_NN_TC, seed=4)
+    nn.push(host)
     for step in range(2):
+        bh, tp, pis, zs, idx = dev.replay_sample_hist(16, seed=100 + step)      # the draw the device step is about to make
         loss_d = dev.train_step_from_replay(16, seed=100 + step)
-        bh, tp, pis, zs, idx = host.replay_sample_hist(16, seed=100 + step)
         loss_h = host.train_step(bh, tp, pis, zs)
-        assert loss_d == loss_h, (step, loss_d, loss_h)
+        assert abs(loss_d - loss_h) <= 2e-6 * abs(loss_h), (step, loss_d, loss_h)   # the loss terms are summed with float atomics
     for k in range(3):
         assert np.array_equal(dev.net_get_params(k), host.net_get_params(k)), k
         assert all(np.array_equal(a, b) for a, b in zip(dev.net_get_bn_stats(k)[:2], host.net_get_bn_stats(k)[:2])), k
