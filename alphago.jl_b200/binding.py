@@ -58,7 +58,7 @@ class GameHeader(C.Structure):
 class Progress(C.Structure):
     _fields_ = [("moves_played", C.c_int64), ("games_finished", C.c_int64), ("games_started", C.c_int64),
                 ("positions_evaluated", C.c_int64), ("readouts", C.c_int64), ("path_nodes", C.c_int64),
-                ("games_live", C.c_int32), ("error", C.c_int32), ("step_ms", C.c_float), ("reserved", C.c_int32)]
+                ("games_live", C.c_int32), ("error", C.c_int32), ("step_ms", C.c_float), ("arena_prunes", C.c_int32)]
 
 
 # every symbol include/agz.h declares (the CPU test-suite checks the built library exports all of them)
@@ -75,7 +75,7 @@ SYMBOLS = [
     "agz_kernel_launches", "agz_phase_times", "agz_set_timing", "agz_net_flops", "agz_trace_read", "agz_engine_info",
     "agz_match_start", "agz_match_search", "agz_match_play",
     "agz_replay_sample_hist", "agz_train_step", "agz_train_read_grads", "agz_net_get_params", "agz_net_get_bn_stats",
-    "agz_set_option", "agz_get_option", "agz_replay_info", "agz_selftest_division", "agz_train_step_from_replay", "agz_net_forward_debug",
+    "agz_set_option", "agz_get_option", "agz_replay_info", "agz_selftest_division", "agz_train_step_from_replay", "agz_net_forward_debug", "agz_selfplay_stats",
 ]
 KERNEL_NAMES = ["select", "features", "stem_conv", "tower_conv", "heads", "incorporate"]
 
@@ -453,6 +453,11 @@ class Engine:
         out = (C.c_int64 * 4)()
         self._check(self.lib.agz_engine_info(self._h, out))
         return {"nodes_per_game": out[0], "bytes_per_node": out[1], "n_games": out[2], "record_ring": out[3]}
+
+    def selfplay_stats(self):
+        out = (C.c_int64 * 4)()
+        self._check(self.lib.agz_selfplay_stats(self._h, out))
+        return {"duplicate_leaves": out[0], "arena_prunes": out[1], "positions_evaluated": out[2], "readouts": out[3]}
 
     def kernel_launches(self):
         n = C.c_int64()

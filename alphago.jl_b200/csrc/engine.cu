@@ -525,6 +525,7 @@ static int read_progress(agz_engine* e, agz_progress* p) {
   p->positions_evaluated = (int64_t)ctr[CTR_POSITIONS];
   p->readouts = (int64_t)ctr[CTR_READOUTS];
   p->path_nodes = (int64_t)ctr[CTR_PATHNODES];
+  p->arena_prunes = (int32_t)ctr[CTR_PRUNES];
   p->games_live = 0;
   p->error = 0;
   for (auto& g : gs) {
@@ -708,7 +709,6 @@ extern "C" int32_t agz_selfplay_step(agz_engine* e, int32_t rounds, agz_progress
     DCHECK(e, devrt::sync(e->stream));
     int rc = read_progress(e, progress);
     progress->step_ms = 0.f;
-    progress->reserved = 0;
 #if AGZ_CUDA
     cudaEventElapsedTime(&progress->step_ms, e->ev_step[0], e->ev_step[1]);
 #endif
@@ -1244,6 +1244,17 @@ extern "C" int32_t agz_engine_info(agz_engine* e, int64_t out[4]) {
   out[1] = (int64_t)e->bytes_per_node;
   out[2] = e->c.n_games;
   out[3] = e->c.ring_cap;
+  return AGZ_OK;
+}
+
+extern "C" int32_t agz_selfplay_stats(agz_engine* e, int64_t out[4]) {
+  if (!e || !out) return fail(e, AGZ_ERR_ARG, "null argument");
+  unsigned long long ctr[CTR_COUNT];
+  DCHECK(e, devrt::d2h(ctr, e->v.ctr, sizeof(ctr), e->stream));
+  out[0] = (int64_t)ctr[CTR_DUP_LEAVES];
+  out[1] = (int64_t)ctr[CTR_PRUNES];
+  out[2] = (int64_t)ctr[CTR_POSITIONS];
+  out[3] = (int64_t)ctr[CTR_READOUTS];
   return AGZ_OK;
 }
 

@@ -79,6 +79,8 @@ struct Cfg {
 
 enum { CTR_MOVES = 0, CTR_FINISHED, CTR_STARTED, CTR_POSITIONS, CTR_READOUTS, CTR_PATHNODES, CTR_RING_TAIL, CTR_RING_HEAD,
        CTR_MATCH_BUSY,  // match slots still searching
+       CTR_PRUNES,      // arena-pressure prunes (forget_leaves)
+       CTR_DUP_LEAVES,  // leaves of a round that were duplicates of an earlier leaf of the same round (revert_visits!)
        CTR_COUNT };
 
 struct RingHeader {  // mirrors agz_game_header
@@ -548,6 +550,7 @@ struct Warp {
   AGZ_DEV void search_incorporate() {
     const bool seed_mode = st.seed_round != 0;
     const int nleaf = st.nleaf;
+    int n_dup = 0;
     // Lane k fetches everything leaf k needs up front (node id, path length, value, meta word): the leaves are processed in
     // order, but their inputs do not depend on each other except for "expanded by an earlier leaf of this batch", which is the
     // same node id appearing earlier in the batch.
@@ -573,6 +576,7 @@ struct Warp {
         if (flags & F_DONE) { st.err = E_ASSERT; break; }  // @assert !position.done (mcts.jl:196)
         const unsigned same = simt::ballot(lane < kk && my_leaf == leaf);
         const bool dup = (flags & F_EXPANDED) != 0 || same != 0u;   // already expanded (:197-200): revert_visits!
+        n_dup += dup ? 1 : 0;
         if (!dup) {
           if (lane == 0) v.meta[nbase + leaf].flags = (uint8_t)(flags | F_EXPANDED);
           const float* probs = v.eval_pi + b * v.pi_stride;
@@ -589,6 +593,7 @@ struct Warp {
       }
       simt::sync();  // the flag writes of this pass are visible to the next pass's loads
     }
+    if (n_dup) count(CTR_DUP_LEAVES, (unsigned long long)n_dup);
     st.nleaf = 0;
   }
 
@@ -925,9 +930,34 @@ struct Warp {
     const int need = c.readouts + 2 * c.pmax + 4;
     if (st.count + need > c.cap) {
       compact();
+      // The reference's tree is unbounded; here the kept subtree plus one move's growth must fit the game's arena.  Under that
+      // pressure (a very sharp network on a small arena) the least-visited nodes are forgotten, N <= 1 first, then 2, 4, ...: their
+      // statistics stay in the parent's rows (the PUCT scores do not change), only their own expansion is redone when they are
+      // visited again.  Counted in agz_progress.arena_prunes; a game stops with AGZ_ERR_CAPACITY only if even that does not help.
+      for (float thr = 1.f; st.count + need > c.cap && thr < 1.0e9f; thr *= 2.f) {
+        forget_leaves(thr);
+        compact();
+        count(CTR_PRUNES, 1);
+      }
       if (st.count + need > c.cap) { st.err = E_CAPACITY; return st.err; }
     }
     return E_OK;
+  }
+
+  // detach every node (other than the root) whose own visit count is <= thr; compact() then drops it and its descendants
+  AGZ_DEV void forget_leaves(float thr) {
+    const int count = st.count;
+    for (int c0 = 0; c0 < count; c0 += 32) {
+      const int i = c0 + lane;
+      bool drop = false;
+      if (i < count && i != st.root) {
+        const NodeMeta m = load_meta(i);
+        if (m.parent >= 0) drop = v.N[row(m.parent) + m.fmove] <= thr;
+      }
+      simt::sync();
+      if (drop) v.meta[nbase + i].parent = -2;
+    }
+    simt::sync();
   }
 
   // ---- get_feats(node.position) (features.jl:3-26): the last 8 boards come from the node, its ancestors in

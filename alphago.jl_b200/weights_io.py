@@ -130,16 +130,20 @@ def save_weight_list(path, name, arrays):
 
 
 def save_model(nn, models_dir, engine=None):
-    """save_model(nn) (src/train.jl:14-35): weights/agz_{base,value,policy}.bson hold the three Flux `params` lists.  The reference
-    also dumps the whole structs (agz_*.bson); here those files carry what this engine needs from them -- the BatchNorm running
-    statistics (mean, variance) per chain.  With `engine`, the current (trained) parameters are read back from it first."""
+    """save_model(nn) (src/train.jl:14-35): weights/agz_{base,value,policy}.bson hold the three Flux `params` lists in the
+    reference's layout (load_reference_model reads them back).  The reference also dumps the whole Flux structs (agz_*.bson); the
+    files of that name written HERE are an engine-private format carrying what this engine needs from them -- the BatchNorm running
+    statistics per chain as (mean, VARIANCE): statistics held as a moving standard deviation (bn_mode BN_STD, the shipped
+    models/agz_*.bson) are squared on the way out (eps of that convention is 1e-8 vs 1e-5: a 1e-5-relative difference in the folded
+    scale).  With `engine`, the current (trained) parameters are read back from it first."""
     import os
     if engine is not None:
         pull_from_engine(nn, engine)
     os.makedirs(os.path.join(models_dir, "weights"), exist_ok=True)
     for k, (chain, var) in enumerate((("base", "bn_weights"), ("value", "val_weights"), ("policy", "pol_weights"))):
         save_weight_list(os.path.join(models_dir, "weights", "agz_%s.bson" % chain), var, nn.params[k])
-        save_weight_list(os.path.join(models_dir, "agz_%s.bson" % chain), chain + "_bn_stats", [nn.bn_mu[k], nn.bn_sigma[k]])
+        var = np.asarray(nn.bn_sigma[k], np.float32) ** 2 if nn.bn_mode == B.BN_STD else nn.bn_sigma[k]
+        save_weight_list(os.path.join(models_dir, "agz_%s.bson" % chain), chain + "_bn_stats", [nn.bn_mu[k], var])
 
 
 def load_saved_model(models_dir, nn):

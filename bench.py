@@ -270,6 +270,7 @@ def main():
     slots_live = pr.games_live
     # ---- timed region 1: device-resident throughput (`value`) ---------------------------------------------------
     l0 = eng.kernel_launches()
+    stats0 = eng.selfplay_stats()
     g0 = eng.replay_info()["gathered_bytes"]
     sampler = ClockSampler(local)
     sampler.start()
@@ -285,6 +286,7 @@ def main():
     sampler.stop_flag = True
     launches = eng.kernel_launches() - l0
     gathered = eng.replay_info()["gathered_bytes"] - g0
+    stats1 = eng.selfplay_stats()
     moves = pr.moves_played - m0
     fill = (pr.positions_evaluated - p0) / float(args.steps * ROUNDS_PER_STEP * args.games * 8)
     readouts_done, finished = pr.readouts - r0, pr.games_finished - f0
@@ -362,6 +364,8 @@ def main():
             "games_finished_timed": int(tot[4]), "harvested_games_e2e": int(tot[5]), "mean_game_length_e2e": (sum(glen) / len(glen)) if glen else None,
             "replay_gathered_bytes_per_step": tot[3] / world / args.steps,   # tuple bytes every rank appended to its ring per step (all ranks' payload)
             "leaf_fill": fill, "readouts_per_s": readouts_done / tmx[0],
+            "duplicate_leaf_frac": (stats1["duplicate_leaves"] - stats0["duplicate_leaves"]) / max(1, stats1["positions_evaluated"] - stats0["positions_evaluated"]),
+            "arena_prunes": stats1["arena_prunes"],
             "network_tflops": flops_pos * rows / ((kms[2] + kms[3] + kms[4]) / max(1, kln[0]) * 1e-3) / 1e12 if kln[0] else None,
         }
         if legs:

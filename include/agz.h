@@ -128,7 +128,7 @@ typedef struct agz_progress {
   int32_t games_live;
   int32_t error;              /* first per-game error seen (AGZ_ERR_*) or 0 */
   float step_ms;              /* device time of this agz_selfplay_step call (CUDA events on the engine's stream) */
-  int32_t reserved;
+  int32_t arena_prunes;       /* cumulative: times a game's node arena had to forget its least-visited nodes to fit the next search */
 } agz_progress;
 
 /* ---- lifecycle ----------------------------------------------------------------------------- */
@@ -276,6 +276,10 @@ int32_t agz_pos_score(agz_engine* e, const agz_position* in, float* score);     
 int32_t agz_pos_liberties(agz_engine* e, const agz_position* in, uint8_t* liberty_cache);      /* LibertyTracker.liberty_cache (board.jl:99-164), N*N entries */
 
 /* ---- introspection for bench/roofline ---------------------------------------------------------- */
+/* Cumulative since agz_selfplay_start: out[0] = leaves that duplicated an earlier leaf of their own tree_search! round and were
+ * reverted (revert_visits!, mcts.jl:197-200) although a network row was spent on them, out[1] = arena-pressure prunes,
+ * out[2] = network rows evaluated, out[3] = select_leaf calls. */
+int32_t agz_selfplay_stats(agz_engine* e, int64_t out[4]);
 int32_t agz_kernel_launches(agz_engine* e, int64_t* n);  /* kernels of this library launched since create */
 /* out[0] = node arena capacity per game (nodes_per_game, or the default chosen at creation: the worst case max_game_length *
  * (readouts + 2 * parallel) when it fits in 40 % of the free device memory), out[1] = bytes per node, out[2] = n_games,

@@ -43,7 +43,7 @@ end
 
 struct AgzProgress
   moves_played::Int64; games_finished::Int64; games_started::Int64; positions_evaluated::Int64; readouts::Int64; path_nodes::Int64
-  games_live::Int32; error::Int32; step_ms::Float32; reserved::Int32
+  games_live::Int32; error::Int32; step_ms::Float32; arena_prunes::Int32
 end
 
 function check(h::Ptr{Cvoid}, rc::Int32)

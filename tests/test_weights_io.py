@@ -46,3 +46,19 @@ def test_save_model_round_trip(tmp_path):
     # the oracle's independent reader sees the same tensors in the same order
     arrs = obson.find_arrays(obson.load(os.path.join(str(tmp_path), "weights", "agz_base.bson")))
     assert len(arrs) == len(nn.params[0]) and all(np.array_equal(a, b) for a, b in zip(arrs, nn.params[0]))
+
+
+def test_save_model_converts_a_moving_std_to_a_variance(tmp_path):
+    """A network loaded from the shipped files keeps its BatchNorm statistics as a moving standard deviation (BN_STD); save_model
+    writes (mean, variance) and load_saved_model reads them back as BN_VAR_EPS, so the statistics survive the round trip."""
+    from alphago_jl_b200 import weights_io
+    env = agz.GoEnv(5, lib_path="unused")
+    nn = agz.NeuralNet(env, tower_height=1, seed=3)
+    rs = np.random.RandomState(2)
+    nn.bn_sigma = [(0.2 + rs.rand(*m.shape)).astype(np.float32) for m in nn.bn_sigma]
+    nn.bn_mode = agz.BN_STD
+    weights_io.save_model(nn, str(tmp_path))
+    back = weights_io.load_saved_model(str(tmp_path), agz.NeuralNet(env, tower_height=1, seed=4))
+    assert back.bn_mode == agz.BN_VAR_EPS
+    for k in range(3):
+        assert np.array_equal(back.bn_sigma[k], nn.bn_sigma[k] ** 2)
