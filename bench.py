@@ -180,21 +180,24 @@ def leg_19(agz, device, tf_sus, games, rounds, world, rank, dist, name):
             dist.broadcast_object_list(ids, src=0)
             eng.nccl_init(ids[0])
         eng.selfplay_start(-1)
-        eng.selfplay_step(3)
+        # >= 4 s of back-to-back rounds first: the roofline denominator is the SUSTAINED tensor peak (MEASURED_PEAKS.json: 4 s of
+        # back-to-back GEMMs); a leg timed from a cool start would run at burst clocks and "beat" it
+        pr = eng.selfplay_step(3)
+        pr = eng.selfplay_step(max(1, int(4000.0 / max(1.0, pr.step_ms / 3))))
         pr = eng.selfplay_step(rounds)                   # plain rounds: device time of the whole round
         ms_round = pr.step_ms / rounds
         if name == "c3":
             eng.replay_gather()
         eng.set_timing(True)
         eng.phase_times(reset=True)
-        eng.selfplay_step(2)
+        eng.selfplay_step(4)
         kms, kln = eng.phase_times(reset=True)
         eng.set_timing(False)
         fpos, fconv = eng.net_flops()
         rows = games * 8
         conv_ms = kms[3] / max(1, kln[3])
         net_ms = (kms[2] + kms[3] + kms[4]) / max(1, kln[0])
-        out = {"workload": "19x19, %d games x 8 leaves = %d positions per batch, tower_height 19, 256 filters, positions from live self-play" % (games, rows),
+        out = {"workload": "19x19, %d games x 8 leaves = %d positions per batch, tower_height 19, 256 filters, positions from live self-play; timed after >= 4 s of back-to-back rounds (sustained clocks)" % (games, rows),
                "ms_per_round": ms_round, "network_ms_per_batch": net_ms, "positions_per_s": rows / (net_ms * 1e-3),
                "network_tflops": fpos * rows / (net_ms * 1e-3) / 1e12,
                "roofline": {"bound": "tensor", "kernel": "conv3x3_tc5_kernel / conv3x3_tc6_kernel", "achieved": fconv * rows / (conv_ms * 1e-3) / 1e12, "peak": tf_sus,
@@ -218,6 +221,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-legs", action="store_true", help="skip the C5 / C4 / C3 legs")
     ap.add_argument("--pipeline", type=int, default=0, help="option schedule.pipeline (two half batches on separate streams)")
+    ap.add_argument("--precision", type=int, default=1, help="option conv.precision: 1 = fp16 operands (default), 2 = split precision (hi + lo fp16 pairs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -238,7 +242,7 @@ def main():
     env = agz.GoEnv(BOARD, device=local)
     nn = agz.NeuralNet(env, tower_height=TOWER, seed=0)
     eng = agz.Engine(BOARD, n_games=args.games, readouts=READOUTS, tower_height=TOWER, seed=0, device=local, world_size=world, rank=rank,
-                     evaluator=agz.EVAL_NN_TC, options={"selfplay.stagger_rounds": args.burnin * ROUNDS_PER_STEP, "schedule.pipeline": args.pipeline})
+                     evaluator=agz.EVAL_NN_TC, options={"selfplay.stagger_rounds": args.burnin * ROUNDS_PER_STEP, "schedule.pipeline": args.pipeline, "conv.precision": args.precision})
     nn.push(eng)
     if world > 1:  # NCCL communicator of the replay all-gather: rank 0's unique id goes round through torch.distributed
         ids = [eng.nccl_unique_id() if rank == 0 else None]
@@ -345,7 +349,7 @@ def main():
         achieved = conv_flops_pos * rows / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": tot[0] / tmx[0], "unit": "moves/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": 1e3 * tmx[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "ms_per_step": 1e3 * tmx[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == 1 else "f16x2-split",
             "data": "synthetic",
             "config": {"workload": "C2: 9x9 Go, %d concurrent self-play games per GPU, 400 readouts/move (50 rounds x 8 leaves per step), tower_height 6, 256 filters, random-init weights seed 0, empty-board starts, finished games refilled" % args.games,
                        "step": "50 tree_search rounds over all games (select -> leaf features -> stem + 12 tower convs -> heads -> incorporate/move logic, one stream) + replay pack / all-gather of the games that finished",

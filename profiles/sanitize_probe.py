@@ -46,5 +46,13 @@ if len(sys.argv) > 1 and sys.argv[1] == "nn":   # the network kernels too (tcgen
     rs = np.random.RandomState(0)
     bh = rs.randint(-1, 2, size=(8, 8, 81)).astype(np.int8)
     loss = eng.train_step(bh, np.ones(8, np.int8), rs.dirichlet(np.ones(82), size=8).astype(np.float32), np.ones(8, np.int8))
-    print("nn ok", pr.moves_played, pr.error, loss, flush=True)
+    for _ in range(200):                       # finish the games, then the device-resident replay -> train path and split precision
+        pr = eng.selfplay_step(8)
+        if pr.games_finished >= 2:
+            break
+    eng.replay_gather()
+    loss2 = eng.train_step_from_replay(8, seed=1)
+    eng.set_option("conv.precision", 2)
+    eng.net_forward_debug(agz.EVAL_NN_TC, bh, np.ones(8, np.int8), want_trunk=True)
+    print("nn ok", pr.moves_played, pr.error, loss, loss2, flush=True)
     eng.close()
