@@ -233,3 +233,23 @@ def test_injected_tap_error_is_caught_and_bisected():
         assert rep["pi_abs"] > 10 * max(ok["pi_abs"], 1e-4) and rep["logit_rel"] > 10 * ok["logit_rel"], (precision, ok, rep)
         assert nn_parity.first_bad_block(eng, agz.EVAL_NN_TC, poss, ref, T, bound) == bad + 1, precision
     eng.close()
+
+
+@pytest.mark.gpu
+def test_reference_julia_outputs():
+    """Pins the network against the reference itself -- once somebody has run tests/golden/gen_golden.jl (needs Julia + Flux +
+    BSON.jl, absent from this image) and committed its output.  Until then: skipped, and NN parity stays "unpinned"."""
+    import json
+    path = os.path.join(os.path.dirname(GOLD), "agz_shipped_9x9_julia.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/agz_shipped_9x9_julia.json has not been generated (no Julia in this image)")
+    ref = json.load(open(path))
+    g = np.load(GOLD)
+    pi_j, v_j = np.array(ref["pi"], np.float32), np.array(ref["v"], np.float32)
+    assert np.abs(g["pi"] - pi_j).max() <= 1e-5 and np.abs(g["v"] - v_j).max() <= 1e-5, "the fp32 oracle differs from the reference's Flux network"
+    eng = agz.Engine(9, lib_path=lib_for("cuda"), n_games=4, tower_height=0)
+    eng.net_set_params(0, g["base"]); eng.net_set_params(1, g["value"]); eng.net_set_params(2, g["policy"])
+    for k, name in enumerate(("base", "value", "policy")):
+        eng.net_set_bn_stats(k, g["bn_mu_" + name], g["bn_sigma_" + name], agz.BN_STD)
+    pi, v = eng.net_forward(agz.EVAL_NN_TC, g["boards_hist"], g["to_play"])
+    assert np.abs(pi - pi_j).max() <= TOL_TC and np.abs(v - v_j).max() <= TOL_TC
