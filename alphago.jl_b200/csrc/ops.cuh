@@ -211,7 +211,8 @@ struct LeafFeaturesF32Op {
 namespace devrt {
 template <class Op> struct MinBlocks;
 // 7 CTAs = 28 warps per SM (72 registers): 8192 trees fill 148 SMs in 1.98 waves; measured on C5 against 8 / 6 / 5 CTAs per SM:
-// 0.207 ms vs 0.218 / 0.237 / 0.219 ms per round
+// 0.207 ms vs 0.218 / 0.237 / 0.219 ms per round (round 1); again in round 2 with the leaner kernel, same box: 7 -> 0.1805,
+// 8 (64 registers) -> 0.1822, 9 (56 registers) -> 0.1967 ms per round
 template <> struct MinBlocks<agz::SelectOp<3, 1>> { static const int v = 7; };
 template <> struct MinBlocks<agz::SelectOp<6, 1>> { static const int v = 6; };
 template <> struct MinBlocks<agz::IncorporateOp<3>> { static const int v = 7; };

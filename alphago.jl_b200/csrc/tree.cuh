@@ -264,6 +264,23 @@ struct Warp {
     simt::sync();
   }
 
+  // apply_path for the path the last select_leaf left in the lanes' registers (plen <= 32)
+  AGZ_DEV void apply_path_regs(int plen, int op, float value) {
+    if (lane < plen) {
+      const float add = op == OP_BACKUP ? value : (op == OP_VLOSS_ADD ? (float)reg_tp : (float)(-reg_tp));
+      if (reg_slot != SLOT_ROOT) v.W[reg_slot] = simt::fadd(v.W[reg_slot], add);
+    }
+    const unsigned long long s0 = simt::shfl((unsigned)(reg_slot == SLOT_ROOT ? 1u : 0u), 0);
+    if (s0) {
+      const int tp0 = simt::shfl(reg_tp, 0);
+      const float add = op == OP_BACKUP ? value : (op == OP_VLOSS_ADD ? (float)tp0 : (float)(-tp0));
+      st.root_W = simt::fadd(st.root_W, add);
+    }
+    if (op == OP_VLOSS_ADD) st.vloss_balance += plen;
+    if (op == OP_VLOSS_REVERT) st.vloss_balance -= plen;
+    simt::sync();
+  }
+
   // Rebuild the path root..node by walking parent pointers (used by the single-node hooks only).
   AGZ_DEV int build_path(int node, PathEnt* path) {
     int len = 0;
@@ -286,6 +303,11 @@ struct Warp {
   }
 
   // ---- select_leaf (mcts.jl:108-138) ------------------------------------------------------------
+  // Lane d of the warp also keeps path entry d (d < 32) in its registers (reg_slot / reg_tp), so that the virtual loss or the
+  // terminal backup that follows the descent does not have to read the path back from memory.
+  unsigned long long reg_slot;
+  int reg_tp;
+
   AGZ_DEV int select_leaf(int from, PathEnt* path, int& plen, NodeMeta* leaf_meta = nullptr) {
     uint32_t sel_idx = st.sel_ctr++;
     int move_no = -1;   // position.n of the root (RNG key of the tie-break draw): known for free when the descent starts at the root
@@ -332,6 +354,7 @@ struct Warp {
         e.slot = slot; e.node = cur; e.to_play = m.to_play;
         path[depth] = e;
       }
+      if (lane == depth) { reg_slot = slot; reg_tp = m.to_play; }
       if (!(m.flags & F_EXPANDED)) break;
       if (depth + 1 >= c.maxd) { st.err = E_ASSERT; break; }
       if (prefetch) {   // the most-visited child is where a sharp policy goes next: its rows travel while this level is scored
@@ -473,6 +496,7 @@ struct Warp {
           e.slot = (unsigned long long)(r + best); e.node = child; e.to_play = cm.to_play;
           path[depth] = e;
         }
+        if (lane == depth) { reg_slot = (unsigned long long)(r + best); reg_tp = cm.to_play; }
         if (leaf_meta) *leaf_meta = cm;
         cur = child;
         break;
@@ -506,10 +530,14 @@ struct Warp {
         const uint32_t* lb = bits_of(leaf);
         float sc = bits_score(B, bits_load(B, lb, lb + c.KB), c.komi);
         float value = sc > 0.f ? 1.f : (sc < 0.f ? -1.f : 0.f);
-        apply_path(path, plen, OP_BACKUP, value);
+        if (plen <= 32) apply_path_regs(plen, OP_BACKUP, value);
+        else apply_path(path, plen, OP_BACKUP, value);
         continue;
       }
-      if (!seed_mode) apply_path(path, plen, OP_VLOSS_ADD, 0.f);
+      if (!seed_mode) {
+        if (plen <= 32) apply_path_regs(plen, OP_VLOSS_ADD, 0.f);
+        else apply_path(path, plen, OP_VLOSS_ADD, 0.f);
+      }
       if (lane == 0) {
         v.leaf_node[(size_t)g * c.pmax + nleaf] = leaf;
         v.leaf_plen[(size_t)g * c.pmax + nleaf] = plen;
