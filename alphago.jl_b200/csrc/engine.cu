@@ -76,7 +76,6 @@ struct agz_engine {
   int pipeline;              // 1: two half batches on two streams (tree work of one hides under the network of the other)
   ReplayState* replay;
 #endif
-  int duo;                   // option tree.duo: -1 auto, 0 one warp per tree, 1 two trees per warp (tree_duo.cuh; boards up to 9x9)
   int fuse_dummy;            // option dummy.fused_rounds
   long long replay_cap;      // option replay.capacity (0 = memory_size default of src/train.jl:38)
 };
@@ -347,7 +346,6 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   e->d_match_active = nullptr;
   e->d_match_ids = nullptr;
   e->fuse_dummy = 1;
-  e->duo = -1;
   e->replay_cap = 0;
   if (rc) {
     int code = fail(nullptr, AGZ_ERR_CUDA, "device allocation failed (n_games=%d, nodes_per_game=%d)", c.n_games, c.cap);
@@ -392,12 +390,6 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
 extern "C" int32_t agz_set_option(agz_engine* e, const char* key, int64_t value) {
   if (!e || !key) return fail(e, AGZ_ERR_ARG, "null argument");
   if (!strcmp(key, "dummy.fused_rounds")) { e->fuse_dummy = value != 0; return AGZ_OK; }
-  if (!strcmp(key, "tree.duo")) {
-    if (value < -1 || value > 1) return fail(e, AGZ_ERR_ARG, "tree.duo must be -1 (auto), 0 or 1");
-    if (value == 1 && e->c.KA != 3) return fail(e, AGZ_ERR_ARG, "tree.duo = 1 needs a board of at most 9x9");
-    e->duo = (int)value;
-    return AGZ_OK;
-  }
   if (!strcmp(key, "selfplay.stagger_rounds")) {
     if (value < 0) return fail(e, AGZ_ERR_ARG, "selfplay.stagger_rounds must be >= 0");
     e->c.stagger_rounds = value;   // read by the next agz_selfplay_start
@@ -437,7 +429,6 @@ extern "C" int32_t agz_set_option(agz_engine* e, const char* key, int64_t value)
 extern "C" int32_t agz_get_option(agz_engine* e, const char* key, int64_t* value) {
   if (!e || !key || !value) return fail(e, AGZ_ERR_ARG, "null argument");
   if (!strcmp(key, "dummy.fused_rounds")) { *value = e->fuse_dummy; return AGZ_OK; }
-  if (!strcmp(key, "tree.duo")) { *value = e->duo; return AGZ_OK; }
   if (!strcmp(key, "selfplay.stagger_rounds")) { *value = e->c.stagger_rounds; return AGZ_OK; }
 #if AGZ_CUDA
   if (!strcmp(key, "schedule.pipeline")) { *value = e->pipeline; return AGZ_OK; }
@@ -560,22 +551,11 @@ extern "C" int32_t agz_selfplay_start(agz_engine* e, int64_t total_games) {
   return AGZ_OK;
 }
 
-// Two trees per warp (tree_duo.cuh) pays when there are thousands of trees per GPU (the tree kernels are then issue bound); with
-// few trees per SM a descent is a latency chain and one warp per tree with child prefetch is the better shape.
-static bool use_duo(const agz_engine* e) {
-  if (e->c.KA != 3) return false;
-  return e->duo == 1;   // measured slower than one warp per tree on C5 (profiles/r02_tree_duo_experiment.md): never chosen automatically
-}
-
 static int one_round(agz_engine* e) {
 #if AGZ_CUDA
   if (e->timing) cudaEventRecord(e->ev[0], e->stream);
 #endif
-  const bool duo = use_duo(e);
-  if (duo) {
-    DuoSelectOp<3> op{e->c, e->v};
-    DCHECK(e, devrt::launch_warps(op, (e->c.n_games + 1) / 2, e->smem_per_warp, e->stream));
-  } else if (e->c.n_games >= 2048) {
+  if (e->c.n_games >= 2048) {
     DISPATCH_KA(e, {
       SelectOp<KA, 1> op{e->c, e->v, -1, e->c.parallel, 0};
       DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
@@ -595,15 +575,10 @@ static int one_round(agz_engine* e) {
     for (int i = 1; i <= 5; ++i) cudaEventRecord(e->ev[i], e->stream);
   }
 #endif
-  if (duo) {
-    DuoIncorporateOp<3> op{e->c, e->v};
-    DCHECK(e, devrt::launch_warps(op, (e->c.n_games + 1) / 2, e->smem_per_warp, e->stream));
-  } else {
-    DISPATCH_KA(e, {
-      IncorporateOp<KA> op{e->c, e->v, -1, 0};
-      DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
-    });
-  }
+  DISPATCH_KA(e, {
+    IncorporateOp<KA> op{e->c, e->v, -1, 0};
+    DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));
+  });
   e->launches += 1;
 #if AGZ_CUDA
   if (e->timing) {
@@ -709,10 +684,7 @@ extern "C" int32_t agz_selfplay_step(agz_engine* e, int32_t rounds, agz_progress
   // DummyNet evaluator: all rounds of the call in one launch per game (ops.cuh DummyRoundsOp); per-kernel timing and the option
   // dummy.fused_rounds = 0 keep the split
   if (rounds > 0 && e->fuse_dummy && e->evaluator == AGZ_EVAL_DUMMY && !e->timing) {
-    if (use_duo(e)) {
-      DuoRoundsOp<3> op{e->c, e->v, rounds};
-      DCHECK(e, devrt::launch_warps(op, (e->c.n_games + 1) / 2, e->smem_per_warp, e->stream));
-    } else if (e->c.n_games >= 2048) {
+    if (e->c.n_games >= 2048) {
       DISPATCH_KA(e, {
         DummyRoundsOp<KA, 1> op{e->c, e->v, rounds};
         DCHECK(e, devrt::launch_warps(op, e->c.n_games, e->smem_per_warp, e->stream));

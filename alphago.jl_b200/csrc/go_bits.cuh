@@ -21,36 +21,26 @@
 
 namespace agz {
 
-// W = lanes of the group that owns the position: 32 (a warp per tree) or 16 (half a warp per tree, N <= 15; tree_duo.cuh).  With
-// W = 16 the two halves of the warp run these functions in lock step on two positions: every collective is reached by all 32
-// threads, so loops and guards are decided by any_warp() (an extra flood step or a guarded block entered for the other half's sake
-// changes nothing: the floods are idempotent and the guarded blocks do nothing on empty sets), data by the half's own any()/ballot().
-template <int W>
-struct BitsCtxT {
-  typedef simt::G<W> S;
+struct BitsCtx {
   int N, KB, lane;
   uint32_t full;  // all on-board bits of this lane's line, 0 for lanes >= N
 };
-typedef BitsCtxT<32> BitsCtx;
 
 struct Lines {
   uint32_t b, w;  // this lane's line of black / white stones
 };
 
-template <int W>
-AGZ_DEV BitsCtxT<W> bits_ctx_w(int N, int KB) {
-  BitsCtxT<W> B;
+AGZ_DEV BitsCtx bits_ctx(int N, int KB) {
+  BitsCtx B;
   B.N = N;
   B.KB = KB;
-  B.lane = simt::G<W>::lane();
+  B.lane = simt::lane();
   B.full = B.lane < N ? ((1u << N) - 1u) : 0u;
   return B;
 }
-AGZ_DEV BitsCtx bits_ctx(int N, int KB) { return bits_ctx_w<32>(N, KB); }
 
 // line `lane` of a stored bitplane (KB words, flat bit p = N*j + i)
-template <int W>
-AGZ_DEV uint32_t bits_line(const BitsCtxT<W>& B, const uint32_t* plane) {
+AGZ_DEV uint32_t bits_line(const BitsCtx& B, const uint32_t* plane) {
   uint32_t r = 0;
   if (B.lane < B.N) {
     const int bit = B.N * B.lane, w0 = bit >> 5, s = bit & 31;
@@ -62,8 +52,7 @@ AGZ_DEV uint32_t bits_line(const BitsCtxT<W>& B, const uint32_t* plane) {
   return r;
 }
 
-template <int W>
-AGZ_DEV Lines bits_load(const BitsCtxT<W>& B, const uint32_t* black, const uint32_t* white) {
+AGZ_DEV Lines bits_load(const BitsCtx& B, const uint32_t* black, const uint32_t* white) {
   Lines L;
   L.b = bits_line(B, black);
   L.w = bits_line(B, white);
@@ -71,21 +60,20 @@ AGZ_DEV Lines bits_load(const BitsCtxT<W>& B, const uint32_t* black, const uint3
 }
 
 // flat words of a line set; every lane receives all KB words (KW >= KB keeps them in registers)
-template <int KW, int W>
-AGZ_DEV void bits_pack(const BitsCtxT<W>& B, uint32_t line, uint32_t (&out)[KW]) {
+template <int KW>
+AGZ_DEV void bits_pack(const BitsCtx& B, uint32_t line, uint32_t (&out)[KW]) {
   const int bit = B.N * B.lane, w0 = bit >> 5, s = bit & 31;
   const uint32_t lo = line << s;
   const uint32_t hi = s ? (line >> (32 - s)) : 0u;
 #pragma unroll
   for (int k = 0; k < KW; ++k) {
     out[k] = 0;
-    if (k < B.KB) out[k] = simt::G<W>::reduce_or((w0 == k ? lo : 0u) | (w0 + 1 == k ? hi : 0u));
+    if (k < B.KB) out[k] = simt::reduce_or((w0 == k ? lo : 0u) | (w0 + 1 == k ? hi : 0u));
   }
 }
 
 // board bytes (-1 W / 0 / +1 B, flat order) <-> lines; used by the position hooks only
-template <int W>
-AGZ_DEV Lines bits_from_bytes(const BitsCtxT<W>& B, const int8_t* board) {
+AGZ_DEV Lines bits_from_bytes(const BitsCtx& B, const int8_t* board) {
   Lines L;
   L.b = 0;
   L.w = 0;
@@ -99,38 +87,34 @@ AGZ_DEV Lines bits_from_bytes(const BitsCtxT<W>& B, const int8_t* board) {
   return L;
 }
 
-template <int W>
-AGZ_DEV void bits_to_bytes(const BitsCtxT<W>& B, const Lines& L, int8_t* board) {
+AGZ_DEV void bits_to_bytes(const BitsCtx& B, const Lines& L, int8_t* board) {
   if (B.lane < B.N) {
     for (int i = 0; i < B.N; ++i) board[B.N * B.lane + i] = (int8_t)((int)((L.b >> i) & 1u) - (int)((L.w >> i) & 1u));
   }
 }
 
 // the points adjacent to a point of x (lanes >= N hold 0, so lane -1 = lane 31 and lane N read as empty lines)
-template <int W>
-AGZ_DEV uint32_t bits_nbr4(const BitsCtxT<W>& B, uint32_t x) {
-  const uint32_t l = simt::G<W>::shfl(x, B.lane - 1);
-  const uint32_t r = simt::G<W>::shfl(x, B.lane + 1);
+AGZ_DEV uint32_t bits_nbr4(const BitsCtx& B, uint32_t x) {
+  const uint32_t l = simt::shfl(x, B.lane - 1);
+  const uint32_t r = simt::shfl(x, B.lane + 1);
   return ((x << 1) | (x >> 1) | l | r) & B.full;
 }
 
 // everything connected to `seed` through points of `mask`
-template <int W>
-AGZ_DEV uint32_t bits_flood(const BitsCtxT<W>& B, uint32_t seed, uint32_t mask) {
+AGZ_DEV uint32_t bits_flood(const BitsCtx& B, uint32_t seed, uint32_t mask) {
   uint32_t g = seed & mask;
   for (;;) {
     const uint32_t n1 = (g | bits_nbr4(B, g)) & mask;
     const uint32_t n2 = (n1 | bits_nbr4(B, n1)) & mask;
     const bool changed = n2 != g;
     g = n2;
-    if (!simt::G<W>::any_warp(changed)) break;
+    if (!simt::any(changed)) break;
   }
   return g;
 }
 
 // two independent floods in one loop (their shuffles overlap)
-template <int W>
-AGZ_DEV void bits_flood2(const BitsCtxT<W>& B, uint32_t& g0, uint32_t mask0, uint32_t& g1, uint32_t mask1) {
+AGZ_DEV void bits_flood2(const BitsCtx& B, uint32_t& g0, uint32_t mask0, uint32_t& g1, uint32_t mask1) {
   g0 &= mask0;
   g1 &= mask1;
   for (;;) {
@@ -141,45 +125,42 @@ AGZ_DEV void bits_flood2(const BitsCtxT<W>& B, uint32_t& g0, uint32_t mask0, uin
     const bool changed = (a2 != g0) || (c2 != g1);
     g0 = a2;
     g1 = c2;
-    if (!simt::G<W>::any_warp(changed)) break;
+    if (!simt::any(changed)) break;
   }
 }
 
-template <int W>
-AGZ_DEV int bits_count(const BitsCtxT<W>&, uint32_t x) { return simt::G<W>::reduce_add(simt::popc(x)); }
+AGZ_DEV int bits_count(uint32_t x) { return simt::reduce_add(simt::popc(x)); }
 
 // the lowest point of a non-empty set as a one-bit set (warp-uniform choice)
-template <int W>
-AGZ_DEV uint32_t bits_lowest(const BitsCtxT<W>& B, uint32_t x, unsigned nonzero_lanes) {
+AGZ_DEV uint32_t bits_lowest(const BitsCtx& B, uint32_t x, unsigned nonzero_lanes) {
   const int dl = simt::ffs(nonzero_lanes) - 1;
-  const uint32_t dv = simt::G<W>::shfl(x, dl);
+  const uint32_t dv = simt::shfl(x, dl);
   return B.lane == dl ? (dv & (0u - dv)) : 0u;
 }
 
 // Play `color` at flat point c.  Returns 0, or 1 when check_legal is set and the point is occupied or the move is
 // suicide (L is then unchanged).  ko_out = the point the opponent may not retake, or -1 (board.jl:473,487-491);
 // ncap_out = stones captured.
-template <int W>
-AGZ_DEV int bits_play(const BitsCtxT<W>& B, Lines& L, int c, int color, bool check_legal, int& ko_out, int& ncap_out) {
+AGZ_DEV int bits_play(const BitsCtx& B, Lines& L, int c, int color, bool check_legal, int& ko_out, int& ncap_out) {
   ko_out = -1;
   ncap_out = 0;
   const int cj = c / B.N, ci = c - cj * B.N;
   const uint32_t cbit = B.lane == cj ? (1u << ci) : 0u;
   uint32_t mine = color == 1 ? L.b : L.w, opp = color == 1 ? L.w : L.b;
-  if (check_legal && simt::G<W>::any(((mine | opp) & cbit) != 0u)) return 1;   // check_legal callers are warp-per-tree code (W = 32)
+  if (check_legal && simt::any(((mine | opp) & cbit) != 0u)) return 1;
   const uint32_t nb = bits_nbr4(B, cbit);
-  const bool koish = !simt::G<W>::any((nb & ~opp) != 0u);  // is_koish: every neighbour holds the opponent's colour
+  const bool koish = !simt::any((nb & ~opp) != 0u);  // is_koish: every neighbour holds the opponent's colour
   mine |= cbit;
   uint32_t empty = B.full & ~(mine | opp);
   int ncap = 0, cap_point = -1;
-  if (simt::G<W>::any_warp((nb & opp) != 0u)) {
+  if (simt::any((nb & opp) != 0u)) {
     const uint32_t alive = bits_flood(B, opp & bits_nbr4(B, empty), opp);
     const uint32_t dead = opp & ~alive;
-    const unsigned dm = simt::G<W>::ballot(dead != 0u);
-    if (simt::G<W>::nz_warp(dm)) {   // (a half without dead stones computes ncap = 0 and removes nothing)
-      ncap = bits_count(B, dead);
+    const unsigned dm = simt::ballot(dead != 0u);
+    if (dm) {
+      ncap = bits_count(dead);
       const int dl = simt::ffs(dm) - 1;
-      const uint32_t dv = simt::G<W>::shfl(dead, dl);
+      const uint32_t dv = simt::shfl(dead, dl);
       cap_point = dl * B.N + simt::ffs(dv) - 1;
       opp &= ~dead;
       empty |= dead;
@@ -187,7 +168,7 @@ AGZ_DEV int bits_play(const BitsCtxT<W>& B, Lines& L, int c, int color, bool che
   }
   if (check_legal) {  // suicide (board.jl:264-266): the played stone's group has no liberty after the captures
     const uint32_t grp = bits_flood(B, cbit, mine);
-    if (!simt::G<W>::any((bits_nbr4(B, grp) & empty) != 0u)) return 1;
+    if (!simt::any((bits_nbr4(B, grp) & empty) != 0u)) return 1;
   }
   L.b = color == 1 ? mine : opp;
   L.w = color == 1 ? opp : mine;
@@ -197,14 +178,13 @@ AGZ_DEV int bits_play(const BitsCtxT<W>& B, Lines& L, int c, int color, bool che
 }
 
 // all_legal_moves for `to_play`: the legal points of this lane's line (pass is always legal and not part of the set)
-template <int W>
-AGZ_DEV uint32_t bits_legal(const BitsCtxT<W>& B, const Lines& L, int to_play, int ko) {
+AGZ_DEV uint32_t bits_legal(const BitsCtx& B, const Lines& L, int to_play, int ko) {
   const uint32_t S = to_play == 1 ? L.b : L.w, O = to_play == 1 ? L.w : L.b;
   const uint32_t E = B.full & ~(S | O);
   const uint32_t open = E & bits_nbr4(B, E);  // an empty neighbour: never suicide
   const uint32_t cand = E & ~open;
   uint32_t legal = open;
-  if (simt::G<W>::any_warp(cand != 0u)) {
+  if (simt::any(cand != 0u)) {
     // groups owning a liberty that is not a candidate: friendly ones make every adjacent candidate legal (they keep
     // that liberty), enemy ones cannot be captured by a candidate
     const uint32_t on = bits_nbr4(B, open);
@@ -213,19 +193,19 @@ AGZ_DEV uint32_t bits_legal(const BitsCtxT<W>& B, const Lines& L, int to_play, i
     legal |= cand & bits_nbr4(B, f1);
     uint32_t srem = S & ~f1, orem = O & ~o1;  // groups whose liberties are all candidates (rare)
     for (;;) {
-      const unsigned m = simt::G<W>::ballot(srem != 0u);
-      if (!simt::G<W>::nz_warp(m)) break;   // (a half with nothing left floods the empty set)
+      const unsigned m = simt::ballot(srem != 0u);
+      if (!m) break;
       const uint32_t g = bits_flood(B, bits_lowest(B, srem, m), S);
       const uint32_t libs = bits_nbr4(B, g) & E;
-      if (bits_count(B, libs) >= 2) legal |= libs;  // a friendly group with a liberty besides the point
+      if (bits_count(libs) >= 2) legal |= libs;  // a friendly group with a liberty besides the point
       srem &= ~g;
     }
     for (;;) {
-      const unsigned m = simt::G<W>::ballot(orem != 0u);
-      if (!simt::G<W>::nz_warp(m)) break;   // (a half with nothing left floods the empty set)
+      const unsigned m = simt::ballot(orem != 0u);
+      if (!m) break;
       const uint32_t g = bits_flood(B, bits_lowest(B, orem, m), O);
       const uint32_t libs = bits_nbr4(B, g) & E;
-      if (bits_count(B, libs) == 1) legal |= libs;  // an enemy group in atari: the point captures it
+      if (bits_count(libs) == 1) legal |= libs;  // an enemy group in atari: the point captures it
       orem &= ~g;
     }
   }
@@ -237,13 +217,12 @@ AGZ_DEV uint32_t bits_legal(const BitsCtxT<W>& B, const Lines& L, int to_play, i
 }
 
 // Tromp-Taylor area score from Black's view: Float32(#B - #W) - komi  (board.jl:511-533)
-template <int W>
-AGZ_DEV float bits_score(const BitsCtxT<W>& B, const Lines& L, float komi) {
+AGZ_DEV float bits_score(const BitsCtx& B, const Lines& L, float komi) {
   const uint32_t E = B.full & ~(L.b | L.w);
   uint32_t rb = E & bits_nbr4(B, L.b), rw = E & bits_nbr4(B, L.w);
   bits_flood2(B, rb, E, rw, E);
-  const int nb = bits_count(B, L.b | (rb & ~rw));
-  const int nw = bits_count(B, L.w | (rw & ~rb));
+  const int nb = bits_count(L.b | (rb & ~rw));
+  const int nw = bits_count(L.w | (rw & ~rb));
   return simt::fsub((float)(nb - nw), komi);
 }
 

@@ -4,7 +4,6 @@
 #pragma once
 #include "../../include/agz.h"
 #include "tree.cuh"
-#include "tree_duo.cuh"
 
 namespace agz {
 
@@ -182,48 +181,6 @@ struct DummyRoundsOp {
   }
 };
 
-// The same three kernels with two games per warp (tree_duo.cuh; option tree.duo): warp wi owns slots 2*wi and 2*wi + 1.
-template <int KA>
-struct DuoSelectOp {
-  Cfg c;
-  View v;
-  AGZ_DEV void operator()(int wi, char*) const {
-    Duo<KA> d(c, v, 2 * wi, c.n_games);
-    d.search_select();
-    d.store_state();
-  }
-};
-
-template <int KA>
-struct DuoIncorporateOp {
-  Cfg c;
-  View v;
-  AGZ_DEV void operator()(int wi, char* smem) const {
-    Duo<KA> d(c, v, 2 * wi, c.n_games);
-    d.search_incorporate();
-    d.after_round(smem);
-    d.store_state();
-  }
-};
-
-template <int KA>
-struct DuoRoundsOp {
-  Cfg c;
-  View v;
-  int rounds;
-  AGZ_DEV void operator()(int wi, char* smem) const {
-    Duo<KA> d(c, v, 2 * wi, c.n_games);
-    for (int r = 0; r < rounds; ++r) {
-      d.search_select();
-      simt::sync();  // the leaf records written by lane 0 of each half are read by every lane below
-      d.search_incorporate();
-      d.after_round(smem);
-      if (!simt::G<16>::any_warp(d.valid && d.st.phase != PH_IDLE)) break;
-    }
-    d.store_state();
-  }
-};
-
 // get_feats for every leaf collected this round, reference layout: out[b][17][N2] float (N x N x 17 x B)
 template <int KA>
 struct LeafFeaturesF32Op {
@@ -251,9 +208,6 @@ struct LeafFeaturesF32Op {
 
 }  // namespace agz
 #if AGZ_CUDA
-#ifndef AGZ_DUO_CTAS
-#define AGZ_DUO_CTAS 5   // resident CTAs per SM the two-trees-per-warp kernels are compiled for (register cap 65536 / (128 * v))
-#endif
 namespace devrt {
 template <class Op> struct MinBlocks;
 // 7 CTAs = 28 warps per SM (72 registers): 8192 trees fill 148 SMs in 1.98 waves; measured on C5 against 8 / 6 / 5 CTAs per SM:
@@ -267,11 +221,6 @@ template <int KA, int OCC> struct TraceTag<agz::SelectOp<KA, OCC>> { static cons
 template <int KA> struct TraceTag<agz::IncorporateOp<KA>> { static const int v = 2; };
 template <> struct MinBlocks<agz::DummyRoundsOp<3, 1>> { static const int v = 7; };
 template <> struct MinBlocks<agz::DummyRoundsOp<6, 1>> { static const int v = 6; };
-template <int KA> struct MinBlocks<agz::DuoSelectOp<KA>> { static const int v = AGZ_DUO_CTAS; };
-template <int KA> struct MinBlocks<agz::DuoIncorporateOp<KA>> { static const int v = AGZ_DUO_CTAS; };
-template <int KA> struct MinBlocks<agz::DuoRoundsOp<KA>> { static const int v = AGZ_DUO_CTAS; };
-template <int KA> struct TraceTag<agz::DuoSelectOp<KA>> { static const int v = 1; };
-template <int KA> struct TraceTag<agz::DuoIncorporateOp<KA>> { static const int v = 2; };
 }  // namespace devrt
 #endif
 namespace agz {

@@ -68,56 +68,6 @@ AGZ_DEV void trace_rec(unsigned long long* tr, int tag, unsigned long long t0) {
   }
 }
 AGZ_DEV bool trace_cta() { return threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1); }
-
-// ---- lane groups.  G<32> is the warp itself.  G<16> is one half of a warp that plays two trees at once (tree_duo.cuh): the two
-// halves run in LOCK STEP -- every collective below is executed by all 32 threads with the full member mask (one SHFL / VOTE / REDUX
-// instruction, no WARPSYNC.EXCLUSIVE serialisation of the halves) and returns, to each thread, the result over its own half.  Code
-// written against G<16> must therefore keep its control flow warp-uniform wherever a collective is reached: loops and guards use
-// any_warp(), per-half conditions become predicates.
-template <int W> struct G;
-template <> struct G<32> {
-  static constexpr int width = 32;
-  AGZ_DEV static int lane() { return threadIdx.x & 31; }
-  AGZ_DEV static int half() { return 0; }
-  AGZ_DEV static void sync() { __syncwarp(); }
-  AGZ_DEV static unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
-  AGZ_DEV static bool any(bool p) { return __any_sync(0xffffffffu, p); }
-  AGZ_DEV static bool any_warp(bool p) { return __any_sync(0xffffffffu, p); }
-  AGZ_DEV static bool nz_warp(unsigned group_uniform) { return group_uniform != 0u; }   // "non-zero in some group of the warp"
-  template <class T> AGZ_DEV static T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-  template <class T> AGZ_DEV static T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
-  AGZ_DEV static unsigned reduce_or(unsigned v) { return __reduce_or_sync(0xffffffffu, v); }
-  AGZ_DEV static int reduce_add(int v) { return __reduce_add_sync(0xffffffffu, v); }
-  AGZ_DEV static unsigned reduce_max(unsigned v) { return __reduce_max_sync(0xffffffffu, v); }
-};
-template <> struct G<16> {
-  static constexpr int width = 16;
-  AGZ_DEV static int lane() { return threadIdx.x & 15; }
-  AGZ_DEV static int half() { return (threadIdx.x >> 4) & 1; }
-  AGZ_DEV static void sync() { __syncwarp(); }
-  AGZ_DEV static unsigned ballot(bool p) { return (__ballot_sync(0xffffffffu, p) >> (threadIdx.x & 16)) & 0xffffu; }
-  AGZ_DEV static bool any(bool p) { return ballot(p) != 0u; }
-  AGZ_DEV static bool any_warp(bool p) { return __any_sync(0xffffffffu, p); }
-  AGZ_DEV static bool nz_warp(unsigned group_uniform) { return __any_sync(0xffffffffu, group_uniform != 0u); }
-  template <class T> AGZ_DEV static T shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src, 16); }
-  template <class T> AGZ_DEV static T shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m, 16); }
-  // REDUX has no segmented form: one full-warp reduction per half over values that are neutral in the other half
-  AGZ_DEV static unsigned reduce_or(unsigned v) {
-    const bool h = (threadIdx.x & 16) != 0;
-    const unsigned a = __reduce_or_sync(0xffffffffu, h ? 0u : v), b = __reduce_or_sync(0xffffffffu, h ? v : 0u);
-    return h ? b : a;
-  }
-  AGZ_DEV static int reduce_add(int v) {
-    const bool h = (threadIdx.x & 16) != 0;
-    const int a = __reduce_add_sync(0xffffffffu, h ? 0 : v), b = __reduce_add_sync(0xffffffffu, h ? v : 0);
-    return h ? b : a;
-  }
-  AGZ_DEV static unsigned reduce_max(unsigned v) {
-    const bool h = (threadIdx.x & 16) != 0;
-    const unsigned a = __reduce_max_sync(0xffffffffu, h ? 0u : v), b = __reduce_max_sync(0xffffffffu, h ? v : 0u);
-    return h ? b : a;
-  }
-};
 }  // namespace simt
 
 #else  // ------------------------------------------------------------------ host emulation (tests only)
@@ -133,7 +83,6 @@ struct EmuWarp {
   ucontext_t ctx[32];
   int cur;
   uint64_t slot[2][32];
-  int tag[2][32];      // op kind of the collective each lane deposited (divergence check of the half-warp groups)
   uint32_t ncoll[32];  // collectives issued per lane (parity selects the slot buffer)
   void (*fn)(void*);
   void* arg;
@@ -160,7 +109,6 @@ inline T exchange_(T v, int src) {
   uint64_t raw = 0;
   memcpy(&raw, &v, sizeof(T));
   w->slot[par][me] = raw;
-  w->tag[par][me] = 0;
   barrier();
   T r;
   memcpy(&r, &w->slot[par][src & 31], sizeof(T));
@@ -171,7 +119,6 @@ inline unsigned ballot(bool p) {
   int me = w->cur;
   int par = w->ncoll[me]++ & 1;
   w->slot[par][me] = p ? 1 : 0;
-  w->tag[par][me] = 0;
   barrier();
   unsigned m = 0;
   for (int i = 0; i < 32; ++i) m |= (unsigned)(w->slot[par][i] & 1) << i;
@@ -183,7 +130,6 @@ inline unsigned reduce_or(unsigned v) {
   int me = w->cur;
   int par = w->ncoll[me]++ & 1;
   w->slot[par][me] = v;
-  w->tag[par][me] = 0;
   barrier();
   unsigned m = 0;
   for (int i = 0; i < 32; ++i) m |= (unsigned)w->slot[par][i];
@@ -194,7 +140,6 @@ inline int reduce_add(int v) {
   int me = w->cur;
   int par = w->ncoll[me]++ & 1;
   w->slot[par][me] = (uint64_t)(uint32_t)v;
-  w->tag[par][me] = 0;
   barrier();
   int m = 0;
   for (int i = 0; i < 32; ++i) m += (int)(uint32_t)w->slot[par][i];
@@ -222,7 +167,6 @@ inline unsigned reduce_max(unsigned v) {
   int me = w->cur;
   int par = w->ncoll[me]++ & 1;
   w->slot[par][me] = v;
-  w->tag[par][me] = 0;
   barrier();
   unsigned m = 0;
   for (int i = 0; i < 32; ++i) m = (unsigned)w->slot[par][i] > m ? (unsigned)w->slot[par][i] : m;
@@ -239,98 +183,5 @@ inline long long dbits(double a) { long long r; memcpy(&r, &a, 8); return r; }
 inline unsigned fbits(float a) { unsigned r; memcpy(&r, &a, 4); return r; }
 inline double bitsd(long long a) { double r; memcpy(&r, &a, 8); return r; }
 inline uint32_t mulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
-
-// lane groups (see the CUDA half of this file): G<16> collectives are issued by all 32 fibers in lock step and return the result
-// over the caller's own half.  Every collective records an op tag; a mismatch between the lanes of a rotation means the device
-// code let the halves' control flow diverge around a collective, which the CUDA build would hang or miscompute on.
-void emu_divergence(const char* what);
-template <int W> struct G;
-template <> struct G<32> {
-  static constexpr int width = 32;
-  static int lane() { return simt::lane(); }
-  static int half() { return 0; }
-  static void sync() { simt::sync(); }
-  static unsigned ballot(bool p) { return simt::ballot(p); }
-  static bool any(bool p) { return simt::any(p); }
-  static bool any_warp(bool p) { return simt::any(p); }
-  static bool nz_warp(unsigned group_uniform) { return group_uniform != 0u; }
-  template <class T> static T shfl(T v, int src) { return simt::exchange_(v, src); }
-  template <class T> static T shfl_xor(T v, int m) { return simt::exchange_(v, simt::lane() ^ m); }
-  static unsigned reduce_or(unsigned v) { return simt::reduce_or(v); }
-  static int reduce_add(int v) { return simt::reduce_add(v); }
-  static unsigned reduce_max(unsigned v) { return simt::reduce_max(v); }
-};
-template <> struct G<16> {
-  static constexpr int width = 16;
-  static int lane() { return g_warp->cur & 15; }
-  static int half() { return (g_warp->cur >> 4) & 1; }
-  // all 32 lanes deposit (tag, value), rotate, and read the 16 values of their own half
-  static void gather_(int tag, uint64_t mine, uint64_t (&out)[16]) {
-    EmuWarp* w = g_warp;
-    const int me = w->cur;
-    const int par = w->ncoll[me]++ & 1;
-    w->slot[par][me] = mine;
-    w->tag[par][me] = tag;
-    barrier();
-    for (int i = 0; i < 32; ++i)
-      if (w->tag[par][i] != tag) emu_divergence("the two halves of a duo warp reached different collectives");
-    for (int i = 0; i < 16; ++i) out[i] = w->slot[par][(me & 16) | i];
-  }
-  static void sync() { uint64_t o[16]; gather_(1, 0, o); }
-  static unsigned ballot(bool p) {
-    uint64_t o[16];
-    gather_(2, p ? 1 : 0, o);
-    unsigned m = 0;
-    for (int i = 0; i < 16; ++i) m |= (unsigned)(o[i] & 1) << i;
-    return m;
-  }
-  static bool any(bool p) { return ballot(p) != 0u; }
-  static bool any_warp(bool p) {
-    EmuWarp* w = g_warp;
-    const int me = w->cur;
-    const int par = w->ncoll[me]++ & 1;
-    w->slot[par][me] = p ? 1 : 0;
-    w->tag[par][me] = 3;
-    barrier();
-    bool r = false;
-    for (int i = 0; i < 32; ++i) {
-      if (w->tag[par][i] != 3) emu_divergence("the two halves of a duo warp reached different collectives");
-      r = r || (w->slot[par][i] & 1);
-    }
-    return r;
-  }
-  static bool nz_warp(unsigned group_uniform) { return any_warp(group_uniform != 0u); }
-  template <class T> static T shfl(T v, int src) {
-    static_assert(sizeof(T) <= 8, "");
-    uint64_t raw = 0, o[16];
-    memcpy(&raw, &v, sizeof(T));
-    gather_(4, raw, o);
-    T r;
-    memcpy(&r, &o[src & 15], sizeof(T));
-    return r;
-  }
-  template <class T> static T shfl_xor(T v, int m) { return shfl(v, (lane() ^ m) & 15); }
-  static unsigned reduce_or(unsigned v) {
-    uint64_t o[16];
-    gather_(5, v, o);
-    unsigned m = 0;
-    for (int i = 0; i < 16; ++i) m |= (unsigned)o[i];
-    return m;
-  }
-  static int reduce_add(int v) {
-    uint64_t o[16];
-    gather_(6, (uint64_t)(uint32_t)v, o);
-    int m = 0;
-    for (int i = 0; i < 16; ++i) m += (int)(uint32_t)o[i];
-    return m;
-  }
-  static unsigned reduce_max(unsigned v) {
-    uint64_t o[16];
-    gather_(7, v, o);
-    unsigned m = 0;
-    for (int i = 0; i < 16; ++i) m = (unsigned)o[i] > m ? (unsigned)o[i] : m;
-    return m;
-  }
-};
 }  // namespace simt
 #endif

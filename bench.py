@@ -141,15 +141,11 @@ def tree_bytes_per_readout(N, d):
     return (d - 1) * 13 * A + 16 * A + 8 * N * N + 16 * d
 
 
-def leg_c5(agz, device, hbm, options=None, lib_path=None):
+def leg_c5(agz, device, hbm):
     """BASELINE config C5: MCTS-only, 9x9, uniform prior / value 0 (DummyNet), 8192 trees x 1600 readouts per move."""
     trees, readouts, rounds = 8192, 1600, 200
-    eng = agz.Engine(9, n_games=trees, readouts=readouts, tower_height=1, seed=0, evaluator=agz.EVAL_DUMMY, nodes_per_game=3600, device=device,
-                     **({"lib_path": lib_path} if lib_path else {}))
+    eng = agz.Engine(9, n_games=trees, readouts=readouts, tower_height=1, seed=0, evaluator=agz.EVAL_DUMMY, nodes_per_game=3600, device=device)
     try:
-        for k, val in (options or {}).items():
-            eng.set_option(k, val)
-        duo = eng.get_option("tree.duo") != 0
         eng.selfplay_start(-1)
         pr0 = eng.selfplay_step(rounds + 10)              # warm-up: past the first move of every tree
         ms, pr1 = 0.0, pr0
@@ -161,8 +157,7 @@ def leg_c5(agz, device, hbm, options=None, lib_path=None):
         d = pn / max(1, ro)
         bpr = tree_bytes_per_readout(9, d)
         achieved = ro * bpr / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": "k_warps<%s> (select_leaf + expand + virtual loss + incorporate + backup + move logic, %s, %d rounds per launch)" % (
-                    "DuoRoundsOp<3>" if duo else "DummyRoundsOp<3,1>", "two trees per warp" if duo else "one warp per tree", rounds),
+        return {"bound": "hbm", "kernel": "k_warps<DummyRoundsOp<3,1>> (select_leaf + expand + virtual loss + incorporate + backup + move logic, one warp per tree, %d rounds per launch)" % rounds,
                 "workload": "C5: MCTS-only 9x9, uniform prior (DummyNet), %d trees x %d readouts/move; %d x %d rounds timed after %d warm-up rounds" % (trees, readouts, reps, rounds, rounds + 10),
                 "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                 "bytes_per_readout": bpr, "mean_path_nodes": d, "readouts_per_launch": ro / reps, "ms_per_launch": ms / reps, "ms_per_round": ms / (reps * rounds),

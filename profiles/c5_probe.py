@@ -13,8 +13,6 @@ import pkg  # noqa: E402
 agz = pkg.load()
 if len(sys.argv) > 1 and sys.argv[1] == "ncu":
     eng = agz.Engine(9, n_games=8192, readouts=1600, tower_height=1, seed=0, evaluator=agz.EVAL_DUMMY, nodes_per_game=3600)
-    if len(sys.argv) > 2:
-        eng.set_option("tree.duo", int(sys.argv[2]))       # 0: one warp per tree, 1: two trees per warp
     eng.selfplay_start(-1)
     eng.selfplay_step(210)
     eng.selfplay_step(210)

@@ -4,18 +4,12 @@
 #define AGZ_EMU 1
 #include "../../alphago.jl_b200/csrc/simt.h"
 
-#include <stdio.h>
 #include <stdlib.h>
 
 namespace simt {
 thread_local EmuWarp* g_warp = nullptr;
 
 static const size_t kStack = 512 * 1024;
-
-void emu_divergence(const char* what) {
-  fprintf(stderr, "agz emulator: %s\n", what);
-  abort();
-}
 
 static void fiber_entry() {
   EmuWarp* w = g_warp;
