@@ -2,7 +2,7 @@
 
 Names, argument meaning and error behaviour follow the reference (0-based indices instead of Julia's 1-based):
   GoEnv (src/game/go/go.jl:1-26), GoPosition + play_move!/pass_move!/all_legal_moves/score/result
-  (src/game/go/board.jl), NeuralNet (src/neural_net.jl:13-73), MCTSPlayer / MCTSNode and their functions
+  (src/game/go/board.jl), GomokuEnv / GomokuPosition (src/game/gomoku/gomoku.jl, board.jl), Position (src/game/env.jl), NeuralNet (src/neural_net.jl:13-73), MCTSPlayer / MCTSNode and their functions
   (src/mcts.jl, src/mcts_play.jl), selfplay (src/selfplay.jl:1-45).
 Everything that computes runs in CUDA kernels behind the C ABI; this file only marshals.
 """
@@ -30,16 +30,18 @@ class GoEnv:
         self._util = None
         self._fwd = {}
 
+    game_kwargs = property(lambda s: {})                  # agz_config fields that select the game (AGZ_GAME_GO is the default)
+
     def forward_engine(self, tower_height):
         """A small engine whose network has `tower_height` blocks, for NeuralNet.__call__ (one per tower height)."""
         if tower_height not in self._fwd:
-            self._fwd[tower_height] = B.Engine(self.N, lib_path=self.lib_path, n_games=8, readouts=8, device=self.device, tower_height=tower_height)
+            self._fwd[tower_height] = B.Engine(self.N, lib_path=self.lib_path, **self.game_kwargs, n_games=8, readouts=8, device=self.device, tower_height=tower_height)
         return self._fwd[tower_height]
 
     def util_engine(self):
         """A one-slot engine used for position-level calls (rules run on the device)."""
         if self._util is None:
-            self._util = B.Engine(self.N, lib_path=self.lib_path, n_games=1, readouts=8, device=self.device)
+            self._util = B.Engine(self.N, lib_path=self.lib_path, **self.game_kwargs, n_games=1, readouts=8, device=self.device)
         return self._util
 
 
@@ -63,6 +65,25 @@ def from_kgs(s, env):                                     # coords.jl:25-34
 
 def to_kgs(coord, env):                                   # coords.jl:37
     return "pass" if coord is None else "%s%d" % (_KGS_COLUMNS[coord[1]], env.N - coord[0])
+
+
+class GomokuEnv(GoEnv):
+    """GomokuEnv(board_size = 15, connect_row = 5, planes = 17) (src/game/gomoku/gomoku.jl:1-19): N^2 actions, no pass."""
+
+    def __init__(self, board_size=15, connect_row=5, planes=17, lib_path=None, device=0):
+        super().__init__(board_size, planes, lib_path, device)
+        self.n_in_row = connect_row
+        self.action_space = board_size * board_size
+
+    game_kwargs = property(lambda s: {"game": B.GAME_GOMOKU, "n_in_row": s.n_in_row})
+
+
+def Go(n):                                                # src/game/env.jl:2
+    return GoEnv(n)
+
+
+def Position(env, **kw):                                  # src/game/env.jl:1,4
+    return GomokuPosition(env, **kw) if isinstance(env, GomokuEnv) else GoPosition(env, **kw)
 
 
 # ------------------------------------------------------------------ GoPosition (board.jl:271-306)
@@ -108,16 +129,38 @@ class GoPosition:
         return pos
 
 
+class GomokuPosition(GoPosition):
+    """GomokuPosition(env; board, n, recent, to_play) (src/game/gomoku/board.jl:25-58): `done` / `winner` come from
+    has_game_ended on construction (:97-129), evaluated by the device rules."""
+
+    def __init__(self, env, board=None, n=0, recent=None, to_play=BLACK, history=None, **_):
+        super().__init__(env, board=board, n=n, komi=0.0, recent=recent, to_play=to_play, history=history)
+        if board is None:
+            self.winner, self.done = 0, False
+        else:
+            self.winner = int(env.util_engine().pos_score(self.to_c()))
+            self.done = self.winner != 0 or not (self.board == EMPTY).any()
+
+
 def play_move(pos_or_player, c, color=None):
-    """play_move!(pos, c) (board.jl:451-509) or play_move!(player, c) (mcts_play.jl:26-50)."""
+    """play_move!(pos, c) (board.jl:451-509; gomoku board.jl:137-169) or play_move!(player, c) (mcts_play.jl:26-50)."""
     if isinstance(pos_or_player, MCTSPlayer):
         return pos_or_player.play_move(c)
     pos = pos_or_player
     env = pos.env
+    if isinstance(pos, GomokuPosition):
+        assert not pos.done                                   # @assert !new_pos.done (gomoku board.jl:144)
+        if c is None:
+            raise IllegalMove()
     cp = pos.to_c()
     if color is not None:
         cp.to_play = color
     out = env.util_engine().pos_play_move(cp, to_flat(c, env))
+    if isinstance(pos, GomokuPosition):
+        N2 = env.N * env.N
+        board = np.frombuffer(out.board, dtype=np.int8, count=N2).reshape(env.N, env.N, order="F").copy()
+        hist = [np.frombuffer(out.hist[k], dtype=np.int8, count=N2).reshape(env.N, env.N, order="F").copy() for k in range(out.n_hist)]
+        return GomokuPosition(env, board=board, n=out.n, recent=pos.recent + [(cp.to_play, c)], to_play=out.to_play, history=hist)
     return GoPosition.from_c(env, out, pos.recent + [(cp.to_play, c)])
 
 
@@ -142,8 +185,10 @@ def result(pos):                                          # board.jl:535-544
     return 1 if s > 0 else (-1 if s < 0 else 0)
 
 
-def result_string(pos):                                   # board.jl:546-555
+def result_string(pos):                                   # board.jl:546-555; gomoku board.jl:184-193
     s = score(pos)
+    if isinstance(pos, GomokuPosition):
+        return "B" if s > 0 else ("W" if s < 0 else "DRAW")
     return "B+%.1f" % s if s > 0 else ("W+%.1f" % abs(s) if s < 0 else "DRAW")
 
 
@@ -222,7 +267,7 @@ class NeuralNet:
 
     def __call__(self, positions):
         """(nn::NeuralNet)(positions) -> (pi: A x B, v: B) (neural_net.jl:57-68); a single Position gives (pi, v)."""
-        single = isinstance(positions, GoPosition)
+        single = isinstance(positions, GoPosition)   # (GomokuPosition is a GoPosition here)
         plist = [positions] if single else list(positions)
         eng = self.env.forward_engine(self.tower_height)   # the engine's network shape is fixed at creation (tower_height)
         self.push(eng)
@@ -276,6 +321,8 @@ class MCTSNode:
     def position(self):
         v, env = self._view(), self.player.env
         board = np.array(v.board[:env.N * env.N], np.int8).reshape(env.N, env.N, order="F")
+        if isinstance(env, GomokuEnv):
+            return GomokuPosition(env, board=board, n=v.n, to_play=v.to_play)
         pos = GoPosition(env, board=board, n=v.n, komi=self.player.engine.cfg.komi, ko=None if v.ko < 0 else from_flat(v.ko, env),
                          recent=[(-v.to_play, None)] if v.last_move_pass else [], to_play=v.to_play)
         pos.done = bool(v.done)
@@ -305,7 +352,7 @@ class MCTSPlayer:
         self.seed, self.game_id = seed, game_id
         self.result, self.result_string = 0, ""
         self.recent = []
-        self.engine = B.Engine(env.N, lib_path=env.lib_path, n_games=1, readouts=num_readouts, tau_threshold=self.tau_threshold,
+        self.engine = B.Engine(env.N, lib_path=env.lib_path, **env.game_kwargs, n_games=1, readouts=num_readouts, tau_threshold=self.tau_threshold,
                                resign_threshold=resign_threshold, seed=seed, max_parallel=max_parallel, device=env.device,
                                nodes_per_game=nodes_per_game, tower_height=getattr(network, "tower_height", 1))
         self._bind_network()
@@ -342,10 +389,10 @@ class MCTSPlayer:
             self.engine.cfg.komi = 7.5
             self.engine.tree_init(0, None, self.game_id)
         else:
-            if abs(pos.komi - self.engine.cfg.komi) > 0:
+            if not isinstance(pos, GomokuPosition) and abs(pos.komi - self.engine.cfg.komi) > 0:
                 # komi lives in the engine config: rebuild the handle for a non-default komi
                 self.engine.close()
-                self.engine = B.Engine(self.env.N, lib_path=self.env.lib_path, n_games=1, readouts=self.num_readouts,
+                self.engine = B.Engine(self.env.N, lib_path=self.env.lib_path, **self.env.game_kwargs, n_games=1, readouts=self.num_readouts,
                                        tau_threshold=self.tau_threshold, resign_threshold=self.resign_threshold, seed=self.seed,
                                        max_parallel=64, komi=pos.komi, device=self.env.device,
                                        tower_height=getattr(self.network, "tower_height", 1))
@@ -380,6 +427,8 @@ class MCTSPlayer:
     def play_move(self, c):                                # mcts_play.jl:26-50
         to_play = self.root._view().to_play
         try:
+            if c is None and isinstance(self.env, GomokuEnv):   # no pass in this game; the reference's `catch` swallows the error
+                raise IllegalMove()
             self.engine.tree_play_move(0, to_flat(c, self.env))
         except IllegalMove:
             print("Illegal move")
@@ -402,7 +451,7 @@ class MCTSPlayer:
         pis = self.searches_pi
         assert len(pis) == self.root._view().n
         positions, results = [], []
-        pos = GoPosition(self.env, komi=self.komi)
+        pos = Position(self.env, komi=self.komi)
         for color, mv in self.recent:
             positions.append(pos)
             results.append(self.result)
@@ -447,7 +496,7 @@ def evaluate(env, black_net, white_net, num_games=400, ro=800, verbose=False, se
     engines = []
     try:
         for k, net in enumerate((black_net, white_net)):
-            eng = B.Engine(env.N, lib_path=env.lib_path, n_games=G, readouts=ro, tau_threshold=-1, inject_noise=0,
+            eng = B.Engine(env.N, lib_path=env.lib_path, **env.game_kwargs, n_games=G, readouts=ro, tau_threshold=-1, inject_noise=0,
                            resign_threshold=resign_threshold, seed=seed + k, device=env.device,
                            tower_height=getattr(net, "tower_height", 1), **engine_overrides)
             engines.append(eng)
@@ -544,7 +593,7 @@ def train(env, num_games=25000, memory_size=500000, batch_size=32, epochs=1, ckp
     from . import weights_io
     cur_nn = model if model is not None else NeuralNet(env, tower_height=tower_height, seed=seed)
     conc = concurrent or min(num_games, 1024)
-    eng = B.Engine(env.N, lib_path=env.lib_path, n_games=conc, readouts=readouts, seed=seed, device=env.device,
+    eng = B.Engine(env.N, lib_path=env.lib_path, **env.game_kwargs, n_games=conc, readouts=readouts, seed=seed, device=env.device,
                    tower_height=cur_nn.tower_height, evaluator=cur_nn.evaluator, options={"replay.capacity": memory_size}, **engine_overrides)
     losses = []
     try:
@@ -610,7 +659,7 @@ class SelfPlayResult:
 
     def extract_data(self):
         positions, results = [], []
-        pos, color = GoPosition(self.env), BLACK
+        pos, color = Position(self.env), BLACK
         for mv in self.moves:
             positions.append(pos)
             results.append(self.result)
@@ -622,7 +671,7 @@ def selfplay(env, nn, num_ro=800, seed=0, n_games=1, concurrent=None, options=No
     """selfplay(env, nn, num_ro) -> player; with n_games > 1 plays that many games concurrently on the GPU and
     returns a list (game ids 0..n_games-1).  `nn` is a NeuralNet or a DummyNet-like object.  `options`: agz_set_option keys."""
     conc = concurrent or n_games
-    eng = B.Engine(env.N, lib_path=env.lib_path, n_games=conc, readouts=num_ro, seed=seed, device=env.device,
+    eng = B.Engine(env.N, lib_path=env.lib_path, **env.game_kwargs, n_games=conc, readouts=num_ro, seed=seed, device=env.device,
                    tower_height=getattr(nn, "tower_height", 1), options=options, **engine_overrides)
     try:
         if isinstance(nn, NeuralNet):

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libagz.so")
 
 AGZ_OK, ERR_ILLEGAL_MOVE, ERR_ASSERT, ERR_CUDA, ERR_NCCL, ERR_ARG, ERR_CAPACITY = 0, 1, 2, 3, 4, 5, 6
 EVAL_DUMMY, EVAL_NN_TC, EVAL_NN_F32 = 0, 1, 2
+GAME_GO, GAME_GOMOKU = 0, 1
 BN_VAR_EPS, BN_STD = 0, 1
 CHAIN_BASE, CHAIN_VALUE, CHAIN_POLICY = 0, 1, 2
 MAX_POINTS, MAX_ACTIONS, HIST = 361, 362, 7
@@ -32,7 +33,8 @@ class Config(C.Structure):
                 ("max_parallel", C.c_int32), ("komi", C.c_float), ("resign_threshold", C.c_double),
                 ("resign_disable_frac", C.c_double), ("n_games", C.c_int32), ("readouts", C.c_int32),
                 ("nodes_per_game", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("world_size", C.c_int32),
-                ("rank", C.c_int32), ("record_ring", C.c_int32), ("evaluator", C.c_int32), ("inject_noise", C.c_int32)]
+                ("rank", C.c_int32), ("record_ring", C.c_int32), ("evaluator", C.c_int32), ("inject_noise", C.c_int32),
+                ("game", C.c_int32), ("n_in_row", C.c_int32)]
 
 
 class Position(C.Structure):
@@ -63,7 +65,7 @@ class Progress(C.Structure):
 
 # every symbol include/agz.h declares (the CPU test-suite checks the built library exports all of them)
 SYMBOLS = [
-    "agz_config_default", "agz_engine_create", "agz_engine_destroy", "agz_last_error", "agz_version",
+    "agz_config_default", "agz_config_default_game", "agz_engine_create", "agz_engine_destroy", "agz_last_error", "agz_version",
     "agz_net_set_params", "agz_net_set_bn_stats", "agz_net_param_count", "agz_net_bn_count", "agz_net_forward",
     "agz_features", "agz_set_dummy_evaluator", "agz_set_evaluator", "agz_selfplay_start", "agz_selfplay_step",
     "agz_selfplay_harvest", "agz_selfplay_run", "agz_replay_gather", "agz_replay_read", "agz_replay_sample", "agz_nccl_unique_id",
@@ -119,7 +121,8 @@ class Engine:
         self.lib = load_library(lib_path)
         self.cfg = Config()
         self._h = C.c_void_p()
-        self._check(self.lib.agz_config_default(C.byref(self.cfg), board_n), None)
+        game, n_in_row = overrides.pop("game", GAME_GO), overrides.pop("n_in_row", 5)
+        self._check(self.lib.agz_config_default_game(C.byref(self.cfg), game, board_n, n_in_row), None)   # GoEnv(N) / GomokuEnv(N, n_in_row)
         for k, v in overrides.items():
             if not hasattr(self.cfg, k):
                 raise TypeError("unknown config field %r" % k)
@@ -131,7 +134,7 @@ class Engine:
         self._h = h
         self.N = self.cfg.board_n
         self.N2 = self.N * self.N
-        self.A = self.N2 + 1
+        self.A = self.N2 + (1 if self.cfg.game == GAME_GO else 0)   # env.action_space
         self.L = self.cfg.max_game_length + 2
         for k, v in (options or {}).items():
             self.set_option(k, v)
@@ -278,7 +281,7 @@ class Engine:
         n = C.c_int32()
         self._check(self.lib.agz_selfplay_harvest(self._h, C.c_int32(max_records), hd, _ptr(mv, C.c_int16), _ptr(q, C.c_float),
                                                   _ptr(pi, C.c_float), _ptr(vis, C.c_float), C.byref(n)))
-        return [GameRecord(hd[i], mv[i], q[i], pi[i], vis[i]) for i in range(n.value)]
+        return [GameRecord(hd[i], mv[i], q[i], pi[i], vis[i], self.cfg.game) for i in range(n.value)]
 
     def selfplay_harvest_discard(self, max_records=1 << 20):
         """Release finished-game records without copying them to the host."""
@@ -291,7 +294,7 @@ class Engine:
         hd, mv, q, pi, vis = self._record_buffers(max(mine, 1))
         self._check(self.lib.agz_selfplay_run(self._h, C.c_int32(total_games), hd, _ptr(mv, C.c_int16), _ptr(q, C.c_float),
                                               _ptr(pi, C.c_float), _ptr(vis, C.c_float)))
-        return [GameRecord(hd[i], mv[i], q[i], pi[i], vis[i]) for i in range(mine)]
+        return [GameRecord(hd[i], mv[i], q[i], pi[i], vis[i], self.cfg.game) for i in range(mine)]
 
     def replay_gather(self):
         n = C.c_int64()
@@ -518,8 +521,9 @@ class Engine:
 class GameRecord:
     """What `selfplay` leaves in the returned MCTSPlayer (searches_pi, qs, result, result_string) + the move list."""
 
-    def __init__(self, hd, moves, qs, pis, visits):
+    def __init__(self, hd, moves, qs, pis, visits, game=GAME_GO):
         n = hd.n_moves
+        self.game = game
         self.game_id, self.n_moves, self.result, self.resigned = hd.game_id, n, hd.result, bool(hd.resigned)
         self.final_score, self.resign_threshold = hd.final_score, hd.resign_threshold
         self.moves = moves[:n].copy()
@@ -531,6 +535,8 @@ class GameRecord:
     def result_string(self):          # set_result! (mcts_play.jl:100-108) / result_string (board.jl:546-555)
         if self.resigned:
             return "B+R" if self.result == 1 else "W+R"
+        if self.game == GAME_GOMOKU:  # result_string (src/game/gomoku/board.jl:184-193); final_score = the winner's colour
+            return "B" if self.final_score > 0 else ("W" if self.final_score < 0 else "DRAW")
         if self.final_score > 0:
             return "B+%.1f" % self.final_score
         if self.final_score < 0:

@@ -118,10 +118,16 @@ extern "C" int32_t agz_version(void) { return 100; }
 
 extern "C" const char* agz_last_error(agz_engine* e) { return e ? e->err : g_err; }
 
-extern "C" int32_t agz_config_default(agz_config* cfg, int32_t board_n) {
+extern "C" int32_t agz_config_default(agz_config* cfg, int32_t board_n) { return agz_config_default_game(cfg, AGZ_GAME_GO, board_n, 0); }
+
+extern "C" int32_t agz_config_default_game(agz_config* cfg, int32_t game, int32_t board_n, int32_t n_in_row) {
   if (!cfg || board_n < 2 || board_n > AGZ_MAX_N) return fail(nullptr, AGZ_ERR_ARG, "board_n must be in [2, %d]", AGZ_MAX_N);
+  if (game != AGZ_GAME_GO && game != AGZ_GAME_GOMOKU) return fail(nullptr, AGZ_ERR_ARG, "unknown game %d", game);
+  if (game == AGZ_GAME_GOMOKU && (n_in_row < 2 || n_in_row > board_n)) return fail(nullptr, AGZ_ERR_ARG, "n_in_row must be in [2, board_n]");
   memset(cfg, 0, sizeof(*cfg));
-  const int N = board_n, A = N * N + 1;
+  const int N = board_n, A = N * N + (game == AGZ_GAME_GO ? 1 : 0);   // env.action_space (go.jl:12, gomoku.jl:12)
+  cfg->game = game;
+  cfg->n_in_row = game == AGZ_GAME_GOMOKU ? n_in_row : 0;
   cfg->board_n = N;
   cfg->planes = 17;
   cfg->filters = 256;
@@ -181,6 +187,8 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   if (cfg->parallel_readouts < 1 || cfg->max_parallel < cfg->parallel_readouts) return fail(nullptr, AGZ_ERR_ARG, "need 1 <= parallel_readouts <= max_parallel");
   if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(nullptr, AGZ_ERR_ARG, "bad rank/world_size");
   if (cfg->max_game_length < 1 || cfg->max_game_length > 32000) return fail(nullptr, AGZ_ERR_ARG, "bad max_game_length");
+  if (cfg->game != AGZ_GAME_GO && cfg->game != AGZ_GAME_GOMOKU) return fail(nullptr, AGZ_ERR_ARG, "unknown game %d", cfg->game);
+  if (cfg->game == AGZ_GAME_GOMOKU && (cfg->n_in_row < 2 || cfg->n_in_row > N)) return fail(nullptr, AGZ_ERR_ARG, "n_in_row must be in [2, board_n]");
 #if AGZ_CUDA
   {
     int ndev = 0;
@@ -235,7 +243,10 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   Cfg& c = e->c;
   c.N = N;
   c.N2 = N * N;
-  c.A = N * N + 1;
+  c.game = cfg->game == AGZ_GAME_GOMOKU ? GAME_GOMOKU : GAME_GO;
+  c.n_in_row = cfg->n_in_row;
+  c.pass = c.game == GAME_GO ? N * N : -1;
+  c.A = N * N + (c.game == GAME_GO ? 1 : 0);
   int ka = (c.A + 31) / 32;
   c.KA = ka <= 3 ? 3 : (ka <= 6 ? 6 : 12);
   c.AS = c.KA * 32;
@@ -357,7 +368,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   devrt::h2d(e->d_dummy_pi, pri.data(), pri.size() * sizeof(float), e->stream);
 #if AGZ_CUDA
   {
-    NNShape s{N, cfg->planes, cfg->filters, cfg->tower_height};
+    NNShape s{N, cfg->planes, cfg->filters, cfg->tower_height, c.A};
     char nerr[256] = "";
     if (cfg->planes != 17) {
       agz_engine_destroy(e);
@@ -1118,7 +1129,7 @@ extern "C" int32_t agz_tree_read_node(agz_engine* e, int32_t slot, int32_t node,
     out->board[p] = (int8_t)(b - w);
     out->legal[p] = (int8_t)((bits[2 * c.KB + (p >> 5)] >> (p & 31)) & 1);
   }
-  out->legal[c.N2] = 1;
+  if (c.pass >= 0) out->legal[c.pass] = 1;
   if (m.parent < 0) { out->N = gs.root_N; out->W = gs.root_W; }
   else {
     const size_t pr = ((size_t)slot * c.cap + m.parent) * c.AS + m.fmove;
@@ -1286,7 +1297,7 @@ extern "C" int32_t agz_phase_times(agz_engine* e, float ms[AGZ_NKERNELS], int64_
 // ------------------------------------------------------------------------------------------- network ABI
 extern "C" int32_t agz_net_flops(agz_engine* e, double* per_position, double* per_tower_conv_position) {
   if (!e) return fail(nullptr, AGZ_ERR_ARG, "null engine");
-  const double N2 = (double)e->c.N2, C = e->cfg.filters, A = N2 + 1;
+  const double N2 = (double)e->c.N2, C = e->cfg.filters, A = (double)e->c.A;
   const double conv = 2.0 * 9 * C * C * N2;
   if (per_tower_conv_position) *per_tower_conv_position = conv;
   if (per_position) *per_position = 2.0 * 9 * e->cfg.planes * C * N2 + e->cfg.tower_height * 2.0 * conv + 2.0 * (3 * C * N2) + 2.0 * (256 * N2 + 256) + 2.0 * (A * 2 * N2);

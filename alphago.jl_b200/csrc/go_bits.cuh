@@ -226,4 +226,18 @@ AGZ_DEV float bits_score(const BitsCtx& B, const Lines& L, float komi) {
   return simt::fsub((float)(nb - nw), komi);
 }
 
+// Gomoku (src/game/gomoku/board.jl:97-129 has_game_ended): does the stone set x hold k in a row -- along a line, across lines, or
+// on either diagonal?  Lane j holds line j (lanes >= N hold 0), so the three cross-line directions are k-1 shuffles.
+AGZ_DEV bool bits_k_in_row(const BitsCtx& B, uint32_t x, int k) {
+  uint32_t h = x, v = x, d1 = x, d2 = x;
+  for (int t = 1; t < k; ++t) {
+    const uint32_t up = simt::shfl(x, B.lane + t);
+    h &= x >> t;
+    v &= up;
+    d1 &= up >> t;
+    d2 &= up << t;
+  }
+  return simt::any((h | v | d1 | d2) != 0u);
+}
+
 }  // namespace agz

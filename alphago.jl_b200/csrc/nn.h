@@ -15,7 +15,9 @@ struct NNet;
 
 struct NNShape {
   int N, planes, filters, tower;
+  int actions;   // outputs of the policy head = env.action_space (neural_net.jl:30): N^2 + 1 for Go, N^2 for Gomoku; 0 = N^2 + 1
 };
+inline int nn_actions(const NNShape& s) { return s.actions > 0 ? s.actions : s.N * s.N + 1; }
 
 NNet* nn_create(const NNShape& s, int max_batch, char* err, size_t errlen);
 void nn_destroy(NNet* n);

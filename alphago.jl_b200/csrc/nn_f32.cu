@@ -18,7 +18,7 @@ static size_t value_count(const NNShape& s) {
   return C + 3 + 256 * N2 + 256 + 256 + 1;
 }
 static size_t policy_count(const NNShape& s) {
-  size_t C = s.filters, N2 = (size_t)s.N * s.N, A = N2 + 1;
+  size_t C = s.filters, N2 = (size_t)s.N * s.N, A = (size_t)nn_actions(s);
   return 2 * C + 6 + A * 2 * N2 + A;
 }
 
@@ -32,7 +32,7 @@ size_t nn_bn_count(const NNet* n, int chain) {
 }
 
 double nn_flops_per_position(const NNShape& s) {
-  double N2 = (double)s.N * s.N, C = s.filters, A = N2 + 1;
+  double N2 = (double)s.N * s.N, C = s.filters, A = (double)nn_actions(s);
   double stem = 2 * 9 * s.planes * C * N2;
   double tower = (double)s.tower * 2 * (2 * 9 * C * C * N2);
   double heads = 2 * (3 * C * N2) + 2 * (256 * N2 + 256) + 2 * (A * 2 * N2);
@@ -52,7 +52,7 @@ NNet* nn_create(const NNShape& s, int max_batch, char* err, size_t errlen) {
   NNet* n = new NNet();
   n->s = s;
   n->N2 = s.N * s.N;
-  n->A = n->N2 + 1;
+  n->A = nn_actions(s);
   n->C = s.filters;
   n->max_batch = max_batch;
   n->ready = false;
@@ -283,13 +283,13 @@ __global__ void __launch_bounds__(256) heads_f32_kernel(const float* __restrict_
                                                         const float* __restrict__ D1W, const float* __restrict__ D1b,
                                                         const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                         const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
-                                                        float* __restrict__ v, int C, int N2, float* __restrict__ raw) {
+                                                        float* __restrict__ v, int C, int N2, int A, float* __restrict__ raw) {
   extern __shared__ float sm[];
   float* vf = sm;             // [N2]
   float* pf = sm + N2;        // [2*N2], index p + N2*c
   float* hid = sm + 3 * N2;   // [256]
   float* red = hid + 256;     // [256]
-  const int b = blockIdx.x, tid = threadIdx.x, A = N2 + 1;
+  const int b = blockIdx.x, tid = threadIdx.x;
   const float* x = trunk + (size_t)b * C * N2;
   for (int p = tid; p < N2; p += 256) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -428,7 +428,7 @@ int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cuda
   if (dbg && dbg->trunk) cudaMemcpyAsync(dbg->trunk, h, (size_t)B * C * N2 * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (n_blocks < n->s.tower) return (int)cudaGetLastError();
   const size_t hsm = (size_t)(3 * N2 + 512) * sizeof(float);
-  heads_f32_kernel<<<B, 256, hsm, s>>>(h, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb, pi, v, C, N2,
+  heads_f32_kernel<<<B, 256, hsm, s>>>(h, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW, n->f_Pb, pi, v, C, N2, n->A,
                                        dbg ? dbg->raw : nullptr);
   if (ev) cudaEventRecord(ev[3], s);
   return (int)cudaGetLastError();

@@ -664,11 +664,11 @@ __global__ void __launch_bounds__(256) heads_tc_kernel(const __half* __restrict_
                                                        const float* __restrict__ D1W, const float* __restrict__ D1b,
                                                        const float* __restrict__ D2W, const float* __restrict__ D2b,
                                                        const float* __restrict__ PW, const float* __restrict__ Pb, float* __restrict__ pi,
-                                                       float* __restrict__ v, int B, int N,
+                                                       float* __restrict__ v, int B, int N, int A,
                                                        unsigned long long* trace, const float4* __restrict__ pre, float* __restrict__ raw, int split) {
   const unsigned long long trace_t0 = trace ? simt::gtimer() : 0ULL;
   extern __shared__ float sm[];
-  const int N2 = N * N, A = N2 + 1;
+  const int N2 = N * N;
   float* vf = sm;                       // [HPB][N2]
   float* pf = vf + HPB * N2;            // [HPB][2*N2], index p + N2*c
   float* hid = pf + HPB * 2 * N2;       // [HPB][256]
@@ -1312,7 +1312,7 @@ int nn_forward_tc(NNet* n, int B, float* pi, float* v, cudaStream_t s, char* err
   if (n_blocks < t->T) return cudaGetLastError() == cudaSuccess ? 0 : 1;   // debug: a truncated tower has no heads
   const size_t hsm = heads_smem(n->N2, n->A);
   heads_tc_kernel<<<(B + HPB - 1) / HPB, 256, hsm, s>>>(split ? t->sact[h] : t->act[h] + roff * 256, n->f_vw, n->f_pw, n->f_head_aff_d, n->f_D1W, n->f_D1b, n->f_D2W, n->f_D2b, n->f_PW,
-                                                        n->f_Pb, pi, v, B, t->N, t->trace, fuse ? t->head_pre + roff : nullptr, dbg ? dbg->raw : nullptr, split ? 1 : 0);
+                                                        n->f_Pb, pi, v, B, t->N, n->A, t->trace, fuse ? t->head_pre + roff : nullptr, dbg ? dbg->raw : nullptr, split ? 1 : 0);
   if (ev) cudaEventRecord(ev[3], s);
   cudaError_t e2 = cudaGetLastError();
   if (e2 != cudaSuccess) { snprintf(err, errlen, "heads launch: %s", cudaGetErrorString(e2)); return 1; }

@@ -122,7 +122,7 @@ struct MatchOp {
           if ((double)qp < w.st.resign_thr) {
             resign = 1;
             const uint32_t* lb = w.bits_of(w.st.root);
-            sc = bits_score(w.B, bits_load(w.B, lb, lb + c.KB), c.komi);
+            sc = game_score(c, w.B, bits_load(w.B, lb, lb + c.KB));
           } else {
             mv = w.pick_move();
           }
@@ -144,7 +144,7 @@ struct MatchOp {
             if (w.terminal(nm)) {
               done = 1;
               const uint32_t* lb = w.bits_of(w.st.root);
-              sc = bits_score(w.B, bits_load(w.B, lb, lb + c.KB), c.komi);
+              sc = game_score(c, w.B, bits_load(w.B, lb, lb + c.KB));
             }
           }
         }
@@ -371,9 +371,10 @@ struct HookOp {
         w.pos = bits_from_bytes(w.B, p->board);
         int status = 0, ko = -1, ncap = 0;
         const int mv = h.fmove;
-        if (mv != c.N2) {
+        bool ended = false;
+        if (mv != c.pass) {
           if (mv == p->ko) status = E_ILLEGAL;
-          else if (bits_play(w.B, w.pos, mv, p->to_play, true, ko, ncap)) status = E_ILLEGAL;
+          else if (game_play(c, w.B, w.pos, mv, p->to_play, true, ko, ncap, ended)) status = E_ILLEGAL;
         }
         if (status == 0) {
           bits_to_bytes(w.B, w.pos, o->board);
@@ -388,9 +389,9 @@ struct HookOp {
             o->n_hist = p->n_hist < 7 ? p->n_hist + 1 : 7;
             o->n = p->n + 1;
             o->to_play = -p->to_play;
-            o->ko = mv == c.N2 ? -1 : ko;
-            o->last_move_pass = mv == c.N2;
-            o->done = (mv == c.N2 && p->last_move_pass) ? 1 : 0;
+            o->ko = mv == c.pass ? -1 : ko;
+            o->last_move_pass = mv == c.pass;
+            o->done = ((mv == c.pass && p->last_move_pass) || ended) ? 1 : 0;
             o->caps[0] = p->caps[0] + (p->to_play == 1 ? ncap : 0);
             o->caps[1] = p->caps[1] + (p->to_play == 1 ? 0 : ncap);
             o->komi = p->komi;
@@ -402,16 +403,18 @@ struct HookOp {
       case HK_POS_LEGAL: {  // all_legal_moves (board.jl:393-424)
         const agz_position* p = h.pos_in;
         w.pos = bits_from_bytes(w.B, p->board);
-        const uint32_t legal = bits_legal(w.B, w.pos, p->to_play, p->ko);
+        const uint32_t legal = game_legal(c, w.B, w.pos, p->to_play, p->ko);
         if (lane < c.N)
           for (int i = 0; i < c.N; ++i) h.legal_out[c.N * lane + i] = (int8_t)((legal >> i) & 1u);
-        if (lane == 0) h.legal_out[c.N2] = 1;
+        if (lane == 0 && c.pass >= 0) h.legal_out[c.pass] = 1;
         finish(w, 0, 0, 0.f);
         return;
       }
       case HK_POS_SCORE: {
         const agz_position* p = h.pos_in;
-        float sc = bits_score(w.B, bits_from_bytes(w.B, p->board), p->komi);
+        Cfg cc = c;
+        cc.komi = p->komi;
+        float sc = game_score(cc, w.B, bits_from_bytes(w.B, p->board));
         finish(w, 0, 0, sc);
         return;
       }

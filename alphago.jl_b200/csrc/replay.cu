@@ -140,7 +140,7 @@ struct PackOp {
   __device__ void operator()(int wi, char* smem) const {
     (void)smem;
     const int lane = threadIdx.x & 31;
-    const BitsCtx B = bits_ctx(c.N, c.KB);   // Go rules on bitboard lines in registers (go_bits.cuh)
+    const BitsCtx B = bits_ctx(c.N, c.KB);   // the game's rules on bitboard lines in registers (go_bits.cuh, tree.cuh game_play)
     Lines pos;
     pos.b = 0;
     pos.w = 0;
@@ -164,9 +164,10 @@ struct PackOp {
       }
       __syncwarp();
       const int mv = v.ring_moves[(size_t)rslot * L + t];
-      if (mv != c.N2) {
+      if (mv != c.pass) {
         int ko, ncap;
-        bits_play(B, pos, mv, to_play, false, ko, ncap);
+        bool ended;
+        game_play(c, B, pos, mv, to_play, false, ko, ncap, ended);
       }
       to_play = -to_play;
       __syncwarp();

@@ -29,6 +29,7 @@ enum { PH_IDLE = 0, PH_SEED = 1, PH_SEARCH = 2, PH_WAIT_RING = 3, PH_MANUAL = 4,
 enum { F_EXPANDED = 1, F_DONE = 2, F_LASTPASS = 4 };
 enum { E_OK = 0, E_ILLEGAL = 1, E_ASSERT = 2, E_CAPACITY = 6 };
 enum { OP_VLOSS_ADD = 0, OP_VLOSS_REVERT = 1, OP_BACKUP = 2, OP_REVERT_VISITS = 3 };
+enum { GAME_GO = 0, GAME_GOMOKU = 1 };  // the two games behind the reference's Position interface (src/game/env.jl)
 static const unsigned long long SLOT_ROOT = ~0ULL;
 
 struct alignas(16) NodeMeta {  // 16 bytes, moved as one 128-bit word
@@ -66,6 +67,8 @@ struct GameState {
 
 struct Cfg {
   int N, N2, A, KA, AS, KB;
+  int game, n_in_row;  // GAME_GO (A = N^2 + 1) | GAME_GOMOKU (A = N^2: no pass; n_in_row stones win, gomoku.jl:1-19)
+  int pass;            // the flat pass move N^2, or -1 when the game has none
   int cap, maxd, pmax;
   int max_game_length, tau_threshold, readouts, parallel;
   int n_games, world, rank, inject_noise;
@@ -115,6 +118,35 @@ struct View {
   const double* rcp;          // rcp[k] = RN(1/k), k in [1, rcp_n): the divisor 1 + N(child) of the PUCT score is a small integer
   int rcp_n;
 };
+
+// ---- the Position interface (src/game/env.jl): play_move!, all_legal_moves, score dispatched on the game ------------------------
+// score: Go = Tromp-Taylor area score (board.jl:511-533); Gomoku = the winner's colour (gomoku board.jl:171), 0 for a full board
+AGZ_DEV float game_score(const Cfg& c, const BitsCtx& B, const Lines& L) {
+  if (c.game == GAME_GOMOKU) return bits_k_in_row(B, L.b, c.n_in_row) ? 1.f : (bits_k_in_row(B, L.w, c.n_in_row) ? -1.f : 0.f);
+  return bits_score(B, L, c.komi);
+}
+// the legal points of this lane's line (a pass, where the game has one, is always legal and not part of the set)
+AGZ_DEV uint32_t game_legal(const Cfg& c, const BitsCtx& B, const Lines& L, int to_play, int ko) {
+  if (c.game == GAME_GOMOKU) return B.full & ~(L.b | L.w);  // gomoku board.jl:95
+  return bits_legal(B, L, to_play, ko);
+}
+// Play `color` at flat point mv (not a pass).  Returns 0, or 1 when check_legal is set and the move is illegal (L unchanged).
+// done_out: the move ended the game (Gomoku: n_in_row made, or the board is full; Go ends by two passes, never here).
+AGZ_DEV int game_play(const Cfg& c, const BitsCtx& B, Lines& L, int mv, int color, bool check_legal, int& ko_out, int& ncap_out, bool& done_out) {
+  done_out = false;
+  if (c.game == GAME_GOMOKU) {  // gomoku board.jl:137-169
+    ko_out = -1;
+    ncap_out = 0;
+    const int cj = mv / B.N, ci = mv - cj * B.N;
+    const uint32_t cbit = B.lane == cj ? (1u << ci) : 0u;
+    if (check_legal && simt::any(((L.b | L.w) & cbit) != 0u)) return 1;
+    if (color == 1) L.b |= cbit; else L.w |= cbit;
+    const bool five = bits_k_in_row(B, color == 1 ? L.b : L.w, c.n_in_row);
+    done_out = five || !simt::any((B.full & ~(L.b | L.w)) != 0u);
+    return 0;
+  }
+  return bits_play(B, L, mv, color, check_legal, ko_out, ncap_out);
+}
 
 template <int KA>
 struct Warp {
@@ -187,7 +219,7 @@ struct Warp {
     bits_pack<KA>(B, pos.b, bw);
     bits_pack<KA>(B, pos.w, ww);
     uint32_t legal = 0;
-    if (!skip_legal) legal = bits_legal(B, pos, to_play, ko);
+    if (!skip_legal) legal = game_legal(c, B, pos, to_play, ko);
     bits_pack<KA>(B, legal, lw);
     uint32_t* bp = bits_of(node);
 #pragma unroll
@@ -211,7 +243,7 @@ struct Warp {
   AGZ_DEV int create_child(int parent, const NodeMeta& pm, int move, bool check_legal, NodeMeta* child_meta = nullptr) {
     if (st.count >= c.cap) { st.err = E_CAPACITY; return -1; }
     const uint32_t* pb = bits_of(parent);
-    if (check_legal && move != c.N2) {
+    if (check_legal && move != c.pass) {
       uint32_t lw = pb[2 * c.KB + (move >> 5)];
       if (!((lw >> (move & 31)) & 1u)) { st.err = E_ILLEGAL; return -1; }
     }
@@ -221,13 +253,14 @@ struct Warp {
     int n = pm.n + 1;
     int ko = -1, flags = 0, ncap = 0;
     bool term;
-    if (move == c.N2) {  // pass_move! (board.jl:426-440)
+    if (move == c.pass) {  // pass_move! (board.jl:426-440)
       flags = F_LASTPASS | ((pm.flags & F_LASTPASS) ? F_DONE : 0);
-      term = (flags & F_DONE) || n >= c.max_game_length;
     } else {
-      bits_play(B, pos, move, color, false, ko, ncap);
-      term = n >= c.max_game_length;
+      bool ended;
+      game_play(c, B, pos, move, color, false, ko, ncap, ended);
+      if (ended) flags = F_DONE;
     }
+    term = (flags & F_DONE) || n >= c.max_game_length;
     const NodeMeta cm = write_node(idx, parent, move, n, ko, -color, flags, term);
     if (child_meta) *child_meta = cm;
     simt::sync();
@@ -380,7 +413,7 @@ struct Warp {
           if (q) simt::prefetch_l2(q);
         }
       }
-      const int pass = c.N2;
+      const int pass = c.pass;   // -1 when the game has no pass: no action index equals it and F_LASTPASS is never set
       int best;
       // HACK of the reference: after a pass, look at the double pass first (mcts.jl:119-126)
       bool pass_first = false;
@@ -528,7 +561,7 @@ struct Warp {
       n_pathnodes += (unsigned long long)plen;
       if (terminal(lm)) {  // game over: back up the true result, do not evaluate (mcts_play.jl:80-84)
         const uint32_t* lb = bits_of(leaf);
-        float sc = bits_score(B, bits_load(B, lb, lb + c.KB), c.komi);
+        float sc = game_score(c, B, bits_load(B, lb, lb + c.KB));
         float value = sc > 0.f ? 1.f : (sc < 0.f ? -1.f : 0.f);
         if (plen <= 32) apply_path_regs(plen, OP_BACKUP, value);
         else apply_path(path, plen, OP_BACKUP, value);
@@ -741,7 +774,7 @@ struct Warp {
       cum[k] = simt::fadd(x, carry);
       carry = simt::shfl(cum[k], 31);
     }
-    const int last = c.N2 - 1;  // cdf[end-1]: pass is excluded from the normaliser
+    const int last = c.A - 2;  // cdf[end-1]: pass is excluded from the normaliser (in a game without pass: the last board point, as the reference does)
     float denom = 0.f;
 #pragma unroll
     for (int k = 0; k < KA; ++k)
@@ -1143,7 +1176,7 @@ struct Warp {
     const NodeMeta nm = load_meta(st.root);
     if (terminal(nm)) {  // is_done(root) (selfplay.jl:39-42)
       const uint32_t* lb = bits_of(st.root);
-      float sc = bits_score(B, bits_load(B, lb, lb + c.KB), c.komi);
+      float sc = game_score(c, B, bits_load(B, lb, lb + c.KB));
       st.final_score = sc;
       st.result = sc > 0.f ? 1 : (sc < 0.f ? -1 : 0);
       st.resigned = 0;

@@ -9,7 +9,8 @@
  *   - plain C types only; the caller owns every host buffer, the library owns all device memory;
  *   - every function returns an int32 status (AGZ_OK = 0); agz_last_error() describes the last failure;
  *   - one engine per GPU, driven by one host thread; calls are blocking; streams/graphs are private;
- *   - indices are 0-based: flat move f = N*col + row (the reference's 1-based fmove minus 1), pass = N*N;
+ *   - indices are 0-based: flat move f = N*col + row (the reference's 1-based fmove minus 1), pass = N*N (Go; Gomoku has no pass
+ *     and N*N actions);
  *   - arrays that the reference holds column-major (W x H x C x B, A x B) keep that memory order.
  *   - there is NO CPU fallback: agz_engine_create fails with AGZ_ERR_CUDA when no sm_100 device is present.
  */
@@ -35,6 +36,12 @@ extern "C" {
 #define AGZ_MAX_POINTS 361
 #define AGZ_MAX_ACTIONS 362
 #define AGZ_HIST 7             /* board deltas kept per position (board.jl:505-506) */
+
+/* games behind the reference's Position interface (src/game/env.jl): Go(n) = GoEnv(n) (src/game/go/go.jl:1-26) and
+ * GomokuEnv(board_size, connect_row) (src/game/gomoku/gomoku.jl:1-19: action_space = N^2, no pass, every empty point legal, the
+ * game ends on n_in_row stones in a line or a full board; score = the winner's colour, src/game/gomoku/board.jl:93-193) */
+#define AGZ_GAME_GO 0
+#define AGZ_GAME_GOMOKU 1
 
 /* evaluator kinds */
 #define AGZ_EVAL_DUMMY 0       /* fixed priors + value: DummyNet of test/test_mcts_player.jl:10-32; BASELINE config 5 */
@@ -78,6 +85,8 @@ typedef struct agz_config {
   int32_t record_ring;        /* finished-game records kept on device until harvested (0 = 2*n_games) */
   int32_t evaluator;          /* AGZ_EVAL_* */
   int32_t inject_noise;       /* 1 (selfplay.jl:23); 0 for play/evaluate-style search */
+  int32_t game;               /* AGZ_GAME_GO | AGZ_GAME_GOMOKU (GoEnv / GomokuEnv) */
+  int32_t n_in_row;           /* GomokuEnv.n_in_row (5); ignored for Go */
 } agz_config;
 
 /* GoPosition (board.jl:271-306) as a POD.  board[f] with f = N*col+row, values -1 W / 0 / +1 B.
@@ -133,6 +142,8 @@ typedef struct agz_progress {
 
 /* ---- lifecycle ----------------------------------------------------------------------------- */
 int32_t agz_config_default(agz_config* cfg, int32_t board_n);  /* GoEnv(N), MCTSRules(env), MCTSPlayer defaults */
+/* the same for either game: GoEnv(N) or GomokuEnv(N, n_in_row) (noise_alpha = Float32(0.03*361/action_space), mcts.jl:22) */
+int32_t agz_config_default_game(agz_config* cfg, int32_t game, int32_t board_n, int32_t n_in_row);
 int32_t agz_engine_create(const agz_config* cfg, agz_engine** out);
 void agz_engine_destroy(agz_engine* e);
 const char* agz_last_error(agz_engine* e);                      /* valid until the next call on e (e may be NULL) */

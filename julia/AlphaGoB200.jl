@@ -17,7 +17,7 @@
 # With Flux present, `NeuralNet(env, flux_nn)` copies the parameters of an AlphaGo.NeuralNet (base_net / value / policy chains).
 module AlphaGoB200
 
-export GoEnv, NeuralNet, MCTSPlayer, B200Engine, IllegalMove, selfplay, extract_data, get_replay_batch, train, evaluate,
+export GoEnv, GomokuEnv, Go, GameEnv, NeuralNet, MCTSPlayer, B200Engine, IllegalMove, selfplay, extract_data, get_replay_batch, train, evaluate,
        set_option!, get_option, load_weights!, read_weights
 
 const libagz = get(ENV, "LIBAGZ", joinpath(@__DIR__, "..", "alphago.jl_b200", "libagz.so"))
@@ -35,6 +35,7 @@ struct AgzConfig
   komi::Float32; resign_threshold::Float64; resign_disable_frac::Float64
   n_games::Int32; readouts::Int32; nodes_per_game::Int32; seed::UInt64
   device::Int32; world_size::Int32; rank::Int32; record_ring::Int32; evaluator::Int32; inject_noise::Int32
+  game::Int32; n_in_row::Int32
 end
 
 struct AgzGameHeader
@@ -54,35 +55,46 @@ function check(h::Ptr{Cvoid}, rc::Int32)
   error("libagz error $rc: $msg")
 end
 
-# ---- GoEnv (go.jl:1-26) -----------------------------------------------------------------------------------------------------
-struct GoEnv
+# ---- GameEnv: GoEnv (go.jl:1-26) and GomokuEnv (gomoku/gomoku.jl:1-19) -------------------------------------------------------
+abstract type GameEnv end
+struct GoEnv <: GameEnv
   N::Int; action_space::Int; planes::Int; max_action_space::Int
 end
 GoEnv(board_size::Int = 19, planes::Int = 17) = GoEnv(board_size, board_size^2 + 1, (planes - 1) ÷ 2, 361)
+struct GomokuEnv <: GameEnv
+  N::Int; n_in_row::Int; action_space::Int; planes::Int; max_action_space::Int
+end
+GomokuEnv(board_size::Int = 15, connect_row::Int = 5, planes::Int = 17) = GomokuEnv(board_size, connect_row, board_size^2, (planes - 1) ÷ 2, 361)
+Go(n) = GoEnv(n)                                                             # game/env.jl:2
+const AGZ_GAME_GO = Int32(0)
+const AGZ_GAME_GOMOKU = Int32(1)
+game_of(::GoEnv) = (AGZ_GAME_GO, Int32(0))
+game_of(env::GomokuEnv) = (AGZ_GAME_GOMOKU, Int32(env.n_in_row))
 
-to_flat0(c::Nothing, env::GoEnv) = env.N^2                                   # coords.jl:5-7, 0-based
-to_flat0(c::Tuple{Int,Int}, env::GoEnv) = env.N * (c[2] - 1) + (c[1] - 1)
-from_flat0(f::Integer, env::GoEnv) = f == env.N^2 ? nothing : (Int(f % env.N) + 1, Int(f ÷ env.N) + 1)
+to_flat0(c::Nothing, env::GameEnv) = env.N^2                                 # coords.jl:5-7, 0-based (not an action of Gomoku)
+to_flat0(c::Tuple{Int,Int}, env::GameEnv) = env.N * (c[2] - 1) + (c[1] - 1)
+from_flat0(f::Integer, env::GameEnv) = f == env.N^2 ? nothing : (Int(f % env.N) + 1, Int(f ÷ env.N) + 1)
 
 # ---- engine handle ----------------------------------------------------------------------------------------------------------
 mutable struct B200Engine
   h::Ptr{Cvoid}
   cfg::AgzConfig
-  env::GoEnv
+  env::GameEnv
 end
 
 """One engine = one GPU.  Keyword arguments are the fields of agz_config that callers of the reference set through
 `MCTSPlayer(...)` / `train(...)` kwargs; everything else keeps the reference's defaults (agz_config_default)."""
-function B200Engine(env::GoEnv; n_games::Int = 1024, readouts::Int = 800, tower_height::Int = 19, seed::Integer = 0, device::Int = 0,
+function B200Engine(env::GameEnv; n_games::Int = 1024, readouts::Int = 800, tower_height::Int = 19, seed::Integer = 0, device::Int = 0,
                     two_player_mode::Bool = false, resign_threshold::Float64 = -0.9, evaluator::Int32 = AGZ_EVAL_NN_TC,
                     world_size::Int = 1, rank::Int = 0, nodes_per_game::Int = 0)
   r = Ref{AgzConfig}()
-  check(C_NULL, ccall((:agz_config_default, libagz), Int32, (Ref{AgzConfig}, Int32), r, env.N))
+  game, n_in_row = game_of(env)
+  check(C_NULL, ccall((:agz_config_default_game, libagz), Int32, (Ref{AgzConfig}, Int32, Int32, Int32), r, game, env.N, n_in_row))
   c = r[]
   c = AgzConfig(c.board_n, c.planes, c.filters, tower_height, c.c_puct, c.noise_weight, c.noise_alpha, c.max_game_length,
                 two_player_mode ? Int32(-1) : c.tau_threshold, c.parallel_readouts, c.max_parallel, c.komi, resign_threshold,
                 c.resign_disable_frac, n_games, readouts, nodes_per_game, UInt64(seed), device, world_size, rank, 0, evaluator,
-                two_player_mode ? Int32(0) : Int32(1))
+                two_player_mode ? Int32(0) : Int32(1), c.game, c.n_in_row)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   check(C_NULL, ccall((:agz_engine_create, libagz), Int32, (Ref{AgzConfig}, Ref{Ptr{Cvoid}}), c, h))
   e = B200Engine(h[], c, env)
@@ -111,7 +123,7 @@ W1,b1,W2,b2,β1,γ1,β2,γ2 (resnet.jl:3-5); value = Conv, BatchNorm, Dense, Den
 `bn_mu` / `bn_sigma` per chain in layer order; `bn_mode` = AGZ_BN_VAR_EPS (Flux 0.10.4: σ² with ε = 1e-5) or AGZ_BN_STD (shipped
 models/agz_*.bson: moving standard deviation)."""
 mutable struct NeuralNet
-  env::GoEnv
+  env::GameEnv
   tower_height::Int
   params::Vector{Vector{Array{Float32}}}        # [base, value, policy]
   bn_mu::Vector{Vector{Float32}}
@@ -124,7 +136,7 @@ glorot_uniform(dims...) = (rand(Float32, dims...) .- 0.5f0) .* sqrt(24.0f0 / sum
 
 """NeuralNet(env; tower_height = 19): Flux-default initialisation restated (Glorot-uniform Conv / Dense weights, zero biases,
 BatchNorm γ = 1, β = 0, μ = 0, σ² = 1), same shapes as neural_net.jl:16-30."""
-function NeuralNet(env::GoEnv; tower_height::Int = 19)
+function NeuralNet(env::GameEnv; tower_height::Int = 19)
   N, C, P = env.N, 256, 2 * env.planes + 1
   z(n) = zeros(Float32, n); o(n) = ones(Float32, n)
   base = Array{Float32}[glorot_uniform(3, 3, P, C), z(C), z(C), o(C)]
@@ -141,7 +153,7 @@ end
 return the chain's parameter arrays in Flux `params` order and `flux_batchnorms(chain)` its BatchNorm layers in order; with
 Flux 0.10.4 these are `collect(Flux.params(chain))` and the `BatchNorm` entries of a walk over `chain.layers` (ResidualBlock:
 its `norm_layers`, resnet.jl:3-5).  Passed in as functions so that this file does not depend on Flux."""
-function NeuralNet(env::GoEnv, flux_nn; tower_height::Int, flux_params::Function, flux_batchnorms::Function, cpu::Function = identity)
+function NeuralNet(env::GameEnv, flux_nn; tower_height::Int, flux_params::Function, flux_batchnorms::Function, cpu::Function = identity)
   chains = (flux_nn.base_net, flux_nn.value, flux_nn.policy)
   ps = [Array{Float32}[Array{Float32}(cpu(p)) for p in flux_params(ch)] for ch in chains]
   mu = [reduce(vcat, [vec(Float32.(cpu(b.μ))) for b in flux_batchnorms(ch)]) for ch in chains]
@@ -203,7 +215,7 @@ struct RootView
   komi::Float32
 end
 struct MCTSPlayer
-  env::GoEnv
+  env::GameEnv
   root::RootView
   searches_π::Vector{Vector{Float32}}
   qs::Vector{Float32}
@@ -214,20 +226,23 @@ struct MCTSPlayer
   game_id::Int64
 end
 
-function result_string(hd::AgzGameHeader)                 # set_result! (mcts_play.jl:100-108), result_string (board.jl:546-555)
+function result_string(hd::AgzGameHeader, env::GameEnv = GoEnv())   # set_result! (mcts_play.jl:100-108), result_string (board.jl:546-555)
   hd.resigned != 0 && return hd.result == 1 ? "B+R" : "W+R"
+  if env isa GomokuEnv                                    # gomoku/board.jl:184-193: final_score carries the winner's colour
+    return hd.final_score > 0 ? "B" : (hd.final_score < 0 ? "W" : "DRAW")
+  end
   hd.final_score > 0 && return "B+" * string(round(hd.final_score; digits = 1))
   hd.final_score < 0 && return "W+" * string(round(abs(hd.final_score); digits = 1))
   "DRAW"
 end
 
-function players_from_records(env::GoEnv, readouts::Int, hd::Vector{AgzGameHeader}, moves::Matrix{Int16}, qs::Matrix{Float32},
+function players_from_records(env::GameEnv, readouts::Int, hd::Vector{AgzGameHeader}, moves::Matrix{Int16}, qs::Matrix{Float32},
                               pis::Array{Float32,3}, n::Int)
   out = MCTSPlayer[]
   for g in 1:n
     nm = Int(hd[g].n_moves)
     mv = Union{Nothing,Tuple{Int,Int}}[from_flat0(moves[t, g], env) for t in 1:nm]
-    push!(out, MCTSPlayer(env, RootView(nm, mv, 7.5f0), [pis[:, t, g] for t in 1:nm], qs[1:nm, g], Int(hd[g].result), result_string(hd[g]),
+    push!(out, MCTSPlayer(env, RootView(nm, mv, 7.5f0), [pis[:, t, g] for t in 1:nm], qs[1:nm, g], Int(hd[g].result), result_string(hd[g], env),
                           readouts, hd[g].resign_threshold, hd[g].game_id))
   end
   out
@@ -235,7 +250,7 @@ end
 
 """selfplay(env, nn, num_ro = 800; n_games = 1) -> the finished player (n_games == 1, like src/selfplay.jl:1) or a Vector of them:
 all games run concurrently on the GPU, game ids 0 … n_games-1 key the random streams (oracle/rng.py)."""
-function selfplay(env::GoEnv, nn::NeuralNet, num_ro::Int = 800; n_games::Int = 1, seed::Integer = 0, device::Int = 0, engine = nothing)
+function selfplay(env::GameEnv, nn::NeuralNet, num_ro::Int = 800; n_games::Int = 1, seed::Integer = 0, device::Int = 0, engine = nothing)
   e = engine === nothing ? B200Engine(env; n_games = n_games, readouts = num_ro, tower_height = nn.tower_height, seed = seed, device = device) : engine
   load_weights!(e, nn)
   L = Int(e.cfg.max_game_length) + 2; A = env.action_space
@@ -278,7 +293,7 @@ end
 triggers `epochs` optimisation steps on one uniform batch of the replay ring once `start_training_after` tuples are there --
 the reference's ratio of steps to games.  Sampling, feature building and the step stay on the device
 (agz_train_step_from_replay); the host only sees the loss."""
-function train(env::GoEnv; num_games::Int = 25000, memory_size::Int = 500000, batch_size::Int = 32, epochs::Int = 1, ckp_freq::Int = 1000,
+function train(env::GameEnv; num_games::Int = 25000, memory_size::Int = 500000, batch_size::Int = 32, epochs::Int = 1, ckp_freq::Int = 1000,
                readouts::Int = 800, tower_height::Int = 19, model = nothing, start_training_after::Int = 50000, concurrent::Int = 1024,
                seed::Integer = 0, lr::Float32 = 2f-2, momentum::Float32 = 9f-1, on_checkpoint = nn -> nothing, verbose::Bool = true)
   cur_nn = model === nothing ? NeuralNet(env; tower_height = tower_height) : model
@@ -305,7 +320,7 @@ function train(env::GoEnv; num_games::Int = 25000, memory_size::Int = 500000, ba
                            e.h, batch_size, UInt64(seed) * 1000003 + UInt64(done) * 131 + UInt64(ep), lr, momentum, loss))
           acc += loss[]
         end
-        verbose && println("Episode $done over. Loss: $(acc / epochs). Winner: $(result_string(hd[r])). Moves: $(hd[r].n_moves).")
+        verbose && println("Episode $done over. Loss: $(acc / epochs). Winner: $(result_string(hd[r], env)). Moves: $(hd[r].n_moves).")
       end
       if done ÷ ckp_freq > last_ckp
         last_ckp = done ÷ ckp_freq
@@ -320,7 +335,7 @@ function train(env::GoEnv; num_games::Int = 25000, memory_size::Int = 500000, ba
 end
 
 # ---- evaluate (neural_net.jl:103-158): all gating games at once, one engine per player ----------------------------------------
-function evaluate(env::GoEnv, black_net::NeuralNet, white_net::NeuralNet; num_games::Int = 400, ro::Int = 800, seed::Integer = 0, verbose::Bool = false)
+function evaluate(env::GameEnv, black_net::NeuralNet, white_net::NeuralNet; num_games::Int = 400, ro::Int = 800, seed::Integer = 0, verbose::Bool = false)
   G = num_games
   engines = [B200Engine(env; n_games = G, readouts = ro, tower_height = net.tower_height, seed = seed + k - 1, two_player_mode = true)
              for (k, net) in enumerate((black_net, white_net))]

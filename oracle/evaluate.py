@@ -7,7 +7,7 @@ the black player draws with (seed_black, game id), the white player with (seed_w
 Reference quirk kept on purpose: the win counter reads `result(black.root.position)` (:150), i.e. the area score of the
 final position, even when the game ended by resignation.
 """
-from . import go
+from . import game, go
 from . import mcts as M
 from . import mcts_play as P
 
@@ -34,10 +34,10 @@ def play_match_game(env, black_net, white_net, ro, seed_black, seed_white, game_
         move = P.pick_move(active)                                           # :135-138
         P.play_move(active, move)
         P.play_move(inactive, move)
-        moves.append(go.to_flat(move, env))
+        moves.append(game.to_flat(move, env))
         num_move += 1
         if P.is_done(active):                                                # :140-146
-            winner = go.result(active.root.position)
+            winner = game.result(active.root.position)
             P.set_result(active, winner, False)
             P.set_result(inactive, winner, False)
             break
@@ -48,7 +48,7 @@ def evaluate(env, black_net, white_net, num_games=400, ro=800, seed=0, resign_th
     games_won = 0
     for i in range(num_games):
         black, white, moves = play_match_game(env, black_net, white_net, ro, seed, seed + 1, i, resign_threshold)
-        won = go.result(black.root.position) == go.BLACK                     # :150
+        won = game.result(black.root.position) == go.BLACK                     # :150
         games_won += int(won)
         if details is not None:
             details.append({"moves": moves, "result": black.result, "result_string": black.result_string, "black_won": won})

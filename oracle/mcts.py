@@ -5,7 +5,7 @@ Float32; Q is Float32; U and the score comparison are Float64 because `c_puct`
 is a Float64 global (mcts.jl:11, 86-92).
 """
 import numpy as np
-from . import go, rng
+from . import game, go, rng
 
 c_puct = 0.96                                            # mcts.jl:11
 dirichlet_noise_weight = 0.25                            # mcts.jl:13
@@ -88,7 +88,7 @@ class MCTSNode:                                          # mcts.jl:41-82
 
 
 def legal_moves(x):                                      # mcts.jl:84
-    return go.all_legal_moves(x.position)
+    return game.all_legal_moves(x.position)
 
 
 def child_Q(x):                                          # mcts.jl:89 (Float32)
@@ -118,7 +118,7 @@ def select_leaf(root):                                   # mcts.jl:108-138
         if not current.is_expanded:
             break
         pos = current.position
-        if len(pos.recent) != 0 and pos.recent[-1].move is None and current.child_N[pass_move] == 0:
+        if game.is_go(pos.env) and len(pos.recent) != 0 and pos.recent[-1].move is None and current.child_N[pass_move] == 0:   # Go only (mcts.jl:121)
             current = maybe_add_child(current, pass_move)
             depth += 1
             continue
@@ -135,7 +135,7 @@ def select_leaf(root):                                   # mcts.jl:108-138
 
 def maybe_add_child(node, fcoord):                       # mcts.jl:140-147
     if fcoord not in node.children:
-        new_pos = go.play_move(node.position, go.from_flat(fcoord, node.position.env))
+        new_pos = game.play_move(node.position, game.from_flat(fcoord, node.position.env))
         node.children[fcoord] = MCTSNode(new_pos, fcoord, node)
     return node.children[fcoord]
 

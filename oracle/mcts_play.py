@@ -1,6 +1,6 @@
 """Search player: restatement of src/mcts_play.jl.  TEST INFRASTRUCTURE."""
 import numpy as np
-from . import go, rng
+from . import game, go, rng
 from . import mcts as M
 
 f32 = np.float32
@@ -32,7 +32,7 @@ def play_move(player, c):                                # mcts_play.jl:26-50
         player.searches_N.append(root.child_N.copy())
     player.qs.append(f32(root.Q))
     try:
-        player.root = M.maybe_add_child(root, go.to_flat(c, root.position.env))
+        player.root = M.maybe_add_child(root, game.to_flat(c, root.position.env))
     except go.IllegalMove:
         if not player.two_player_mode:
             player.searches_pi.pop()
@@ -60,7 +60,7 @@ def pick_move(player):                                   # mcts_play.jl:52-71
         selection = rng.u53(r[0], r[1])
         fcoord = int(np.searchsorted(cdf.astype(np.float64), selection, side="left"))
         assert root.child_N[fcoord] != 0
-    return go.from_flat(fcoord, root.position.env)
+    return game.from_flat(fcoord, root.position.env)
 
 
 def tree_search(player, parallel_readouts=8):            # mcts_play.jl:73-98
@@ -70,7 +70,7 @@ def tree_search(player, parallel_readouts=8):            # mcts_play.jl:73-98
         failsafe += 1
         leaf = M.select_leaf(player.root)
         if M.is_done(leaf):
-            value = go.result(leaf.position)
+            value = game.result(leaf.position)
             M.backup_value(leaf, value, player.root)
             continue
         M.add_virtual_loss(leaf, player.root)
@@ -88,13 +88,13 @@ def set_result(player, winner, was_resign):              # mcts_play.jl:100-108
     if was_resign:
         s = "B+R" if winner == go.BLACK else "W+R"
     else:
-        s = go.result_string(player.root.position)
+        s = game.result_string(player.root.position)
     player.result_string = s
 
 
 def initialize_game(player, pos=None):                   # mcts_play.jl:110-118
     if pos is None:
-        pos = go.GoPosition(player.env)
+        pos = game.Position(player.env)
     player.rng.reset_root()
     player.root = M.MCTSNode(pos, rng_ctx=player.rng)
     player.result = 0
@@ -115,7 +115,7 @@ def extract_data(player):                                # mcts_play.jl:126-139
     assert len(player.searches_pi) == player.root.position.n
     positions, results = [], []
     pis = [p.copy() for p in player.searches_pi]
-    for pwc in go.replay_position(player.root.position, player.result):
+    for pwc in game.replay_position(player.root.position, player.result):
         positions.append(pwc.position)
         results.append(pwc.result)
     return positions, pis, results

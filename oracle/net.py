@@ -63,10 +63,10 @@ def glorot_uniform(rs, *dims):
 class NeuralNet:
     """neural_net.jl:7-33.  Parameters are numpy arrays in Flux shapes."""
 
-    def __init__(self, N=19, tower_height=19, filters=256, planes=17, seed=0):
+    def __init__(self, N=19, tower_height=19, filters=256, planes=17, seed=0, action_space=None):
         rs = np.random.RandomState(seed)
         self.N, self.T, self.C, self.planes = N, tower_height, filters, planes
-        A = N * N + 1
+        A = N * N + 1 if action_space is None else action_space   # env.action_space (neural_net.jl:30): N^2 for Gomoku
         C = filters
         self.stem_W = glorot_uniform(rs, 3, 3, planes, C); self.stem_b = np.zeros(C, np.float32); self.stem_bn = BN(C)
         self.blocks = []

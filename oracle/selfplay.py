@@ -1,6 +1,6 @@
 """Self-play driver: restatement of src/selfplay.jl.  TEST INFRASTRUCTURE."""
 import numpy as np
-from . import go, rng
+from . import game, go, rng
 from . import mcts as M
 from . import mcts_play as P
 
@@ -33,6 +33,6 @@ def selfplay(env, nn, num_ro=800, seed=0, game_id=0, resign_threshold=-0.9, resi
         if on_move is not None:
             on_move(player, move)
         if M.is_done(player.root):
-            P.set_result(player, go.result(player.root.position), False)
+            P.set_result(player, game.result(player.root.position), False)
             break
     return player

@@ -52,7 +52,7 @@ def test_no_cpu_fallback():
 
 def test_struct_sizes_match_header():
     # sizes computed from the C declarations in include/agz.h
-    assert ctypes.sizeof(agz.Config) == 128
+    assert ctypes.sizeof(agz.Config) == 136
     assert ctypes.sizeof(agz.Position) == 2924
     assert ctypes.sizeof(agz.NodeView) == 9456
     assert ctypes.sizeof(agz.binding.GameHeader) == 32
