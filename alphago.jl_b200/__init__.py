@@ -5,6 +5,7 @@ from .binding import (Engine, Config, Position, NodeView, GameRecord, IllegalMov
                       SYMBOLS, EVAL_DUMMY, EVAL_NN_TC, EVAL_NN_F32, BN_VAR_EPS, BN_STD, CHAIN_BASE, CHAIN_VALUE,
                       CHAIN_POLICY, GAME_GO, GAME_GOMOKU)
 from . import api
+from . import gtp
 from .api import (GoEnv, GoPosition, GomokuEnv, GomokuPosition, Go, result_string, NeuralNet, MCTSPlayer, MCTSNode, selfplay, evaluate, train, play, MatchGame, initialize_game, tree_search, pick_move,
                   play_move, should_resign, is_done, set_result, extract_data, select_leaf, incorporate_results,
                   maybe_add_child, add_virtual_loss, revert_virtual_loss, inject_noise, to_flat, from_flat, from_kgs,

@@ -181,8 +181,45 @@ def test_nn_selfplay_matches_oracle_tree():
         assert list(r.moves) == [ogm.to_flat(m.move, oenv) for m in op.root.position.recent], gid
         assert np.array_equal(np.array(op.searches_N), r.visits)
         assert r.result == op.result and r.result_string == op.result_string
-    # the replay ring packs Gomoku tuples with the same rules: boards of tuple t = the position before move t
-    n = eng.replay_gather()
-    assert n == sum(r.n_moves for r in recs)
     for e in (helper, eng):
         e.close()
+
+
+@pytest.mark.gpu
+def test_replay_tuples_and_training_step():
+    """extract_data / replay_position (gomoku board.jl:195-217) on the device: the ring's tuples are the positions before each move
+    replayed with the Gomoku rules, pi is N^2 wide, z = the game's result; one optimisation step runs on them (train.jl:66-70)."""
+    N = 7
+    eng = agz.Engine(N, lib_path=lib_for("cuda"), n_games=4, readouts=16, seed=21, tower_height=1, game=agz.GAME_GOMOKU, n_in_row=4)
+    eng.set_dummy_evaluator(None, 0.0)
+    eng.selfplay_start(6)
+    for _ in range(400):
+        pr = eng.selfplay_step(16)
+        if pr.games_finished == 6:
+            break
+    assert pr.games_finished == 6 and pr.error == 0
+    total = eng.replay_gather()
+    recs = eng.selfplay_harvest(16)
+    assert total == sum(r.n_moves for r in recs) and total > 0
+    boards, tp, pis, zs = eng.replay_read(0, total)
+    assert pis.shape == (total, N * N)
+    oenv = ogm.GomokuEnv(N, 4)
+    expected = []
+    for r in recs:
+        pos = ogm.GomokuPosition(oenv)
+        for t, m in enumerate(r.moves):
+            expected.append((pos.board.flatten(order="F").copy(), pos.to_play, r.searches_pi[t], r.result))
+            pos = ogm.play_move(pos, ogm.from_flat(int(m), oenv))
+        assert pos.done or r.resigned
+    used = set()
+    for k in range(total):
+        hit = next((i for i, (b, p, pi, z) in enumerate(expected)
+                    if i not in used and p == tp[k] and z == zs[k] and np.array_equal(b, boards[k]) and np.array_equal(pi, pis[k])), None)
+        assert hit is not None, k
+        used.add(hit)
+    nn = agz.NeuralNet(agz.GomokuEnv(N, 4, lib_path=lib_for("cuda")), tower_height=1, seed=1)
+    nn.push(eng)
+    l0 = eng.train_step_from_replay(16, seed=1)
+    l1 = eng.train_step_from_replay(16, seed=1)
+    assert np.isfinite(l0) and np.isfinite(l1) and l1 < l0          # the same batch again: the loss went down
+    eng.close()
