@@ -40,7 +40,7 @@ struct TraceTag {
 };
 
 template <class Op>
-__global__ void __launch_bounds__(128, MinBlocks<Op>::v) k_warps(const Op op, int n_warps, int smem_per_warp) {
+__global__ void __launch_bounds__(128, MinBlocks<Op>::v) k_warps(const __grid_constant__ Op op, int n_warps, int smem_per_warp) {
   extern __shared__ __align__(16) char smem[];
   const int wib = threadIdx.x >> 5;
   const int w = blockIdx.x * 4 + wib;

@@ -72,6 +72,24 @@ AGZ_DEV void bits_pack(const BitsCtx& B, uint32_t line, uint32_t (&out)[KW]) {
   }
 }
 
+// three planes at once (a new node's black / white / legal planes): the per-word lane predicates are shared
+template <int KW>
+AGZ_DEV void bits_pack3(const BitsCtx& B, uint32_t l0, uint32_t l1, uint32_t l2, uint32_t (&o0)[KW], uint32_t (&o1)[KW], uint32_t (&o2)[KW]) {
+  const int bit = B.N * B.lane, w0 = bit >> 5, s = bit & 31;
+  const uint32_t lo0 = l0 << s, lo1 = l1 << s, lo2 = l2 << s;
+  const uint32_t hi0 = s ? (l0 >> (32 - s)) : 0u, hi1 = s ? (l1 >> (32 - s)) : 0u, hi2 = s ? (l2 >> (32 - s)) : 0u;
+#pragma unroll
+  for (int k = 0; k < KW; ++k) {
+    o0[k] = 0; o1[k] = 0; o2[k] = 0;
+    if (k < B.KB) {
+      const bool a = w0 == k, b = w0 + 1 == k;
+      o0[k] = simt::reduce_or((a ? lo0 : 0u) | (b ? hi0 : 0u));
+      o1[k] = simt::reduce_or((a ? lo1 : 0u) | (b ? hi1 : 0u));
+      o2[k] = simt::reduce_or((a ? lo2 : 0u) | (b ? hi2 : 0u));
+    }
+  }
+}
+
 // board bytes (-1 W / 0 / +1 B, flat order) <-> lines; used by the position hooks only
 AGZ_DEV Lines bits_from_bytes(const BitsCtx& B, const int8_t* board) {
   Lines L;

@@ -67,7 +67,12 @@ struct IncorporateOp {
     const int g = only_slot >= 0 ? only_slot : slot0 + wi;
     Warp<KA> w(c, v, g, smem);
     w.search_incorporate();
-    if (only_slot < 0) w.after_round();
+    if (only_slot < 0 && w.after_round_due()) {
+      w.store_state();
+      simt::sync();
+      after_round_cold<KA>(&c, &v, g, smem);
+      w.st = v.gs[g];
+    }
     w.st.seed_round = 0;
     w.store_state();
   }
@@ -173,7 +178,12 @@ struct DummyRoundsOp {
       else { w.st.nleaf = 0; w.st.seed_round = 0; }
       simt::sync();  // the leaf records written by lane 0 are read by every lane below
       w.search_incorporate();
-      w.after_round();
+      if (w.after_round_due()) {
+        w.store_state();
+        simt::sync();
+        after_round_cold<KA>(&c, &v, g, smem);
+        w.st = v.gs[g];
+      }
       w.st.seed_round = 0;
       if (w.st.phase == PH_IDLE) break;
     }

@@ -11,9 +11,14 @@
 #define AGZ_CUDA 1
 #include <cuda_runtime.h>
 #define AGZ_DEV __device__ __forceinline__
+#define AGZ_COLD __device__ __noinline__
 
 namespace simt {
+#if AGZ_LANE_ASM
+AGZ_DEV int lane() { int l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }   // not rematerialisable: stays in a register
+#else
 AGZ_DEV int lane() { return threadIdx.x & 31; }
+#endif
 AGZ_DEV void sync() { __syncwarp(); }
 AGZ_DEV unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 AGZ_DEV bool any(bool p) { return __any_sync(0xffffffffu, p); }
@@ -73,6 +78,7 @@ AGZ_DEV bool trace_cta() { return threadIdx.x == 0 && (blockIdx.x == 0 || blockI
 #else  // ------------------------------------------------------------------ host emulation (tests only)
 #define AGZ_CUDA 0
 #define AGZ_DEV inline
+#define AGZ_COLD inline
 #include <math.h>
 #include <string.h>
 #include <ucontext.h>

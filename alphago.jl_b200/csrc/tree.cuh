@@ -148,6 +148,17 @@ AGZ_DEV int game_play(const Cfg& c, const BitsCtx& B, Lines& L, int mv, int colo
   return bits_play(B, L, mv, color, check_legal, ko_out, ncap_out);
 }
 
+// position of the n-th (0-based) set bit of m (n < popc(m)): five popcount halvings instead of clearing n bits one by one
+AGZ_DEV int nth_set_bit(unsigned m, int n) {
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const int cnt = simt::popc((m >> pos) & ((1u << w) - 1u));
+    if (n >= cnt) { n -= cnt; pos += w; }
+  }
+  return pos;
+}
+
 template <int KA>
 struct Warp {
   const Cfg& c;
@@ -216,11 +227,9 @@ struct Warp {
   // Write a node whose position is `pos` (terminal nodes carry no legal-move mask: `skip_legal`).
   AGZ_DEV NodeMeta write_node(int node, int parent, int fmove, int n, int ko, int to_play, int flags, bool skip_legal) {
     uint32_t bw[KA], ww[KA], lw[KA];
-    bits_pack<KA>(B, pos.b, bw);
-    bits_pack<KA>(B, pos.w, ww);
     uint32_t legal = 0;
     if (!skip_legal) legal = game_legal(c, B, pos, to_play, ko);
-    bits_pack<KA>(B, legal, lw);
+    bits_pack3<KA>(B, pos.b, pos.w, legal, bw, ww, lw);
     uint32_t* bp = bits_of(node);
 #pragma unroll
     for (int k = 0; k < KA; ++k) {
@@ -499,9 +508,7 @@ struct Warp {
           int cntk = simt::popc(tm[k]);
           if (!found) {
             if (pick < cntk) {
-              unsigned mk = tm[k];
-              for (int t = 0; t < pick; ++t) mk &= mk - 1;  // drop the `pick` lowest set bits
-              best = k * 32 + simt::ffs(mk) - 1;
+              best = k * 32 + nth_set_bit(tm[k], pick);
               found = true;
             } else {
               pick -= cntk;
@@ -627,10 +634,18 @@ struct Warp {
       }
       simt::sync();  // every lane has read its flags before any lane rewrites them below
       const int kn = nleaf - k0 < 32 ? nleaf - k0 : 32;
+      PathEnt pre;
+      pre.slot = SLOT_ROOT; pre.node = 0; pre.to_play = 0;
+      if (lane < simt::shfl(my_plen, 0)) pre = path_of(k0)[lane];
       for (int kk = 0; kk < kn; ++kk) {
         const int k = k0 + kk;
         const PathEnt* path = path_of(k);
         const int leaf = simt::shfl(my_leaf, kk), plen = simt::shfl(my_plen, kk), flags = simt::shfl(my_flags, kk);
+        PathEnt nxt = pre;   // the next leaf's path entries travel while this leaf is finished
+        {
+          const int plen_next = simt::shfl(my_plen, (kk + 1) & 31);
+          if (kk + 1 < kn && lane < plen_next) nxt = path_of(k + 1)[lane];
+        }
         const float value = simt::shfl(my_value, kk);
         const size_t b = (size_t)g * c.pmax + k;
         // revert_virtual_loss!, then incorporate_results! (mcts_play.jl:92-95, mcts.jl:188-213)
@@ -640,17 +655,20 @@ struct Warp {
         n_dup += dup ? 1 : 0;
         if (!dup) {
           if (lane == 0) v.meta[nbase + leaf].flags = (uint8_t)(flags | F_EXPANDED);
-          const float* probs = v.eval_pi + b * v.pi_stride;
-          const size_t r = row(leaf);
+          const float* probs = v.eval_pi + b * v.pi_stride + lane;
+          const size_t r = row(leaf) + lane;
+          float* Pr = v.P + r;
+          float* Wr = v.W + r;
+          const int left = c.A - lane;   // lane's entries q*32 with q*32 < left are actions
 #pragma unroll
           for (int q = 0; q < KA; ++q) {
-            int a = q * 32 + lane;
-            bool in = a < c.A;
-            v.P[r + a] = in ? probs[a] : 0.f;
-            v.W[r + a] = in ? value : 0.f;  // children start from the parent's value (mcts.jl:211)
+            const bool in = q * 32 < left;
+            Pr[q * 32] = in ? probs[q * 32] : 0.f;
+            Wr[q * 32] = in ? value : 0.f;  // children start from the parent's value (mcts.jl:211)
           }
         }
-        finish_path(path, plen, !seed_mode, dup, value);
+        finish_path(path, plen, !seed_mode, dup, value, pre);
+        pre = nxt;
       }
       simt::sync();  // the flag writes of this pass are visible to the next pass's loads
     }
@@ -660,12 +678,15 @@ struct Warp {
 
   // revert_virtual_loss! followed by backup_value!(value) (fresh leaf) or by revert_visits! (duplicate): one read-modify-write per
   // path entry instead of two; every W slot sees the same two fp32 additions in the same order as the two separate passes.
-  AGZ_DEV void finish_path(const PathEnt* path, int plen, bool had_vloss, bool dup, float value) {
+  // `pre` = path[lane] (lane < plen), loaded by the caller while the previous leaf was being finished: the entry loads of successive
+  // leaves are independent, only their read-modify-writes (shared ancestors) are ordered.
+  AGZ_DEV void finish_path(const PathEnt* path, int plen, bool had_vloss, bool dup, float value, const PathEnt& pre) {
     simt::sync();
     for (int d0 = 0; d0 < plen; d0 += 32) {
       int d = d0 + lane;
       if (d < plen) {
-        PathEnt e = path[d];
+        PathEnt e = pre;
+        if (d0) e = path[d];
         if (e.slot != SLOT_ROOT) {
           if (had_vloss || !dup) {
             float w = v.W[e.slot];
@@ -677,9 +698,9 @@ struct Warp {
         }
       }
     }
-    PathEnt e0 = path[0];
-    if (e0.slot == SLOT_ROOT) {
-      if (had_vloss) st.root_W = simt::fadd(st.root_W, (float)(-e0.to_play));
+    const int root0 = simt::shfl((int)(pre.slot == SLOT_ROOT ? 1 : 0), 0), tp0 = simt::shfl(pre.to_play, 0);   // path[0]
+    if (root0) {
+      if (had_vloss) st.root_W = simt::fadd(st.root_W, (float)(-tp0));
       if (!dup) st.root_W = simt::fadd(st.root_W, value);
       if (dup) st.root_N = simt::fsub(st.root_N, 1.0f);
     }
@@ -750,9 +771,7 @@ struct Warp {
         int cntk = simt::popc(tm[k]);
         if (best < 0) {
           if (pick < cntk) {
-            unsigned mk = tm[k];
-            for (int t = 0; t < pick; ++t) mk &= mk - 1;
-            best = k * 32 + simt::ffs(mk) - 1;
+            best = k * 32 + nth_set_bit(tm[k], pick);
           } else {
             pick -= cntk;
           }
@@ -1131,6 +1150,15 @@ struct Warp {
   }
 
   // ---- selfplay.jl:22-43, evaluated once per round after the leaves have been incorporated -----------
+  // Nearly always nothing is due (the search has not reached its visit target yet): the kernels test that inline and call the
+  // per-move logic out of line (after_round_cold below), which keeps pick_move / play_move! / compaction / noise / game end --
+  // nine tenths of the code -- out of the instruction stream of the search loop.
+  AGZ_DEV bool after_round_due() const {
+    const bool searching = (st.phase == PH_SEARCH || st.phase == PH_MATCH_SEARCH) && st.root_N < st.target_N;
+    const bool idle = st.phase == PH_IDLE || st.phase == PH_MANUAL || st.phase == PH_MATCH_WAIT || (st.phase == PH_SEED && !st.seed_round);
+    return !(st.err == 0 && (searching || idle));
+  }
+
   AGZ_DEV void after_round() {
     if (st.err) {
       if (st.phase == PH_MATCH_SEARCH && lane == 0) simt::atomic_add(&v.ctr[CTR_MATCH_BUSY], ~0ULL);
@@ -1187,5 +1215,14 @@ struct Warp {
     st.target_N = simt::fadd(st.root_N, (float)c.readouts);
   }
 };
+
+// the per-move logic of one game, out of line: the caller has stored the game's state and reloads it afterwards
+template <int KA>
+AGZ_COLD void after_round_cold(const Cfg* c, const View* v, int g, char* smem) {
+  Warp<KA> w(*c, *v, g, smem);
+  w.after_round();
+  w.store_state();
+  simt::sync();
+}
 
 }  // namespace agz

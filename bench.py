@@ -141,10 +141,11 @@ def tree_bytes_per_readout(N, d):
     return (d - 1) * 13 * A + 16 * A + 8 * N * N + 16 * d
 
 
-def leg_c5(agz, device, hbm):
+def leg_c5(agz, device, hbm, lib_path=None):
     """BASELINE config C5: MCTS-only, 9x9, uniform prior / value 0 (DummyNet), 8192 trees x 1600 readouts per move."""
     trees, readouts, rounds = 8192, 1600, 200
-    eng = agz.Engine(9, n_games=trees, readouts=readouts, tower_height=1, seed=0, evaluator=agz.EVAL_DUMMY, nodes_per_game=3600, device=device)
+    eng = agz.Engine(9, n_games=trees, readouts=readouts, tower_height=1, seed=0, evaluator=agz.EVAL_DUMMY, nodes_per_game=3600, device=device,
+                     **({"lib_path": lib_path} if lib_path else {}))
     try:
         eng.selfplay_start(-1)
         pr0 = eng.selfplay_step(rounds + 10)              # warm-up: past the first move of every tree
