@@ -206,68 +206,126 @@ int nn_commit(NNet* n, cudaStream_t s, char* err, size_t errlen) {
 // ----------------------------------------------------------------------------------------------------------
 // fp32 kernels.  Activations: [B][C][N2] with point p = N*j + i (i fastest) = the reference's W x H x C x B.
 
-static const int COT = 16, CIT = 16;
+// Register-tiled direct convolution: a CTA of 128 threads computes COT = 32 output channels x PT = 48 consecutive points of one
+// board; thread (ty, tx) owns channels co0 + 4*ty .. +3 and points p0 + tx + 16*q, q < 3 (12 accumulators; a training batch is a
+// small problem, and small thread tiles are what keeps enough warps on 148 SMs).  Per input channel and
+// tap it reads one float4 of weights (layout [ci][tap][co] in global and shared memory, a broadcast within a half warp) and 6 inputs from the zero-haloed
+// board in shared memory: 4 shared loads per 12 FMAs.  Input channels arrive in chunks of CIT through a two-stage cp.async pipeline
+// (the halo is zeroed once; only interior points are ever written).  Every accumulator still sums its (ci, tap) products in ascending
+// order with one fmaf each -- the same arithmetic, bit for bit, as a one-output-per-thread loop (which this kernel replaced: 1 shared
+// load per FMA, 9 TFLOP/s).
+static const int COT = 32, CIT = 8, PT = 96, PQ = 6, CONV_THREADS = 128;
 
-__global__ void __launch_bounds__(128) conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                          const float* __restrict__ scale, const float* __restrict__ shift,
-                                                          const float* __restrict__ res, float* __restrict__ out, int Cin, int Cout,
-                                                          int N, int relu) {
-  extern __shared__ float sm[];
+static size_t conv_f32_stage(int N) { return (size_t)((CIT * (N + 2) * (N + 2) + 3) / 4 * 4 + CIT * 9 * COT); }   // floats per stage
+static size_t conv_f32_smem(int N) { return 2 * conv_f32_stage(N) * sizeof(float); }
+static int conv_f32_chunks(int N) { return (N * N + PT - 1) / PT; }
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(K)); }
+// r / n for 0 <= r < 2^20 and small n, without the integer-division sequence: (r + 0.5) / n is at least 0.5 / n away from an integer
+__device__ __forceinline__ int small_div(int r, float inv_n) { return __float2int_rz(((float)r + 0.5f) * inv_n); }
+
+__global__ void __launch_bounds__(CONV_THREADS) conv3x3_f32_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                   const float* __restrict__ res, float* __restrict__ out, int Cin, int Cout,
+                                                                   int N, int relu, int chunks) {
+  extern __shared__ __align__(16) float sm[];
   const int N2 = N * N, NP = N + 2, NPP = NP * NP;
-  float* sin = sm;                      // [CIT][NPP], zero halo
-  float* sw = sm + CIT * NPP;           // [COT][CIT][9]
-  const int b = blockIdx.x, co0 = blockIdx.y * COT, tid = threadIdx.x;
-  float acc[COT][3];
-#pragma unroll
-  for (int c = 0; c < COT; ++c)
-#pragma unroll
-    for (int q = 0; q < 3; ++q) acc[c][q] = 0.f;
-  for (int ci0 = 0; ci0 < Cin; ci0 += CIT) {
-    for (int x = tid; x < CIT * NPP; x += 128) {
-      int ci = x / NPP, r = x % NPP, jj = r / NP - 1, ii = r % NP - 1;
-      float val = 0.f;
-      if (ci0 + ci < Cin && ii >= 0 && ii < N && jj >= 0 && jj < N) val = in[((size_t)b * Cin + ci0 + ci) * N2 + jj * N + ii];
-      sin[x] = val;
+  const int in_floats = (CIT * NPP + 3) / 4 * 4, stage = in_floats + CIT * 9 * COT;
+  const float inv_n = 1.0f / (float)N;
+  const int b = blockIdx.x / chunks, p0 = (blockIdx.x % chunks) * PT, co0 = blockIdx.y * COT, tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  for (int x = tid; x < 2 * stage; x += CONV_THREADS) sm[x] = 0.f;   // halos (and channels past Cin / Cout) stay zero
+  __syncthreads();
+  auto fill = [&](int buf, int ci0) {
+    float* sin = sm + buf * stage;     // [CIT][NPP]
+    float* sw = sin + in_floats;       // [CIT][9][COT]
+    for (int ci = 0; ci < CIT && ci0 + ci < Cin; ++ci) {
+      const float* src = in + ((size_t)b * Cin + ci0 + ci) * N2;
+      for (int p = tid; p < N2; p += CONV_THREADS) {
+        const int jj = small_div(p, inv_n), ii = p - jj * N;
+        cp_async4(sin + ci * NPP + (jj + 1) * NP + ii + 1, src + p);
+      }
     }
-    for (int x = tid; x < COT * CIT * 9; x += 128) {
-      int co = x / (CIT * 9), r = x % (CIT * 9), ci = r / 9, t = r % 9;
-      sw[x] = (ci0 + ci < Cin && co0 + co < Cout) ? w[((size_t)(co0 + co) * Cin + ci0 + ci) * 9 + t] : 0.f;
-    }
-    __syncthreads();
+    // weights arrive as w[ci][tap][co] (output channel fastest): a row of COT channels is contiguous in both memories
+    const bool vec = (Cout & 3) == 0;
+    for (int x = tid; x < CIT * 9 * (COT / 4); x += CONV_THREADS) {
+      const int row = x / (COT / 4), c4 = (x % (COT / 4)) * 4;   // row = ci * 9 + tap inside the chunk
+      if (ci0 * 9 + row < Cin * 9) {
+        const float* src = w + ((size_t)ci0 * 9 + row) * Cout + co0 + c4;
+        float* dst = sw + row * COT + c4;
+        if (vec && co0 + c4 + 3 < Cout) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+        } else {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      int p = tid + q * 128;
-      if (p < N2) {
-        int jj = p / N, ii = p % N;
-        for (int ci = 0; ci < CIT; ++ci) {
-          float x[9];
-#pragma unroll
-          for (int kj = 0; kj < 3; ++kj)
-#pragma unroll
-            for (int ki = 0; ki < 3; ++ki) x[kj * 3 + ki] = sin[ci * NPP + (jj + kj) * NP + (ii + ki)];
-#pragma unroll
-          for (int c = 0; c < COT; ++c) {
-            const float* wp = sw + (c * CIT + ci) * 9;
-            float a = acc[c][q];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) a = fmaf(wp[t], x[t], a);
-            acc[c][q] = a;
-          }
+          for (int e = 0; e < 4; ++e)
+            if (co0 + c4 + e < Cout) cp_async4(dst + e, src + e);
         }
       }
     }
+    cp_async_commit();
+  };
+  int base[PQ];                                  // index of the window's corner (jj-1, ii-1) in the padded board = jj*NP + ii
+#pragma unroll
+  for (int q = 0; q < PQ; ++q) {
+    const int p = p0 + tx + 16 * q;
+    const int jj = small_div(p, inv_n);
+    base[q] = p < N2 ? jj * NP + (p - jj * N) : 0;
+  }
+  float acc[4][PQ];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int q = 0; q < PQ; ++q) acc[c][q] = 0.f;
+  fill(0, 0);
+  int buf = 0;
+  for (int ci0 = 0; ci0 < Cin; ci0 += CIT, buf ^= 1) {
+    if (ci0 + CIT < Cin) {
+      fill(buf ^ 1, ci0 + CIT);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
+    const float* sin = sm + buf * stage;
+    const float* sw = sin + in_floats;
+    const int nci = Cin - ci0 < CIT ? Cin - ci0 : CIT;
+    for (int ci = 0; ci < nci; ++ci) {
+      const float* xi = sin + ci * NPP;
+      const float4* wp = reinterpret_cast<const float4*>(sw + ci * 9 * COT + 4 * ty);
+#pragma unroll
+      for (int kj = 0; kj < 3; ++kj)
+#pragma unroll
+        for (int ki = 0; ki < 3; ++ki) {
+          const float4 wv = wp[(kj * 3 + ki) * (COT / 4)];
+          const int off = kj * NP + ki;
+#pragma unroll
+          for (int q = 0; q < PQ; ++q) {
+            const float x = xi[base[q] + off];
+            acc[0][q] = fmaf(wv.x, x, acc[0][q]);
+            acc[1][q] = fmaf(wv.y, x, acc[1][q]);
+            acc[2][q] = fmaf(wv.z, x, acc[2][q]);
+            acc[3][q] = fmaf(wv.w, x, acc[3][q]);
+          }
+        }
+    }
+    __syncthreads();   // this stage is refilled by the next iteration's prefetch
   }
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    int p = tid + q * 128;
-    if (p < N2) {
+  for (int c = 0; c < 4; ++c) {
+    const int co = co0 + 4 * ty + c;
+    if (co < Cout) {
+      const float sc = scale[co], sh = shift[co];
 #pragma unroll
-      for (int c = 0; c < COT; ++c) {
-        int co = co0 + c;
-        if (co < Cout) {
-          size_t o = ((size_t)b * Cout + co) * N2 + p;
-          float y = acc[c][q] * scale[co] + shift[co];
+      for (int q = 0; q < PQ; ++q) {
+        const int p = p0 + tx + 16 * q;
+        if (p < N2) {
+          const size_t o = ((size_t)b * Cout + co) * N2 + p;
+          float y = acc[c][q] * sc + sh;
           if (res) y += res[o];
           if (relu) y = fmaxf(y, 0.f);
           out[o] = y;
@@ -369,13 +427,14 @@ long long nn_f32_launches_per_forward(const NNet* n) { return 1 + 2 * n->s.tower
 // plain launch of the fp32 convolution for other translation units (train.cu: forward and data-gradient convolutions)
 int conv3x3_f32_launch(const float* in, const float* w, const float* scale, const float* shift, const float* res, float* out, int B, int Cin,
                        int Cout, int N, int relu, cudaStream_t s) {
-  const size_t smem = (size_t)(CIT * (N + 2) * (N + 2) + COT * CIT * 9) * sizeof(float);
+  const size_t smem = conv_f32_smem(N);
   static int attr_n = -1;
   if (attr_n != N) {
     if (cudaFuncSetAttribute(conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     attr_n = N;
   }
-  conv3x3_f32_kernel<<<dim3(B, (Cout + COT - 1) / COT), 128, smem, s>>>(in, w, scale, shift, res, out, Cin, Cout, N, relu);
+  const int chunks = conv_f32_chunks(N);
+  conv3x3_f32_kernel<<<dim3(B * chunks, (Cout + COT - 1) / COT), CONV_THREADS, smem, s>>>(in, w, scale, shift, res, out, Cin, Cout, N, relu, chunks);
   return (int)cudaGetLastError();
 }
 
@@ -386,14 +445,14 @@ static int upload_f32_weights(NNet* n, cudaStream_t s) {
   if (nn_fold_layers(n, convs, err, sizeof(err), true)) return (int)cudaErrorInvalidValue;
   for (size_t l = 0; l < convs.size(); ++l) {
     const ConvLayerHost& L = convs[l];
-    // device layout w[co][ci][t], t = kj*3 + ki for the input offset (dj, di) = (kj-1, ki-1):
+    // device layout w[ci][t][co] (output channel fastest), t = kj*3 + ki for the input offset (dj, di) = (kj-1, ki-1):
     // Flux Conv is a true convolution, so tap (ki, kj) of the correlation uses W[2-ki, 2-kj]
     std::vector<float> w((size_t)L.cout * L.cin * 9);
     for (int co = 0; co < L.cout; ++co)
       for (int ci = 0; ci < L.cin; ++ci)
         for (int kj = 0; kj < 3; ++kj)
           for (int ki = 0; ki < 3; ++ki)
-            w[((size_t)co * L.cin + ci) * 9 + kj * 3 + ki] = L.w[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)L.cin * co];
+            w[((size_t)ci * 9 + kj * 3 + ki) * L.cout + co] = L.w[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)L.cin * co];
     cudaMemcpyAsync(n->f_w[l], w.data(), w.size() * 4, cudaMemcpyHostToDevice, s);
     cudaStreamSynchronize(s);
   }
@@ -411,17 +470,18 @@ int nn_forward_f32(NNet* n, const float* feats, int B, float* pi, float* v, cuda
   }
   for (int i = 0; i < 3; ++i)
     if (!n->f_act[i]) CUDA_TRY(cudaMalloc((void**)&n->f_act[i], (size_t)n->max_batch * C * N2 * sizeof(float)));
-  const size_t smem = (size_t)(CIT * (N + 2) * (N + 2) + COT * CIT * 9) * sizeof(float);
+  const size_t smem = conv_f32_smem(N);
   CUDA_TRY(cudaFuncSetAttribute(conv3x3_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(B, (C + COT - 1) / COT);
+  const int chunks = conv_f32_chunks(N);
+  dim3 grid(B * chunks, (C + COT - 1) / COT);
   if (ev) cudaEventRecord(ev[0], s);
-  conv3x3_f32_kernel<<<grid, 128, smem, s>>>(feats, n->f_w[0], n->f_scale[0], n->f_shift[0], nullptr, n->f_act[0], n->s.planes, C, N, 1);
+  conv3x3_f32_kernel<<<grid, CONV_THREADS, smem, s>>>(feats, n->f_w[0], n->f_scale[0], n->f_shift[0], nullptr, n->f_act[0], n->s.planes, C, N, 1, chunks);
   if (ev) cudaEventRecord(ev[1], s);
   float *h = n->f_act[0], *t1 = n->f_act[1], *t2 = n->f_act[2];
   const int n_blocks = (dbg && dbg->n_blocks >= 0 && dbg->n_blocks < n->s.tower) ? dbg->n_blocks : n->s.tower;
   for (int t = 0; t < n_blocks; ++t) {
-    conv3x3_f32_kernel<<<grid, 128, smem, s>>>(h, n->f_w[1 + 2 * t], n->f_scale[1 + 2 * t], n->f_shift[1 + 2 * t], nullptr, t1, C, C, N, 1);
-    conv3x3_f32_kernel<<<grid, 128, smem, s>>>(t1, n->f_w[2 + 2 * t], n->f_scale[2 + 2 * t], n->f_shift[2 + 2 * t], h, t2, C, C, N, 1);
+    conv3x3_f32_kernel<<<grid, CONV_THREADS, smem, s>>>(h, n->f_w[1 + 2 * t], n->f_scale[1 + 2 * t], n->f_shift[1 + 2 * t], nullptr, t1, C, C, N, 1, chunks);
+    conv3x3_f32_kernel<<<grid, CONV_THREADS, smem, s>>>(t1, n->f_w[2 + 2 * t], n->f_scale[2 + 2 * t], n->f_shift[2 + 2 * t], h, t2, C, C, N, 1, chunks);
     float* tmp = h; h = t2; t2 = tmp;
   }
   if (ev) cudaEventRecord(ev[2], s);

@@ -12,7 +12,7 @@
 // autograd), "parity unpinned" by the reference itself.
 //
 // This is the caller-side row of SURVEY 8(f), not the self-play hot path: a step is one 32-position minibatch per game
-// (train.jl:68), ~0.01 % of the loop's arithmetic, so the kernels are plain fp32 SIMT (the convolutions reuse the tiled
+// (train.jl:68), ~0.01 % of the loop's arithmetic, so the kernels are fp32 SIMT (the convolutions reuse the register-tiled
 // fp32 kernel of the cross-check path for forward and data gradients; the weight gradient has its own tiled kernel).
 // Parameters live in three flat device buffers in Flux `params` order (what save_model writes, train.jl:27-33).
 #include <math.h>
@@ -26,7 +26,7 @@
 
 namespace agz {
 
-// fp32 3x3 convolution of the cross-check path (nn_f32.cu): out = relu?(scale * corr(in, w) + shift (+ res)) with
+// w[ci][t][co] (output channel fastest), t = kj*3 + ki = correlation tap (dj, di) = (kj-1, ki-1)
 // w[co][ci][t], t = kj*3 + ki = correlation tap (dj, di) = (kj-1, ki-1)
 int conv3x3_f32_launch(const float* in, const float* w, const float* scale, const float* shift, const float* res, float* out, int B, int Cin,
                        int Cout, int N, int relu, cudaStream_t s);
@@ -56,27 +56,29 @@ struct TrainState {
   // backward scratch
   float *dA, *dS, *dT, *dZ;         // [B][C][N2]
   float *dhz, *dha, *dhid, *dlogit, *dvpre;
-  float *wc, *wd, *dwc;             // reordered weights / weight gradient of the current layer [C][C][9]
+  float *wc, *wd, *dwc, *dwpart;    // reordered weights / weight gradient of the current layer [C][C][9]; its WG_SPLIT partial sums
   float *ones, *zeros;              // [C]
   float *red;                       // small reduction scratch
   bool dirty;                       // device parameters are newer than the host copy in NNet
 };
 
 // ------------------------------------------------------------------------------------------------ small kernels
-// Flux W[a + 3b + 9ci + 9Cin*co] (true convolution) -> correlation layout w[co][ci][kj*3+ki] with (ki, kj) = (2-a, 2-b)
+// Flux W[a + 3b + 9ci + 9Cin*co] (true convolution) -> correlation layout of the fp32 convolution kernel (nn_f32.cu):
+// w[ci][kj*3+ki][co] (output channel fastest) with (ki, kj) = (2-a, 2-b)
 __global__ void k_flux_to_corr(const float* __restrict__ W, float* __restrict__ wc, int Cin, int Cout) {
   const size_t total = (size_t)Cout * Cin * 9;
   for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x) {
-    const int t = (int)(x % 9), ci = (int)((x / 9) % Cin), co = (int)(x / ((size_t)9 * Cin));
+    const int co = (int)(x % Cout), t = (int)((x / Cout) % 9), ci = (int)(x / ((size_t)9 * Cout));
     const int kj = t / 3, ki = t % 3;
     wc[x] = W[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)Cin * co];
   }
 }
-// data-gradient weights: dx = corr(dz, wd) with wd[ci][co][t] = wc[co][ci][8 - t]
+// data-gradient weights: dx = corr(dz, wd), a convolution from Cout to Cin channels whose weight for (input co, tap t, output ci) is
+// the forward weight of (ci, tap 8 - t, co): wd[co][t][ci] (its output channel ci fastest)
 __global__ void k_flux_to_dgrad(const float* __restrict__ W, float* __restrict__ wd, int Cin, int Cout) {
   const size_t total = (size_t)Cout * Cin * 9;
   for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x) {
-    const int t = (int)(x % 9), co = (int)((x / 9) % Cout), ci = (int)(x / ((size_t)9 * Cout));
+    const int ci = (int)(x % Cin), t = (int)((x / Cin) % 9), co = (int)(x / ((size_t)9 * Cin));
     const int t2 = 8 - t, kj = t2 / 3, ki = t2 % 3;
     wd[x] = W[(size_t)(2 - ki) + 3 * (2 - kj) + 9 * (size_t)ci + 9 * (size_t)Cin * co];
   }
@@ -187,45 +189,120 @@ __global__ void k_add(float* __restrict__ y, const float* __restrict__ x, size_t
 }
 
 // weight gradient of a 3x3 convolution in correlation layout: dwc[co][ci][t] = sum_b sum_p dz[b][co][p] * in[b][ci][p + off(t)]
-static const int WG_CO = 16, WG_CI = 16;
-__global__ void __launch_bounds__(256) k_conv_wgrad(const float* __restrict__ in, const float* __restrict__ dz, float* __restrict__ dwc, int B,
-                                                    int Cin, int Cout, int N) {
+// A CTA of 128 threads owns 32 output x 16 input channels; a thread owns 2 x 2 channels and all 9 taps (36 accumulators).  Walking
+// a board row, the 3 x 3 input window slides: each step loads one new column (3 values per input channel) and one gradient per
+// output channel -- 8 shared loads per 36 FMAs (the one-pair-per-thread loop this replaced did 10 per 9).  The tiles of the next
+// board travel by cp.async while the current one is accumulated.  590 k outputs at 36 per thread are only 512 warps, so the batch is
+// split WG_SPLIT ways over gridDim.z into partial sums that k_wgrad_reduce adds in a fixed order (deterministic).
+static const int WG_CO = 32, WG_CI = 16, WG_THREADS = 128, WG_SPLIT = 4;
+static size_t wgrad_stage(int N) { return (size_t)((WG_CI * (N + 2) * (N + 2) + 8 + 3) / 4 * 4 + WG_CO * N * N); }   // floats per stage
+static size_t wgrad_smem(int N) { return 2 * wgrad_stage(N) * sizeof(float); }
+
+__device__ __forceinline__ void wg_cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+}
+
+__global__ void __launch_bounds__(WG_THREADS) k_conv_wgrad(const float* __restrict__ in, const float* __restrict__ dz, float* __restrict__ part,
+                                                           int B, int Cin, int Cout, int N) {
   extern __shared__ float sm[];
   const int N2 = N * N, NP = N + 2, NPP = NP * NP;
-  float* sin = sm;               // [WG_CI][NPP] zero halo
-  float* sdz = sm + WG_CI * NPP; // [WG_CO][N2]
+  const int in_floats = (WG_CI * NPP + 8 + 3) / 4 * 4, stage = in_floats + WG_CO * N2;
+  const float inv_n = 1.0f / (float)N;
   const int co0 = blockIdx.x * WG_CO, ci0 = blockIdx.y * WG_CI, tid = threadIdx.x;
-  const int co = tid / WG_CI, ci = tid % WG_CI;   // 16 x 16 threads, 9 taps each
-  float acc[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-  for (int b = 0; b < B; ++b) {
-    for (int x = tid; x < WG_CI * NPP; x += 256) {
-      const int c = x / NPP, r = x % NPP, jj = r / NP - 1, ii = r % NP - 1;
-      float val = 0.f;
-      if (ci0 + c < Cin && ii >= 0 && ii < N && jj >= 0 && jj < N) val = in[((size_t)b * Cin + ci0 + c) * N2 + jj * N + ii];
-      sin[x] = val;
-    }
-    for (int x = tid; x < WG_CO * N2; x += 256) {
-      const int c = x / N2, p = x % N2;
-      sdz[x] = co0 + c < Cout ? dz[((size_t)b * Cout + co0 + c) * N2 + p] : 0.f;
-    }
-    __syncthreads();
-    const float* xi = sin + ci * NPP;
-    const float* dzo = sdz + co * N2;
-    for (int jj = 0; jj < N; ++jj)
-      for (int ii = 0; ii < N; ++ii) {
-        const float g = dzo[jj * N + ii];
-#pragma unroll
-        for (int kj = 0; kj < 3; ++kj)
-#pragma unroll
-          for (int ki = 0; ki < 3; ++ki) acc[kj * 3 + ki] = fmaf(g, xi[(jj + kj) * NP + (ii + ki)], acc[kj * 3 + ki]);
+  const int per = (B + (int)gridDim.z - 1) / (int)gridDim.z, b_lo = blockIdx.z * per, b_hi = min(B, b_lo + per);
+  const int tc = tid >> 3, ti = tid & 7;   // output channels co0 + 2*tc + {0,1}, input channels ci0 + 2*ti + {0,1}
+  for (int x = tid; x < 2 * stage; x += WG_THREADS) sm[x] = 0.f;   // halos, the 8 floats past the last board, channels past Cin / Cout
+  __syncthreads();
+  auto fill = [&](int buf, int b) {
+    float* sin = sm + buf * stage;   // [WG_CI][NPP] zero halo (+ 8 zero floats: the sliding window reads up to 2 columns past a row)
+    float* sdz = sin + in_floats;    // [WG_CO][N2]
+    for (int c = 0; c < WG_CI && ci0 + c < Cin; ++c) {
+      const float* src = in + ((size_t)b * Cin + ci0 + c) * N2;
+      for (int p = tid; p < N2; p += WG_THREADS) {
+        const int jj = __float2int_rz(((float)p + 0.5f) * inv_n), ii = p - jj * N;
+        wg_cp_async4(sin + c * NPP + (jj + 1) * NP + ii + 1, src + p);
       }
-    __syncthreads();
-  }
-  if (co0 + co < Cout && ci0 + ci < Cin) {
+    }
+    for (int c = 0; c < WG_CO && co0 + c < Cout; ++c) {
+      const float* src = dz + ((size_t)b * Cout + co0 + c) * N2;
+      for (int p = tid; p < N2; p += WG_THREADS) wg_cp_async4(sdz + c * N2 + p, src + p);
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  float acc[2][2][9];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) dwc[((size_t)(co0 + co) * Cin + ci0 + ci) * 9 + t] = acc[t];
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[a][c][t] = 0.f;
+  if (b_lo < b_hi) fill(0, b_lo);
+  for (int b = b_lo; b < b_hi; ++b) {
+    const int buf = (b - b_lo) & 1;
+    if (b + 1 < b_hi) {
+      fill(buf ^ 1, b + 1);
+      asm volatile("cp.async.wait_group 1;");
+    } else {
+      asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();
+    const float* x0 = sm + buf * stage + (2 * ti) * NPP;
+    const float* x1 = x0 + NPP;
+    const float* g0 = sm + buf * stage + in_floats + (2 * tc) * N2;
+    const float* g1 = g0 + N2;
+    for (int jj = 0; jj < N; ++jj) {
+      const float* r0 = x0 + jj * NP;
+      const float* r1 = x1 + jj * NP;
+      float w0[2][3], w1[2][3], w2[2][3];   // window columns [input channel][kj]
+#pragma unroll
+      for (int kj = 0; kj < 3; ++kj) {
+        w0[0][kj] = r0[kj * NP]; w0[1][kj] = r1[kj * NP];
+        w1[0][kj] = r0[kj * NP + 1]; w1[1][kj] = r1[kj * NP + 1];
+      }
+#define AGZ_WG_STEP(II, CA, CB, CC)                                                                \
+      {                                                                                            \
+        _Pragma("unroll") for (int kj = 0; kj < 3; ++kj) { CC[0][kj] = r0[kj * NP + (II) + 2]; CC[1][kj] = r1[kj * NP + (II) + 2]; } \
+        if ((II) < N) {                                                                            \
+          const float ga = g0[jj * N + (II)], gb = g1[jj * N + (II)];                              \
+          _Pragma("unroll") for (int c = 0; c < 2; ++c)                                            \
+          _Pragma("unroll") for (int kj = 0; kj < 3; ++kj) {                                       \
+            acc[0][c][kj * 3 + 0] = fmaf(ga, CA[c][kj], acc[0][c][kj * 3 + 0]);                    \
+            acc[0][c][kj * 3 + 1] = fmaf(ga, CB[c][kj], acc[0][c][kj * 3 + 1]);                    \
+            acc[0][c][kj * 3 + 2] = fmaf(ga, CC[c][kj], acc[0][c][kj * 3 + 2]);                    \
+            acc[1][c][kj * 3 + 0] = fmaf(gb, CA[c][kj], acc[1][c][kj * 3 + 0]);                    \
+            acc[1][c][kj * 3 + 1] = fmaf(gb, CB[c][kj], acc[1][c][kj * 3 + 1]);                    \
+            acc[1][c][kj * 3 + 2] = fmaf(gb, CC[c][kj], acc[1][c][kj * 3 + 2]);                    \
+          }                                                                                        \
+        }                                                                                          \
+      }
+      for (int ii = 0; ii < N; ii += 3) {
+        AGZ_WG_STEP(ii, w0, w1, w2)
+        AGZ_WG_STEP(ii + 1, w1, w2, w0)
+        AGZ_WG_STEP(ii + 2, w2, w0, w1)
+      }
+#undef AGZ_WG_STEP
+    }
+    __syncthreads();   // this stage is refilled by the next iteration's prefetch
+  }
+  float* dst = part + (size_t)blockIdx.z * Cout * Cin * 9;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int co = co0 + 2 * tc + a, ci = ci0 + 2 * ti + c;
+      if (co < Cout && ci < Cin) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) dst[((size_t)co * Cin + ci) * 9 + t] = acc[a][c][t];
+      }
+    }
+}
+
+// dwc = ((part0 + part1) + part2) + part3
+__global__ void k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dwc, size_t n, int splits) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float a = part[i];
+    for (int k = 1; k < splits; ++k) a += part[(size_t)k * n + i];
+    dwc[i] = a;
   }
 }
 
@@ -395,7 +472,7 @@ void train_destroy(TrainState* t) {
   cudaFree(t->hid); cudaFree(t->vout); cudaFree(t->logits); cudaFree(t->prob); cudaFree(t->d_pi); cudaFree(t->d_z);
   cudaFree(t->dA); cudaFree(t->dS); cudaFree(t->dT); cudaFree(t->dZ);
   cudaFree(t->dhz); cudaFree(t->dha); cudaFree(t->dhid); cudaFree(t->dlogit); cudaFree(t->dvpre);
-  cudaFree(t->wc); cudaFree(t->wd); cudaFree(t->dwc); cudaFree(t->ones); cudaFree(t->zeros); cudaFree(t->red);
+  cudaFree(t->wc); cudaFree(t->wd); cudaFree(t->dwc); cudaFree(t->dwpart); cudaFree(t->ones); cudaFree(t->zeros); cudaFree(t->red);
   delete t;
 }
 
@@ -436,7 +513,7 @@ TrainState* train_create(const NNet* n, int max_batch, char* err, size_t errlen)
   ok = ok && dm(&t->hid, B * 256) && dm(&t->vout, B) && dm(&t->logits, B * A) && dm(&t->prob, B * A) && dm(&t->d_pi, B * A) && dm(&t->d_z, B);
   ok = ok && dm(&t->dA, B * C * N2) && dm(&t->dS, B * C * N2) && dm(&t->dT, B * C * N2) && dm(&t->dZ, B * C * N2);
   ok = ok && dm(&t->dhz, B * 3 * N2) && dm(&t->dha, B * 3 * N2) && dm(&t->dhid, B * 256) && dm(&t->dlogit, B * A) && dm(&t->dvpre, B);
-  ok = ok && dm(&t->wc, 9 * C * C) && dm(&t->wd, 9 * C * C) && dm(&t->dwc, 9 * C * C) && dm(&t->ones, C) && dm(&t->zeros, C) && dm(&t->red, (size_t)8);
+  ok = ok && dm(&t->wc, 9 * C * C) && dm(&t->wd, 9 * C * C) && dm(&t->dwc, 9 * C * C) && dm(&t->dwpart, (size_t)WG_SPLIT * 9 * C * C) && dm(&t->ones, C) && dm(&t->zeros, C) && dm(&t->red, (size_t)8);
   if (!ok) { snprintf(err, errlen, "device allocation for training failed (batch %d)", max_batch); train_destroy(t); return nullptr; }
   std::vector<float> one(C, 1.f);
   cudaMemcpy(t->ones, one.data(), C * sizeof(float), cudaMemcpyHostToDevice);
@@ -588,7 +665,7 @@ static int train_step_core(TrainState* t, int B, float eta, float rho, float* lo
   float* Pb = t->P[0];
   float* Gb = t->G[0];
   cudaMemsetAsync(t->red, 0, 8 * sizeof(float), s);
-  const size_t wsm = (size_t)(WG_CI * (N + 2) * (N + 2) + WG_CO * N2) * sizeof(float);
+  const size_t wsm = wgrad_smem(N);
   cudaFuncSetAttribute(k_conv_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm);
 
   // ---- forward, train mode (neural_net.jl:57-68 with train = true)
@@ -666,7 +743,8 @@ static int train_step_core(TrainState* t, int B, float eta, float rho, float* lo
     k_bn_bwd_reduce<<<C, 256, 0, s>>>(dout, t->a[l], t->z[l], mean, inv, B, C, N2, Gb + o.beta, Gb + o.gamma);
     k_bn_bwd_apply<<<grid_for(act), 256, 0, s>>>(dout, t->a[l], t->z[l], mean, inv, Pb + o.gamma, Gb + o.beta, Gb + o.gamma, t->dZ, gshort, B, C, N2);
     k_channel_sum<<<C, 256, 0, s>>>(t->dZ, B, C, N2, Gb + o.b);
-    k_conv_wgrad<<<dim3((C + WG_CO - 1) / WG_CO, (o.cin + WG_CI - 1) / WG_CI), 256, wsm, s>>>(in, t->dZ, t->dwc, B, o.cin, C, N);
+    k_conv_wgrad<<<dim3((C + WG_CO - 1) / WG_CO, (o.cin + WG_CI - 1) / WG_CI, WG_SPLIT), WG_THREADS, wsm, s>>>(in, t->dZ, t->dwpart, B, o.cin, C, N);
+    k_wgrad_reduce<<<grid_for((size_t)9 * o.cin * C), 256, 0, s>>>(t->dwpart, t->dwc, (size_t)9 * o.cin * C, WG_SPLIT);
     k_corr_to_flux<<<grid_for((size_t)9 * o.cin * C), 256, 0, s>>>(t->dwc, Gb + o.W, o.cin, C);
     if (din) {
       k_flux_to_dgrad<<<grid_for((size_t)9 * o.cin * C), 256, 0, s>>>(Pb + o.W, t->wd, o.cin, C);
