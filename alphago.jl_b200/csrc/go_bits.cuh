@@ -24,6 +24,7 @@ namespace agz {
 struct BitsCtx {
   int N, KB, lane;
   uint32_t full;  // all on-board bits of this lane's line, 0 for lanes >= N
+  float inv_n;    // 1 / N: flat point -> line without an integer division (bits_point)
 };
 
 struct Lines {
@@ -36,7 +37,15 @@ AGZ_DEV BitsCtx bits_ctx(int N, int KB) {
   B.KB = KB;
   B.lane = simt::lane();
   B.full = B.lane < N ? ((1u << N) - 1u) : 0u;
+  B.inv_n = 1.0f / (float)N;
   return B;
+}
+
+// line j and position i of flat point c = N*j + i (c < 2^20): (c + 0.5) / N is at least 0.5 / N away from an integer, so the rounded
+// float product truncates to the exact quotient
+AGZ_DEV void bits_point(const BitsCtx& B, int c, int& cj, int& ci) {
+  cj = (int)(((float)c + 0.5f) * B.inv_n);
+  ci = c - cj * B.N;
 }
 
 // line `lane` of a stored bitplane (KB words, flat bit p = N*j + i)
@@ -162,7 +171,8 @@ AGZ_DEV uint32_t bits_lowest(const BitsCtx& B, uint32_t x, unsigned nonzero_lane
 AGZ_DEV int bits_play(const BitsCtx& B, Lines& L, int c, int color, bool check_legal, int& ko_out, int& ncap_out) {
   ko_out = -1;
   ncap_out = 0;
-  const int cj = c / B.N, ci = c - cj * B.N;
+  int cj, ci;
+  bits_point(B, c, cj, ci);
   const uint32_t cbit = B.lane == cj ? (1u << ci) : 0u;
   uint32_t mine = color == 1 ? L.b : L.w, opp = color == 1 ? L.w : L.b;
   if (check_legal && simt::any(((mine | opp) & cbit) != 0u)) return 1;

@@ -169,7 +169,8 @@ struct Warp {
   Lines pos;     // the position being worked on: this lane's board line of black / white stones (go_bits.cuh)
   char* smem;    // per-warp scratch of the shared-memory rules code (go_rules.cuh; liberty-cache hook only)
   GameState st;  // register copy (warp-uniform); written back by store_state()
-  size_t nbase;
+  unsigned nbase;   // first node of this game's arena: all arenas together hold < 2^31 nodes (a node is > 400 bytes), so node indices are
+                    // 32-bit and only the final products are widened (one IMAD.WIDE instead of 64-bit adds and multiplies)
   bool prefetch;  // latency mode (few trees per SM): pull the most-visited child's rows into L2 while this level is scored
 
   AGZ_DEV Warp(const Cfg& c_, const View& v_, int g_, char* smem_) : c(c_), v(v_), g(g_), lane(simt::lane()), smem(smem_) {
@@ -177,7 +178,7 @@ struct Warp {
     pos.b = 0;
     pos.w = 0;
     st = v.gs[g];
-    nbase = (size_t)g * c.cap;
+    nbase = (unsigned)g * (unsigned)c.cap;
     prefetch = false;
   }
   AGZ_DEV void store_state() {
@@ -185,8 +186,8 @@ struct Warp {
     if (lane == 0) v.gs[g] = st;
   }
   // AS = 32*KA and the bit planes' node stride 3*KA are compile-time constants here (the planes themselves sit KB words apart)
-  AGZ_DEV size_t row(int node) const { return (nbase + node) * (size_t)(KA * 32); }
-  AGZ_DEV uint32_t* bits_of(int node) const { return v.bits + (nbase + node) * (size_t)(3 * KA); }
+  AGZ_DEV size_t row(int node) const { return (size_t)(nbase + (unsigned)node) * (unsigned)(KA * 32); }
+  AGZ_DEV uint32_t* bits_of(int node) const { return v.bits + (size_t)(nbase + (unsigned)node) * (unsigned)(3 * KA); }
   // element `idx` of a per-lane register array, as a select chain (a dynamically indexed array would be spilled to local memory)
   template <class T>
   AGZ_DEV static T pick(const T (&a)[KA], int idx) {
@@ -198,14 +199,14 @@ struct Warp {
   AGZ_DEV NodeMeta load_meta(int node) const {
 #if AGZ_CUDA
     NodeMeta m;   // one 16-byte load instead of a load per field
-    *reinterpret_cast<uint4*>(&m) = *reinterpret_cast<const uint4*>(v.meta + nbase + node);
+    *reinterpret_cast<uint4*>(&m) = *reinterpret_cast<const uint4*>(v.meta + (nbase + (unsigned)node));
     return m;
 #else
     return v.meta[nbase + node];
 #endif
   }
   AGZ_DEV bool terminal(const NodeMeta& m) const { return (m.flags & F_DONE) || m.n >= c.max_game_length; }
-  AGZ_DEV PathEnt* path_of(int k) const { return v.path + ((size_t)g * c.pmax + k) * c.maxd; }
+  AGZ_DEV PathEnt* path_of(int k) const { return v.path + (size_t)((unsigned)g * (unsigned)c.pmax + (unsigned)k) * (unsigned)c.maxd; }
   AGZ_DEV void count(int which, unsigned long long n) {
     if (lane == 0) simt::atomic_add(&v.ctr[which], n);
   }
@@ -501,18 +502,17 @@ struct Warp {
           U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_SELECT, (uint32_t)move_no, sel_idx, (uint32_t)depth);
           pick = (int)simt::mulhi(rr.x, (uint32_t)total);
         }
+        // the pick-th tied child in action order: every lane ranks its own candidates (ties before it in its word + the words before)
         best = pass;
-        bool found = false;
+        {
+          const unsigned lt = (1u << lane) - 1u;
+          int before = 0;
 #pragma unroll
-        for (int k = 0; k < KA; ++k) {
-          int cntk = simt::popc(tm[k]);
-          if (!found) {
-            if (pick < cntk) {
-              best = k * 32 + nth_set_bit(tm[k], pick);
-              found = true;
-            } else {
-              pick -= cntk;
-            }
+          for (int k = 0; k < KA; ++k) {
+            const bool it = ((tm[k] >> lane) & 1u) != 0u && before + simt::popc(tm[k] & lt) == pick;
+            const unsigned who = simt::ballot(it);
+            if (who) best = k * 32 + simt::ffs(who) - 1;
+            before += simt::popc(tm[k]);
           }
         }
       }
