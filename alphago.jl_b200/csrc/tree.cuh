@@ -502,18 +502,20 @@ struct Warp {
           U4 rr = rng_draw(c.seed, st.game_id_lo, SITE_SELECT, (uint32_t)move_no, sel_idx, (uint32_t)depth);
           pick = (int)simt::mulhi(rr.x, (uint32_t)total);
         }
-        // the pick-th tied child in action order: every lane ranks its own candidates (ties before it in its word + the words before)
-        best = pass;
+        // the pick-th tied child in action order: every lane ranks its own candidates (ties before it in its word + the words before);
+        // exactly one (lane, word) has rank `pick`, found with one warp maximum
         {
           const unsigned lt = (1u << lane) - 1u;
           int before = 0;
+          unsigned mine = 0u;   // action + 1 of this lane's candidate with rank `pick`, or 0
 #pragma unroll
           for (int k = 0; k < KA; ++k) {
             const bool it = ((tm[k] >> lane) & 1u) != 0u && before + simt::popc(tm[k] & lt) == pick;
-            const unsigned who = simt::ballot(it);
-            if (who) best = k * 32 + simt::ffs(who) - 1;
+            mine = it ? (unsigned)(k * 32 + lane + 1) : mine;
             before += simt::popc(tm[k]);
           }
+          const unsigned hit = simt::reduce_max(mine);
+          best = hit ? (int)hit - 1 : pass;
         }
       }
       const int ok = best >> 5, ol = best & 31;
