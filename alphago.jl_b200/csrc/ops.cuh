@@ -52,7 +52,7 @@ struct SelectOp {
       w.st.nleaf = 0;
       w.st.seed_round = 0;
     }
-    w.store_state();
+    w.store_hot();
   }
 };
 
@@ -68,13 +68,13 @@ struct IncorporateOp {
     Warp<KA> w(c, v, g, smem);
     w.search_incorporate();
     if (only_slot < 0 && w.after_round_due()) {
-      w.store_state();
+      w.store_hot();
       simt::sync();
       after_round_cold<KA>(&c, &v, g, smem);
       w.st = v.gs[g];
     }
     w.st.seed_round = 0;
-    w.store_state();
+    w.store_hot();
   }
 };
 
@@ -179,7 +179,7 @@ struct DummyRoundsOp {
       simt::sync();  // the leaf records written by lane 0 are read by every lane below
       w.search_incorporate();
       if (w.after_round_due()) {
-        w.store_state();
+        w.store_hot();
         simt::sync();
         after_round_cold<KA>(&c, &v, g, smem);
         w.st = v.gs[g];
@@ -187,7 +187,7 @@ struct DummyRoundsOp {
       w.st.seed_round = 0;
       if (w.st.phase == PH_IDLE) break;
     }
-    w.store_state();
+    w.store_hot();
   }
 };
 

@@ -48,21 +48,28 @@ struct alignas(16) PathEnt {  // 16 bytes; where this path node's own N / W live
   int32_t to_play;
 };
 
-struct GameState {
-  int32_t phase, root, count, err;
-  float root_N, root_W, target_N;
-  int32_t n_moves;       // plies recorded for the current game
-  uint32_t sel_ctr, noise_ctr;
-  uint32_t game_id_lo;
-  int32_t hist_len;
-  double resign_thr;
-  int64_t game_id;
+struct alignas(16) GameState {
+  // written by every search round: the first 32 bytes, stored as two 16-byte words (Warp::store_hot) so that the fields below do
+  // not have to stay live in registers through the search kernels
+  float root_N, root_W;
+  int32_t count, err;
+  uint32_t sel_ctr;
   int32_t nleaf, seed_round;
   int32_t vloss_balance;  // path entries with a virtual loss outstanding
+  // read by the search, written by the per-move logic
+  int32_t phase, root;
+  float target_N;
+  uint32_t game_id_lo;
+  // per-move logic only
+  int32_t n_moves;       // plies recorded for the current game
+  uint32_t noise_ctr;
+  int32_t hist_len;
   int32_t result, resigned;
   float final_score;
   int32_t delay;          // PH_DELAY: rounds left before the first game of this slot starts
   int32_t pad;
+  double resign_thr;
+  int64_t game_id;
 };
 
 struct Cfg {
@@ -184,6 +191,15 @@ struct Warp {
   AGZ_DEV void store_state() {
     simt::sync();
     if (lane == 0) v.gs[g] = st;
+  }
+  // what a search round changes (the leading 32 bytes of GameState)
+  AGZ_DEV void store_hot() {
+    simt::sync();
+    if (lane == 0) {
+      GameState* d = v.gs + g;
+      d->root_N = st.root_N; d->root_W = st.root_W; d->count = st.count; d->err = st.err;
+      d->sel_ctr = st.sel_ctr; d->nleaf = st.nleaf; d->seed_round = st.seed_round; d->vloss_balance = st.vloss_balance;
+    }
   }
   // AS = 32*KA and the bit planes' node stride 3*KA are compile-time constants here (the planes themselves sit KB words apart)
   AGZ_DEV size_t row(int node) const { return (size_t)(nbase + (unsigned)node) * (unsigned)(KA * 32); }
