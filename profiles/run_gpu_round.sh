@@ -9,7 +9,7 @@ T0=$(date +%s)
 stamp() { echo "$1 rc=$2 $(( $(date +%s)-T0 ))s" | tee -a $O/${TAG}_times.log; }
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; stamp pytest $?
 tail -3 $O/${TAG}_pytest.log
-timeout 500 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; stamp bench $?
+timeout 600 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; stamp bench $?
 timeout 300 python bench.py --steps 6 --warmup 3 --no-legs --no-cpu-baseline --precision 2 > $O/${TAG}_bench_split.json 2> $O/${TAG}_bench_split.err; stamp bench_split $?
 if [ "$2" != "skip-ncu" ]; then
 # launch list of one steady-state step: skip the burn-in (112 steps x 50 rounds x 17 launches + gathers) by counting from the end is not
@@ -26,6 +26,7 @@ ncu -i $R/tree_c5.ncu-rep --page source --csv --print-source sass > $O/${TAG}_tr
 gzip -f $O/${TAG}_*_source_*.csv
 stamp export 0
 fi
+timeout 120 python profiles/train_probe.py > $O/${TAG}_train.jsonl 2>&1; stamp train $?
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python profiles/sanitize_probe.py nn > $O/${TAG}_sanitizer_memcheck.log 2>&1; stamp memcheck $?
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python profiles/sanitize_probe.py > $O/${TAG}_sanitizer_racecheck.log 2>&1; stamp racecheck $?
 tail -2 $O/${TAG}_sanitizer_memcheck.log $O/${TAG}_sanitizer_racecheck.log

@@ -25,6 +25,19 @@ for N, ro, cap in ((9, 24, 0), (19, 16, 0), (9, 16, 60)):
     eng.replay_sample_hist(4, seed=1)
     print(N, ro, cap, "games", len(recs), "moves", sum(r.n_moves for r in recs), "tuples", n, flush=True)
     eng.close()
+# Gomoku (the second game of the Position interface): whole games, replay packing
+eng = agz.Engine(9, n_games=4, readouts=16, seed=2, game=agz.GAME_GOMOKU, n_in_row=5)
+eng.set_dummy_evaluator(None, 0.0)
+eng.selfplay_start(4)
+for _ in range(4000):
+    pr = eng.selfplay_step(16)
+    n = eng.replay_gather()
+    eng.selfplay_harvest(8)
+    if pr.games_finished == 4 or pr.error:
+        break
+assert pr.error == 0 and pr.games_finished == 4
+print("gomoku ok", n, flush=True)
+eng.close()
 eng = agz.Engine(9, n_games=3, readouts=16, tau_threshold=-1, inject_noise=0)
 eng.set_dummy_evaluator(None, 0.0)
 eng.match_start()
