@@ -13,6 +13,8 @@ Pinning status
   reference's own unit tests (`test/test_go.jl`, `test/test_mcts.jl`,
   `test/test_mcts_player.jl`, `test/test_features.jl`) in
   `tests/test_oracle_*.py`.
+* Gomoku (`gomoku.py`, dispatched by `game.py` like the reference's `Position` interface): the reference has no test for
+  this game; pinned only by hand-checked cases derived from src/game/gomoku/board.jl (`tests/test_oracle_gomoku.py`).
 * Random draws (tie-breaks, Dirichlet noise, soft-pick): the reference draws
   from Julia's global RNG (MersenneTwister + Distributions.jl) which cannot be
   reproduced here (no Julia).  The oracle and the engine share ONE explicit
