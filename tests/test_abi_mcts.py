@@ -429,6 +429,73 @@ def test_selfplay_matches_oracle_bulk():
     check_selfplay_parity(env19, 19, 16, seeds=[4], n_games=2, max_game_length=60)
 
 
+@pytest.mark.gpu
+def test_19x19_sharp_policy_long_game():
+    """19x19, 800 readouts, a sharp (one-hot-like) prior that sends nearly every readout down one line, so the
+    re-used subtree keeps ~800 nodes per move.  (i) With the default arena (worst case max_game_length * (readouts + 2 * parallel))
+    60 moves are played without error or pruning and the first moves equal the oracle's bit for bit; (ii) with an arena of one move
+    worth (+ 150 nodes) the game still plays its 60 moves: the least-visited nodes are forgotten (arena_prunes > 0), every move is legal."""
+    N, R, L = 19, 800, 60
+    A_ = N * N + 1
+    pri = np.full(A_, 1e-5, f32)
+    pri[3 * N + 3] = 1.0
+    pri[15 * N + 15] = 0.5
+    pri /= pri.sum()
+    net = DummyNet(A_, fake_priors=pri, fake_value=0.2)
+    oenv = ogo.GoEnv(N)
+    lib = lib_for("cuda")
+    eng = agz.Engine(N, lib_path=lib, n_games=2, readouts=R, seed=3, max_game_length=L)
+    eng.set_dummy_evaluator(pri, 0.2)
+    eng.selfplay_start(2)
+    for _ in range(400):
+        pr = eng.selfplay_step(100)
+        if pr.games_finished == 2:
+            break
+    assert pr.games_finished == 2 and pr.error == 0 and pr.arena_prunes == 0
+    recs = sorted(eng.selfplay_harvest(4), key=lambda r: r.game_id)
+    eng.close()
+    assert all(r.n_moves == L or r.resigned for r in recs)
+    OM.MAX_GAME_LENGTH_OVERRIDE = L
+    try:
+        class Stop(Exception):
+            pass
+
+        moves_checked = 3
+        seen = []
+
+        def on_move(player, move):
+            seen.append(player)
+            if len(player.searches_pi) >= moves_checked:
+                raise Stop()
+
+        try:
+            osp.selfplay(oenv, net, R, seed=3, game_id=0, on_move=on_move)
+        except Stop:
+            pass
+        op = seen[-1]
+        r = recs[0]
+        k = min(moves_checked, r.n_moves)
+        assert [ogo.to_flat(m.move, oenv) for m in op.root.position.recent][:k] == list(r.moves[:k])
+        assert np.array_equal(np.array(op.searches_N[:k]), r.visits[:k])
+        assert np.array_equal(np.array(op.searches_pi[:k], dtype=f32), r.searches_pi[:k])
+    finally:
+        OM.MAX_GAME_LENGTH_OVERRIDE = None
+    small = agz.Engine(N, lib_path=lib, n_games=2, readouts=R, seed=3, max_game_length=L, nodes_per_game=R + 20 + 150)
+    small.set_dummy_evaluator(pri, 0.2)
+    small.selfplay_start(2)
+    for _ in range(400):
+        pr = small.selfplay_step(100)
+        if pr.games_finished == 2:
+            break
+    assert pr.games_finished == 2 and pr.error == 0 and pr.arena_prunes > 0
+    for r in small.selfplay_harvest(4):
+        pos = ogo.GoPosition(oenv)
+        for m in r.moves:
+            pos = ogo.play_move(pos, ogo.from_flat(int(m), oenv))      # raises IllegalMove on an illegal move
+        assert r.n_moves == L or r.resigned or pos.done
+    small.close()
+
+
 # ------------------------------------------------------------ BASELINE full size (C2): size-independent properties
 @pytest.mark.gpu
 def test_c2_full_size_properties():
