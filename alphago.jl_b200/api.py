@@ -483,7 +483,9 @@ def _bind(eng, net):
         eng.set_evaluator(B.EVAL_DUMMY)
 
 
-def _score_string(s):
+def _score_string(s, env=None):
+    if isinstance(env, GomokuEnv):                          # result_string of src/game/gomoku/board.jl:184-193
+        return "B" if s > 0 else ("W" if s < 0 else "DRAW")
     return "B+%.1f" % s if s > 0 else ("W+%.1f" % abs(s) if s < 0 else "DRAW")
 
 
@@ -522,7 +524,7 @@ def evaluate(env, black_net, white_net, num_games=400, ro=800, verbose=False, se
                 games[g].moves.append(int(mv[g]))
             for g in np.flatnonzero(alive & done):                  # is_done(active) (:140-146)
                 games[g].result = 1 if sc[g] > 0 else (-1 if sc[g] < 0 else 0)
-                games[g].result_string = _score_string(float(sc[g]))
+                games[g].result_string = _score_string(float(sc[g]), env)
                 black_score[g] = sc[g]
                 alive[g] = False
             num_move += 1

@@ -103,12 +103,14 @@ def test_training_reduces_the_loss_on_a_fixed_batch():
     eng.close()
 
 
-def test_train_loop_selfplay_replay_train(tmp_path):
+@pytest.mark.parametrize("game", ["go", "gomoku"])
+def test_train_loop_selfplay_replay_train(tmp_path, game):
     """train(env; ...) (src/train.jl:38-92): self-play fills the replay ring, every finished game triggers one optimisation step on
-    a uniform batch once `start_training_after` tuples are there, checkpoints go through save_model."""
+    a uniform batch once `start_training_after` tuples are there, checkpoints go through save_model.  Both games of the reference's
+    GameEnv (GoEnv, GomokuEnv) go through the same loop."""
     lib_for("cuda")
     from alphago_jl_b200 import weights_io
-    env = agz.GoEnv(5)
+    env = agz.GoEnv(5) if game == "go" else agz.GomokuEnv(6, 4)
     nn0 = agz.NeuralNet(env, tower_height=1, seed=2)
     before = [np.concatenate([a.flatten(order="F") for a in lst]) for lst in nn0.params]
     nn = agz.train(env, num_games=24, batch_size=16, readouts=16, tower_height=1, model=nn0, start_training_after=40, concurrent=8,
