@@ -49,13 +49,15 @@ struct alignas(16) PathEnt {  // 16 bytes; where this path node's own N / W live
 };
 
 struct alignas(16) GameState {
-  // written by every search round: the first 32 bytes, stored as two 16-byte words (Warp::store_hot) so that the fields below do
-  // not have to stay live in registers through the search kernels
+  // written by every search round: the first 48 bytes (Warp::store_hot), so that the fields below do not have to stay live in
+  // registers through the search kernels
   float root_N, root_W;
   int32_t count, err;
   uint32_t sel_ctr;
   int32_t nleaf, seed_round;
   int32_t vloss_balance;  // path entries with a virtual loss outstanding
+  int32_t tiny_values;    // an evaluator value with 0 < |v| < 2^-70 was incorporated: the PUCT quotients take the IEEE divisions
+  int32_t hot_pad[3];
   // read by the search, written by the per-move logic
   int32_t phase, root;
   float target_N;
@@ -192,13 +194,14 @@ struct Warp {
     simt::sync();
     if (lane == 0) v.gs[g] = st;
   }
-  // what a search round changes (the leading 32 bytes of GameState)
+  // what a search round changes (the leading fields of GameState)
   AGZ_DEV void store_hot() {
     simt::sync();
     if (lane == 0) {
       GameState* d = v.gs + g;
       d->root_N = st.root_N; d->root_W = st.root_W; d->count = st.count; d->err = st.err;
       d->sel_ctr = st.sel_ctr; d->nleaf = st.nleaf; d->seed_round = st.seed_round; d->vloss_balance = st.vloss_balance;
+      d->tiny_values = st.tiny_values;
     }
   }
   // AS = 32*KA and the bit planes' node stride 3*KA are compile-time constants here (the planes themselves sit KB words apart)
@@ -460,14 +463,13 @@ struct Warp {
         double rc[KA];
         // Take the IEEE divisions when a divisor could lie past the table -- N(child) <= N(node) in a search, only the test hooks
         // (PH_MANUAL trees, agz_tree_set_stats) can break that -- or when a Float32 quotient could be subnormal (0 < |w| < 2^-100).
-        bool odd = st.phase == PH_MANUAL || !(simt::fadd(cur_N, 2.0f) < (float)v.rcp_n);
-        unsigned tiny = 0u;
+        // The latter is decided per game, not per child: every W is a sum of +-1 (virtual losses, game results) and evaluator
+        // values; as long as every non-zero value seen had |v| >= 2^-70 all of them are multiples of 2^-93, and so is every
+        // rounded partial sum (exact below 2^-69, a multiple of a larger ulp above), hence no non-zero W lies below 2^-93.
+        // search_incorporate raises st.tiny_values on the first smaller value and the game takes the IEEE path from then on.
+        const bool odd = st.phase == PH_MANUAL || st.tiny_values != 0 || !(simt::fadd(cur_N, 2.0f) < (float)v.rcp_n);
 #pragma unroll
-        for (int k = 0; k < KA; ++k) {
-          den[k] = simt::fadd(1.0f, n[k]);
-          tiny |= ((simt::fbits(w[k]) << 1) - 1u) < ((27u << 24) - 1u) ? 1u : 0u;   // exponent field below 27 and not +-0
-        }
-        odd = odd || simt::any(tiny != 0u);
+        for (int k = 0; k < KA; ++k) den[k] = simt::fadd(1.0f, n[k]);
         double s[KA];
         double mx = -1.0e300;
         if (!odd) {
@@ -672,6 +674,7 @@ struct Warp {
         const bool dup = (flags & F_EXPANDED) != 0 || same != 0u;   // already expanded (:197-200): revert_visits!
         n_dup += dup ? 1 : 0;
         if (!dup) {
+          if (((simt::fbits(value) << 1) - 1u) < ((57u << 24) - 1u)) st.tiny_values = 1;   // 0 < |value| < 2^-70 (select_leaf)
           if (lane == 0) v.meta[nbase + leaf].flags = (uint8_t)(flags | F_EXPANDED);
           const float* probs = v.eval_pi + b * v.pi_stride + lane;
           const size_t r = row(leaf) + lane;
@@ -1097,6 +1100,7 @@ struct Warp {
     st.n_moves = 0;
     st.nleaf = 0;
     st.vloss_balance = 0;
+    st.tiny_values = 0;
     st.err = 0;
     st.result = 0;
     st.resigned = 0;

@@ -366,6 +366,13 @@ def test_selfplay_parity_sweep():
                 check_selfplay_parity(e, N, ro, seeds=[seed], priors_seed=ps, value=val, n_games=ng)
 
 
+def test_tiny_evaluator_values_take_the_exact_division_path(env):
+    """The reciprocal-table quotients are exact only while W / (1 + N) stays a normal Float32; an evaluator value below 2^-70 flags
+    the game (GameState.tiny_values) and its PUCT scores use IEEE divisions from then on.  1e-35 / k reaches the subnormals."""
+    check_selfplay_parity(env, 9, 16, seeds=[4], priors_seed=9, value=1e-35, n_games=2)
+    check_selfplay_parity(env, 9, 16, seeds=[4], priors_seed=9, value=-3e-41, n_games=2)
+
+
 def test_selfplay_concurrent_games_match_oracle(env):
     check_selfplay_parity(env, 9, 16, seeds=[3], n_games=3)
 
