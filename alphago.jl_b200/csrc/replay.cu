@@ -182,6 +182,7 @@ static int grow(unsigned char** p, size_t* cap, size_t need) {
   *cap = 0;   // a failed allocation must not leave a stale capacity behind a null pointer
   size_t n = need + need / 2 + 4096;
   if (cudaMalloc((void**)p, n) != cudaSuccess) return 1;
+  cudaMemset(*p, 0, n);   // tuples are padded to 16 bytes: the padding travels with every copy and must not be uninitialised memory
   *cap = n;
   return 0;
 }

@@ -28,6 +28,8 @@ stamp export 0
 fi
 timeout 120 python profiles/train_probe.py > $O/${TAG}_train.jsonl 2>&1; stamp train $?
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python profiles/sanitize_probe.py nn > $O/${TAG}_sanitizer_memcheck.log 2>&1; stamp memcheck $?
+timeout 600 compute-sanitizer --tool synccheck --error-exitcode 9 python profiles/sanitize_probe.py nn > $O/${TAG}_sanitizer_synccheck.log 2>&1; stamp synccheck $?
+timeout 600 compute-sanitizer --tool initcheck --error-exitcode 9 python profiles/sanitize_probe.py nn > $O/${TAG}_sanitizer_initcheck.log 2>&1; stamp initcheck $?
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python profiles/sanitize_probe.py > $O/${TAG}_sanitizer_racecheck.log 2>&1; stamp racecheck $?
 tail -2 $O/${TAG}_sanitizer_memcheck.log $O/${TAG}_sanitizer_racecheck.log
 cat $O/${TAG}_bench.json | cut -c1-300; cat $O/${TAG}_bench_split.json | cut -c1-200
