@@ -321,6 +321,7 @@ extern "C" int32_t agz_engine_create(const agz_config* cfg, agz_engine** out) {
   rc |= dalloc(e, &v.ring_pi, (size_t)c.ring_cap * L * c.A);
   rc |= dalloc(e, &v.ring_vis, (size_t)c.ring_cap * L * c.A);
   rc |= dalloc(e, &v.ctr, (size_t)CTR_COUNT);
+  rc |= dalloc(e, &v.noise_g, G * c.AS);
   // rcp[k] = RN(1/k): the PUCT score divides by 1 + N(child), and N(child) never exceeds the visits a game can accumulate on one
   // line (max_game_length searches of readouts + 2*parallel visits); larger divisors (test hooks) take the IEEE-division path
   {

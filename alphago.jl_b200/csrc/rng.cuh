@@ -81,21 +81,25 @@ AGZ_DEV double det_pow(double x, double y) {
 }
 
 // Gamma(alpha, 1), 0 < alpha < 1: Ahrens & Dieter (1974) GS.  Counter = (action, (noise_call << 16) | attempt).
+// One attempt: x = the candidate, returns whether it is accepted (b = 1 + alpha / e).
+AGZ_DEV bool gamma_small_attempt(double alpha, double b, uint64_t seed, uint32_t game_id, uint32_t move_no, uint32_t a, uint32_t noise_call,
+                                 uint32_t t, double& x) {
+  U4 r = rng_draw(seed, game_id, SITE_NOISE, move_no, a, (noise_call << 16) | t);
+  double u1 = u52c(r.x, r.y), u2 = u52c(r.z, r.w);
+  double p = simt::dmul(b, u1);
+  if (p <= 1.0) {
+    x = det_exp(simt::ddiv(det_log(p), alpha));
+    return u2 <= det_exp(-x);
+  }
+  x = -det_log(simt::ddiv(simt::dsub(b, p), alpha));
+  return u2 <= det_exp(simt::dmul(simt::dsub(alpha, 1.0), det_log(x)));
+}
+// the sampler: at most 64 attempts (the last candidate is returned if none was accepted)
 AGZ_DEV double gamma_small(double alpha, uint64_t seed, uint32_t game_id, uint32_t move_no, uint32_t a, uint32_t noise_call) {
   const double b = simt::dadd(1.0, simt::ddiv(alpha, 2.718281828459045));
   double x = 0.0;
-  for (uint32_t t = 0; t < 64; ++t) {
-    U4 r = rng_draw(seed, game_id, SITE_NOISE, move_no, a, (noise_call << 16) | t);
-    double u1 = u52c(r.x, r.y), u2 = u52c(r.z, r.w);
-    double p = simt::dmul(b, u1);
-    if (p <= 1.0) {
-      x = det_exp(simt::ddiv(det_log(p), alpha));
-      if (u2 <= det_exp(-x)) return x;
-    } else {
-      x = -det_log(simt::ddiv(simt::dsub(b, p), alpha));
-      if (u2 <= det_exp(simt::dmul(simt::dsub(alpha, 1.0), det_log(x)))) return x;
-    }
-  }
+  for (uint32_t t = 0; t < 64; ++t)
+    if (gamma_small_attempt(alpha, b, seed, game_id, move_no, a, noise_call, t, x)) return x;
   return x;
 }
 

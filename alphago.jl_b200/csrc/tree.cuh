@@ -124,6 +124,7 @@ struct View {
   float *ring_q, *ring_pi, *ring_vis;
   unsigned long long* ctr;
   unsigned long long* trace;  // kernel timeline trace buffer (simt.h) or nullptr
+  double* noise_g;            // [slot][AS] scratch of inject_noise!: the gamma variates of the Dirichlet draw
   const double* rcp;          // rcp[k] = RN(1/k), k in [1, rcp_n): the divisor 1 + N(child) of the PUCT score is a small integer
   int rcp_n;
 };
@@ -734,6 +735,35 @@ struct Warp {
     const size_t r = row(st.root);
     const uint32_t move_no = (uint32_t)load_meta(st.root).n;
     const uint32_t call = st.noise_ctr++;
+    // The A gamma variates are rejection samples whose draws are keyed by (action, attempt), not by lane, so the lanes share them
+    // as a work list: a lane that gets its variate accepted takes the next unassigned action.  A fixed three-actions-per-lane
+    // split runs 3 x (the slowest of 32 rejection loops) attempts; this runs ~A x 1.35 / 32.  This is most of the per-move tail
+    // of the incorporate kernel (the warps of games that do not move have long finished).
+    double* gs = v.noise_g + (size_t)g * (KA * 32);
+    {
+      const double b = simt::dadd(1.0, simt::ddiv(c.noise_alpha, 2.718281828459045));
+      const unsigned lt = (1u << lane) - 1u;
+      int a = lane, next = 32;
+      uint32_t t = 0;
+      for (;;) {
+        const bool have = a < c.A;
+        if (!simt::any(have)) break;
+        bool fin = false;
+        if (have) {
+          double x = 0.0;
+          fin = gamma_small_attempt(c.noise_alpha, b, c.seed, st.game_id_lo, move_no, (uint32_t)a, call, t, x) || t == 63;
+          ++t;
+          if (fin) gs[a] = x;
+        }
+        const unsigned done = simt::ballot(fin);
+        if (fin) {
+          a = next + simt::popc(done & lt);
+          t = 0;
+        }
+        next += simt::popc(done);
+      }
+      simt::sync();
+    }
     double gm[KA];
     double acc = 0.0;
 #pragma unroll
@@ -741,7 +771,7 @@ struct Warp {
       int a = k * 32 + lane;
       gm[k] = 0.0;
       if (a < c.A) {
-        gm[k] = gamma_small(c.noise_alpha, c.seed, st.game_id_lo, move_no, (uint32_t)a, call);
+        gm[k] = gs[a];
         acc = simt::dadd(acc, gm[k]);
       }
     }
