@@ -36,7 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 BOARD, GAMES, READOUTS, TOWER, ROUNDS_PER_STEP = 9, 1024, 400, 6, 50
 METRIC = "self-play moves/sec (9x9, 400 readouts)"
 # DRAM bytes per tower-conv launch (8192 positions) from the committed ncu --set full capture of this workload
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 0.5 * ((340.96 + 300.13) + (680.70 + 313.13)) * 1e6
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 0.5 * ((341.14 + 299.02) + (680.71 + 314.34)) * 1e6
 
 
 def peaks():
@@ -362,7 +362,7 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "conv3x3_tc5_kernel / conv3x3_tc6_kernel (tower 3x3 conv 256->256, fp16 tcgen05 cta_group::2 + TMA im2col; tc6 = second conv of a block, shortcut tile by TMA)",
                          "measured_in": "CUDA events around every kernel, sequential schedule, %d steps of the same workload right after the timed region" % min(2, args.steps), "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
                          "frac": achieved / tf_sus, "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH if args.games == GAMES else None,
-                         "traffic_detail": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full on this workload (profiles/r01_conv3x3_tc_ncu_full.md): tc5 341.0 + 300.1 MB, tc6 680.7 + 313.1 MB, mean of the two; algorithmic 680 / 1020 MB",
+                         "traffic_detail": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full on this workload (profiles/r02_conv_raw.csv): tc5 341.1 + 299.0 MB, tc6 680.7 + 314.3 MB, mean of the two; algorithmic 680 / 1020 MB",
                          "peak_source": src + " bf16 sustained",
                          "flops_per_launch": conv_flops_pos * rows, "ms_per_launch": conv_ms},
             "kernel_ms_per_round": {n: kms[i] / max(1, kln[0]) for i, n in enumerate(agz.binding.KERNEL_NAMES)},
